@@ -1,0 +1,142 @@
+// Flat-arena optimiser step: global grad L2 norm -> clip -> Adam, plus the fp32 -> bf16 (hi, lo) split.
+// Replaces torch.nn.utils.clip_grad_norm_ (ctools/torch_utils/grad_clip.py:141-144) + torch.optim.Adam.step
+// (rl_learner.py:73-80,132: betas (0, 0.99), eps 1e-5, no weight decay) — ~1.2 k foreach launches in the
+// reference — by two streaming passes over one contiguous fp32 arena; the DP average 1/world of
+// DistModule.sync_gradients (ctools/utils/dist_helper.py:421-431) is folded into the same pass.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kPartials = 1024;
+constexpr int kThreads = 256;
+
+__global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ partial) {
+    float acc = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = n / 4;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = g4[i];
+        acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc += g[i] * g[i];
+    __shared__ float red[kThreads / 32];
+    acc = dsb::warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < kThreads / 32; ++i) t += red[i];
+        partial[blockIdx.x] = t;
+    }
+}
+
+__global__ void norm_finish_kernel(const float* __restrict__ partial, int np, float* __restrict__ norm_out) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) acc += (double)partial[i];
+    __shared__ double red[32];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+        norm_out[0] = (float)sqrt(t);
+    }
+}
+
+__device__ __forceinline__ void split_store(float x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t i) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, const float* __restrict__ norm, float max_norm,
+                            float grad_scale, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
+                            __nv_bfloat16* __restrict__ sh, __nv_bfloat16* __restrict__ sl) {
+    float scale = grad_scale;
+    if (norm) {
+        // clip_grad_norm_: clip_coef = max_norm / (total_norm + 1e-6), clamped to 1
+        const float total = norm[0] * grad_scale;
+        scale *= fminf(1.0f, max_norm / (total + 1e-6f));
+    }
+    const float step_size = lr / bc1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gi = g[i] * scale;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        const float pi = p[i] - step_size * (mi / denom);
+        p[i] = pi;
+        if (sh) split_store(pi, sh, sl, i);
+    }
+}
+
+__global__ void split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                             __nv_bfloat16* __restrict__ lo, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = n / 4;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    uint2* h2 = reinterpret_cast<uint2*>(hi);
+    uint2* l2 = reinterpret_cast<uint2*>(lo);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = x4[i];
+        const __nv_bfloat162 ha = __floats2bfloat162_rn(v.x, v.y), hb = __floats2bfloat162_rn(v.z, v.w);
+        const float2 fa = __bfloat1622float2(ha), fb = __bfloat1622float2(hb);
+        const __nv_bfloat162 la = __floats2bfloat162_rn(v.x - fa.x, v.y - fa.y);
+        const __nv_bfloat162 lb = __floats2bfloat162_rn(v.z - fb.x, v.w - fb.y);
+        h2[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
+        l2[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
+    }
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        split_store(x[i], hi, lo, i);
+}
+
+inline unsigned grid_for(int64_t n, int per_thread) {
+    int64_t blocks = (n / per_thread + kThreads - 1) / kThreads;
+    const int64_t cap = 148 * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+}  // namespace
+
+extern "C" int dsb_sumsq_partials(void) { return kPartials; }
+
+extern "C" int dsb_grad_norm(const float* grad, int64_t n, float* partial, float* norm_out, dsb_stream_t stream) {
+    DSB_REQUIRE(grad && partial && norm_out && n > 0, "grad_norm: bad argument");
+    DSB_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0, "grad_norm: grad must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    sumsq_kernel<<<kPartials, kThreads, 0, s>>>(grad, n, partial);
+    int rc = dsb::check_launch("grad_norm/sumsq");
+    if (rc) return rc;
+    norm_finish_kernel<<<1, 256, 0, s>>>(partial, kPartials, norm_out);
+    return dsb::check_launch("grad_norm/finish");
+}
+
+extern "C" int dsb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                             const float* norm, float max_norm, float grad_scale, float lr, float beta1, float beta2,
+                             float eps, int t, void* shadow_hi, void* shadow_lo, dsb_stream_t stream) {
+    DSB_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && t >= 1, "adam_step: bad argument");
+    DSB_REQUIRE(!shadow_hi == !shadow_lo, "adam_step: shadow_hi and shadow_lo go together");
+    const float bc1 = 1.0f - powf(beta1, (float)t);
+    const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)t));
+    adam_kernel<<<grid_for(n, 4), kThreads, 0, (cudaStream_t)stream>>>(
+        param, grad, exp_avg, exp_avg_sq, n, norm, max_norm, grad_scale, lr, beta1, beta2, eps, bc1, bc2_sqrt,
+        (__nv_bfloat16*)shadow_hi, (__nv_bfloat16*)shadow_lo);
+    return dsb::check_launch("adam_step");
+}
+
+extern "C" int dsb_split_bf16(const float* x, void* hi, void* lo, int64_t n, dsb_stream_t stream) {
+    DSB_REQUIRE(x && hi && lo && n >= 0, "split_bf16: bad argument");
+    if (n == 0) return DSB_OK;
+    DSB_REQUIRE(((reinterpret_cast<uintptr_t>(x) & 15) | (reinterpret_cast<uintptr_t>(hi) & 7) |
+                 (reinterpret_cast<uintptr_t>(lo) & 7)) == 0, "split_bf16: misaligned pointer");
+    split_kernel<<<grid_for(n, 8), kThreads, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
+    return dsb::check_launch("split_bf16");
+}

@@ -1,0 +1,220 @@
+"""``Model`` — drop-in for ``distar.agent.default.model.Model`` (DI-star model/model.py:22-189).
+
+Same constructor, method names, keyword arguments, returned dict keys and ``state_dict`` keys as the reference,
+so ``Agent`` (agent.py:127,312,503,725,737), ``RLLearner._train`` (rl_learner.py:102) and ``SLLearner._train``
+(sl_learner.py:50) can use it unchanged.  Internals are B200-first:
+
+* all trainable parameters live in ONE contiguous fp32 arena (``flat_param``) with a matching gradient arena
+  (``flat_grad``); the per-tensor ``nn.Parameter`` objects the reference API exposes are views into them.  The
+  data-parallel exchange is therefore a single NCCL all-reduce of ``flat_grad`` (dist.py) and the optimiser a
+  two-kernel pass over the arena (ops.FlatAdam) instead of 394-894 per-tensor calls.
+* the compute is ``policy_net.Net`` driving the sm_100a kernels of libdistar_b200.so.
+"""
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .constants import SELECTED_UNITS_ACTION_MASK
+from .params import init_state_dict
+from .policy_net import BASELINE_ATAN, HEADS, MAX_SELECTED_UNITS_NUM, Net
+from .spec import BASELINES, is_trainable, param_specs
+
+
+class _Node(nn.Module):
+    """Anonymous container used to rebuild the reference's module tree from dotted state_dict names."""
+
+
+def _cfg_get(cfg, path, default):
+    cur = cfg
+    for k in path.split('.'):
+        if isinstance(cur, dict) and k in cur:
+            cur = cur[k]
+        elif hasattr(cur, k) and not isinstance(cur, dict):
+            cur = getattr(cur, k)
+        else:
+            return default
+    return cur
+
+
+class _Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+def _to_cfg(d):
+    return _Cfg({k: _to_cfg(v) for k, v in d.items()}) if isinstance(d, dict) else d
+
+
+class Model(nn.Module):
+    def __init__(self, cfg={}, use_value_network=False, temperature=None, seed: Optional[int] = None,
+                 gemm_terms: int = 3, sample_rng: str = 'cuda'):
+        super().__init__()
+        sx = int(_cfg_get(cfg, 'model.spatial_x', 160))
+        sy = int(_cfg_get(cfg, 'model.spatial_y', 152))
+        self.spatial_x, self.spatial_y = sx, sy
+        self.temperature = float(temperature if temperature is not None else _cfg_get(cfg, 'model.temperature', 1.0))
+        if _cfg_get(cfg, 'learner.use_value_feature', False):
+            raise NotImplementedError('use_value_feature=True (ValueEncoder) is outside the hot-path scope')
+        enabled = list(_cfg_get(cfg, 'model.enable_baselines', BASELINES)) if use_value_network else []
+        self.baselines = [b for b in BASELINES if b in enabled]
+        self.only_update_baseline = bool(_cfg_get(cfg, 'model.only_update_baseline', False))
+        self.gemm_terms, self.sample_rng = gemm_terms, sample_rng
+        # attributes callers read (agent.py:107-108,148)
+        self.cfg = _to_cfg({'encoder': {'core_lstm': {'num_layers': 3, 'hidden_size': 384, 'input_size': 1536}},
+                            'temperature': self.temperature, 'spatial_x': sx, 'spatial_y': sy,
+                            'enable_baselines': self.baselines})
+        self._specs = param_specs(sx, sy, self.baselines)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+        sd = init_state_dict(seed, sx, sy, self.baselines, perturb=0.0)
+        n_train = sum(int(torch.tensor(s).prod()) if len(s) else 1 for _, s, k in self._specs if is_trainable(k))
+        self._offsets = {}
+        flat = torch.empty(n_train, dtype=torch.float32)
+        off = 0
+        for name, shape, kind in self._specs:
+            if not is_trainable(kind):
+                continue
+            n = sd[name].numel()
+            off = (off + 3) // 4 * 4          # 16-byte alignment of every tensor inside the arena
+            self._offsets[name] = (off, n, tuple(shape))
+            off += n
+        flat = torch.zeros(off, dtype=torch.float32)
+        self._arena_numel = off
+        object.__setattr__(self, '_flat_param', flat)
+        object.__setattr__(self, '_flat_grad', torch.zeros_like(flat))
+        self._params: Dict[str, nn.Parameter] = {}
+        for name, shape, kind in self._specs:
+            node = self
+            parts = name.split('.')
+            for p in parts[:-1]:
+                if not hasattr(node, p):
+                    node.add_module(p, _Node())
+                node = getattr(node, p)
+            if is_trainable(kind):
+                o, n, shp = self._offsets[name]
+                flat[o:o + n].copy_(sd[name].reshape(-1))
+                prm = nn.Parameter(flat[o:o + n].view(shp))
+            else:
+                prm = nn.Parameter(sd[name], requires_grad=False)
+            node.register_parameter(parts[-1], prm)
+            self._params[name] = prm
+        self.policy.action_type_head.race = 'zerg'          # agent.py:148 sets this attribute
+        self._bind_grads()
+        self._su_mask = torch.tensor(SELECTED_UNITS_ACTION_MASK, dtype=torch.bool)
+
+    # ---------------------------------------------------------------- arena plumbing
+    @property
+    def flat_param(self) -> torch.Tensor:
+        return self._flat_param
+
+    @property
+    def flat_grad(self) -> torch.Tensor:
+        return self._flat_grad
+
+    def _bind_grads(self):
+        for name, (o, n, shp) in self._offsets.items():
+            p = self._params[name]
+            p.data = self._flat_param[o:o + n].view(shp)
+            p.grad = self._flat_grad[o:o + n].view(shp)
+
+    def _apply(self, fn, recurse=True):
+        """Move the arena as a whole (``.cuda()``, ``.to()``, ``.share_memory()``) and re-bind the views."""
+        new_flat = fn(self._flat_param)
+        object.__setattr__(self, '_flat_param', new_flat)
+        object.__setattr__(self, '_flat_grad', torch.zeros_like(new_flat))
+        for name, p in self._params.items():
+            if name not in self._offsets:
+                p.data = fn(p.data)
+        self._bind_grads()
+        self._su_mask = fn(self._su_mask)
+        return self
+
+    def zero_grad(self, set_to_none: bool = False):
+        self._flat_grad.zero_()
+        self._bind_grads()
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        missing, unexpected = [], [k for k in state_dict if k not in self._params]
+        with torch.no_grad():
+            for name, p in self._params.items():
+                if name in state_dict:
+                    p.data.copy_(state_dict[name].to(p.device))
+                else:
+                    missing.append(name)
+        if strict and (missing or unexpected):
+            raise RuntimeError('load_state_dict: missing %s unexpected %s' % (missing[:5], unexpected[:5]))
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    # ---------------------------------------------------------------- compute
+    def _net(self) -> Net:
+        return Net(self._params, self.spatial_x, self.spatial_y, self.temperature, self.gemm_terms, self.sample_rng)
+
+    def forward(self, spatial_info, entity_info, scalar_info, entity_num, hidden_state):
+        """model.py:46-54."""
+        out = self.compute_logp_action(spatial_info, entity_info, scalar_info, entity_num, hidden_state)
+        return out['action_info'], out['selected_units_num'], out['hidden_state']
+
+    def compute_logp_action(self, spatial_info, entity_info, scalar_info, entity_num, hidden_state, **kwargs):
+        """model.py:56-74: encoder -> one LSTM step -> sampling policy -> per-head log-prob of the sample."""
+        net = self._net()
+        lstm_input, scalar_context, _bf, entity_embeddings, map_skip = net.encoder(
+            spatial_info, entity_info, scalar_info, entity_num)
+        lstm_out, out_state = net.lstm('core_lstm', lstm_input.unsqueeze(0), hidden_state, 3)
+        action, su_num, logit, extra = net.policy_sample(lstm_out.squeeze(0), entity_embeddings, map_skip,
+                                                        scalar_context, entity_num, self._su_mask)
+        logp = {}
+        for k, a in action.items():
+            logp[k] = torch.log_softmax(logit[k], dim=-1).gather(-1, a.unsqueeze(-1)).squeeze(-1)
+        return {'action_info': action, 'action_logp': logp, 'selected_units_num': su_num, 'entity_num': entity_num,
+                'hidden_state': out_state, 'logit': logit, 'extra_units': extra}
+
+    def compute_teacher_logit(self, spatial_info, entity_info, scalar_info, entity_num, hidden_state,
+                              selected_units_num, action_info, **kwargs):
+        """model.py:76-93."""
+        net = self._net()
+        lstm_input, scalar_context, _bf, entity_embeddings, map_skip = net.encoder(
+            spatial_info, entity_info, scalar_info, entity_num)
+        lstm_out, out_state = net.lstm('core_lstm', lstm_input.unsqueeze(0), hidden_state, 3)
+        _a, su_num, logit = net.policy_train(lstm_out.squeeze(0), entity_embeddings, map_skip, scalar_context,
+                                             entity_num, action_info, selected_units_num)
+        return {'logit': logit, 'hidden_state': out_state, 'entity_num': entity_num, 'selected_units_num': su_num}
+
+    def rl_learner_forward(self, spatial_info, entity_info, scalar_info, entity_num, hidden_state, action_info,
+                           selected_units_num, behaviour_logp, teacher_logit, mask, reward, step, batch_size,
+                           unroll_len, **kwargs):
+        """model.py:95-168.  Observation rows are time-major [(T+1)*B]; policy runs on the first T*B rows."""
+        net = self._net()
+        B, T = batch_size, unroll_len
+        flat_action = {k: v.flatten(0, 1) for k, v in action_info.items()}
+        flat_su_num = selected_units_num.flatten(0, 1)
+        lstm_input, scalar_context, baseline_feature, entity_embeddings, map_skip = net.encoder(
+            spatial_info, entity_info, scalar_info, entity_num)
+        state0 = [(h.view(-1, B, h.shape[-1])[0], c.view(-1, B, c.shape[-1])[0]) for h, c in hidden_state]
+        lstm_out, _ = net.lstm('core_lstm', lstm_input.view(-1, B, lstm_input.shape[-1]), state0, 3)
+        lstm_out = lstm_out.reshape(-1, lstm_out.shape[-1])
+        _a, _n, logits = net.policy_train(lstm_out[:-B], entity_embeddings[:-B], [m[:-B] for m in map_skip],
+                                          scalar_context[:-B], entity_num[:-B], flat_action, flat_su_num)
+        critic_input = lstm_out.detach() if self.only_update_baseline else lstm_out
+        values = {k: net.value_baseline(k, critic_input).view(T + 1, B) for k in self.baselines}
+        logits = {k: v.view(T, B, *v.shape[1:]) for k, v in logits.items()}
+        su = logits['selected_units']
+        logits['selected_units'] = F.pad(su, (0, 0, 0, MAX_SELECTED_UNITS_NUM - su.shape[2]), 'constant', -1e9)
+        return {'unroll_len': T, 'batch_size': B, 'selected_units_num': selected_units_num,
+                'target_logit': logits, 'value': values, 'action_log_prob': behaviour_logp,
+                'teacher_logit': teacher_logit, 'mask': mask, 'action': action_info, 'reward': reward,
+                'step': step}
+
+    def sl_train(self, spatial_info, entity_info, scalar_info, entity_num, selected_units_num, traj_lens,
+                 hidden_state, action_info, **kwargs):
+        """model.py:170-189 (observation rows batch-major [B*T])."""
+        net = self._net()
+        B = len(traj_lens)
+        lstm_input, scalar_context, _bf, entity_embeddings, map_skip = net.encoder(
+            spatial_info, entity_info, scalar_info, entity_num)
+        x = lstm_input.view(-1, lstm_input.shape[0] // B, lstm_input.shape[-1]).permute(1, 0, 2)
+        lstm_out, out_state = net.lstm('core_lstm', x, hidden_state, 3)
+        lstm_out = lstm_out.permute(1, 0, 2).reshape(-1, lstm_out.shape[-1])
+        action, su_num, logits = net.policy_train(lstm_out, entity_embeddings, map_skip, scalar_context, entity_num,
+                                                  action_info, selected_units_num)
+        return logits, action, out_state

@@ -1,0 +1,441 @@
+"""Host-side dataflow of the AlphaStar policy: encoders -> core LSTM -> auto-regressive heads -> baselines.
+
+This file is the *orchestration* of the hot path: it decides shapes, masks and the
+order of work, and hands the heavy steps to the kernels in ``ops`` (tcgen05 split GEMM for every tileable
+fc_block, scatter_connection, categorical sampling ...).  Steps that have no hand-written kernel yet are
+plain device-side torch calls (cuBLAS / cuDNN / ATen: library code, listed per row in DESIGN.md §coverage).
+Parameters arrive as ``P[name]`` with the reference's state_dict names.
+
+Semantics follow the reference (DI-star ``distar/agent/default/model``) including its quirks:
+  * pooled entity mean uses relu(x) because the reference's shared ReLU is in-place (entity_encoder.py:39,81-85)
+  * effect planes always light flat pixel 0 (zero-padded index lists, spatial_encoder.py:62-69)
+  * (x, y) clamped in the scatter (module_utils.py:18-19); learned end token at slot entity_num
+    (action_arg_head.py:118-129); LSTM carries the layer-normed cell state (lstm.py:150)
+  * teacher-forced selected-units loop runs max(selected_units_num) steps for the whole batch, rows with
+    selected_units_num == 0 are not normalised (action_arg_head.py:179-200); logits padded to 64 with -1e9
+    (model.py:156-158); delay logits are not divided by the temperature (action_arg_head.py:41-47)
+"""
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+Tensor = torch.Tensor
+HEADS = ['action_type', 'delay', 'queued', 'selected_units', 'target_unit', 'target_location']
+MAX_SELECTED_UNITS_NUM = 64
+MAX_ENTITY_NUM = 512
+NUM_ACTIONS = 327
+
+ENTITY_FIELDS = [  # (name, kind, width): actor_critic_default_config.yaml:264-364
+    ('unit_type', 'o', 260), ('alliance', 'o', 5), ('cargo_space_taken', 'o', 9),
+    ('build_progress', 'u', 1), ('health_ratio', 'u', 1), ('shield_ratio', 'u', 1), ('energy_ratio', 'u', 1),
+    ('display_type', 'o', 5), ('x', 'b', 11), ('y', 'b', 11), ('cloak', 'o', 5), ('is_blip', 'o', 2),
+    ('is_powered', 'o', 2), ('mineral_contents', 'u', 1), ('vespene_contents', 'u', 1),
+    ('cargo_space_max', 'o', 9), ('assigned_harvesters', 'o', 24), ('weapon_cooldown', 'o', 32),
+    ('order_length', 'o', 9), ('order_id_0', 'o', 327), ('order_id_1', 'o', 49), ('is_hallucination', 'o', 2),
+    ('buff_id_0', 'o', 50), ('buff_id_1', 'o', 50), ('addon_unit_type', 'o', 9), ('is_active', 'o', 2),
+    ('order_progress_0', 'u', 1), ('order_progress_1', 'u', 1), ('order_id_2', 'o', 49), ('order_id_3', 'o', 49),
+    ('is_in_cargo', 'o', 2), ('attack_upgrade_level', 'o', 4), ('armor_upgrade_level', 'o', 4),
+    ('shield_upgrade_level', 'o', 4), ('last_selected_units', 'o', 2), ('last_targeted_unit', 'o', 2),
+]
+SCALAR_FIELDS = [  # (name, kind, vocab/in, ctx, baseline): yaml:146-219, scalar_encoder.py:99-132
+    ('agent_statistics', 'fc', 10, False, True), ('home_race', 'emb', 5, True, False),
+    ('away_race', 'emb', 5, True, False), ('upgrades', 'fc', 90, False, True),
+    ('unit_counts_bow', 'fc', 260, False, True), ('last_delay', 'emb', 128, False, False),
+    ('last_queued', 'emb', 2, False, False), ('last_action_type', 'emb', 327, False, False),
+    ('cumulative_stat', 'fc', 167, True, True), ('beginning_order', 'bo', 214, True, True),
+    ('unit_type_bool', 'fc', 260, True, False), ('enemy_unit_type_bool', 'fc', 260, True, False),
+    ('unit_order_type', 'fc', 269, True, False),
+]
+SPATIAL_ONEHOT = [('visibility_map', 4), ('creep', 2), ('player_relative', 5), ('alerts', 2), ('pathable', 2),
+                  ('buildable', 2)]
+SPATIAL_EFFECTS = ['effect_PsiStorm', 'effect_NukeDot', 'effect_LiberatorDefenderZone', 'effect_BlindingCloud',
+                   'effect_CorrosiveBile', 'effect_LurkerSpines']
+BASELINE_ATAN = {'winloss': True, 'build_order': False, 'built_unit': False, 'effect': False, 'upgrade': False,
+                 'battle': False}
+
+
+class Net:
+    """Functional network over a parameter mapping.  ``terms`` = products per tensor-core GEMM (3 = fp32-class)."""
+
+    def __init__(self, P: Dict[str, Tensor], spatial_x: int, spatial_y: int, temperature: float = 1.0,
+                 terms: int = 3, rng: str = 'cuda'):
+        self.P, self.W, self.H, self.T, self.terms, self.rng = P, spatial_x, spatial_y, temperature, terms, rng
+
+    # -------------------------------------------------------------------------------------- primitives
+    def fc(self, name: str, x: Tensor, relu: bool = False) -> Tensor:
+        return ops.linear(x, self.P[name + '.0.weight'], self.P[name + '.0.bias'], relu, self.terms)
+
+    def conv(self, name: str, x: Tensor, pad: int, relu: bool = False) -> Tensor:
+        y = F.conv2d(x, self.P[name + '.0.weight'], self.P[name + '.0.bias'], padding=pad)
+        return torch.relu(y) if relu else y
+
+    def ln(self, name: str, x: Tensor) -> Tensor:
+        return F.layer_norm(x, (x.shape[-1],), self.P[name + '.weight'], self.P[name + '.bias'], 1e-5)
+
+    def sample(self, logits: Tensor) -> Tensor:
+        return ops.sample_categorical(logits, rng=self.rng)[0]
+
+    # -------------------------------------------------------------------------------------- transformer
+    def attention(self, pre: str, x: Tensor, key_mask: Optional[Tensor], heads: int, hd: int) -> Tensor:
+        """module_utils.py:88-111."""
+        B, N, _ = x.shape
+        q, k, v = self.fc(pre + '.attention_pre', x).view(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
+        score = torch.matmul(q, k.transpose(2, 3)) / math.sqrt(hd)
+        if key_mask is not None:
+            score = score.masked_fill(~key_mask.view(B, 1, 1, N), -1e9)
+        a = torch.matmul(torch.softmax(score, dim=-1), v).permute(0, 2, 1, 3).reshape(B, N, heads * hd)
+        return self.fc(pre + '.project', a)
+
+    def transformer(self, pre: str, x: Tensor, key_mask, heads: int, hd: int, post_ln: bool) -> Tensor:
+        """module_utils.py:130-151,191-199."""
+        x = self.fc(pre + '.embedding', x, relu=True)
+        for i in range(3):
+            lp = '%s.layers.%d' % (pre, i)
+            if post_ln:
+                x = self.ln(lp + '.layernorm1', x + self.attention(lp + '.attention', x, key_mask, heads, hd))
+                m = self.fc(lp + '.mlp.1', self.fc(lp + '.mlp.0', x, relu=True), relu=True)
+                x = self.ln(lp + '.layernorm2', x + m)
+            else:
+                x = x + self.attention(lp + '.attention', self.ln(lp + '.layernorm1', x), key_mask, heads, hd)
+                x = x + self.fc(lp + '.mlp.1', self.fc(lp + '.mlp.0', self.ln(lp + '.layernorm2', x), relu=True),
+                                relu=True)
+        return x
+
+    # -------------------------------------------------------------------------------------- encoders
+    def scalar_encoder(self, s: Dict[str, Tensor]):
+        """obs_encoder/scalar_encoder.py:99-132 (K8)."""
+        P, pre = self.P, 'encoder.scalar_encoder.encode_modules.'
+        dev = s['time'].device
+        outs, ctx, base = [], [], []
+        for name, kind, din, is_ctx, is_base in SCALAR_FIELDS:
+            if kind == 'emb':
+                e = torch.relu(F.embedding(s[name].long().clamp(max=din - 1), P[pre + name + '.weight']))
+            elif kind == 'fc':
+                e = self.fc(pre + name, s[name].float(), relu=True)
+            else:
+                bo, loc = s['beginning_order'].long(), s['bo_location'].long()
+                B = bo.shape[0]
+                bits = torch.arange(9, -1, -1, device=dev)
+                tok = torch.cat([F.one_hot(bo, 174).float(),
+                                 torch.eye(20, device=dev).unsqueeze(0).expand(B, -1, -1),
+                                 (((loc % self.W).unsqueeze(-1) >> bits) & 1).float(),
+                                 (((loc // self.W).unsqueeze(-1) >> bits) & 1).float()], dim=2)
+                t = self.transformer(pre + 'beginning_order.transformer', tok, None, 2, 8, post_ln=False)
+                e = self.fc(pre + 'beginning_order.embedd_fc', t.mean(dim=1), relu=True)
+            outs.append(e)
+            if is_ctx:
+                ctx.append(e)
+            if is_base:
+                base.append(e)
+        pa = P['encoder.scalar_encoder.position_array']
+        t = s['time'].float().unsqueeze(1)
+        te = torch.stack([torch.sin(t * pa[0::2]), torch.cos(t * pa[1::2])], dim=2).reshape(t.shape[0], -1)
+        outs.append(te)
+        return torch.cat(outs, 1), torch.cat(ctx, 1), torch.cat(base, 1)
+
+    def entity_features(self, e: Dict[str, Tensor], pad_to: int = 1024) -> Tensor:
+        """997-wide expansion of entity_encoder.py:59-78, zero padded to a GEMM-tileable width."""
+        dev = e['x'].device
+        cols = []
+        bits = torch.arange(10, -1, -1, device=dev)
+        for name, kind, w in ENTITY_FIELDS:
+            v = e[name]
+            if kind == 'o':
+                cols.append(F.one_hot(v.long().clamp(max=w - 1), w).float())
+            elif kind == 'b':
+                cols.append(((v.long().unsqueeze(-1) >> bits) & 1).float())
+            else:
+                cols.append(v.float().unsqueeze(-1))
+        width = sum(c.shape[-1] for c in cols)
+        if pad_to > width:
+            cols.append(torch.zeros(*cols[0].shape[:-1], pad_to - width, device=dev))
+        return torch.cat(cols, dim=-1)
+
+    def entity_encoder(self, e: Dict[str, Tensor], entity_num: Tensor):
+        """obs_encoder/entity_encoder.py:59-96 (K1-K4)."""
+        P, pre = self.P, 'encoder.entity_encoder.'
+        for name, kind, w in ENTITY_FIELDS:
+            if kind == 'o' and e[name].dtype in (torch.int8, torch.int16, torch.int32, torch.int64):
+                if bool((e[name] < 0).any()):
+                    raise RuntimeError('negative categorical id in entity field %s' % name)
+        feats = self.entity_features(e)
+        E = feats.shape[1]
+        mask = torch.arange(E, device=feats.device).unsqueeze(0) < entity_num.unsqueeze(1)
+        w = P[pre + 'transformer.embedding.0.weight']
+        w_pad = F.pad(w, (0, feats.shape[-1] - w.shape[1]))
+        x = ops.linear(feats, w_pad, P[pre + 'transformer.embedding.0.bias'], True, self.terms)
+        for i in range(3):
+            lp = '%stransformer.layers.%d' % (pre, i)
+            x = self.ln(lp + '.layernorm1', x + self.attention(lp + '.attention', x, mask, 2, 128))
+            m = self.fc(lp + '.mlp.1', self.fc(lp + '.mlp.0', x, relu=True), relu=True)
+            x = self.ln(lp + '.layernorm2', x + m)
+        x = torch.relu(x)
+        entity_embeddings = self.fc(pre + 'entity_fc', x, relu=True)
+        pooled = (x * mask.unsqueeze(2)).sum(dim=1) / entity_num.unsqueeze(-1)
+        return entity_embeddings, self.fc(pre + 'embed_fc', pooled, relu=True), mask
+
+    def spatial_encoder(self, sp: Dict[str, Tensor], scatter_map: Tensor):
+        """obs_encoder/spatial_encoder.py:51-90 (K7)."""
+        pre = 'encoder.spatial_encoder.'
+        N, H, W = sp['height_map'].shape
+        planes = [sp['height_map'].float().unsqueeze(1) / 256]
+        for name, n in SPATIAL_ONEHOT:
+            planes.append(F.one_hot(sp[name].long(), n).permute(0, 3, 1, 2).float())
+        for name in SPATIAL_EFFECTS:
+            p = torch.zeros(N, H * W, device=scatter_map.device)
+            p.scatter_(1, sp[name].long(), 1.0)
+            planes.append(p.view(N, 1, H, W))
+        planes.append(scatter_map)
+        x = self.conv(pre + 'project', torch.cat(planes, dim=1), 0, relu=True)
+        skips = []
+        for i in range(3):
+            skips.append(x)
+            x = self.conv(pre + 'downsample.%d' % i, F.max_pool2d(x, 2, 2), 1, relu=True)
+        for i in range(4):
+            skips.append(x)
+            r = self.conv(pre + 'res.%d.conv2' % i, self.conv(pre + 'res.%d.conv1' % i, x, 1, relu=True), 1)
+            x = torch.relu(r + x)
+        return self.fc(pre + 'fc', x.reshape(N, -1), relu=True), skips
+
+    def encoder(self, spatial_info, entity_info, scalar_info, entity_num):
+        """model/encoder.py:28-45."""
+        embedded_scalar, scalar_context, baseline_feature = self.scalar_encoder(scalar_info)
+        entity_embeddings, embedded_entity, mask = self.entity_encoder(entity_info, entity_num)
+        project = self.fc('encoder.scatter_project', entity_embeddings, relu=True)
+        scatter_map = ops.scatter_connection(project, entity_info['x'], entity_info['y'], entity_num, self.H, self.W)
+        embedded_spatial, map_skip = self.spatial_encoder(spatial_info, scatter_map)
+        lstm_input = torch.cat([embedded_scalar, embedded_entity, embedded_spatial], dim=-1)
+        return lstm_input, scalar_context, baseline_feature, entity_embeddings, map_skip
+
+    # -------------------------------------------------------------------------------------- LSTM
+    def lstm_cell(self, pre: str, ig: Tensor, h: Tensor, c: Tensor):
+        """LayerNormLSTMCell with the input half (LN_i(x W_ih^T)) precomputed: lstm.py:138-153."""
+        hg = self.ln(pre + '.layernorm_h', h @ self.P[pre + '.weight_hh'].t())
+        i, f, g, o = (ig + hg).chunk(4, 1)
+        c2 = self.ln(pre + '.layernorm_c', torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g))
+        return torch.sigmoid(o) * torch.tanh(c2), c2
+
+    def lstm(self, pre: str, x: Tensor, state: List[Tuple[Tensor, Tensor]], layers: int):
+        """StackedLSTM over [L,B,D] (lstm.py:161-167,223-234).  The input projection of a whole layer is one
+        GEMM over all timesteps (the layer-major loop order of the reference makes that legal)."""
+        out_state = []
+        for l in range(layers):
+            cp = '%s.layers.%d.cell' % (pre, l)
+            L, B, D = x.shape
+            ig = self.ln(cp + '.layernorm_i', ops.linear(x.reshape(L * B, D), self.P[cp + '.weight_ih'], None, False,
+                                                         self.terms)).view(L, B, -1)
+            h, c = state[l]
+            ys = []
+            for t in range(L):
+                h, c = self.lstm_cell(cp, ig[t], h, c)
+                ys.append(h)
+            x = torch.stack(ys)
+            out_state.append((h, c))
+        return x, out_state
+
+    # -------------------------------------------------------------------------------------- heads
+    def glu(self, name: str, x: Tensor, ctx: Tensor) -> Tensor:
+        return self.fc(name + '.layer2', torch.sigmoid(self.fc(name + '.layer1', ctx)) * x)
+
+    def action_type_head(self, lstm_out, scalar_context, action_type=None):
+        """head/action_type_head.py:48-67 (K10)."""
+        pre = 'policy.action_type_head.'
+        x = self.fc(pre + 'project', lstm_out, relu=True)
+        for i in range(2):
+            r = torch.relu(self.ln(pre + 'res.%d.fc1.1' % i, self.fc(pre + 'res.%d.fc1' % i, x)))
+            r = self.ln(pre + 'res.%d.fc2.1' % i, self.fc(pre + 'res.%d.fc2' % i, r))
+            x = torch.relu(r + x)
+        logits = self.glu(pre + 'action_fc', x, scalar_context) / self.T
+        if action_type is None:
+            action_type = self.sample(logits)
+        # one_hot(a) @ W^T == gather of weight columns
+        w1 = self.P[pre + 'action_map_fc1.0.weight']
+        e1 = torch.relu(w1.t()[action_type.long()] + self.P[pre + 'action_map_fc1.0.bias'])
+        e1 = self.glu(pre + 'glu1', self.fc(pre + 'action_map_fc2', e1), scalar_context)
+        return logits, action_type, e1 + self.glu(pre + 'glu2', lstm_out, scalar_context)
+
+    def arg_head(self, pre: str, emb, n: int, use_temperature: bool, action=None):
+        """DelayHead / QueuedHead: head/action_arg_head.py:41-53,73-86 (K11)."""
+        x = self.fc(pre + 'fc3', self.fc(pre + 'fc2', self.fc(pre + 'fc1', emb, relu=True), relu=True))
+        if use_temperature:
+            x = x / self.T
+        if action is None:
+            action = self.sample(x)
+        w1 = self.P[pre + 'embed_fc1.0.weight']
+        e = torch.relu(w1.t()[action.long()] + self.P[pre + 'embed_fc1.0.bias'])
+        return x, action, emb + self.fc(pre + 'embed_fc2', e)
+
+    def su_keys(self, entity_embeddings, entity_num):
+        """_get_key_mask, action_arg_head.py:118-143."""
+        pre = 'policy.selected_units_head.'
+        N, E, _ = entity_embeddings.shape
+        key = self.fc(pre + 'key_fc', entity_embeddings)
+        slot = torch.arange(E + 1, device=key.device).unsqueeze(0)
+        is_end = (slot == entity_num.unsqueeze(1)).unsqueeze(-1)
+        key = torch.where(is_end, self.P[pre + 'end_embedding'].view(1, 1, -1),
+                          F.pad(key, (0, 0, 0, 1)))
+        return key, slot < (entity_num + 1).unsqueeze(1), slot
+
+    def su_embed(self, key, weights, normalise):
+        """masked mean of selected keys -> embed_fc2(relu(embed_fc1)): action_arg_head.py:196-199,290-293.
+        weights [..., E+1] (0/1), key [N,E+1,32]."""
+        pre = 'policy.selected_units_head.'
+        s = torch.matmul(weights, key) if weights.dim() == 3 else (key * weights.unsqueeze(2)).sum(dim=1)
+        cnt = weights.sum(dim=-1, keepdim=True)
+        s = torch.where(normalise, s / cnt, s)
+        return self.fc(pre + 'embed_fc2', self.fc(pre + 'embed_fc1', s, relu=True))
+
+    def selected_units_train(self, emb0, entity_embeddings, entity_num, selected_units_num, selected_units):
+        """Teacher-forced pointer network (action_arg_head.py:168-216) in its step-parallel form
+        (SURVEY.md Appendix B.1): everything but the 32-wide LN-LSTM is computed for all steps at once."""
+        pre = 'policy.selected_units_head.'
+        N = emb0.shape[0]
+        key, valid, slot = self.su_keys(entity_embeddings, entity_num)
+        S = max(int(selected_units_num.max()), 1)
+        su = selected_units[:, :S].long()
+        onehot = su.unsqueeze(-1) == slot.unsqueeze(1)                               # [N,S,E+1]
+        ended = torch.cummax((su == entity_num.unsqueeze(1)).long(), dim=1)[0].bool()  # end_flag after step i
+        picked = torch.cummax((onehot & ~ended.unsqueeze(-1)).long(), dim=1)[0].float()  # cumulative one-hot
+        normalise = (selected_units_num != 0).view(N, 1, 1)
+        emb_steps = emb0.unsqueeze(1) + self.su_embed(key, picked, normalise)         # ae after step i
+        ae = torch.cat([emb0.unsqueeze(1), emb_steps[:, :-1]], dim=1)                 # ae feeding step i
+        q = self.fc(pre + 'query_fc2', self.fc(pre + 'query_fc1', ae, relu=True))     # [N,S,32]
+        cp = pre + 'lstm.layers.0.cell'
+        ig = self.ln(cp + '.layernorm_i', q @ self.P[cp + '.weight_ih'].t())
+        h = torch.zeros(N, 32, device=emb0.device)
+        c = torch.zeros(N, 32, device=emb0.device)
+        hs = []
+        for i in range(S):
+            h, c = self.lstm_cell(cp, ig[:, i], h, c)
+            hs.append(h)
+        logits = torch.matmul(torch.stack(hs, dim=1), key.transpose(1, 2))            # [N,S,E+1]
+        # mask recurrence: step 0 end slot off; step i>=1: all valid slots minus every unit chosen before i
+        chosen_before = torch.cummax(onehot.long(), dim=1)[0].bool()
+        chosen_before = torch.cat([torch.zeros_like(chosen_before[:, :1]), chosen_before[:, :-1]], dim=1)
+        step_mask = valid.unsqueeze(1) & ~chosen_before
+        step_mask[:, 0] = valid & (slot != entity_num.unsqueeze(1))
+        logits = logits.masked_fill(~step_mask, -1e9)
+        return logits, emb_steps[:, -1], selected_units_num
+
+    def selected_units_sample(self, emb0, entity_embeddings, entity_num, su_mask):
+        """Sampling pointer network, action_arg_head.py:262-314 (K12; sequential, early exit when all rows ended)."""
+        pre = 'policy.selected_units_head.'
+        N = emb0.shape[0]
+        dev = emb0.device
+        rows = torch.arange(N, device=dev)
+        key, valid, slot = self.su_keys(entity_embeddings, entity_num)
+        step_mask = valid & (slot != entity_num.unsqueeze(1))
+        num = torch.full((N,), MAX_SELECTED_UNITS_NUM, dtype=torch.long, device=dev)
+        num[~su_mask] = 0
+        end_flag = ~su_mask
+        picked = torch.zeros(N, key.shape[1], device=dev)
+        cp = pre + 'lstm.layers.0.cell'
+        h = torch.zeros(N, 32, device=dev)
+        c = torch.zeros(N, 32, device=dev)
+        ae = emb0
+        results, logits = [], []
+        result = None
+        for i in range(MAX_SELECTED_UNITS_NUM):
+            if i > 0:
+                if i == 1:
+                    step_mask[rows, entity_num] = True
+                step_mask[rows, result] = False
+            q = self.fc(pre + 'query_fc2', self.fc(pre + 'query_fc1', ae, relu=True))
+            h, c = self.lstm_cell(cp, self.ln(cp + '.layernorm_i', q @ self.P[cp + '.weight_ih'].t()), h, c)
+            step_logits = (h.unsqueeze(1) * key).sum(dim=2).masked_fill(~step_mask, -1e9) / self.T
+            result = self.sample(step_logits)
+            num = torch.where((result == entity_num) & ~end_flag, torch.full_like(num, i + 1), num)
+            end_flag = end_flag | (result == entity_num)
+            results.append(result)
+            logits.append(step_logits)
+            picked[rows[~end_flag], result[~end_flag]] = 1
+            ae = emb0 + self.su_embed(key, picked, (picked.sum(dim=1, keepdim=True) != 0))
+            if bool(end_flag.all()):
+                break
+        extra = torch.zeros(N, MAX_ENTITY_NUM + 1, device=dev)
+        return torch.stack(logits, dim=1), torch.stack(results, dim=1), ae, num, extra
+
+    def target_unit_head(self, emb, entity_embeddings, entity_num, target_unit=None):
+        """action_arg_head.py:343-363 (K13)."""
+        pre = 'policy.target_unit_head.'
+        key = self.fc(pre + 'key_fc', entity_embeddings)
+        q = self.fc(pre + 'query_fc2', self.fc(pre + 'query_fc1', emb, relu=True))
+        logits = torch.matmul(key, q.unsqueeze(-1)).squeeze(-1)
+        E = entity_embeddings.shape[1]
+        valid = torch.arange(E, device=emb.device).unsqueeze(0) < entity_num.unsqueeze(1)
+        logits = logits.masked_fill(~valid, -1e9) / self.T
+        if target_unit is None:
+            target_unit = self.sample(logits)
+        return logits, target_unit
+
+    def location_head(self, emb, map_skip, location=None):
+        """action_arg_head.py:417-450 (K14)."""
+        pre = 'policy.location_head.'
+        N = emb.shape[0]
+        h8, w8 = map_skip[-1].shape[2:]
+        x = self.fc(pre + 'project_embed', emb, relu=True).reshape(N, 4, h8, w8)
+        x = self.conv(pre + 'conv1', torch.relu(torch.cat([x, map_skip[-1]], dim=1)), 0, relu=True)
+        for i in range(4):
+            x = x + map_skip[len(map_skip) - i - 1]
+            rp = pre + 'res.%d.' % i
+            r = self.conv(rp + 'conv2', self.conv(rp + 'conv1', x, 1, relu=True), 1)
+            g = x
+            for j in range(4):
+                g = self.conv(rp + 'GateWeightG.%d' % j, g, 0, relu=(j < 3))
+            x = torch.relu(torch.tanh(r * torch.sigmoid(g)) * self.P[rp + 'UpdateSP'] + x)
+        for i in range(3):
+            x = self.conv(pre + 'upsample.%d' % i, F.interpolate(x, scale_factor=2., mode='bilinear'), 1,
+                          relu=(i < 2))
+        logits = x.reshape(N, -1) / self.T
+        if location is None:
+            location = self.sample(logits)
+        return logits, location
+
+    def value_baseline(self, name: str, x: Tensor) -> Tensor:
+        """model/value.py:31-39 (K16)."""
+        pre = 'value_networks.%s.' % name
+        x = self.fc(pre + 'project', x, relu=True)
+        for i in range(16):
+            r = self.fc(pre + 'res.%d.fc2' % i, self.fc(pre + 'res.%d.fc1' % i, x, relu=True))
+            x = self.ln(pre + 'res.%d.norm' % i, r + x)
+        v = F.linear(x, self.P[pre + 'value_fc.0.weight'], self.P[pre + 'value_fc.0.bias']).squeeze(1)
+        if BASELINE_ATAN[name]:
+            v = (2.0 / math.pi) * torch.atan((math.pi / 2.0) * v)
+        return v
+
+    # -------------------------------------------------------------------------------------- policy
+    def policy_sample(self, lstm_out, entity_embeddings, map_skip, scalar_context, entity_num, su_action_mask):
+        """model/policy.py:22-48."""
+        logit, action = {}, {}
+        logit['action_type'], action['action_type'], emb = self.action_type_head(lstm_out, scalar_context)
+        logit['delay'], action['delay'], emb = self.arg_head('policy.delay_head.', emb, 128, False)
+        logit['queued'], action['queued'], emb = self.arg_head('policy.queued_head.', emb, 2, True)
+        su_mask = su_action_mask.to(emb.device)[action['action_type']]
+        logit['selected_units'], action['selected_units'], emb, su_num, extra = self.selected_units_sample(
+            emb, entity_embeddings, entity_num, su_mask)
+        logit['target_unit'], action['target_unit'] = self.target_unit_head(emb, entity_embeddings, entity_num)
+        logit['target_location'], action['target_location'] = self.location_head(emb, map_skip)
+        return action, su_num, logit, extra
+
+    def policy_train(self, lstm_out, entity_embeddings, map_skip, scalar_context, entity_num, action_info,
+                     selected_units_num):
+        """model/policy.py:50-73."""
+        logit, action = {}, {}
+        logit['action_type'], action['action_type'], emb = self.action_type_head(
+            lstm_out, scalar_context, action_info['action_type'])
+        logit['delay'], action['delay'], emb = self.arg_head('policy.delay_head.', emb, 128, False,
+                                                             action_info['delay'])
+        logit['queued'], action['queued'], emb = self.arg_head('policy.queued_head.', emb, 2, True,
+                                                               action_info['queued'])
+        logit['selected_units'], emb, su_num = self.selected_units_train(
+            emb, entity_embeddings, entity_num, selected_units_num, action_info['selected_units'])
+        action['selected_units'] = None   # the reference returns None here (action_arg_head.py:166,314)
+        logit['target_unit'], action['target_unit'] = self.target_unit_head(
+            emb, entity_embeddings, entity_num, action_info['target_unit'])
+        logit['target_location'], action['target_location'] = self.location_head(
+            emb, map_skip, action_info['target_location'])
+        return action, su_num, logit

@@ -1,0 +1,103 @@
+/* distar_b200 — C-ABI of the B200-native AlphaStar policy hot path (libdistar_b200.so).
+ *
+ * The reference (opendilab/DI-star @ 12b1c69) is pure Python/PyTorch: it has no FFI of its own, so the
+ * "binding" a maintainer adds is the ctypes stub in INTEGRATION.md (distar_b200/lib.py is that stub).
+ * Every entry point below replaces a block of PyTorch-eager calls in the reference; the file:line it
+ * replaces is cited per function (paths relative to distar/agent/default/).
+ *
+ * Conventions
+ *  - plain device pointers + sizes; the caller (PyTorch) owns every buffer including workspaces;
+ *    the library never allocates, frees or synchronises, and keeps no state beyond cached
+ *    cudaFuncSetAttribute calls and TMA descriptors built per call on the host stack.
+ *  - all work is enqueued on `stream` (CUDA-graph capturable unless noted).
+ *  - return 0 on success, negative dsb_status on failure; dsb_last_error() gives a thread-local message.
+ *  - tensors are dense row-major unless a stride argument says otherwise.
+ */
+#ifndef DISTAR_B200_H_
+#define DISTAR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dsb_stream_t; /* cudaStream_t */
+
+enum dsb_status { DSB_OK = 0, DSB_ERR_ARG = -1, DSB_ERR_CUDA = -2, DSB_ERR_UNSUPPORTED = -3 };
+
+const char* dsb_last_error(void);
+int dsb_version(void);
+/* number of kernels launched by this library in the calling process since load (bench gpu_launches). */
+int64_t dsb_launch_count(void);
+
+/* ---- scatter_connection  (model/module_utils.py:11-34 'add' + masking of model/encoder.py:37-38) ----
+ * out[n,c,y,x] = sum_{e < entity_num[n], clamp(ey)=y, clamp(ex)=x} project[n,e,c]   (entity order, deterministic)
+ * project [N,E,C=32] f32, ex/ey [N,E] u8, entity_num [N] i64 (NULL = all E valid), out [N,32,H,W] f32 (H=W=128).
+ * Every output element is written exactly once (no memset pass). */
+int dsb_scatter_connection_fwd(const float* project, const uint8_t* ex, const uint8_t* ey, const int64_t* entity_num,
+                               float* out, int N, int E, int H, int W, dsb_stream_t stream);
+/* grad_project[n,e,c] = grad_out[n,c,clamp(ey),clamp(ex)] for e < entity_num[n], else 0. */
+int dsb_scatter_connection_bwd(const float* grad_out, const uint8_t* ex, const uint8_t* ey, const int64_t* entity_num,
+                               float* grad_project, int N, int E, int H, int W, dsb_stream_t stream);
+
+/* ---- V-trace / UPGO / TD(lambda) return scans  (rl_training/as_rl_utils.py:157-218,265-312; call sites :15,:40,:238) ----
+ * reward [F,T,B], value [F,T+1,B] (bootstrap row already zeroed where terminal, rl_loss.py:47-49),
+ * rho [R,T,B] clipped importance ratios (R = 6 heads), gamma_td [F] (device), lambda_td scalar.
+ * vtrace_adv [F,R,T,B]  (gamma=1, lambda=1, c=rho),  upgo_adv [R,T,B] = rho*(G - V[:T]) on field 0 (winloss),
+ * td_return [F,T,B].  One thread per (column b, item); the T loop lives in registers. */
+int dsb_return_scan(const float* reward, const float* value, const float* rho, const float* gamma_td, float lambda_td,
+                    float* vtrace_adv, float* upgo_adv, float* td_return, int F, int R, int T, int B,
+                    dsb_stream_t stream);
+
+/* ---- per-row categorical statistics  (rl_loss.py:63-90; as_rl_utils.py:52-103; sl_loss.py CE) ----
+ * For each of `rows` rows of `logits` [rows,C] (and optional `teacher` [rows,C]) with label action[rows] (i64):
+ *   lse[r] = (row max, log sum exp(z - max)) as two floats, logp[r] = (logits[r,a]-max)-logsum,
+ *   entropy[r] = -sum p log p, kl[r] = sum pt (log pt - log p), lse_t[r] likewise two floats for the teacher.
+ * Masked classes carry -1e9 as in the reference.  teacher/kl/lse_t may be NULL. */
+int dsb_categorical_stats_fwd(const float* logits, const float* teacher, const int64_t* action, float* lse,
+                              float* logp, float* entropy, float* kl, float* lse_t, int64_t rows, int C,
+                              dsb_stream_t stream);
+/* grad_logits[r,j] = g_logp[r]*(1[j==a]-p_j) - g_ent[r]*p_j*(log p_j + H_r) + g_kl[r]*(p_j - pt_j)
+ * (g_* are per-row upstream gradients; entropy = H_r from the forward). */
+int dsb_categorical_stats_bwd(const float* logits, const float* teacher, const int64_t* action, const float* lse,
+                              const float* entropy, const float* lse_t, const float* g_logp, const float* g_ent,
+                              const float* g_kl, float* grad_logits, int64_t rows, int C, dsb_stream_t stream);
+
+/* ---- masked categorical sampling  (torch.multinomial(softmax(x),1) sites: head/action_type_head.py:57-58,
+ *      head/action_arg_head.py:46-47,79-80,147-148,361-362,448-449) ----
+ * index[r] = argmax_j softmax(logits[r])_j / q[r,j]  (first max wins), q ~ Exp(1) supplied by the caller so the
+ * RNG stream is the reference's; also returns logp[r] = log_softmax(logits[r])[index[r]] (model.py:67-71). */
+int dsb_sample_categorical(const float* logits, const float* q, int64_t* index, float* logp, int64_t rows, int C,
+                           dsb_stream_t stream);
+
+/* ---- fp32 -> (hi, lo) bf16 split used by the split-precision tensor-core GEMM ---- */
+int dsb_split_bf16(const float* x, void* hi, void* lo, int64_t n, dsb_stream_t stream);
+
+/* ---- tcgen05 GEMM:  C[M,N] = act( A[M,K] . W[N,K]^T + bias[N] )   (fc_block, nn_module.py:231-270) ----
+ * A and W are given as bf16 (hi, lo) pairs, both K-major (row-major with K contiguous), K % 64 == 0,
+ * N % 128 == 0 (N <= 4096), M arbitrary.  terms = 1: hi*hi only (plain bf16); terms = 3: hi*hi + hi*lo + lo*hi
+ * (fp32-class product, ~2^-16 relative).  Accumulation is fp32 in TMEM.
+ * C fp32 [M,N] (ldc = N).  Optional c_hi/c_lo (bf16 [M,N]) receive the split of the result so the next GEMM
+ * needs no separate split pass.  relu != 0 applies max(.,0).  bias may be NULL. */
+int dsb_gemm_bf16_split(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                        float* c, void* c_hi, void* c_lo, int64_t M, int N, int K, int terms, int relu,
+                        dsb_stream_t stream);
+
+/* ---- fused grad-norm -> clip -> Adam over the flat arena  (rl_learner.py:73-80,125,132; grad_clip.py:141-144) ----
+ * step 1: dsb_sumsq partial sums of grad^2 into `partial` [>= dsb_sumsq_partials()] then a finishing reduction
+ *         into norm_out[0] = sqrt(sum) (all on device, no host sync).
+ * step 2: dsb_adam_step reads norm_out on device: scale = min(1, max_norm/(norm*grad_scale + 1e-6)) * grad_scale
+ *         (grad_scale = 1/world folds the DP average, dist_helper.py:421-431), then Adam(beta1,beta2,eps, no decay)
+ *         with bias correction for step `t` (1-based); optionally refreshes the bf16 hi/lo shadow of the weights. */
+int dsb_sumsq_partials(void);
+int dsb_grad_norm(const float* grad, int64_t n, float* partial, float* norm_out, dsb_stream_t stream);
+int dsb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* norm,
+                  float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps, int t,
+                  void* shadow_hi, void* shadow_lo, dsb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISTAR_B200_H_ */

@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — learner samples/sec of the AlphaStar policy hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                  # our CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  # the CPU oracle port of the reference
+    torchrun ... bench.py --gpus N ...                                    # one rank per GPU (driver launches this)
+
+A step = ``RLLearner._train`` on one synthetic learner batch: rl_learner_forward -> ReinforcementLoss ->
+backward -> (N>1: one NCCL all-reduce of the flat gradient arena) -> clip -> Adam.  Workload at N=1 is
+BASELINE.json configs[3]/metric: per-rank batch 128, unroll 32, 512 entities, 128x128 spatial (weak scaling:
+every rank trains its own 128 trajectories).  `value` = world * B * T / step_time with the batch resident in HBM;
+`e2e` = same through the public API with the batch copied from pinned host memory every step and the loss read
+back.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=128, help='trajectories per rank (BASELINE: 128)')
+    ap.add_argument('--unroll', type=int, default=32, help='unroll length (BASELINE: 32)')
+    ap.add_argument('--encoder-chunk', type=int, default=264)
+    ap.add_argument('--terms', type=int, default=3, help='tensor-core products per GEMM: 3 = fp32-class (parity), 1 = bf16')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--cpu-batch', type=int, default=4)
+    ap.add_argument('--cpu-unroll', type=int, default=8)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.samples, self.stop_flag, self.index = [], False, index
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(',')]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        self.thread.join(timeout=3)
+        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace('.', '').isdigit())
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        mx = [int(float(s[1])) for s in self.samples if s[1].replace('.', '').isdigit()]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_rate(batch, unroll, repeats=2, threads=None):
+    """The reference's CPU PyTorch path, as restated by the oracle (kind 'port'): rl_learner_forward + loss +
+    backward on a bounded sample.  Returns (frames/s, seconds per step, cores)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import alphastar_ref as O
+    from distar_b200.params import init_state_dict
+    from distar_b200.synth import synth_rl_batch, tree_clone
+    cores = threads or os.cpu_count()
+    torch.set_num_threads(cores)
+    sd = init_state_dict(seed=0)
+    P = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    data = synth_rl_batch(batch, unroll, seed=0)
+
+    def one():
+        for p in P.values():
+            p.grad = None
+        info = O.rl_loss(O.rl_learner_forward(P, **tree_clone(data)))
+        info['total_loss'].backward()
+        return float(info['total_loss'])
+    one()
+    best = float('inf')
+    for _ in range(repeats):
+        t = time.time()
+        one()
+        best = min(best, time.time() - t)
+    return batch * unroll / best, best, cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    times = []
+    cores = os.cpu_count()
+    # each "step" is one bounded sample (cpu_batch x cpu_unroll frames)
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import alphastar_ref as O
+    from distar_b200.params import init_state_dict
+    from distar_b200.synth import synth_rl_batch, tree_clone
+    torch.set_num_threads(cores)
+    sd = init_state_dict(seed=0)
+    P = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    data = synth_rl_batch(args.cpu_batch, args.cpu_unroll, seed=0)
+
+    def one():
+        for p in P.values():
+            p.grad = None
+        info = O.rl_loss(O.rl_learner_forward(P, **tree_clone(data)))
+        info['total_loss'].backward()
+    for _ in range(max(args.warmup, 1)):
+        one()
+    for _ in range(args.steps):
+        t = time.time()
+        one()
+        times.append(time.time() - t)
+    ms = 1e3 * sum(times) / len(times)
+    frames = args.cpu_batch * args.cpu_unroll
+    value = frames / (ms / 1e3)
+    sample = 'oracle port of the reference CPU path: rl_learner_forward+loss+backward on B=%d x T=%d frames/step' % (
+        args.cpu_batch, args.cpu_unroll)
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'learner samples/sec (unroll=32, 512 ent, 128^2 spatial)', 'value': value,
+        'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'RL learner step, 512 entities, 128x128 spatial; CPU arm times a bounded sample',
+                   'batch_per_step': args.cpu_batch, 'unroll': args.cpu_unroll},
+        'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0}))
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def tree_bytes(tree):
+    from distar_b200.synth import tree_map
+    n = [0]
+    tree_map(lambda t: n.__setitem__(0, n[0] + t.numel() * t.element_size()) or t, tree)
+    return n[0]
+
+
+def kernel_rooflines(dev, peaks):
+    """Stand-alone CUDA-event timings of the two kernels BASELINE.json names, at the bench shapes."""
+    from distar_b200 import ops
+    out = {}
+    # scatter_connection: N rows of the bench batch; output 2 MiB/obs >> L2, so no flush needed
+    N, E = 1056, 512
+    proj = torch.randn(N, E, 32, device=dev)
+    ex = torch.randint(0, 128, (N, E), device=dev, dtype=torch.uint8)
+    ey = torch.randint(0, 128, (N, E), device=dev, dtype=torch.uint8)
+    en = torch.full((N,), E, device=dev, dtype=torch.int64)
+    for _ in range(3):
+        ops.scatter_connection(proj, ex, ey, en, 128, 128)
+    s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+    reps = 10
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(reps):
+        ops.scatter_connection(proj, ex, ey, en, 128, 128)
+    e.record()
+    torch.cuda.synchronize()
+    dt = s.elapsed_time(e) / reps / 1e3
+    bytes_per_obs = 32 * 128 * 128 * 4 + E * 32 * 4 + E * 2
+    ach = N * bytes_per_obs / dt / 1e9
+    out['scatter_connection'] = {'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                                 'frac': ach / peaks['hbm_gbs'], 'traffic': None, 'us_per_launch': dt * 1e6,
+                                 'shape': 'N=%d obs, 512 entities, 32ch, 128x128' % N,
+                                 'peak_source': peaks['source']}
+    # entity-transformer MLP GEMM: [M,256] x [1024,256]^T, M = 256 obs * 512 tokens, 3-term split
+    M, K, Nn = 256 * 512, 256, 1024
+    a = torch.randn(M, K, device=dev)
+    w = torch.randn(Nn, K, device=dev) / 16
+    b = torch.randn(Nn, device=dev)
+    a_hi, a_lo = ops.split_bf16(a)
+    w_hi, w_lo = ops.split_bf16(w)
+    for terms in (3, 1):
+        for _ in range(3):
+            ops.gemm_split(a_hi, a_lo, w_hi, w_lo, b, True, terms)
+        torch.cuda.synchronize()
+        s.record()
+        for _ in range(reps):
+            ops.gemm_split(a_hi, a_lo, w_hi, w_lo, b, True, terms)
+        e.record()
+        torch.cuda.synchronize()
+        dt = s.elapsed_time(e) / reps / 1e3
+        flops = 2.0 * M * K * Nn * terms
+        ach = flops / dt / 1e12
+        out['entity_mlp_gemm_terms%d' % terms] = {
+            'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
+            'frac': ach / peaks['bf16_tflops'], 'traffic': None, 'us_per_launch': dt * 1e6,
+            'shape': 'M=%d K=%d N=%d, %d bf16 MMA terms (tensor-core flops counted)' % (M, K, Nn, terms),
+            'peak_source': peaks['source']}
+    return out
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d['bf16_tflops'], 'source': 'measured (MEASURED_PEAKS.json)'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from distar_b200 import lib
+    from distar_b200.learner import RLLearner
+    from distar_b200.model import Model
+    from distar_b200.synth import synth_rl_batch, tree_map
+    lib.load()
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl b200 needs a CUDA device: the product path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl')
+    B, T = args.batch, args.unroll
+    cfg = {'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': ['winloss']}}
+    model = Model(cfg, use_value_network=True, seed=0, gemm_terms=args.terms, encoder_chunk=args.encoder_chunk).cuda()
+    learner = RLLearner(model, 'MP0', None, lr=1e-5, max_norm=1.0)
+    host = synth_rl_batch(B, T, seed=1000 * rank)
+    host = tree_map(lambda t: t.pin_memory(), host)
+    h2d = tree_bytes(host)
+    resident = tree_map(lambda t: t.to(dev, non_blocking=True), host)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+        s.record()
+        for _ in range(steps):
+            step_fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps
+
+    def step_resident():
+        # the loss zeroes value[-1] in place of the model OUTPUT only; inputs are never modified
+        learner._train(resident)
+
+    last_loss = [None]
+
+    def step_e2e():
+        data = tree_map(lambda t: t.to(dev, non_blocking=True), host)
+        info = learner._train(data)
+        last_loss[0] = info['total_loss'].item()           # device -> host read of the step result
+
+    for _ in range(args.warmup):
+        step_resident()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = lib.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = lib.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    e2e = None
+    if not args.no_e2e:
+        step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+        e2e = {'value': world * B * T / (ms_e2e / 1e3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': 4 + 4 * 45, 'ms_per_step': ms_e2e}
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    roofs = kernel_rooflines(dev, peaks)
+    line = {
+        'metric': 'learner samples/sec (unroll=32, 512 ent, 128^2 spatial)', 'value': world * B * T / (ms / 1e3),
+        'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32 (bf16x3 split products on tcgen05, fp32 accumulate)' if args.terms == 3 else 'bf16',
+        'data': 'synthetic',
+        'config': {'workload': 'RL learner step (rl_learner_forward + V-trace/UPGO/TD/entropy/KL loss + backward + '
+                               'clip + Adam), BASELINE configs[3] per rank',
+                   'batch_per_gpu': B, 'unroll': T, 'entities': 512, 'spatial': '128x128', 'global_batch': world * B,
+                   'parallelism': 'dp%d' % world, 'encoder_chunk': args.encoder_chunk,
+                   'l2': 'inputs and activations (GBs per step) far exceed the 126 MB L2; no flush needed'},
+        'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches),
+        'roofline': roofs['entity_mlp_gemm_terms3'] if args.terms == 3 else roofs['entity_mlp_gemm_terms1'],
+        'rooflines': roofs,
+    }
+    if not args.no_cpu_baseline:
+        v, sec, cores = cpu_reference_rate(args.cpu_batch, args.cpu_unroll)
+        line['cpu_baseline'] = {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                                'sample': 'oracle port, rl_learner_forward+loss+backward, B=%d x T=%d frames, best of 2 '
+                                          '(%.1f s/step)' % (args.cpu_batch, args.cpu_unroll, sec)}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

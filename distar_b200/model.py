@@ -20,6 +20,8 @@ from .constants import SELECTED_UNITS_ACTION_MASK
 from .params import init_state_dict
 from .policy_net import BASELINE_ATAN, HEADS, MAX_SELECTED_UNITS_NUM, Net
 from .spec import BASELINES, is_trainable, param_specs
+from .synth import tree_map
+from torch.utils.checkpoint import checkpoint as torch_checkpoint
 
 
 class _Node(nn.Module):
@@ -48,7 +50,8 @@ def _to_cfg(d):
 
 class Model(nn.Module):
     def __init__(self, cfg={}, use_value_network=False, temperature=None, seed: Optional[int] = None,
-                 gemm_terms: int = 3, sample_rng: str = 'cuda'):
+                 gemm_terms: int = 3, sample_rng: str = 'cuda', encoder_chunk: int = 0,
+                 checkpoint_encoder: bool = True):
         super().__init__()
         sx = int(_cfg_get(cfg, 'model.spatial_x', 160))
         sy = int(_cfg_get(cfg, 'model.spatial_y', 152))
@@ -60,6 +63,9 @@ class Model(nn.Module):
         self.baselines = [b for b in BASELINES if b in enabled]
         self.only_update_baseline = bool(_cfg_get(cfg, 'model.only_update_baseline', False))
         self.gemm_terms, self.sample_rng = gemm_terms, sample_rng
+        # observation rows are independent in the encoder: process them in chunks (and, while training,
+        # recompute each chunk's activations in backward) so B=128 x T=32 fits one GPU's HBM.
+        self.encoder_chunk, self.checkpoint_encoder = encoder_chunk, checkpoint_encoder
         # attributes callers read (agent.py:107-108,148)
         self.cfg = _to_cfg({'encoder': {'core_lstm': {'num_layers': 3, 'hidden_size': 384, 'input_size': 1536}},
                             'temperature': self.temperature, 'spatial_x': sx, 'spatial_y': sy,
@@ -150,6 +156,26 @@ class Model(nn.Module):
     def _net(self) -> Net:
         return Net(self._params, self.spatial_x, self.spatial_y, self.temperature, self.gemm_terms, self.sample_rng)
 
+    def _encode(self, net: Net, spatial_info, entity_info, scalar_info, entity_num):
+        N = entity_num.shape[0]
+        chunk = self.encoder_chunk
+        if not chunk or N <= chunk:
+            return net.encoder(spatial_info, entity_info, scalar_info, entity_num)
+
+        def run(sp, en, sc, num):
+            li, ctx, bf, ee, ms = net.encoder(sp, en, sc, num)
+            return (li, ctx, bf, ee) + tuple(ms[3:])          # only the 16x16 skips leave the encoder
+
+        outs = []
+        for s0 in range(0, N, chunk):
+            args = tree_map(lambda t: t[s0:s0 + chunk], (spatial_info, entity_info, scalar_info, entity_num))
+            if self.checkpoint_encoder and torch.is_grad_enabled():
+                outs.append(torch_checkpoint(run, *args, use_reentrant=False))
+            else:
+                outs.append(run(*args))
+        cat = [torch.cat([o[i] for o in outs], dim=0) for i in range(len(outs[0]))]
+        return cat[0], cat[1], cat[2], cat[3], [None, None, None] + cat[4:]
+
     def forward(self, spatial_info, entity_info, scalar_info, entity_num, hidden_state):
         """model.py:46-54."""
         out = self.compute_logp_action(spatial_info, entity_info, scalar_info, entity_num, hidden_state)
@@ -158,8 +184,8 @@ class Model(nn.Module):
     def compute_logp_action(self, spatial_info, entity_info, scalar_info, entity_num, hidden_state, **kwargs):
         """model.py:56-74: encoder -> one LSTM step -> sampling policy -> per-head log-prob of the sample."""
         net = self._net()
-        lstm_input, scalar_context, _bf, entity_embeddings, map_skip = net.encoder(
-            spatial_info, entity_info, scalar_info, entity_num)
+        lstm_input, scalar_context, _bf, entity_embeddings, map_skip = self._encode(
+            net, spatial_info, entity_info, scalar_info, entity_num)
         lstm_out, out_state = net.lstm('core_lstm', lstm_input.unsqueeze(0), hidden_state, 3)
         action, su_num, logit, extra = net.policy_sample(lstm_out.squeeze(0), entity_embeddings, map_skip,
                                                         scalar_context, entity_num, self._su_mask)
@@ -173,8 +199,8 @@ class Model(nn.Module):
                               selected_units_num, action_info, **kwargs):
         """model.py:76-93."""
         net = self._net()
-        lstm_input, scalar_context, _bf, entity_embeddings, map_skip = net.encoder(
-            spatial_info, entity_info, scalar_info, entity_num)
+        lstm_input, scalar_context, _bf, entity_embeddings, map_skip = self._encode(
+            net, spatial_info, entity_info, scalar_info, entity_num)
         lstm_out, out_state = net.lstm('core_lstm', lstm_input.unsqueeze(0), hidden_state, 3)
         _a, su_num, logit = net.policy_train(lstm_out.squeeze(0), entity_embeddings, map_skip, scalar_context,
                                              entity_num, action_info, selected_units_num)
@@ -188,12 +214,12 @@ class Model(nn.Module):
         B, T = batch_size, unroll_len
         flat_action = {k: v.flatten(0, 1) for k, v in action_info.items()}
         flat_su_num = selected_units_num.flatten(0, 1)
-        lstm_input, scalar_context, baseline_feature, entity_embeddings, map_skip = net.encoder(
-            spatial_info, entity_info, scalar_info, entity_num)
+        lstm_input, scalar_context, baseline_feature, entity_embeddings, map_skip = self._encode(
+            net, spatial_info, entity_info, scalar_info, entity_num)
         state0 = [(h.view(-1, B, h.shape[-1])[0], c.view(-1, B, c.shape[-1])[0]) for h, c in hidden_state]
         lstm_out, _ = net.lstm('core_lstm', lstm_input.view(-1, B, lstm_input.shape[-1]), state0, 3)
         lstm_out = lstm_out.reshape(-1, lstm_out.shape[-1])
-        _a, _n, logits = net.policy_train(lstm_out[:-B], entity_embeddings[:-B], [m[:-B] for m in map_skip],
+        _a, _n, logits = net.policy_train(lstm_out[:-B], entity_embeddings[:-B], [(m[:-B] if m is not None else None) for m in map_skip],
                                           scalar_context[:-B], entity_num[:-B], flat_action, flat_su_num)
         critic_input = lstm_out.detach() if self.only_update_baseline else lstm_out
         values = {k: net.value_baseline(k, critic_input).view(T + 1, B) for k in self.baselines}
@@ -210,8 +236,8 @@ class Model(nn.Module):
         """model.py:170-189 (observation rows batch-major [B*T])."""
         net = self._net()
         B = len(traj_lens)
-        lstm_input, scalar_context, _bf, entity_embeddings, map_skip = net.encoder(
-            spatial_info, entity_info, scalar_info, entity_num)
+        lstm_input, scalar_context, _bf, entity_embeddings, map_skip = self._encode(
+            net, spatial_info, entity_info, scalar_info, entity_num)
         x = lstm_input.view(-1, lstm_input.shape[0] // B, lstm_input.shape[-1]).permute(1, 0, 2)
         lstm_out, out_state = net.lstm('core_lstm', x, hidden_state, 3)
         lstm_out = lstm_out.permute(1, 0, 2).reshape(-1, lstm_out.shape[-1])

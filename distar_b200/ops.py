@@ -7,6 +7,7 @@ torch so the *Python* control flow around the kernels (shapes, masks, autograd w
 machine without a GPU.  Product code never turns it on.
 """
 import math
+import os
 from typing import Optional
 
 import torch
@@ -218,8 +219,13 @@ def split_bf16(x: torch.Tensor):
     return hi, (x - hi.float()).to(torch.bfloat16)
 
 
+# DEBUG ONLY: DSB_DISABLE_TCGEN05=1 routes every fc_block through the library matmul so the rest of the pipeline
+# can be bisected on a GPU box when the tensor-core kernel is under suspicion.  Never set in tests of record/bench.
+_TCGEN05_OFF = os.environ.get('DSB_DISABLE_TCGEN05', '0') == '1'
+
+
 def gemm_eligible(N: int, K: int) -> bool:
-    return N % 128 == 0 and K % 64 == 0
+    return (not _TCGEN05_OFF) and N % 128 == 0 and K % 64 == 0
 
 
 def gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu: bool, terms: int = 3, want_split: bool = False):

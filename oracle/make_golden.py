@@ -1,0 +1,102 @@
+"""Dump golden fixtures from the UNMODIFIED reference (run in the authoring container only).
+
+    python oracle/make_golden.py            # writes tests/golden/*.pt
+
+Weights come from distar_b200.params.init_state_dict (seeded, reproducible anywhere) loaded into the reference
+``Model``; inputs from distar_b200.synth (seeded).  The fixtures hold only reference OUTPUTS (plus input
+checksums), so the GPU box — which has no /root/reference — can check the oracle and the CUDA path against
+what the real reference produced.
+"""
+import hashlib
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [os.path.dirname(HERE), HERE]
+
+import ref_import  # noqa: E402
+from distar_b200.params import init_state_dict  # noqa: E402
+from distar_b200.synth import synth_obs, synth_rl_batch, synth_actions, tree_clone, tree_map  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+BASELINES = ('winloss', 'build_order')
+WEIGHT_SEED = 3
+
+
+def checksum(tree) -> str:
+    h = hashlib.sha256()
+
+    def visit(t):
+        h.update(t.detach().cpu().contiguous().view(torch.uint8).numpy().tobytes())
+        return t
+    tree_map(visit, tree)
+    return h.hexdigest()[:16]
+
+
+def infer_case():
+    return synth_obs(3, seed=11, entity_num=torch.tensor([512, 77, 300]))
+
+
+def teacher_case():
+    en = torch.tensor([512, 40, 333, 200])
+    obs = synth_obs(4, seed=12, entity_num=en)
+    g = torch.Generator().manual_seed(1)
+    act, num = synth_actions(4, en, g, max_su=9)
+    num[1] = 0
+    return obs, act, num
+
+
+def rl_case():
+    batch = synth_rl_batch(2, 3, seed=21, entity_num='random', max_su=6)
+    batch['reward']['winloss'][-1, 0] = 1.0
+    return batch
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    model, cfg, mods = ref_import.load_reference(spatial=128, enable_baselines=BASELINES)
+    sd = init_state_dict(seed=WEIGHT_SEED, baselines=BASELINES)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    meta = {'weight_seed': WEIGHT_SEED, 'baselines': list(BASELINES), 'weights_checksum': checksum(sd),
+            'torch': str(torch.__version__)}
+    # ---- config 1/2: sampling forward
+    obs = infer_case()
+    torch.manual_seed(5)
+    with torch.no_grad():
+        r = model.compute_logp_action(**tree_clone(obs))
+    torch.save({'meta': meta, 'input_checksum': checksum(obs), 'rng_seed': 5,
+                'action_info': r['action_info'], 'action_logp': r['action_logp'],
+                'selected_units_num': r['selected_units_num'], 'logit': r['logit'],
+                'hidden_state': r['hidden_state']}, os.path.join(OUT, 'infer.pt'))
+    # ---- teacher-forced forward
+    obs, act, num = teacher_case()
+    with torch.no_grad():
+        r = model.compute_teacher_logit(**tree_clone(obs), selected_units_num=num.clone(), action_info=tree_clone(act))
+    torch.save({'meta': meta, 'input_checksum': checksum((obs, act, num)), 'logit': r['logit'],
+                'hidden_state': r['hidden_state']}, os.path.join(OUT, 'teacher.pt'))
+    # ---- config 4: RL step
+    batch = rl_case()
+    loss_fn = mods['ReinforcementLoss'](cfg.learner, 'MP0')
+    model.zero_grad()
+    out = model.rl_learner_forward(**tree_clone(batch))
+    info = loss_fn.compute_loss(out)
+    info['total_loss'].backward()
+    scalars = {k: (v.item() if torch.is_tensor(v) else float(v)) for k, v in info.items()}
+    grad_norm = {n: p.grad.norm().item() for n, p in model.named_parameters() if p.requires_grad}
+    keep = ['policy.action_type_head.action_fc.layer2.0.bias', 'core_lstm.layers.2.cell.layernorm_c.weight',
+            'encoder.scatter_project.0.weight', 'value_networks.winloss.value_fc.0.weight',
+            'policy.selected_units_head.end_embedding', 'encoder.spatial_encoder.project.0.weight']
+    grads = {n: p.grad.clone() for n, p in model.named_parameters() if n in keep}
+    torch.save({'meta': meta, 'input_checksum': checksum(batch),
+                'target_logit': {k: v.detach() for k, v in out['target_logit'].items()},
+                'value': {k: v.detach() for k, v in out['value'].items()}, 'loss': scalars,
+                'grad_norm': grad_norm, 'grads': grads}, os.path.join(OUT, 'rl_step.pt'))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,156 @@
+"""-m gpu: each CUDA kernel (through the C-ABI) against the CPU oracle / plain fp32 torch on the same seeded inputs."""
+import math
+
+import pytest
+import torch
+
+import alphastar_ref as O
+from distar_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _scatter_case(N, E, H, W, seed, big_coords=False, ragged=True):
+    g = torch.Generator().manual_seed(seed)
+    proj = torch.randn(N, E, 32, generator=g)
+    hi = 256 if big_coords else W
+    ex = torch.randint(0, hi, (N, E), generator=g).to(torch.uint8)
+    ey = torch.randint(0, hi, (N, E), generator=g).to(torch.uint8)
+    # force duplicates: many entities on the same pixel
+    ex[:, : E // 4] = ex[:, :1]
+    ey[:, : E // 4] = ey[:, :1]
+    en = torch.randint(0, E + 1, (N,), generator=g) if ragged else torch.full((N,), E)
+    return proj, ex, ey, en
+
+
+@pytest.mark.parametrize('N,E,H,W,big', [(3, 512, 128, 128, False), (2, 512, 128, 128, True), (1, 37, 128, 128, False),
+                                        (2, 512, 152, 160, True), (5, 300, 128, 128, False)])
+def test_scatter_connection_bit_exact(N, E, H, W, big):
+    proj, ex, ey, en = _scatter_case(N, E, H, W, seed=N * 7 + E, big_coords=big)
+    mask = (torch.arange(E).unsqueeze(0) < en.unsqueeze(1)).unsqueeze(-1)
+    ref = O.scatter_connection(proj * mask, ex, ey, H, W)
+    out = ops.scatter_connection(proj.to(DEV), ex.to(DEV), ey.to(DEV), en.to(DEV), H, W)
+    assert out.shape == (N, 32, H, W) and out.is_contiguous()
+    assert torch.equal(out.cpu(), ref.contiguous()), 'scatter_connection must be bit-exact (deterministic entity order)'
+
+
+def test_scatter_connection_empty_and_full():
+    proj, ex, ey, _ = _scatter_case(2, 512, 128, 128, seed=1, ragged=False)
+    en = torch.tensor([0, 512])
+    out = ops.scatter_connection(proj.to(DEV), ex.to(DEV), ey.to(DEV), en.to(DEV), 128, 128).cpu()
+    assert out[0].abs().sum() == 0
+    assert torch.equal(out[1], O.scatter_connection(proj[1:], ex[1:], ey[1:], 128, 128)[0].contiguous())
+    # linearity: scatter(a + b) == scatter(a) + scatter(b) up to fp32 rounding; checksum: total mass preserved
+    tot = out[1].double().sum().item()
+    assert abs(tot - proj[1].double().sum().item()) < 1e-2
+
+
+def test_scatter_connection_backward():
+    proj, ex, ey, en = _scatter_case(3, 512, 128, 128, seed=5)
+    p = proj.to(DEV).requires_grad_(True)
+    out = ops.scatter_connection(p, ex.to(DEV), ey.to(DEV), en.to(DEV), 128, 128)
+    g = torch.randn(out.shape, generator=torch.Generator().manual_seed(2))
+    out.backward(g.to(DEV))
+    pr = proj.clone().requires_grad_(True)
+    mask = (torch.arange(512).unsqueeze(0) < en.unsqueeze(1)).unsqueeze(-1)
+    O.scatter_connection(pr * mask, ex, ey, 128, 128).backward(g)
+    assert torch.equal(p.grad.cpu(), pr.grad)
+
+
+@pytest.mark.parametrize('F_,T,B', [(1, 32, 128), (3, 7, 5), (6, 64, 33)])
+def test_return_scan_matches_oracle(F_, T, B):
+    g = torch.Generator().manual_seed(T)
+    reward = torch.randn(F_, T, B, generator=g) * 0.3
+    reward[0] = 0
+    reward[0, -1] = torch.randint(-1, 2, (B,), generator=g).float()
+    value = torch.randn(F_, T + 1, B, generator=g)
+    rho = torch.rand(6, T, B, generator=g).clamp(max=1) * 1.0
+    rho[:, :, ::3] = 1.0
+    gam = torch.tensor([1.0, 1.0, 1.0, 1.0, 1.0, 0.997][:F_])
+    vt, up, td = ops.return_scan(reward.to(DEV), value.to(DEV), rho.to(DEV), gam.to(DEV), 0.8)
+    for f in range(F_):
+        for h in range(6):
+            ref = O.vtrace_advantages(rho[h], reward[f], value[f])
+            assert torch.allclose(vt[f, h].cpu(), ref, rtol=1e-6, atol=1e-6), (f, h)
+        ref = O.lambda_returns(reward[f], value[f], float(gam[f]), 0.8)
+        assert torch.allclose(td[f].cpu(), ref, rtol=1e-6, atol=1e-6)
+    ret = O.upgo_returns(reward[0], value[0])
+    for h in range(6):
+        assert torch.allclose(up[h].cpu(), rho[h] * (ret - value[0][:-1]), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize('rows,C,masked', [(300, 327, False), (64, 2, False), (200, 513, True), (40, 16384, False),
+                                           (33, 512, True), (5, 128, False)])
+def test_categorical_stats_fwd_bwd(rows, C, masked):
+    g = torch.Generator().manual_seed(rows + C)
+    z = torch.randn(rows, C, generator=g) * 2
+    t = torch.randn(rows, C, generator=g)
+    if masked:
+        k = torch.randint(1, C, (rows, 1), generator=g)
+        m = torch.arange(C).unsqueeze(0) >= k
+        z = z.masked_fill(m, -1e9)
+        t = t.masked_fill(m, -1e9)
+        z[0] = -1e9          # a fully padded selected-units step
+        t[0] = -1e9
+    a = torch.randint(0, C, (rows,), generator=g)
+    if masked:
+        a = torch.minimum(a, k.squeeze(1) - 1)
+    zr = z.clone().requires_grad_(True)
+    lp = torch.log_softmax(zr, -1)
+    tl = torch.log_softmax(t, -1)
+    r_logp = lp.gather(-1, a.unsqueeze(-1)).squeeze(-1)
+    r_ent = -(lp.exp() * lp).sum(-1)
+    r_kl = (tl.exp() * (tl - lp)).sum(-1)
+    w = torch.randn(3, rows, generator=g)
+    (r_logp * w[0] + r_ent * w[1] + r_kl * w[2]).sum().backward()
+    zd = z.to(DEV).requires_grad_(True)
+    logp, ent, kl = ops.categorical_stats(zd, a.to(DEV), t.to(DEV))
+    wd = w.to(DEV)
+    (logp * wd[0] + ent * wd[1] + kl * wd[2]).sum().backward()
+    assert torch.allclose(logp.cpu(), r_logp.detach(), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(ent.cpu(), r_ent.detach(), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(kl.cpu(), r_kl.detach(), rtol=1e-4, atol=2e-5)
+    assert torch.allclose(zd.grad.cpu(), zr.grad, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('rows,C', [(64, 327), (64, 2), (32, 513), (16, 16384), (128, 128), (7, 512)])
+def test_sampling_matches_torch_multinomial_stream(rows, C):
+    g = torch.Generator().manual_seed(C)
+    z = torch.randn(rows, C, generator=g) * 3
+    if C in (513, 512):
+        z = z.masked_fill(torch.arange(C).unsqueeze(0) >= torch.randint(1, C, (rows, 1), generator=g), -1e9)
+    torch.manual_seed(1234)
+    ref = torch.multinomial(torch.softmax(z, -1), 1)[:, 0]
+    torch.manual_seed(1234)
+    idx, logp = ops.sample_categorical(z.to(DEV), rng='cpu')
+    assert torch.equal(idx.cpu(), ref)
+    assert torch.allclose(logp.cpu(), torch.log_softmax(z, -1).gather(-1, ref.unsqueeze(-1)).squeeze(-1), atol=1e-5)
+
+
+def test_split_bf16_reconstructs():
+    x = torch.randn(1000003, generator=torch.Generator().manual_seed(0)) * 37
+    hi, lo = ops.split_bf16(x.to(DEV))
+    rec = hi.float() + lo.float()
+    assert (rec.cpu() - x).abs().max() <= x.abs().max() * 2 ** -15
+    assert ((rec.cpu() - x).abs() / x.abs().clamp(min=1e-6)).median() < 2 ** -16
+
+
+def test_flat_adam_matches_torch():
+    g = torch.Generator().manual_seed(3)
+    n = 1_000_003
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.0, 0.99), eps=1e-5)
+    p = p0.clone().to(DEV)
+    grad = torch.zeros(n, device=DEV)
+    mine = ops.FlatAdam(p, grad, lr=1e-3, betas=(0.0, 0.99), eps=1e-5, max_norm=1.0)
+    for it in range(3):
+        gr = torch.randn(n, generator=g) * (10.0 if it == 0 else 1e-4)
+        ref.grad = gr.clone()
+        norm_ref = torch.nn.utils.clip_grad_norm_([ref], 1.0)
+        opt.step()
+        grad.copy_(gr.to(DEV))
+        norm = mine.step()
+        assert abs(norm.item() - norm_ref.item()) <= 1e-4 * norm_ref.item()
+        assert torch.allclose(p.cpu(), ref.detach(), rtol=1e-5, atol=1e-6)

@@ -1,0 +1,125 @@
+"""-m gpu: the CUDA model / loss through the reference-shaped API against the CPU oracle and the golden fixtures.
+
+Tolerance: BASELINE.json asks for logits/values within 1e-3 rtol of the fp32 reference.  We test
+max|a-b| <= 1e-3 * max|b| per tensor over the finite (un-masked) entries, masked entries (-1e9) must match exactly,
+and sampled indices must be identical under the reference's RNG stream (sample_rng='cpu')."""
+import os
+
+import pytest
+import torch
+
+import alphastar_ref as O
+import make_golden as G
+from distar_b200.model import Model
+from distar_b200.params import init_state_dict
+from distar_b200.rl_loss import ReinforcementLoss
+from distar_b200.synth import tree_clone, tree_map
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+DEV = 'cuda'
+TOL = 1e-3
+
+
+def close(a, b, name, rtol=TOL):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    fin = b.abs() < 1e8
+    assert torch.equal(fin, a.abs() < 1e8), name
+    if fin.any():
+        scale = max(b[fin].abs().max().item(), 1e-6)
+        err = (a[fin] - b[fin]).abs().max().item()
+        assert err <= rtol * scale, '%s: max err %.3e, scale %.3e' % (name, err, scale)
+
+
+def to_dev(tree):
+    return tree_map(lambda t: t.to(DEV), tree)
+
+
+@pytest.fixture(scope='module')
+def sd():
+    return init_state_dict(seed=G.WEIGHT_SEED, baselines=G.BASELINES)
+
+
+@pytest.fixture(scope='module')
+def model(sd):
+    cfg = {'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': list(G.BASELINES)}}
+    m = Model(cfg, use_value_network=True, seed=0, sample_rng='cpu')
+    m.load_state_dict(sd)
+    return m.cuda()
+
+
+def test_model_lives_in_one_arena(model, sd):
+    assert model.flat_param.is_cuda and model.flat_grad.is_cuda
+    for n, p in model.named_parameters():
+        assert p.is_cuda, n
+        if p.requires_grad:
+            a0, a1 = model.flat_param.data_ptr(), model.flat_param.data_ptr() + model.flat_param.numel() * 4
+            assert a0 <= p.data_ptr() < a1, n
+    for k, v in model.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), k
+
+
+def test_sampling_forward_vs_golden(model):
+    g = torch.load(os.path.join(GOLD, 'infer.pt'))
+    torch.manual_seed(g['rng_seed'])
+    with torch.no_grad():
+        o = model.compute_logp_action(**to_dev(G.infer_case()))
+    for k in O.HEADS:
+        close(o['logit'][k], g['logit'][k], 'logit/' + k)
+        assert torch.equal(o['action_info'][k].cpu(), g['action_info'][k]), 'sampled %s differs' % k
+        close(o['action_logp'][k], g['action_logp'][k], 'logp/' + k)
+    assert torch.equal(o['selected_units_num'].cpu(), g['selected_units_num'])
+    for (h, c), (gh, gc) in zip(o['hidden_state'], g['hidden_state']):
+        close(h, gh, 'h')
+        close(c, gc, 'c')
+
+
+def test_teacher_forward_vs_golden(model):
+    g = torch.load(os.path.join(GOLD, 'teacher.pt'))
+    obs, act, num = G.teacher_case()
+    with torch.no_grad():
+        o = model.compute_teacher_logit(**to_dev(obs), selected_units_num=num.to(DEV), action_info=to_dev(act))
+    for k in O.HEADS:
+        close(o['logit'][k], g['logit'][k], 'logit/' + k)
+
+
+def test_rl_step_vs_golden(model):
+    g = torch.load(os.path.join(GOLD, 'rl_step.pt'))
+    model.zero_grad()
+    out = model.rl_learner_forward(**to_dev(G.rl_case()))
+    info = ReinforcementLoss(None, 'MP0').compute_loss(out)
+    info['total_loss'].backward()
+    for k in O.HEADS:
+        close(out['target_logit'][k], g['target_logit'][k], 'target_logit/' + k)
+    for k, v in g['value'].items():
+        close(out['value'][k], v, 'value/' + k)
+    for k, v in g['loss'].items():
+        got = info[k].item() if torch.is_tensor(info[k]) else info[k]
+        assert abs(got - v) <= 2e-3 * max(1.0, abs(v)), (k, got, v)
+    # gradient norms: the 6-frame batch is ReLU/max-pool-decision sensitive, so this is a 2 % check per tensor
+    gmax = max(g['grad_norm'].values())
+    bad = []
+    for n, p in model.named_parameters():
+        if p.requires_grad:
+            v = g['grad_norm'][n]
+            if abs(p.grad.norm().item() - v) > 2e-2 * max(v, 1e-2 * gmax):
+                bad.append((n, p.grad.norm().item(), v))
+    assert not bad, bad[:5]
+
+
+def test_sl_forward_matches_oracle(model, sd):
+    from distar_b200.synth import synth_obs, synth_actions
+    B, T = 2, 2
+    en = torch.tensor([512, 100, 256, 64])
+    obs = synth_obs(B * T, seed=31, entity_num=en, hidden=False)
+    g = torch.Generator().manual_seed(2)
+    act, num = synth_actions(B * T, en, g, max_su=5)
+    hidden = [(torch.randn(B, 384, generator=g), torch.randn(B, 384, generator=g)) for _ in range(3)]
+    with torch.no_grad():
+        ol, _, _ = O.sl_train(sd, **tree_clone(obs), selected_units_num=num.clone(), traj_lens=[T] * B,
+                              hidden_state=tree_clone(hidden), action_info=tree_clone(act))
+        ml, _, _ = model.sl_train(**to_dev(obs), selected_units_num=num.to(DEV), traj_lens=[T] * B,
+                                  hidden_state=to_dev(hidden), action_info=to_dev(act))
+    for k in O.HEADS:
+        close(ml[k], ol[k], 'sl_logit/' + k)

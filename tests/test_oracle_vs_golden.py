@@ -1,0 +1,74 @@
+"""Pins the oracle against the committed fixtures dumped from the real reference (runs anywhere, CPU)."""
+import os
+
+import pytest
+import torch
+
+import alphastar_ref as O
+import make_golden as G
+from distar_b200.params import init_state_dict
+from distar_b200.synth import tree_clone
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def close(a, b, name, rtol=1e-4):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    fin = b.abs() < 1e8
+    assert torch.equal(fin, a.abs() < 1e8), name
+    if fin.any():
+        scale = max(b[fin].abs().max().item(), 1e-6)
+        err = (a[fin] - b[fin]).abs().max().item()
+        assert err <= rtol * scale, '%s: max err %.3e, scale %.3e' % (name, err, scale)
+
+
+@pytest.fixture(scope='module')
+def sd():
+    return init_state_dict(seed=G.WEIGHT_SEED, baselines=G.BASELINES)
+
+
+def test_fixture_inputs_reproduce(sd):
+    g = torch.load(os.path.join(GOLD, 'infer.pt'))
+    assert g['meta']['weights_checksum'] == G.checksum(sd), 'seeded weights differ on this machine'
+    assert g['input_checksum'] == G.checksum(G.infer_case()), 'seeded inputs differ on this machine'
+
+
+def test_oracle_sampling_forward_vs_golden(sd, su_action_mask):
+    g = torch.load(os.path.join(GOLD, 'infer.pt'))
+    torch.manual_seed(g['rng_seed'])
+    with torch.no_grad():
+        o = O.compute_logp_action(sd, **tree_clone(G.infer_case()), su_action_mask=su_action_mask)
+    for k in O.HEADS:
+        assert torch.equal(o['action_info'][k], g['action_info'][k]), k
+        close(o['logit'][k], g['logit'][k], 'logit/' + k)
+        close(o['action_logp'][k], g['action_logp'][k], 'logp/' + k)
+    assert torch.equal(o['selected_units_num'], g['selected_units_num'])
+
+
+def test_oracle_teacher_forward_vs_golden(sd):
+    g = torch.load(os.path.join(GOLD, 'teacher.pt'))
+    obs, act, num = G.teacher_case()
+    with torch.no_grad():
+        o = O.compute_teacher_logit(sd, **tree_clone(obs), selected_units_num=num, action_info=act)
+    for k in O.HEADS:
+        close(o['logit'][k], g['logit'][k], 'logit/' + k)
+
+
+def test_oracle_rl_step_vs_golden(sd):
+    g = torch.load(os.path.join(GOLD, 'rl_step.pt'))
+    P = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    out = O.rl_learner_forward(P, **tree_clone(G.rl_case()))
+    info = O.rl_loss(out)
+    info['total_loss'].backward()
+    for k in O.HEADS:
+        close(out['target_logit'][k], g['target_logit'][k], 'target_logit/' + k)
+    for k, v in g['value'].items():
+        close(out['value'][k], v, 'value/' + k)
+    for k, v in g['loss'].items():
+        assert abs(info[k].item() - v) <= 1e-4 * max(1.0, abs(v)), (k, info[k].item(), v)
+    gmax = max(g['grad_norm'].values())
+    for n, v in g['grad_norm'].items():
+        assert abs(P[n].grad.norm().item() - v) <= 1e-3 * max(v, 1e-3 * gmax), n
+    for n, v in g['grads'].items():
+        close(P[n].grad, v, 'grad/' + n, rtol=1e-3)

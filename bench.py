@@ -274,6 +274,8 @@ def run_b200(args, rank, world, local_rank):
         info = learner._train(data)
         last_loss[0] = info['total_loss'].item()           # device -> host read of the step result
 
+    if os.environ.get('DSB_ANOMALY') == '1':
+        torch.autograd.set_detect_anomaly(True)
     for _ in range(args.warmup):
         step_resident()
     clocks = ClockSampler(local_rank)

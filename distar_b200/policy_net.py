@@ -58,12 +58,21 @@ BASELINE_ATAN = {'winloss': True, 'build_order': False, 'built_unit': False, 'ef
                  'battle': False}
 
 
+def set_library_precision():
+    """The reference computes in fp32 end to end.  PyTorch lets cuDNN convolutions silently use TF32 (10-bit mantissa),
+    which alone costs ~1e-3 on the location logits; the parts of the path that are still library calls must run in
+    true fp32 to hold the 1e-3 parity contract."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
 class Net:
     """Functional network over a parameter mapping.  ``terms`` = products per tensor-core GEMM (3 = fp32-class)."""
 
     def __init__(self, P: Dict[str, Tensor], spatial_x: int, spatial_y: int, temperature: float = 1.0,
                  terms: int = 3, rng: str = 'cuda'):
         self.P, self.W, self.H, self.T, self.terms, self.rng = P, spatial_x, spatial_y, temperature, terms, rng
+        set_library_precision()
 
     # -------------------------------------------------------------------------------------- primitives
     def fc(self, name: str, x: Tensor, relu: bool = False) -> Tensor:
@@ -387,10 +396,15 @@ class Net:
             for j in range(4):
                 g = self.conv(rp + 'GateWeightG.%d' % j, g, 0, relu=(j < 3))
             x = torch.relu(torch.tanh(r * torch.sigmoid(g)) * self.P[rp + 'UpdateSP'] + x)
-        for i in range(3):
-            x = self.conv(pre + 'upsample.%d' % i, F.interpolate(x, scale_factor=2., mode='bilinear'), 1,
-                          relu=(i < 2))
-        logits = x.reshape(N, -1) / self.T
+        # ATen's bilinear backward launches an invalid grid beyond ~2k rows of this shape: run the decoder in row chunks
+        outs = []
+        for r0 in range(0, N, 1024):
+            u = x[r0:r0 + 1024]
+            for i in range(3):
+                u = self.conv(pre + 'upsample.%d' % i, F.interpolate(u, scale_factor=2., mode='bilinear'), 1,
+                              relu=(i < 2))
+            outs.append(u.reshape(u.shape[0], -1))
+        logits = (outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)) / self.T
         if location is None:
             location = self.sample(logits)
         return logits, location

@@ -12,7 +12,8 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor 128x64 bf16 boxes (SWIZZLE_128B) for A_hi/A_lo/W_hi/W_lo
 //   warp 1      MMA issuer  : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 N128 K16),
 //               tcgen05.commit releases smem stages and publishes the TMEM accumulator
-//   warps 2..5  epilogue    : tcgen05.ld 32x32b -> +bias, ReLU -> fp32 C (and optional bf16 hi/lo split of C)
+//   warps 2..5  epilogue    : tcgen05.ld 32x32b -> +bias, ReLU -> swizzled smem box -> TMA store of fp32 C
+//               (and an optional bf16 hi/lo split of C)
 //   kStages-deep smem ring (mbarrier full/empty) and a 2-deep TMEM accumulator ring (tmem_full/tmem_empty) so
 //   the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
@@ -25,7 +26,9 @@ constexpr int kStages = 3;
 constexpr int kAccStages = 2;
 constexpr int kTileBytes = BM * BK * 2;                 // 16 KiB: one 128x64 bf16 operand tile
 constexpr int kStageBytes = 4 * kTileBytes;             // A_hi, A_lo, W_hi, W_lo
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kStoreBufBytes = 32 * 128;                // one 32-row x 32-col fp32 staging box (128 B rows, SWIZZLE_128B)
+constexpr int kStoreBytes = 4 * 2 * kStoreBufBytes;     // 4 epilogue warps x double buffer
+constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kTmemCols = kAccStages * BN;              // 256
 constexpr int kThreads = 192;
 constexpr int UMMA_K = 16;
@@ -120,14 +123,21 @@ struct GemmParams {
     int N, K, terms, relu;
 };
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                  const GemmParams p) {
+                  const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024 B alignment
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    unsigned char* store_bufs = smem + kStages * kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(store_bufs + kStoreBytes);
     uint64_t* full = bars;                       // [kStages]
     uint64_t* empty = bars + kStages;            // [kStages]
     uint64_t* tmem_full = bars + 2 * kStages;    // [kAccStages]
@@ -221,8 +231,12 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
+        // TMEM -> registers -> (+bias, ReLU) -> swizzled smem box -> TMA store: every global write is a full,
+        // coalesced 128 B line issued by the copy engine; the staging box is double buffered per warp.
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
+        unsigned char* my_bufs = store_bufs + (warp - 2) * 2 * kStoreBufBytes;
         int it = 0;
+        uint32_t chunk_no = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -232,9 +246,14 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             const int64_t row = (int64_t)m0 + q * 32 + lane;
             const bool row_ok = row < p.M;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_no) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+                if (c0 == BN - 32) {               // accumulator fully read: hand TMEM back to the MMA warp early
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                }
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -243,35 +262,43 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     if (p.relu) x = fmaxf(x, 0.f);
                     v[j] = x;
                 }
-                if (row_ok) {
-                    float4* dst = reinterpret_cast<float4*>(p.c + row * p.N + n0 + c0);
+                unsigned char* buf = my_bufs + (chunk_no & 1) * kStoreBufBytes;
+                // the TMA store that last read this buffer (two chunks ago) must have finished reading it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                const uint32_t rowbase = smem_u32(buf) + lane * 128;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    if (p.c_hi) {
-                        uint4* dh = reinterpret_cast<uint4*>(p.c_hi + row * p.N + n0 + c0);
-                        uint4* dl = reinterpret_cast<uint4*>(p.c_lo + row * p.N + n0 + c0);
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t addr = rowbase + (uint32_t)((j ^ (lane & 7)) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                                 "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) tma_store_2d(&map_c, buf, n0 + c0, m0 + q * 32);
+                if (p.c_hi && row_ok) {
+                    uint4* dh = reinterpret_cast<uint4*>(p.c_hi + row * p.N + n0 + c0);
+                    uint4* dl = reinterpret_cast<uint4*>(p.c_lo + row * p.N + n0 + c0);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint32_t h[4], l[4];
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t h[4], l[4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float x0 = v[8 * j + 2 * e], x1 = v[8 * j + 2 * e + 1];
-                                const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
-                                const float2 hf = __bfloat1622float2(hh);
-                                const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
-                                h[e] = *reinterpret_cast<const uint32_t*>(&hh);
-                                l[e] = *reinterpret_cast<const uint32_t*>(&ll);
-                            }
-                            dh[j] = make_uint4(h[0], h[1], h[2], h[3]);
-                            dl[j] = make_uint4(l[0], l[1], l[2], l[3]);
+                        for (int e = 0; e < 4; ++e) {
+                            const float x0 = v[8 * j + 2 * e], x1 = v[8 * j + 2 * e + 1];
+                            const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+                            const float2 hf = __bfloat1622float2(hh);
+                            const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+                            h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                            l[e] = *reinterpret_cast<const uint32_t*>(&ll);
                         }
+                        dh[j] = make_uint4(h[0], h[1], h[2], h[3]);
+                        dl[j] = make_uint4(l[0], l[1], l[2], l[3]);
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
     }
 
     tc_fence_before();
@@ -313,6 +340,21 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols) {
     return DSB_OK;
 }
 
+// fp32 row-major [rows, cols] output, box = 32 x 32, 128 B swizzle (matches the epilogue's staging layout)
+int make_map_c(CUtensorMap* map, const void* base, int64_t rows, int64_t cols) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { dsb::set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DSB_ERR_CUDA; }
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { dsb::set_error("cuTensorMapEncodeTiled(C) failed: %d", (int)r); return DSB_ERR_CUDA; }
+    return DSB_OK;
+}
+
 }  // namespace
 
 extern "C" int dsb_gemm_bf16_split(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
@@ -326,8 +368,9 @@ extern "C" int dsb_gemm_bf16_split(const void* a_hi, const void* a_lo, const voi
                 BN, BK, N, K);
     DSB_REQUIRE((M + BM - 1) / BM * (int64_t)(N / BN) < (1ll << 31), "gemm: too many tiles");
     if (M == 0) return DSB_OK;
-    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo, mc;
     int rc;
+    if ((rc = make_map_c(&mc, c, M, N))) return rc;
     if ((rc = make_map(&ma_hi, a_hi, M, K))) return rc;
     if ((rc = make_map(&mw_hi, w_hi, N, K))) return rc;
     if ((rc = make_map(&ma_lo, terms == 3 ? a_lo : a_hi, M, K))) return rc;
@@ -347,6 +390,6 @@ extern "C" int dsb_gemm_bf16_split(const void* a_hi, const void* a_lo, const voi
     p.M = M; p.N = N; p.K = K; p.terms = terms; p.relu = relu;
     const int64_t tiles = (M + BM - 1) / BM * (int64_t)(N / BN);
     const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
-    gemm_split_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+    gemm_split_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, mc, p);
     return dsb::check_launch("gemm_bf16_split");
 }

@@ -306,6 +306,34 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
 
 
 # ------------------------------------------------------------------------------------------------
+# bilinear x2 up-sampling (location head decoder, K14)
+# ------------------------------------------------------------------------------------------------
+class _Upsample2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        N, C, H, W = x.shape
+        x = x.contiguous()
+        out = torch.empty((N, C, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+        lib.call('dsb_upsample_bilinear2x_fwd', x, out, N * C, H, W)
+        ctx.shape = (N, C, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        N, C, H, W = ctx.shape
+        gin = torch.empty((N, C, H, W), dtype=torch.float32, device=g.device)
+        lib.call('dsb_upsample_bilinear2x_bwd', g.contiguous(), gin, N * C, H, W)
+        return gin
+
+
+def upsample_bilinear2x(x: torch.Tensor) -> torch.Tensor:
+    """F.interpolate(x, scale_factor=2., mode='bilinear') (align_corners=False) on [N,C,H,W] fp32."""
+    if _use_kernel(x):
+        return _Upsample2x.apply(x.float())
+    return F.interpolate(x, scale_factor=2., mode='bilinear')
+
+
+# ------------------------------------------------------------------------------------------------
 # flat-arena optimiser (K20)
 # ------------------------------------------------------------------------------------------------
 class FlatAdam:

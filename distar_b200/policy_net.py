@@ -396,15 +396,9 @@ class Net:
             for j in range(4):
                 g = self.conv(rp + 'GateWeightG.%d' % j, g, 0, relu=(j < 3))
             x = torch.relu(torch.tanh(r * torch.sigmoid(g)) * self.P[rp + 'UpdateSP'] + x)
-        # ATen's bilinear backward launches an invalid grid beyond ~2k rows of this shape: run the decoder in row chunks
-        outs = []
-        for r0 in range(0, N, 1024):
-            u = x[r0:r0 + 1024]
-            for i in range(3):
-                u = self.conv(pre + 'upsample.%d' % i, F.interpolate(u, scale_factor=2., mode='bilinear'), 1,
-                              relu=(i < 2))
-            outs.append(u.reshape(u.shape[0], -1))
-        logits = (outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)) / self.T
+        for i in range(3):
+            x = self.conv(pre + 'upsample.%d' % i, ops.upsample_bilinear2x(x), 1, relu=(i < 2))
+        logits = x.reshape(N, -1) / self.T
         if location is None:
             location = self.sample(logits)
         return logits, location

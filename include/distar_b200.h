@@ -72,6 +72,11 @@ int dsb_categorical_stats_bwd(const float* logits, const float* teacher, const i
 int dsb_sample_categorical(const float* logits, const float* q, int64_t* index, float* logp, int64_t rows, int C,
                            dsb_stream_t stream);
 
+/* ---- bilinear x2 up-sampling, align_corners=False  (F.interpolate at head/action_arg_head.py:439-440) ----
+ * in [NC, H, W] f32 -> out [NC, 2H, 2W]; backward is a deterministic gather (no atomics). */
+int dsb_upsample_bilinear2x_fwd(const float* in, float* out, int64_t NC, int H, int W, dsb_stream_t stream);
+int dsb_upsample_bilinear2x_bwd(const float* grad_out, float* grad_in, int64_t NC, int H, int W, dsb_stream_t stream);
+
 /* ---- fp32 -> (hi, lo) bf16 split used by the split-precision tensor-core GEMM ---- */
 int dsb_split_bf16(const float* x, void* hi, void* lo, int64_t n, dsb_stream_t stream);
 

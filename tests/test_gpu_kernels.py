@@ -154,3 +154,18 @@ def test_flat_adam_matches_torch():
         norm = mine.step()
         assert abs(norm.item() - norm_ref.item()) <= 1e-4 * norm_ref.item()
         assert torch.allclose(p.cpu(), ref.detach(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('N,C,H,W', [(3, 128, 16, 16), (2, 64, 32, 32), (2, 32, 64, 64), (1, 5, 3, 7), (2, 4, 1, 1)])
+def test_upsample_bilinear2x_fwd_bwd(N, C, H, W):
+    g = torch.Generator().manual_seed(H * W)
+    x = torch.randn(N, C, H, W, generator=g)
+    go = torch.randn(N, C, 2 * H, 2 * W, generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref = torch.nn.functional.interpolate(xr, scale_factor=2., mode='bilinear')
+    ref.backward(go)
+    xd = x.to(DEV).requires_grad_(True)
+    out = ops.upsample_bilinear2x(xd)
+    out.backward(go.to(DEV))
+    assert torch.allclose(out.cpu(), ref.detach(), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(xd.grad.cpu(), xr.grad, rtol=1e-5, atol=1e-5)

@@ -1,21 +1,30 @@
-// Split-precision tcgen05 GEMM:  C[M,N] = act(A[M,K] . W[N,K]^T + bias)   — the fc_block workhorse
-// (ctools/torch_utils/network/nn_module.py:231-270) behind the entity transformer's QKV / out-proj / MLP
-// layers (model/module_utils.py:88-139), the LSTM input projection and the value / head MLPs.
+// Split-precision tcgen05 GEMM family:  C = alpha * op(A) . op(B)^T (+ bias, ReLU)
+//
+// One persistent warp-specialised kernel serves every GEMM-shaped piece of the hot path:
+//   * fc_block forward  y = act(x W^T + b)           (ctools/torch_utils/network/nn_module.py:231-270; the entity
+//     transformer's QKV / out-proj / MLP, model/module_utils.py:88-139, LSTM input projection, value/head MLPs)
+//   * its input gradient dX = dY W  and weight gradient dW = dY^T X  (split-K over the token dimension)
+//   * attention scores S = Q K^T, context O = P V and all five attention-backward products, batched over
+//     (observation, head) by pure coordinate arithmetic on ONE tensor map (no per-head copies or transposes).
 //
 // Why "split": the parity contract is 1e-3 on logits against an fp32 reference; plain bf16 operands miss it by
 // >10x and TF32 by ~3x (measured on the CPU oracle).  Each fp32 operand x is therefore
 // carried as a bf16 pair (hi = bf16(x), lo = bf16(x - hi)) and the product is formed on the tensor cores as
 // hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM (relative error ~2^-16).  terms = 1 gives plain bf16.
 //
-// Structure (one CTA per SM, persistent over 128x128 output tiles, m-major tile order so the CTAs that share
-// an A tile run together and A streams from HBM once):
-//   warp 0      TMA producer: cp.async.bulk.tensor 128x64 bf16 boxes (SWIZZLE_128B) for A_hi/A_lo/W_hi/W_lo
-//   warp 1      MMA issuer  : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 N128 K16),
-//               tcgen05.commit releases smem stages and publishes the TMEM accumulator
-//   warps 2..5  epilogue    : tcgen05.ld 32x32b -> +bias, ReLU -> swizzled smem box -> TMA store of fp32 C
-//               (and an optional bf16 hi/lo split of C)
-//   kStages-deep smem ring (mbarrier full/empty) and a 2-deep TMEM accumulator ring (tmem_full/tmem_empty) so
-//   the epilogue of tile i overlaps the MMAs of tile i+1.
+// Operand layouts.  A "K-major" operand is stored with the reduction index contiguous (x[M,K], W[N,K]): one TMA box
+// of 128 rows x 64 k (SWIZZLE_128B).  An "MN-major" operand is stored with the reduction index strided (the natural
+// layout of X and dY when reducing over tokens, of V in P.V, of P in P^T.dO ...): two TMA boxes of 64 k-rows x 64 mn,
+// consumed through MN-major UMMA descriptors (LBO = 8 KiB between the 64-wide halves, SBO = 1 KiB between 8-row
+// k groups).  No transposed copy of any activation is ever materialised.
+//
+// Structure (one CTA per SM, persistent over 128x128 output tiles, n-fastest tile order so CTAs that share an A
+// tile run together and A streams from HBM once):
+//   warp 0      TMA producer : cp.async.bulk.tensor boxes for A_hi/A_lo/B_hi/B_lo into a 3-deep smem ring
+//   warp 1      MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 N128 K16);
+//               tcgen05.commit frees smem stages and publishes the TMEM accumulator (2-deep ring)
+//   warps 2..5  epilogue     : tcgen05.ld 32x32b -> alpha, +bias, ReLU -> swizzled smem box -> TMA store of fp32 C
+//               (optional bf16 hi/lo split of C for a following GEMM)
 #include <cuda.h>
 #include "common.cuh"
 
@@ -25,7 +34,7 @@ constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int kStages = 3;
 constexpr int kAccStages = 2;
 constexpr int kTileBytes = BM * BK * 2;                 // 16 KiB: one 128x64 bf16 operand tile
-constexpr int kStageBytes = 4 * kTileBytes;             // A_hi, A_lo, W_hi, W_lo
+constexpr int kStageBytes = 4 * kTileBytes;             // A_hi, A_lo, B_hi, B_lo
 constexpr int kStoreBufBytes = 32 * 128;                // one 32-row x 32-col fp32 staging box (128 B rows, SWIZZLE_128B)
 constexpr int kStoreBytes = 4 * 2 * kStoreBufBytes;     // 4 epilogue warps x double buffer
 constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -60,6 +69,11 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -73,29 +87,35 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major, SWIZZLE_128B operand tile (rows of 128 B, 8-row groups of 1024 B): cute::UMMA::SmemDescriptor
-// (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30) (=1, unused when swizzled), SBO>>4 [32,46)
-// (=1024 B), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+// cute::UMMA::SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+//   K-major tile  : rows of 128 B (64 k), 8-row groups of 1024 B  -> SBO = 1024, LBO unused (1)
+//   MN-major tile : rows of 128 B (64 mn) indexed by k, 8-k groups of 1024 B -> SBO = 1024; second 64-wide mn half
+//                   8192 B further -> LBO = 8192
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(mn_major ? (8192 >> 4) : 1) << 16;
     d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
 }
-// cute::UMMA::InstrDescriptor: c_format F32=1 [4,6), a/b_format BF16=1 [7,10)/[10,13), K-major both,
-// n_dim = N>>3 [17,23), m_dim = M>>4 [24,29).
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// cute::UMMA::InstrDescriptor: c_format F32=1 [4,6), a/b_format BF16=1 [7,10)/[10,13), a_major [15], b_major [16]
+// (0 = K, 1 = MN), n_dim = N>>3 [17,23), m_dim = M>>4 [24,29).
+__device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
 
-__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                     uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate) : "memory");
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -114,24 +134,56 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-struct GemmParams {
-    const float* bias;
-    float* c;
-    __nv_bfloat16* c_hi;
-    __nv_bfloat16* c_lo;
-    int64_t M;
-    int N, K, terms, relu;
+struct OperandMap {       // tile origin = (col_base + bi*col_inner, row_outer*bo + row_inner*bi), see header
+    int col_base, col_inner, row_outer, row_inner, mn_major;
 };
 
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+struct GemmParams {
+    const float* bias;
+    __nv_bfloat16* c_hi;
+    __nv_bfloat16* c_lo;
+    float alpha;
+    int64_t M;               // valid rows per batch
+    int64_t ldc;             // row stride (elements) of c_hi / c_lo
+    int N, terms, relu;
+    int num_m, num_n, num_k; // tiles per (batch, split); k blocks per split
+    int batch, inner, splits;
+    int c_row_outer, c_row_inner, c_row_split, c_col_base, c_col_inner;
+    OperandMap a, b;
+};
+
+struct TileCoord { int b, s, m0, n0, bo, bi; };
+
+__device__ __forceinline__ TileCoord decode_tile(int tile, const GemmParams& p) {
+    TileCoord t;
+    const int n_i = tile % p.num_n;
+    int r = tile / p.num_n;
+    const int m_i = r % p.num_m;
+    r /= p.num_m;
+    t.s = r % p.splits;
+    t.b = r / p.splits;
+    t.m0 = m_i * BM;
+    t.n0 = n_i * BN;
+    t.bo = t.b / p.inner;
+    t.bi = t.b - t.bo * p.inner;
+    return t;
+}
+
+__device__ __forceinline__ void load_operand(const CUtensorMap* map, uint64_t* bar, unsigned char* dst,
+                                             const OperandMap& o, const TileCoord& t, int mn0, int kg) {
+    const int col0 = o.col_base + t.bi * o.col_inner;
+    const int row0 = o.row_outer * t.bo + o.row_inner * t.bi;
+    if (!o.mn_major) {
+        tma_load_2d(map, bar, dst, col0 + kg, row0 + mn0);                      // box {64 k, 128 rows}
+    } else {
+        tma_load_2d(map, bar, dst, col0 + mn0, row0 + kg);                      // box {64 mn, 64 k} x 2
+        tma_load_2d(map, bar, dst + kTileBytes / 2, col0 + mn0 + 64, row0 + kg);
+    }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                   const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024 B alignment
@@ -145,16 +197,17 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_m = (int)((p.M + BM - 1) / BM), num_n = p.N / BN, num_k = p.K / BK;
-    const int num_tiles = num_m * num_n;
+    const int num_tiles = p.batch * p.splits * p.num_m * p.num_n;
+    const int num_k = p.num_k;
     const bool three = p.terms == 3;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
         if (three) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_lo) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
         }
         for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
@@ -177,16 +230,17 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             uint32_t phase = 0;
             const uint32_t tx = (three ? 4 : 2) * kTileBytes;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+                const TileCoord t = decode_tile(tile, p);
                 for (int kb = 0; kb < num_k; ++kb) {
+                    const int kg = (t.s * num_k + kb) * BK;
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char* st = smem + stage * kStageBytes;
                     mbar_expect_tx(&full[stage], tx);
-                    tma_load_2d(&map_a_hi, &full[stage], st, kb * BK, m0);
-                    tma_load_2d(&map_w_hi, &full[stage], st + 2 * kTileBytes, kb * BK, n0);
+                    load_operand(&map_a_hi, &full[stage], st, p.a, t, t.m0, kg);
+                    load_operand(&map_b_hi, &full[stage], st + 2 * kTileBytes, p.b, t, t.n0, kg);
                     if (three) {
-                        tma_load_2d(&map_a_lo, &full[stage], st + kTileBytes, kb * BK, m0);
-                        tma_load_2d(&map_w_lo, &full[stage], st + 3 * kTileBytes, kb * BK, n0);
+                        load_operand(&map_a_lo, &full[stage], st + kTileBytes, p.a, t, t.m0, kg);
+                        load_operand(&map_b_lo, &full[stage], st + 3 * kTileBytes, p.b, t, t.n0, kg);
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -197,6 +251,11 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
+        const bool a_mn = p.a.mn_major != 0, b_mn = p.b.mn_major != 0;
+        const uint32_t idesc = make_idesc(a_mn, b_mn);
+        // descriptor start-address step (>>4) per UMMA_K: 32 B inside the swizzle row (K-major) or 16 k-rows (MN-major)
+        const uint64_t a_step = a_mn ? (uint64_t)((UMMA_K * 128) >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
+        const uint64_t b_step = b_mn ? (uint64_t)((UMMA_K * 128) >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -208,21 +267,21 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-                    const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + kTileBytes);
-                    const uint64_t w_hi = make_desc(sa + 2 * kTileBytes), w_lo = make_desc(sa + 3 * kTileBytes);
+                    const uint64_t a_hi = make_desc(sa, a_mn), a_lo = make_desc(sa + kTileBytes, a_mn);
+                    const uint64_t b_hi = make_desc(sa + 2 * kTileBytes, b_mn), b_lo = make_desc(sa + 3 * kTileBytes, b_mn);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per K step inside the swizzle span
+                        const uint64_t ao = a_step * k, bo = b_step * k;
                         const uint32_t first = (kb | k) ? 1u : 0u;
                         if (three) {
-                            umma(d_tmem, a_lo + adv, w_hi + adv, first);
-                            umma(d_tmem, a_hi + adv, w_lo + adv, 1u);
-                            umma(d_tmem, a_hi + adv, w_hi + adv, 1u);
+                            umma(d_tmem, a_lo + ao, b_hi + bo, idesc, first);
+                            umma(d_tmem, a_hi + ao, b_lo + bo, idesc, 1u);
+                            umma(d_tmem, a_hi + ao, b_hi + bo, idesc, 1u);
                         } else {
-                            umma(d_tmem, a_hi + adv, w_hi + adv, first);
+                            umma(d_tmem, a_hi + ao, b_hi + bo, idesc, first);
                         }
                     }
-                    umma_commit(&empty[stage]);                       // frees this smem stage when the MMAs retire
+                    umma_commit(&empty[stage]);                         // frees this smem stage when the MMAs retire
                     if (kb == num_k - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
                 }
                 __syncwarp();
@@ -231,7 +290,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
-        // TMEM -> registers -> (+bias, ReLU) -> swizzled smem box -> TMA store: every global write is a full,
+        // TMEM -> registers -> (alpha, +bias, ReLU) -> swizzled smem box -> TMA store: every global write is a full,
         // coalesced 128 B line issued by the copy engine; the staging box is double buffered per warp.
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
         unsigned char* my_bufs = store_bufs + (warp - 2) * 2 * kStoreBufBytes;
@@ -240,11 +299,13 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+            const TileCoord t = decode_tile(tile, p);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const int64_t row = (int64_t)m0 + q * 32 + lane;
-            const bool row_ok = row < p.M;
+            const int row_in_batch = t.m0 + q * 32 + lane;
+            const bool row_ok = row_in_batch < p.M;
+            const int c_row0 = t.bo * p.c_row_outer + t.bi * p.c_row_inner + t.s * p.c_row_split + t.m0 + q * 32;
+            const int c_col0 = p.c_col_base + t.bi * p.c_col_inner + t.n0;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_no) {
                 uint32_t r[32];
@@ -257,8 +318,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(r[j]);
-                    if (p.bias) x += __ldg(p.bias + n0 + c0 + j);
+                    float x = __uint_as_float(r[j]) * p.alpha;
+                    if (p.bias) x += __ldg(p.bias + t.n0 + c0 + j);
                     if (p.relu) x = fmaxf(x, 0.f);
                     v[j] = x;
                 }
@@ -275,10 +336,11 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) tma_store_2d(&map_c, buf, n0 + c0, m0 + q * 32);
+                if (lane == 0) tma_store_2d(&map_c, buf, c_col0 + c0, c_row0);
                 if (p.c_hi && row_ok) {
-                    uint4* dh = reinterpret_cast<uint4*>(p.c_hi + row * p.N + n0 + c0);
-                    uint4* dl = reinterpret_cast<uint4*>(p.c_lo + row * p.N + n0 + c0);
+                    const int64_t off = (int64_t)(c_row0 + lane) * p.ldc + c_col0 + c0;
+                    uint4* dh = reinterpret_cast<uint4*>(p.c_hi + off);
+                    uint4* dl = reinterpret_cast<uint4*>(p.c_lo + off);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         uint32_t h[4], l[4];
@@ -325,56 +387,51 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] tensor, box = [BM rows, BK cols], 128 B swizzle
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols) {
+// 2-D row-major [rows, cols] tensor of `esize`-byte elements, box = [box_rows, box_cols], 128 B swizzle
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int esize, int box_rows, int box_cols) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { dsb::set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DSB_ERR_CUDA; }
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * esize};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = enc(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B,
+                     esize == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { dsb::set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return DSB_ERR_CUDA; }
+    if (r != CUDA_SUCCESS) {
+        dsb::set_error("cuTensorMapEncodeTiled failed: %d (rows %lld cols %lld esize %d)", (int)r, (long long)rows,
+                       (long long)cols, esize);
+        return DSB_ERR_CUDA;
+    }
     return DSB_OK;
 }
 
-// fp32 row-major [rows, cols] output, box = 32 x 32, 128 B swizzle (matches the epilogue's staging layout)
-int make_map_c(CUtensorMap* map, const void* base, int64_t rows, int64_t cols) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) { dsb::set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DSB_ERR_CUDA; }
-    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
-    const cuuint32_t box[2] = {32, 32};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { dsb::set_error("cuTensorMapEncodeTiled(C) failed: %d", (int)r); return DSB_ERR_CUDA; }
-    return DSB_OK;
-}
-
-}  // namespace
-
-extern "C" int dsb_gemm_bf16_split(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
-                                   const float* bias, float* c, void* c_hi, void* c_lo, int64_t M, int N, int K,
-                                   int terms, int relu, dsb_stream_t stream) {
-    DSB_REQUIRE(a_hi && w_hi && c, "gemm: null pointer");
-    DSB_REQUIRE(terms == 1 || terms == 3, "gemm: terms must be 1 or 3");
-    DSB_REQUIRE(terms == 1 || (a_lo && w_lo), "gemm: terms=3 needs the lo halves");
-    DSB_REQUIRE(!c_hi == !c_lo, "gemm: c_hi and c_lo go together");
-    DSB_REQUIRE(M >= 0 && N > 0 && K > 0 && N % BN == 0 && K % BK == 0, "gemm: need N %% %d == 0 and K %% %d == 0 (N=%d K=%d)",
-                BN, BK, N, K);
-    DSB_REQUIRE((M + BM - 1) / BM * (int64_t)(N / BN) < (1ll << 31), "gemm: too many tiles");
-    if (M == 0) return DSB_OK;
-    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo, mc;
+int launch(const dsb_gemm_args& g, cudaStream_t stream) {
+    DSB_REQUIRE(g.a_hi && g.b_hi && g.c, "gemm: null pointer");
+    DSB_REQUIRE(g.terms == 1 || g.terms == 3, "gemm: terms must be 1 or 3");
+    DSB_REQUIRE(g.terms == 1 || (g.a_lo && g.b_lo), "gemm: terms=3 needs the lo halves");
+    DSB_REQUIRE(!g.c_hi == !g.c_lo, "gemm: c_hi and c_lo go together");
+    const int batch = g.batch > 0 ? g.batch : 1, splits = g.splits > 0 ? g.splits : 1, inner = g.inner > 0 ? g.inner : 1;
+    DSB_REQUIRE(g.m >= 0 && g.n > 0 && g.k > 0 && g.n % BN == 0 && g.k % (BK * splits) == 0,
+                "gemm: need n %% %d == 0 and k %% (%d*splits) == 0 (m=%lld n=%d k=%d splits=%d)", BN, BK, (long long)g.m,
+                g.n, g.k, splits);
+    DSB_REQUIRE((batch == 1 && splits == 1) || g.m % BM == 0, "gemm: batched / split-K problems need m %% %d == 0", BM);
+    DSB_REQUIRE(splits == 1 || (!g.bias && !g.relu), "gemm: split-K partial sums take no bias / ReLU");
+    DSB_REQUIRE(g.a_cols % 8 == 0 && g.b_cols % 8 == 0 && g.c_cols % 4 == 0, "gemm: row pitches must be 16-byte multiples");
+    if (g.m == 0) return DSB_OK;
+    const int num_m = (int)((g.m + BM - 1) / BM), num_n = g.n / BN;
+    const int64_t tiles = (int64_t)batch * splits * num_m * num_n;
+    DSB_REQUIRE(tiles < (1ll << 31), "gemm: too many tiles");
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mc;
     int rc;
-    if ((rc = make_map_c(&mc, c, M, N))) return rc;
-    if ((rc = make_map(&ma_hi, a_hi, M, K))) return rc;
-    if ((rc = make_map(&mw_hi, w_hi, N, K))) return rc;
-    if ((rc = make_map(&ma_lo, terms == 3 ? a_lo : a_hi, M, K))) return rc;
-    if ((rc = make_map(&mw_lo, terms == 3 ? w_lo : w_hi, N, K))) return rc;
+    const int a_br = g.a_mn ? 64 : BM, b_br = g.b_mn ? 64 : BN;   // MN-major boxes are 64 k-rows x 64 mn
+    if ((rc = make_map(&ma_hi, g.a_hi, g.a_rows, g.a_cols, 2, a_br, 64))) return rc;
+    if ((rc = make_map(&mb_hi, g.b_hi, g.b_rows, g.b_cols, 2, b_br, 64))) return rc;
+    if ((rc = make_map(&ma_lo, g.terms == 3 ? g.a_lo : g.a_hi, g.a_rows, g.a_cols, 2, a_br, 64))) return rc;
+    if ((rc = make_map(&mb_lo, g.terms == 3 ? g.b_lo : g.b_hi, g.b_rows, g.b_cols, 2, b_br, 64))) return rc;
+    if ((rc = make_map(&mc, g.c, g.c_rows, g.c_cols, 4, 32, 32))) return rc;
     static bool configured = false;
     static int num_sms = 0;
     if (!configured) {
@@ -386,10 +443,34 @@ extern "C" int dsb_gemm_bf16_split(const void* a_hi, const void* a_lo, const voi
         configured = true;
     }
     GemmParams p;
-    p.bias = bias; p.c = c; p.c_hi = (__nv_bfloat16*)c_hi; p.c_lo = (__nv_bfloat16*)c_lo;
-    p.M = M; p.N = N; p.K = K; p.terms = terms; p.relu = relu;
-    const int64_t tiles = (M + BM - 1) / BM * (int64_t)(N / BN);
+    p.bias = g.bias; p.c_hi = (__nv_bfloat16*)g.c_hi; p.c_lo = (__nv_bfloat16*)g.c_lo;
+    p.alpha = g.alpha; p.M = g.m; p.ldc = g.c_cols; p.N = g.n; p.terms = g.terms; p.relu = g.relu;
+    p.num_m = num_m; p.num_n = num_n; p.num_k = g.k / (BK * splits);
+    p.batch = batch; p.inner = inner; p.splits = splits;
+    p.c_row_outer = g.c_row_outer; p.c_row_inner = g.c_row_inner; p.c_row_split = g.c_row_split;
+    p.c_col_base = g.c_col_base; p.c_col_inner = g.c_col_inner;
+    p.a = OperandMap{g.a_col_base, g.a_col_inner, g.a_row_outer, g.a_row_inner, g.a_mn};
+    p.b = OperandMap{g.b_col_base, g.b_col_inner, g.b_row_outer, g.b_row_inner, g.b_mn};
     const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
-    gemm_split_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, mc, p);
-    return dsb::check_launch("gemm_bf16_split");
+    gemm_split_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, p);
+    return dsb::check_launch("gemm_split");
+}
+
+}  // namespace
+
+extern "C" int dsb_gemm_ex(const dsb_gemm_args* args, dsb_stream_t stream) {
+    DSB_REQUIRE(args, "gemm_ex: null args");
+    return launch(*args, (cudaStream_t)stream);
+}
+
+extern "C" int dsb_gemm_bf16_split(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
+                                   const float* bias, float* c, void* c_hi, void* c_lo, int64_t M, int N, int K,
+                                   int terms, int relu, dsb_stream_t stream) {
+    dsb_gemm_args g = {};
+    g.a_hi = a_hi; g.a_lo = a_lo; g.b_hi = w_hi; g.b_lo = w_lo;
+    g.a_rows = M; g.a_cols = K; g.b_rows = N; g.b_cols = K;
+    g.bias = bias; g.alpha = 1.0f; g.relu = relu; g.terms = terms;
+    g.c = c; g.c_rows = M; g.c_cols = N; g.c_hi = c_hi; g.c_lo = c_lo;
+    g.m = M; g.n = N; g.k = K; g.batch = 1; g.inner = 1; g.splits = 1;
+    return launch(g, (cudaStream_t)stream);
 }

@@ -6,24 +6,25 @@
 // each entity's 32-channel row (one coalesced 128 B read) into the tile, then streams the tile out so that every
 // output element is written exactly once with fully coalesced 128 B warp stores.  No memset pass, no int64
 // index tensor, no global atomics.  Algorithmic traffic per obs: 2 MiB written + 64 KiB + 1 KiB read.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
 
 constexpr int kC = 32;        // scatter_dim (actor_critic_default_config.yaml: encoder.scatter.output_dim)
-constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;
+constexpr int kThreadsDefault = 512;
 constexpr int kPad = 4;       // channel stride = npix + 4 floats: keeps 16 B alignment, 4-way (not 32-way) bank conflicts
 
 // Forward, v2.  The map is >= 97 % zeros (<= 512 entities on 16384 pixels), so the shared-memory tile is never
 // cleared nor fully read: an occupancy bitmap says which pixels hold data; the write-out streams 16-byte zero
 // vectors straight from registers and only touches the tile where the bitmap is set.  Per CTA the instruction
 // stream is essentially the 4096 coalesced float4 streaming stores of its 64 KiB output slab.
-template <int ROWS, int WT>   // WT = compile-time map width (0 = runtime)
+template <int ROWS, int WT, int kThreads>   // WT = compile-time map width (0 = runtime)
 __global__ void __launch_bounds__(kThreads)
 scatter_fwd_kernel(const float* __restrict__ project, const uint8_t* __restrict__ ex,
                    const uint8_t* __restrict__ ey, const int64_t* __restrict__ entity_num,
                    float* __restrict__ out, int E, int H, int Wrt) {
+    constexpr int kWarps = kThreads / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int W = WT ? WT : Wrt;
     const int bands = H / ROWS;
@@ -126,7 +127,7 @@ __global__ void scatter_bwd_kernel(const float* __restrict__ grad_out, const uin
 
 }  // namespace
 
-template <int ROWS, int WT>
+template <int ROWS, int WT, int kThreads>
 static int launch_scatter_fwd(const float* project, const uint8_t* ex, const uint8_t* ey, const int64_t* entity_num,
                               float* out, int N, int E, int H, int W, cudaStream_t stream) {
     const size_t smem = (size_t)kC * (ROWS * W + kPad) * sizeof(float) + (size_t)E * sizeof(uint32_t) +
@@ -134,14 +135,14 @@ static int launch_scatter_fwd(const float* project, const uint8_t* ex, const uin
     DSB_REQUIRE(smem <= 220 * 1024, "scatter_connection_fwd: tile does not fit shared memory");
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(scatter_fwd_kernel<ROWS, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(scatter_fwd_kernel<ROWS, WT, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) { dsb::set_error("scatter fwd smem attr: %s", cudaGetErrorString(e)); return DSB_ERR_CUDA; }
         configured = smem;
     }
     const int64_t grid = (int64_t)N * (H / ROWS);
     DSB_REQUIRE(grid < (1ll << 31), "scatter_connection_fwd: grid too large");
-    scatter_fwd_kernel<ROWS, WT><<<(unsigned)grid, kThreads, smem, stream>>>(project, ex, ey, entity_num, out, E, H, W);
+    scatter_fwd_kernel<ROWS, WT, kThreads><<<(unsigned)grid, kThreads, smem, stream>>>(project, ex, ey, entity_num, out, E, H, W);
     return dsb::check_launch("scatter_connection_fwd");
 }
 
@@ -152,13 +153,26 @@ extern "C" int dsb_scatter_connection_fwd(const float* project, const uint8_t* e
     DSB_REQUIRE(N >= 0 && E > 0 && E <= 65535 && H > 0 && W > 0, "scatter_connection_fwd: bad shape");
     if (N == 0) return DSB_OK;
     constexpr int ROWS = 4;
-    DSB_REQUIRE(H % ROWS == 0 && W % 4 == 0 && ROWS * W <= 65535,
-                "scatter_connection_fwd: need H %% %d == 0 and W %% 4 == 0", ROWS);
+    DSB_REQUIRE(H % 8 == 0 && W % 4 == 0 && 8 * W <= 65535, "scatter_connection_fwd: need H %% 8 == 0 and W %% 4 == 0");
     DSB_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "scatter_connection_fwd: out must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    if (W == 128) return launch_scatter_fwd<ROWS, 128>(project, ex, ey, entity_num, out, N, E, H, W, s);
-    if (W == 160) return launch_scatter_fwd<ROWS, 160>(project, ex, ey, entity_num, out, N, E, H, W, s);
-    return launch_scatter_fwd<ROWS, 0>(project, ex, ey, entity_num, out, N, E, H, W, s);
+    static int variant = -1;                 // DEBUG: DSB_SCATTER_VARIANT picks the tile shape for tuning runs
+    if (variant < 0) { const char* v = getenv("DSB_SCATTER_VARIANT"); variant = v ? atoi(v) : 0; }
+    if (W == 128) {
+        switch (variant) {
+            case 1: return launch_scatter_fwd<4, 128, 512>(project, ex, ey, entity_num, out, N, E, H, W, s);
+            case 6: return launch_scatter_fwd<1, 128, 128>(project, ex, ey, entity_num, out, N, E, H, W, s);
+            case 7: return launch_scatter_fwd<1, 128, 256>(project, ex, ey, entity_num, out, N, E, H, W, s);
+            case 8: return launch_scatter_fwd<2, 128, 128>(project, ex, ey, entity_num, out, N, E, H, W, s);
+            case 2: return launch_scatter_fwd<4, 128, 256>(project, ex, ey, entity_num, out, N, E, H, W, s);
+            case 3: return launch_scatter_fwd<8, 128, 512>(project, ex, ey, entity_num, out, N, E, H, W, s);
+            case 4: return launch_scatter_fwd<2, 128, 512>(project, ex, ey, entity_num, out, N, E, H, W, s);
+            case 5: return launch_scatter_fwd<8, 128, 1024>(project, ex, ey, entity_num, out, N, E, H, W, s);
+            default: return launch_scatter_fwd<2, 128, 256>(project, ex, ey, entity_num, out, N, E, H, W, s);
+        }
+    }
+    if (W == 160) return launch_scatter_fwd<2, 160, 256>(project, ex, ey, entity_num, out, N, E, H, W, s);
+    return launch_scatter_fwd<2, 0, 256>(project, ex, ey, entity_num, out, N, E, H, W, s);
 }
 
 extern "C" int dsb_scatter_connection_bwd(const float* grad_out, const uint8_t* ex, const uint8_t* ey,

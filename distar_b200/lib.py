@@ -28,11 +28,33 @@ _SIGNATURES = {
     'dsb_upsample_bilinear2x_fwd': (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     'dsb_upsample_bilinear2x_bwd': (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     'dsb_gemm_bf16_split': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    'dsb_attn_softmax_fwd': (_i, [_vp, _vp, _i, _vp, _vp, _i64, _i, _vp]),
+    'dsb_attn_softmax_bwd': (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i64, _i, _vp]),
     'dsb_sumsq_partials': (_i, []),
     'dsb_grad_norm': (_i, [_vp, _i64, _vp, _vp, _vp]),
     'dsb_adam_step': (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp]),
 }
 
+
+
+class GemmArgs(ctypes.Structure):
+    """mirror of dsb_gemm_args (include/distar_b200.h)"""
+    _fields_ = [('a_hi', _vp), ('a_lo', _vp), ('b_hi', _vp), ('b_lo', _vp),
+                ('a_rows', _i64), ('a_cols', _i64), ('b_rows', _i64), ('b_cols', _i64),
+                ('a_mn', _c.c_int32), ('b_mn', _c.c_int32),
+                ('a_col_base', _c.c_int32), ('a_col_inner', _c.c_int32), ('a_row_outer', _c.c_int32),
+                ('a_row_inner', _c.c_int32),
+                ('b_col_base', _c.c_int32), ('b_col_inner', _c.c_int32), ('b_row_outer', _c.c_int32),
+                ('b_row_inner', _c.c_int32),
+                ('bias', _vp), ('alpha', _f), ('relu', _c.c_int32), ('terms', _c.c_int32),
+                ('c', _vp), ('c_rows', _i64), ('c_cols', _i64), ('c_hi', _vp), ('c_lo', _vp),
+                ('m', _i64), ('n', _c.c_int32), ('k', _c.c_int32),
+                ('batch', _c.c_int32), ('inner', _c.c_int32), ('splits', _c.c_int32),
+                ('c_row_outer', _c.c_int32), ('c_row_inner', _c.c_int32), ('c_row_split', _c.c_int32),
+                ('c_col_base', _c.c_int32), ('c_col_inner', _c.c_int32)]
+
+
+_SIGNATURES['dsb_gemm_ex'] = (_i, [ctypes.POINTER(GemmArgs), _vp])
 EXPORTS = sorted(_SIGNATURES)
 _lib = None
 
@@ -70,6 +92,26 @@ def _ptr(t):
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def gemm_ex(**kw):
+    """dsb_gemm_ex with tensors given by keyword (a_hi, a_lo, b_hi, b_lo, bias, c, c_hi, c_lo) plus the integer fields."""
+    lib = load()
+    g = GemmArgs()
+    keep = []
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor):
+            keep.append(v)
+            v = _ptr(v)
+        setattr(g, k, v if v is not None else None)
+    for name in ('a', 'b'):
+        t = kw[name + '_hi']
+        setattr(g, name + '_rows', t.shape[0])
+        setattr(g, name + '_cols', t.shape[1])
+    g.c_rows, g.c_cols = kw['c'].shape
+    rc = lib.dsb_gemm_ex(ctypes.byref(g), _stream())
+    if rc != 0:
+        raise DsbError('dsb_gemm_ex failed (%d): %s' % (rc, lib.dsb_last_error().decode()))
 
 
 def call(name: str, *args):

@@ -253,11 +253,34 @@ def gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu: bool, terms: int = 3, want_sp
     return c
 
 
-class _SplitLinear(torch.autograd.Function):
-    """y = act(x W^T + b) with forward AND input-gradient GEMMs on tcgen05 (3-term split products).
+def _gemm_ex(**kw) -> None:
+    lib.gemm_ex(**kw)
 
-    The weight gradient dW = dY^T X reduces over the (huge) row dimension; it needs MN-major operands / split-K
-    and is still a library GEMM in this round."""
+
+def _pick_splits(tiles: int, k: int) -> int:
+    """split-K factor for a reduction of length k (tokens) over `tiles` output tiles: fill ~148 SMs, keep >= 512 k per
+    split, and k % (64 * splits) == 0."""
+    s = 1
+    while tiles * s * 2 <= 296 and k % (64 * s * 2) == 0 and k // (s * 2) >= 512:
+        s *= 2
+    return s
+
+
+def weight_grad(g_hi, g_lo, x_hi, x_lo, terms: int = 3) -> torch.Tensor:
+    """dW[N,K] = dY^T X with both operands read in place (MN-major: the reduction runs over rows = tokens), split-K over
+    tokens on the tensor cores, partial tiles summed afterwards."""
+    M, N = g_hi.shape
+    K = x_hi.shape[1]
+    splits = _pick_splits((N // 128) * (K // 128), M)
+    part = torch.empty((splits * N, K), dtype=torch.float32, device=g_hi.device)
+    _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=x_hi, b_lo=x_lo, a_mn=1, b_mn=1, alpha=1.0, terms=terms, c=part, m=N, n=K, k=M,
+             batch=1, inner=1, splits=splits, c_row_split=N)
+    return part.view(splits, N, K).sum(0) if splits > 1 else part
+
+
+class _SplitLinear(torch.autograd.Function):
+    """y = act(x W^T + b): forward, input gradient (dY . W, W read MN-major in place) and weight gradient
+    (dY^T . X, split-K over tokens) all on the tcgen05 kernel with 3-term split products."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, relu, terms):
@@ -265,32 +288,117 @@ class _SplitLinear(torch.autograd.Function):
         a_hi, a_lo = split_bf16(x2)
         w_hi, w_lo = split_bf16(weight)
         y = gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu, terms)
-        ctx.save_for_backward(x2, weight, y if relu else None)
+        ctx.save_for_backward(a_hi, a_lo, w_hi, w_lo, y if relu else None)
         ctx.relu, ctx.terms, ctx.has_bias, ctx.xshape = relu, terms, bias is not None, x.shape
         return y.view(*x.shape[:-1], weight.shape[0])
 
     @staticmethod
     def backward(ctx, gy):
-        x2, weight, y = ctx.saved_tensors
+        a_hi, a_lo, w_hi, w_lo, y = ctx.saved_tensors
         gy2 = gy.reshape(-1, gy.shape[-1])
         if ctx.relu:
             gy2 = gy2 * (y > 0)
         gy2 = gy2.contiguous()
+        M, N = gy2.shape
+        K = a_hi.shape[1]
+        on_gpu = gy2.is_cuda
         gx = gw = gb = None
+        g_hi = g_lo = None
+        if on_gpu and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+            g_hi, g_lo = split_bf16(gy2)
         if ctx.needs_input_grad[0]:
-            N, K = weight.shape
-            if gemm_eligible(K, N):
-                g_hi, g_lo = split_bf16(gy2)
-                wt_hi, wt_lo = split_bf16(weight.t().contiguous())
-                gx = gemm_split(g_hi, g_lo, wt_hi, wt_lo, None, False, ctx.terms)
+            if on_gpu and K % 128 == 0 and N % 64 == 0:
+                gx = torch.empty((M, K), dtype=torch.float32, device=gy2.device)
+                _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=w_hi, b_lo=w_lo, b_mn=1, alpha=1.0, terms=ctx.terms, c=gx, m=M, n=K,
+                         k=N, batch=1, inner=1, splits=1)
             else:
-                gx = gy2 @ weight
+                gx = gy2 @ (w_hi.float() + w_lo.float())
             gx = gx.view(ctx.xshape)
         if ctx.needs_input_grad[1]:
-            gw = gy2.t() @ x2
+            if on_gpu and N % 128 == 0 and K % 128 == 0 and M % 64 == 0 and M >= 128:
+                gw = weight_grad(g_hi, g_lo, a_hi, a_lo, ctx.terms)
+            else:
+                gw = gy2.t() @ (a_hi.float() + a_lo.float())
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gy2.sum(0)
         return gx, gw, gb, None, None
+
+
+class _EntityAttention(torch.autograd.Function):
+    """softmax(Q K^T / sqrt(d) + key mask) V for all (observation, head) pairs of the entity transformer
+    (model/module_utils.py:95-110), forward and backward, as batched tcgen05 GEMMs that address Q, K, V inside the
+    QKV activation by coordinates (no split / permute / contiguous copies) plus two row-softmax kernels."""
+
+    @staticmethod
+    def forward(ctx, qkv, entity_num, heads, hd):
+        NS, W3 = qkv.shape
+        S = 512 if NS % 512 == 0 else None
+        n_obs = entity_num.shape[0]
+        S = NS // n_obs
+        H, D = heads, hd
+        dev = qkv.device
+        q_hi, q_lo = split_bf16(qkv)
+        scores = torch.empty((n_obs * H * S, S), dtype=torch.float32, device=dev)
+        _gemm_ex(a_hi=q_hi, a_lo=q_lo, b_hi=q_hi, b_lo=q_lo, alpha=1.0 / math.sqrt(D), terms=3, c=scores, m=S, n=S, k=D,
+                 batch=n_obs * H, inner=H, splits=1, a_col_base=0, a_col_inner=D, a_row_outer=S,
+                 b_col_base=H * D, b_col_inner=D, b_row_outer=S, c_row_outer=H * S, c_row_inner=S)
+        p_hi = torch.empty((n_obs * H * S, S), dtype=torch.bfloat16, device=dev)
+        p_lo = torch.empty_like(p_hi)
+        lib.call('dsb_attn_softmax_fwd', scores, entity_num, H * S, p_hi, p_lo, n_obs * H * S, S)
+        del scores
+        out = torch.empty((NS, H * D), dtype=torch.float32, device=dev)
+        _gemm_ex(a_hi=p_hi, a_lo=p_lo, b_hi=q_hi, b_lo=q_lo, b_mn=1, alpha=1.0, terms=3, c=out, m=S, n=D, k=S,
+                 batch=n_obs * H, inner=H, splits=1, a_row_outer=H * S, a_row_inner=S,
+                 b_col_base=2 * H * D, b_col_inner=D, b_row_outer=S, c_row_outer=S, c_col_inner=D)
+        ctx.save_for_backward(q_hi, q_lo, p_hi, p_lo, entity_num)
+        ctx.dims = (n_obs, S, H, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        q_hi, q_lo, p_hi, p_lo, entity_num = ctx.saved_tensors
+        n_obs, S, H, D = ctx.dims
+        dev = g_out.device
+        alpha = 1.0 / math.sqrt(D)
+        g_hi, g_lo = split_bf16(g_out.contiguous())
+        dqkv = torch.empty((n_obs * S, 3 * H * D), dtype=torch.float32, device=dev)
+        common = dict(terms=3, batch=n_obs * H, inner=H, splits=1)
+        # dP[q,k] = sum_d dO[q,d] V[k,d]
+        dp = torch.empty((n_obs * H * S, S), dtype=torch.float32, device=dev)
+        _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=q_hi, b_lo=q_lo, alpha=1.0, c=dp, m=S, n=S, k=D,
+                 a_col_inner=D, a_row_outer=S, b_col_base=2 * H * D, b_col_inner=D, b_row_outer=S,
+                 c_row_outer=H * S, c_row_inner=S, **common)
+        # dV[k,d] = sum_q P[q,k] dO[q,d]          (both operands reduce over rows -> MN-major)
+        _gemm_ex(a_hi=p_hi, a_lo=p_lo, b_hi=g_hi, b_lo=g_lo, a_mn=1, b_mn=1, alpha=1.0, c=dqkv, m=S, n=D, k=S,
+                 a_row_outer=H * S, a_row_inner=S, b_col_inner=D, b_row_outer=S,
+                 c_row_outer=S, c_col_base=2 * H * D, c_col_inner=D, **common)
+        ds_hi = torch.empty_like(p_hi)
+        ds_lo = torch.empty_like(p_lo)
+        lib.call('dsb_attn_softmax_bwd', p_hi, p_lo, dp, entity_num, H * S, ds_hi, ds_lo, n_obs * H * S, S)
+        del dp
+        # dQ[q,d] = alpha * sum_k dS[q,k] K[k,d]
+        _gemm_ex(a_hi=ds_hi, a_lo=ds_lo, b_hi=q_hi, b_lo=q_lo, b_mn=1, alpha=alpha, c=dqkv, m=S, n=D, k=S,
+                 a_row_outer=H * S, a_row_inner=S, b_col_base=H * D, b_col_inner=D, b_row_outer=S,
+                 c_row_outer=S, c_col_base=0, c_col_inner=D, **common)
+        # dK[k,d] = alpha * sum_q dS[q,k] Q[q,d]
+        _gemm_ex(a_hi=ds_hi, a_lo=ds_lo, b_hi=q_hi, b_lo=q_lo, a_mn=1, b_mn=1, alpha=alpha, c=dqkv, m=S, n=D, k=S,
+                 a_row_outer=H * S, a_row_inner=S, b_col_base=0, b_col_inner=D, b_row_outer=S,
+                 c_row_outer=S, c_col_base=H * D, c_col_inner=D, **common)
+        return dqkv, None, None, None
+
+
+def entity_attention(qkv: torch.Tensor, entity_num: torch.Tensor, heads: int, hd: int) -> torch.Tensor:
+    """qkv [N, S, 3*heads*hd] (q | k | v, each head-major) -> context [N, S, heads*hd]; keys >= entity_num masked."""
+    N, S, W3 = qkv.shape
+    if _use_kernel(qkv) and S % 128 == 0 and hd % 128 == 0:
+        out = _EntityAttention.apply(qkv.reshape(N * S, W3).contiguous(), entity_num.to(torch.int64).contiguous(), heads, hd)
+        return out.view(N, S, heads * hd)
+    q, k, v = qkv.view(N, S, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    score = torch.matmul(q, k.transpose(2, 3)) / math.sqrt(hd)
+    if entity_num is not None:
+        key_mask = torch.arange(S, device=qkv.device).unsqueeze(0) < entity_num.unsqueeze(1)
+        score = score.masked_fill(~key_mask.view(N, 1, 1, S), -1e9)
+    return torch.matmul(torch.softmax(score, dim=-1), v).permute(0, 2, 1, 3).reshape(N, S, heads * hd)
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = False,

@@ -179,7 +179,9 @@ class Net:
         x = ops.linear(feats, w_pad, P[pre + 'transformer.embedding.0.bias'], True, self.terms)
         for i in range(3):
             lp = '%stransformer.layers.%d' % (pre, i)
-            x = self.ln(lp + '.layernorm1', x + self.attention(lp + '.attention', x, mask, 2, 128))
+            qkv = self.fc(lp + '.attention.attention_pre', x)
+            a = self.fc(lp + '.attention.project', ops.entity_attention(qkv, entity_num, 2, 128))
+            x = self.ln(lp + '.layernorm1', x + a)
             m = self.fc(lp + '.mlp.1', self.fc(lp + '.mlp.0', x, relu=True), relu=True)
             x = self.ln(lp + '.layernorm2', x + m)
         x = torch.relu(x)

@@ -80,15 +80,52 @@ int dsb_upsample_bilinear2x_bwd(const float* grad_out, float* grad_in, int64_t N
 /* ---- fp32 -> (hi, lo) bf16 split used by the split-precision tensor-core GEMM ---- */
 int dsb_split_bf16(const float* x, void* hi, void* lo, int64_t n, dsb_stream_t stream);
 
-/* ---- tcgen05 GEMM:  C[M,N] = act( A[M,K] . W[N,K]^T + bias[N] )   (fc_block, nn_module.py:231-270) ----
- * A and W are given as bf16 (hi, lo) pairs, both K-major (row-major with K contiguous), K % 64 == 0,
- * N % 128 == 0 (N <= 4096), M arbitrary.  terms = 1: hi*hi only (plain bf16); terms = 3: hi*hi + hi*lo + lo*hi
- * (fp32-class product, ~2^-16 relative).  Accumulation is fp32 in TMEM.
- * C fp32 [M,N] (ldc = N).  Optional c_hi/c_lo (bf16 [M,N]) receive the split of the result so the next GEMM
- * needs no separate split pass.  relu != 0 applies max(.,0).  bias may be NULL. */
+/* ---- tcgen05 GEMM family  (fc_block nn_module.py:231-270; attention module_utils.py:88-111; their backward) ----
+ * dsb_gemm_bf16_split:  C[M,N] = act( A[M,K] . W[N,K]^T + bias[N] ),  A and W as bf16 (hi, lo) pairs, K contiguous,
+ * K % 64 == 0, N % 128 == 0, M arbitrary.  terms = 1: hi*hi only (plain bf16); terms = 3: hi*hi + hi*lo + lo*hi
+ * (fp32-class product, ~2^-16 relative).  fp32 accumulation in TMEM.  C fp32 [M,N]; optional c_hi/c_lo (bf16 [M,N])
+ * receive the split of the result so a following GEMM needs no separate split pass. */
 int dsb_gemm_bf16_split(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                         float* c, void* c_hi, void* c_lo, int64_t M, int N, int K, int terms, int relu,
                         dsb_stream_t stream);
+
+/* dsb_gemm_ex: the general form.  For batch b = bo*inner + bi and split s the kernel computes the [m, n] block
+ *     C_b,s = alpha * sum_{k in split s} A_b[i,k] * B_b[j,k]   (+ bias[j], ReLU when splits == 1)
+ * where the operands are sub-blocks of 2-D row-major bf16 tensors addressed by coordinate arithmetic only:
+ *   K-major operand  (x_mn = 0): element (i, k) at row  row_outer*bo + row_inner*bi + i,  col col_base + col_inner*bi + k
+ *   MN-major operand (x_mn = 1): element (i, k) at row  row_outer*bo + row_inner*bi + k,  col col_base + col_inner*bi + i
+ * and C_b,s is written to rows c_row_outer*bo + c_row_inner*bi + c_row_split*s + [0, m), columns
+ * c_col_base + c_col_inner*bi + [0, n) of the fp32 tensor c [c_rows, c_cols].
+ * Examples: S = Q K^T for (obs, head): A = B = the QKV activation, a_col_base 0 / b_col_base 256, col_inner 128,
+ * row_outer 512; O = P V: B = QKV with b_mn = 1; dW = dY^T X: both MN-major, splits > 1 over the token dimension.
+ * Requirements: n % 128 == 0, k % (64*splits) == 0, m % 128 == 0 unless batch == splits == 1. */
+typedef struct dsb_gemm_args {
+    const void *a_hi, *a_lo, *b_hi, *b_lo;   /* bf16 tensors (lo may be NULL when terms == 1) */
+    int64_t a_rows, a_cols, b_rows, b_cols;  /* their full 2-D shapes (cols contiguous) */
+    int32_t a_mn, b_mn;
+    int32_t a_col_base, a_col_inner, a_row_outer, a_row_inner;
+    int32_t b_col_base, b_col_inner, b_row_outer, b_row_inner;
+    const float* bias;
+    float alpha;
+    int32_t relu, terms;
+    float* c;
+    int64_t c_rows, c_cols;
+    void *c_hi, *c_lo;                       /* optional bf16 split of C, same [c_rows, c_cols] layout */
+    int64_t m;
+    int32_t n, k;
+    int32_t batch, inner, splits;
+    int32_t c_row_outer, c_row_inner, c_row_split, c_col_base, c_col_inner;
+} dsb_gemm_args;
+int dsb_gemm_ex(const dsb_gemm_args* args, dsb_stream_t stream);
+
+/* ---- masked softmax of the entity self-attention  (module_utils.py:99-107) ----
+ * scores fp32 [rows, S] (already scaled by 1/sqrt(d) in the Q.K^T epilogue); row r belongs to observation
+ * r / rows_per_obs; keys >= entity_num[obs] are masked to -1e9 as in the reference.  P leaves as a bf16 (hi, lo) pair.
+ * Backward: dS = P * (dP - sum_k dP_k P_k) (0 at masked keys), again as a (hi, lo) pair for the dQ / dK products. */
+int dsb_attn_softmax_fwd(const float* scores, const int64_t* entity_num, int rows_per_obs, void* p_hi, void* p_lo,
+                         int64_t rows, int S, dsb_stream_t stream);
+int dsb_attn_softmax_bwd(const void* p_hi, const void* p_lo, const float* dp, const int64_t* entity_num,
+                         int rows_per_obs, void* ds_hi, void* ds_lo, int64_t rows, int S, dsb_stream_t stream);
 
 /* ---- fused grad-norm -> clip -> Adam over the flat arena  (rl_learner.py:73-80,125,132; grad_clip.py:141-144) ----
  * step 1: dsb_sumsq partial sums of grad^2 into `partial` [>= dsb_sumsq_partials()] then a finishing reduction

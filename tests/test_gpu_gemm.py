@@ -44,3 +44,126 @@ def test_linear_autograd_through_gemm():
     y.backward(go.to(DEV))
     for got, ref, n in [(xd.grad, xr.grad, 'dx'), (wd.grad, wr.grad, 'dw'), (bd.grad, br.grad, 'db')]:
         assert (got.cpu() - ref).abs().max().item() <= 1e-3 * ref.abs().max().item(), n
+
+
+# ------------------------------------------------------------------------------------------ generalised GEMM (dsb_gemm_ex)
+from distar_b200 import lib as _lib
+
+
+def _split(x):
+    return ops.split_bf16(x.to(DEV).contiguous())
+
+
+def _check(c, ref, tol=2e-5):
+    err = (c.double().cpu() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= tol * scale, 'max err %.3e (scale %.3e)' % (err, scale)
+
+
+@pytest.mark.parametrize('M,N,K', [(256, 128, 64), (384, 256, 512)])
+def test_gemm_ex_b_mn_major(M, N, K):
+    g = torch.Generator().manual_seed(1)
+    a = torch.randn(M, K, generator=g)
+    bm = torch.randn(K, N, generator=g) / K ** 0.5          # B stored [K, N]: reduction index strided
+    a_hi, a_lo = _split(a)
+    b_hi, b_lo = _split(bm)
+    c = torch.empty(M, N, device=DEV)
+    _lib.gemm_ex(a_hi=a_hi, a_lo=a_lo, b_hi=b_hi, b_lo=b_lo, b_mn=1, alpha=1.0, terms=3, c=c, m=M, n=N, k=K,
+                 batch=1, inner=1, splits=1)
+    torch.cuda.synchronize()
+    _check(c, a.double() @ bm.double())
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (256, 384, 256)])
+def test_gemm_ex_a_mn_major(M, N, K):
+    g = torch.Generator().manual_seed(2)
+    am = torch.randn(K, M, generator=g)                      # A stored [K, M]
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    a_hi, a_lo = _split(am)
+    b_hi, b_lo = _split(w)
+    c = torch.empty(M, N, device=DEV)
+    _lib.gemm_ex(a_hi=a_hi, a_lo=a_lo, b_hi=b_hi, b_lo=b_lo, a_mn=1, alpha=1.0, terms=3, c=c, m=M, n=N, k=K,
+                 batch=1, inner=1, splits=1)
+    torch.cuda.synchronize()
+    _check(c, am.double().t() @ w.double().t())
+
+
+@pytest.mark.parametrize('tokens,Nw,Kw,splits', [(512, 128, 128, 1), (4096, 256, 1024, 16), (8192, 768, 256, 32)])
+def test_gemm_ex_weight_gradient_split_k(tokens, Nw, Kw, splits):
+    g = torch.Generator().manual_seed(3)
+    dy = torch.randn(tokens, Nw, generator=g)
+    x = torch.randn(tokens, Kw, generator=g)
+    a_hi, a_lo = _split(dy)
+    b_hi, b_lo = _split(x)
+    part = torch.empty(splits * Nw, Kw, device=DEV)
+    _lib.gemm_ex(a_hi=a_hi, a_lo=a_lo, b_hi=b_hi, b_lo=b_lo, a_mn=1, b_mn=1, alpha=1.0, terms=3, c=part, m=Nw, n=Kw,
+                 k=tokens, batch=1, inner=1, splits=splits, c_row_split=Nw)
+    torch.cuda.synchronize()
+    dw = part.view(splits, Nw, Kw).sum(0)
+    _check(dw, dy.double().t() @ x.double(), tol=5e-5)
+
+
+def test_gemm_ex_batched_attention_products():
+    obs, S, H, D = 3, 512, 2, 128
+    g = torch.Generator().manual_seed(4)
+    qkv = torch.randn(obs * S, 3 * H * D, generator=g)
+    q_hi, q_lo = _split(qkv)
+    # scores[o,h] = Q K^T / sqrt(D)
+    sc = torch.empty(obs * H * S, S, device=DEV)
+    _lib.gemm_ex(a_hi=q_hi, a_lo=q_lo, b_hi=q_hi, b_lo=q_lo, alpha=1.0 / D ** 0.5, terms=3, c=sc, m=S, n=S, k=D,
+                 batch=obs * H, inner=H, splits=1, a_col_base=0, a_col_inner=D, a_row_outer=S,
+                 b_col_base=H * D, b_col_inner=D, b_row_outer=S, c_row_outer=H * S, c_row_inner=S)
+    torch.cuda.synchronize()
+    x = qkv.double().view(obs, S, 3, H, D)
+    q, k, v = x[:, :, 0], x[:, :, 1], x[:, :, 2]
+    ref = torch.einsum('oqhd,okhd->ohqk', q, k) / D ** 0.5
+    _check(sc.view(obs, H, S, S), ref)
+    # context[o,h] = P V   (V is MN-major inside the same activation)
+    p = torch.softmax(ref, -1).float().reshape(obs * H * S, S)
+    p_hi, p_lo = _split(p)
+    ctx = torch.empty(obs * S, H * D, device=DEV)     # heads concatenated along the feature axis, as the reference
+    _lib.gemm_ex(a_hi=p_hi, a_lo=p_lo, b_hi=q_hi, b_lo=q_lo, b_mn=1, alpha=1.0, terms=3, c=ctx, m=S, n=D, k=S,
+                 batch=obs * H, inner=H, splits=1, a_row_outer=H * S, a_row_inner=S,
+                 b_col_base=2 * H * D, b_col_inner=D, b_row_outer=S, c_row_outer=S, c_col_inner=D)
+    torch.cuda.synchronize()
+    ref_ctx = torch.einsum('ohqk,okhd->oqhd', p.double().view(obs, H, S, S), v)
+    _check(ctx.view(obs, S, H, D), ref_ctx)
+
+
+def test_linear_autograd_weight_grad_split_k():
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(8, 512, 256, generator=g)
+    w = torch.randn(1024, 256, generator=g) / 16
+    b = torch.randn(1024, generator=g)
+    go = torch.randn(8, 512, 1024, generator=g)
+    # no ReLU here: a pre-activation within rounding of 0 flips the mask and moves dx by a whole term
+    xr, wr, br = [t.double().clone().requires_grad_(True) for t in (x, w, b)]
+    torch.nn.functional.linear(xr, wr, br).backward(go.double())
+    xd, wd, bd = [t.to(DEV).requires_grad_(True) for t in (x, w, b)]
+    ops.linear(xd, wd, bd, relu=False).backward(go.to(DEV))
+    for got, ref, n in [(xd.grad, xr.grad, 'dx'), (wd.grad, wr.grad, 'dw'), (bd.grad, br.grad, 'db')]:
+        err = (got.double().cpu() - ref).abs().max().item()
+        assert err <= 1e-4 * ref.abs().max().item(), (n, err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize('entity_num', [[512, 512, 512], [512, 77, 1], [300, 0, 128]])
+def test_entity_attention_fwd_bwd(entity_num):
+    n, S, H, D = len(entity_num), 512, 2, 128
+    g = torch.Generator().manual_seed(11)
+    qkv = torch.randn(n, S, 3 * H * D, generator=g)
+    go = torch.randn(n, S, H * D, generator=g)
+    en = torch.tensor(entity_num)
+    qr = qkv.double().clone().requires_grad_(True)
+    q, k, v = qr.view(n, S, 3, H, D).permute(2, 0, 3, 1, 4)
+    sc = torch.matmul(q, k.transpose(2, 3)) / D ** 0.5
+    mask = torch.arange(S).unsqueeze(0) < en.unsqueeze(1)
+    sc = sc.masked_fill(~mask.view(n, 1, 1, S), -1e9)
+    ref = torch.matmul(torch.softmax(sc, -1), v).permute(0, 2, 1, 3).reshape(n, S, H * D)
+    ref.backward(go.double())
+    qd = qkv.to(DEV).requires_grad_(True)
+    out = ops.entity_attention(qd, en.to(DEV), H, D)
+    out.backward(go.to(DEV))
+    err = (out.double().cpu() - ref.detach()).abs().max().item()
+    assert err <= 2e-5 * ref.abs().max().item(), ('fwd', err)
+    gerr = (qd.grad.double().cpu() - qr.grad).abs().max().item()
+    assert gerr <= 1e-4 * qr.grad.abs().max().item(), ('bwd', gerr, qr.grad.abs().max().item())

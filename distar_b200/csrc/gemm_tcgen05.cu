@@ -30,15 +30,14 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int BM = 128, BK = 64;                        // BN (64 or 128) is a template parameter
 constexpr int kStages = 3;
 constexpr int kAccStages = 2;
-constexpr int kTileBytes = BM * BK * 2;                 // 16 KiB: one 128x64 bf16 operand tile
+constexpr int kTileBytes = BM * BK * 2;                 // 16 KiB: one 128x64 bf16 operand tile (B tiles use BN*128 B of it)
 constexpr int kStageBytes = 4 * kTileBytes;             // A_hi, A_lo, B_hi, B_lo
 constexpr int kStoreBufBytes = 32 * 128;                // one 32-row x 32-col fp32 staging box (128 B rows, SWIZZLE_128B)
 constexpr int kStoreBytes = 4 * 2 * kStoreBufBytes;     // 4 epilogue warps x double buffer
 constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int kTmemCols = kAccStages * BN;              // 256
 constexpr int kThreads = 192;
 constexpr int UMMA_K = 16;
 
@@ -68,6 +67,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -103,9 +108,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
 }
 // cute::UMMA::InstrDescriptor: c_format F32=1 [4,6), a/b_format BF16=1 [7,10)/[10,13), a_major [15], b_major [16]
 // (0 = K, 1 = MN), n_dim = N>>3 [17,23), m_dim = M>>4 [24,29).
-__device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn) {
+__device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn, int bn) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+           ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -136,10 +141,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 struct OperandMap {       // tile origin = (col_base + bi*col_inner, row_outer*bo + row_inner*bi), see header
     int col_base, col_inner, row_outer, row_inner, mn_major;
+    // implicit-GEMM convolution operand (conv != 0): an NHWC tensor [imgs, H, W, C] read through a 4-D tensor map;
+    // the halo of a 3x3 tap is whatever TMA zero-fills outside the image.
+    int conv, H, W, C, taps;
 };
 
 struct GemmParams {
     const float* bias;
+    const float* residual;   // optional fp32 [c_rows, ldc] added before the ReLU
     __nv_bfloat16* c_hi;
     __nv_bfloat16* c_lo;
     float alpha;
@@ -154,6 +163,7 @@ struct GemmParams {
 
 struct TileCoord { int b, s, m0, n0, bo, bi; };
 
+template <int BN>
 __device__ __forceinline__ TileCoord decode_tile(int tile, const GemmParams& p) {
     TileCoord t;
     const int n_i = tile % p.num_n;
@@ -169,18 +179,49 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const GemmParams& p) 
     return t;
 }
 
+__device__ __forceinline__ void tap_offset(int tap, int taps, int& dy, int& dx) {
+    if (taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; } else { dy = 0; dx = 0; }
+}
+
+// mn0 = first row (A) / column (B) of the output tile this operand tile feeds, kg = first reduction index, width = 128
+// for A, BN for B.
 __device__ __forceinline__ void load_operand(const CUtensorMap* map, uint64_t* bar, unsigned char* dst,
-                                             const OperandMap& o, const TileCoord& t, int mn0, int kg) {
+                                             const OperandMap& o, const TileCoord& t, int mn0, int kg, int width) {
+    if (o.conv) {
+        const int cblocks = o.C / 64;
+        if (!o.mn_major) {
+            // forward / input-gradient convolution: rows = 128 consecutive output pixels (whole image rows),
+            // reduction index = (tap, channel)
+            const int pix0 = mn0, hw = o.H * o.W;
+            const int img = pix0 / hw, y0 = (pix0 - img * hw) / o.W;
+            const int kb = kg / 64, tap = kb / cblocks, cb = kb - tap * cblocks;
+            int dy, dx;
+            tap_offset(tap, o.taps, dy, dx);
+            tma_load_4d(map, bar, dst, cb * 64, dx, y0 + dy, img);               // box {64 c, W, 128/W, 1}
+        } else {
+            // weight-gradient convolution: reduction index = 64 consecutive pixels, columns = (tap, channel)
+            const int hw = o.H * o.W;
+            const int img = kg / hw, y0 = (kg - img * hw) / o.W;
+            for (int h = 0; h < width / 64; ++h) {
+                const int col = mn0 + 64 * h, tap = col / o.C, c = col - tap * o.C;
+                int dy, dx;
+                tap_offset(tap, o.taps, dy, dx);
+                tma_load_4d(map, bar, dst + h * (kTileBytes / 2), c, dx, y0 + dy, img);   // box {64 c, W, 64/W, 1}
+            }
+        }
+        return;
+    }
     const int col0 = o.col_base + t.bi * o.col_inner;
     const int row0 = o.row_outer * t.bo + o.row_inner * t.bi;
     if (!o.mn_major) {
-        tma_load_2d(map, bar, dst, col0 + kg, row0 + mn0);                      // box {64 k, 128 rows}
+        tma_load_2d(map, bar, dst, col0 + kg, row0 + mn0);                      // box {64 k, 128 (or BN) rows}
     } else {
-        tma_load_2d(map, bar, dst, col0 + mn0, row0 + kg);                      // box {64 mn, 64 k} x 2
-        tma_load_2d(map, bar, dst + kTileBytes / 2, col0 + mn0 + 64, row0 + kg);
+        for (int h = 0; h < width / 64; ++h)                                    // box {64 mn, 64 k} per 64-wide half
+            tma_load_2d(map, bar, dst + h * (kTileBytes / 2), col0 + mn0 + 64 * h, row0 + kg);
     }
 }
 
+template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -196,6 +237,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     uint64_t* tmem_empty = tmem_full + kAccStages;
     uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
 
+    constexpr int kTmemColsAlloc = kAccStages * BN;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = p.batch * p.splits * p.num_m * p.num_n;
     const int num_k = p.num_k;
@@ -215,7 +257,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     }
     if (warp == 1) {   // TMEM allocation is warp-collective; the same warp deallocates at the end
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_ptr)),
-                     "n"(kTmemCols) : "memory");
+                     "n"(kTmemColsAlloc) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -228,19 +270,19 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx = (three ? 4 : 2) * kTileBytes;
+            const uint32_t tx = (three ? 2 : 1) * (kTileBytes + BN * 128);
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile(tile, p);
+                const TileCoord t = decode_tile<BN>(tile, p);
                 for (int kb = 0; kb < num_k; ++kb) {
                     const int kg = (t.s * num_k + kb) * BK;
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char* st = smem + stage * kStageBytes;
                     mbar_expect_tx(&full[stage], tx);
-                    load_operand(&map_a_hi, &full[stage], st, p.a, t, t.m0, kg);
-                    load_operand(&map_b_hi, &full[stage], st + 2 * kTileBytes, p.b, t, t.n0, kg);
+                    load_operand(&map_a_hi, &full[stage], st, p.a, t, t.m0, kg, BM);
+                    load_operand(&map_b_hi, &full[stage], st + 2 * kTileBytes, p.b, t, t.n0, kg, BN);
                     if (three) {
-                        load_operand(&map_a_lo, &full[stage], st + kTileBytes, p.a, t, t.m0, kg);
-                        load_operand(&map_b_lo, &full[stage], st + 3 * kTileBytes, p.b, t, t.n0, kg);
+                        load_operand(&map_a_lo, &full[stage], st + kTileBytes, p.a, t, t.m0, kg, BM);
+                        load_operand(&map_b_lo, &full[stage], st + 3 * kTileBytes, p.b, t, t.n0, kg, BN);
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -252,7 +294,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         uint32_t phase = 0;
         int it = 0;
         const bool a_mn = p.a.mn_major != 0, b_mn = p.b.mn_major != 0;
-        const uint32_t idesc = make_idesc(a_mn, b_mn);
+        const uint32_t idesc = make_idesc(a_mn, b_mn, BN);
         // descriptor start-address step (>>4) per UMMA_K: 32 B inside the swizzle row (K-major) or 16 k-rows (MN-major)
         const uint64_t a_step = a_mn ? (uint64_t)((UMMA_K * 128) >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
         const uint64_t b_step = b_mn ? (uint64_t)((UMMA_K * 128) >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
@@ -299,7 +341,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const TileCoord t = decode_tile(tile, p);
+            const TileCoord t = decode_tile<BN>(tile, p);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const int row_in_batch = t.m0 + q * 32 + lane;
@@ -320,6 +362,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 for (int j = 0; j < 32; ++j) {
                     float x = __uint_as_float(r[j]) * p.alpha;
                     if (p.bias) x += __ldg(p.bias + t.n0 + c0 + j);
+                    if (p.residual && row_ok) x += __ldg(p.residual + (int64_t)(c_row0 + lane) * p.ldc + c_col0 + c0 + j);
                     if (p.relu) x = fmaxf(x, 0.f);
                     v[j] = x;
                 }
@@ -367,7 +410,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemColsAlloc) : "memory");
     }
 }
 
@@ -408,34 +451,78 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int
     return DSB_OK;
 }
 
-int launch(const dsb_gemm_args& g, cudaStream_t stream) {
-    DSB_REQUIRE(g.a_hi && g.b_hi && g.c, "gemm: null pointer");
-    DSB_REQUIRE(g.terms == 1 || g.terms == 3, "gemm: terms must be 1 or 3");
-    DSB_REQUIRE(g.terms == 1 || (g.a_lo && g.b_lo), "gemm: terms=3 needs the lo halves");
-    DSB_REQUIRE(!g.c_hi == !g.c_lo, "gemm: c_hi and c_lo go together");
+// 4-D NHWC bf16 tensor [imgs, H, W, C] (C contiguous), box = {64 c, W, box_h, 1}, 128 B swizzle, zero OOB fill
+int make_map_nhwc(CUtensorMap* map, const void* base, int64_t imgs, int H, int W, int C, int box_h) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { dsb::set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DSB_ERR_CUDA; }
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)imgs};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)W, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        dsb::set_error("cuTensorMapEncodeTiled(NHWC) failed: %d (imgs %lld H %d W %d C %d box_h %d)", (int)r,
+                       (long long)imgs, H, W, C, box_h);
+        return DSB_ERR_CUDA;
+    }
+    return DSB_OK;
+}
+
+template <int BN>
+int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
     const int batch = g.batch > 0 ? g.batch : 1, splits = g.splits > 0 ? g.splits : 1, inner = g.inner > 0 ? g.inner : 1;
     DSB_REQUIRE(g.m >= 0 && g.n > 0 && g.k > 0 && g.n % BN == 0 && g.k % (BK * splits) == 0,
                 "gemm: need n %% %d == 0 and k %% (%d*splits) == 0 (m=%lld n=%d k=%d splits=%d)", BN, BK, (long long)g.m,
                 g.n, g.k, splits);
-    DSB_REQUIRE((batch == 1 && splits == 1) || g.m % BM == 0, "gemm: batched / split-K problems need m %% %d == 0", BM);
-    DSB_REQUIRE(splits == 1 || (!g.bias && !g.relu), "gemm: split-K partial sums take no bias / ReLU");
-    DSB_REQUIRE(g.a_cols % 8 == 0 && g.b_cols % 8 == 0 && g.c_cols % 4 == 0, "gemm: row pitches must be 16-byte multiples");
+    DSB_REQUIRE(batch == 1 || g.m % BM == 0, "gemm: batched problems need m %% %d == 0", BM);
+    DSB_REQUIRE(splits == 1 || g.c_row_split % BM == 0, "gemm: split-K needs c_row_split %% %d == 0", BM);
+    DSB_REQUIRE(splits == 1 || (!g.bias && !g.relu && !g.residual), "gemm: split-K partial sums take no bias / ReLU / residual");
+    DSB_REQUIRE(g.c_cols % 4 == 0, "gemm: C row pitch must be a 16-byte multiple");
     if (g.m == 0) return DSB_OK;
     const int num_m = (int)((g.m + BM - 1) / BM), num_n = g.n / BN;
     const int64_t tiles = (int64_t)batch * splits * num_m * num_n;
     DSB_REQUIRE(tiles < (1ll << 31), "gemm: too many tiles");
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mc;
     int rc;
-    const int a_br = g.a_mn ? 64 : BM, b_br = g.b_mn ? 64 : BN;   // MN-major boxes are 64 k-rows x 64 mn
-    if ((rc = make_map(&ma_hi, g.a_hi, g.a_rows, g.a_cols, 2, a_br, 64))) return rc;
-    if ((rc = make_map(&mb_hi, g.b_hi, g.b_rows, g.b_cols, 2, b_br, 64))) return rc;
-    if ((rc = make_map(&ma_lo, g.terms == 3 ? g.a_lo : g.a_hi, g.a_rows, g.a_cols, 2, a_br, 64))) return rc;
-    if ((rc = make_map(&mb_lo, g.terms == 3 ? g.b_lo : g.b_hi, g.b_rows, g.b_cols, 2, b_br, 64))) return rc;
+    const void* a_lo = g.terms == 3 ? g.a_lo : g.a_hi;
+    const void* b_lo = g.terms == 3 ? g.b_lo : g.b_hi;
+    if (g.a_conv) {
+        DSB_REQUIRE(!g.a_mn && batch == 1 && splits == 1, "gemm: conv A operand is K-major, unbatched");
+        DSB_REQUIRE(g.conv_c % 64 == 0 && (g.conv_taps == 1 || g.conv_taps == 9) && g.conv_w <= 128 && 128 % g.conv_w == 0 &&
+                    g.conv_h % (128 / g.conv_w) == 0, "gemm: unsupported conv geometry H=%d W=%d C=%d taps=%d", g.conv_h,
+                    g.conv_w, g.conv_c, g.conv_taps);
+        DSB_REQUIRE(g.k == g.conv_taps * g.conv_c && g.m == (int64_t)g.conv_imgs * g.conv_h * g.conv_w,
+                    "gemm: conv A dims mismatch (m=%lld k=%d)", (long long)g.m, g.k);
+        if ((rc = make_map_nhwc(&ma_hi, g.a_hi, g.conv_imgs, g.conv_h, g.conv_w, g.conv_c, 128 / g.conv_w))) return rc;
+        if ((rc = make_map_nhwc(&ma_lo, a_lo, g.conv_imgs, g.conv_h, g.conv_w, g.conv_c, 128 / g.conv_w))) return rc;
+    } else {
+        DSB_REQUIRE(g.a_cols % 8 == 0, "gemm: A row pitch must be a 16-byte multiple");
+        const int a_br = g.a_mn ? 64 : BM;
+        if ((rc = make_map(&ma_hi, g.a_hi, g.a_rows, g.a_cols, 2, a_br, 64))) return rc;
+        if ((rc = make_map(&ma_lo, a_lo, g.a_rows, g.a_cols, 2, a_br, 64))) return rc;
+    }
+    if (g.b_conv) {
+        DSB_REQUIRE(g.b_mn && batch == 1, "gemm: conv B operand (weight gradient) is MN-major, unbatched");
+        DSB_REQUIRE(g.conv_c % 64 == 0 && (g.conv_taps == 1 || g.conv_taps == 9) && g.conv_w <= 64 && 64 % g.conv_w == 0 &&
+                    g.conv_h % (64 / g.conv_w) == 0, "gemm: unsupported conv geometry H=%d W=%d C=%d taps=%d", g.conv_h,
+                    g.conv_w, g.conv_c, g.conv_taps);
+        DSB_REQUIRE(g.n == g.conv_taps * g.conv_c && g.k == (int64_t)g.conv_imgs * g.conv_h * g.conv_w,
+                    "gemm: conv B dims mismatch (n=%d k=%d)", g.n, g.k);
+        if ((rc = make_map_nhwc(&mb_hi, g.b_hi, g.conv_imgs, g.conv_h, g.conv_w, g.conv_c, 64 / g.conv_w))) return rc;
+        if ((rc = make_map_nhwc(&mb_lo, b_lo, g.conv_imgs, g.conv_h, g.conv_w, g.conv_c, 64 / g.conv_w))) return rc;
+    } else {
+        DSB_REQUIRE(g.b_cols % 8 == 0, "gemm: B row pitch must be a 16-byte multiple");
+        const int b_br = g.b_mn ? 64 : BN;
+        if ((rc = make_map(&mb_hi, g.b_hi, g.b_rows, g.b_cols, 2, b_br, 64))) return rc;
+        if ((rc = make_map(&mb_lo, b_lo, g.b_rows, g.b_cols, 2, b_br, 64))) return rc;
+    }
     if ((rc = make_map(&mc, g.c, g.c_rows, g.c_cols, 4, 32, 32))) return rc;
     static bool configured = false;
     static int num_sms = 0;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(gemm_split_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) { dsb::set_error("gemm smem attr: %s", cudaGetErrorString(e)); return DSB_ERR_CUDA; }
         int dev = 0;
         cudaGetDevice(&dev);
@@ -443,17 +530,29 @@ int launch(const dsb_gemm_args& g, cudaStream_t stream) {
         configured = true;
     }
     GemmParams p;
-    p.bias = g.bias; p.c_hi = (__nv_bfloat16*)g.c_hi; p.c_lo = (__nv_bfloat16*)g.c_lo;
+    p.bias = g.bias; p.residual = g.residual; p.c_hi = (__nv_bfloat16*)g.c_hi; p.c_lo = (__nv_bfloat16*)g.c_lo;
     p.alpha = g.alpha; p.M = g.m; p.ldc = g.c_cols; p.N = g.n; p.terms = g.terms; p.relu = g.relu;
     p.num_m = num_m; p.num_n = num_n; p.num_k = g.k / (BK * splits);
     p.batch = batch; p.inner = inner; p.splits = splits;
     p.c_row_outer = g.c_row_outer; p.c_row_inner = g.c_row_inner; p.c_row_split = g.c_row_split;
     p.c_col_base = g.c_col_base; p.c_col_inner = g.c_col_inner;
-    p.a = OperandMap{g.a_col_base, g.a_col_inner, g.a_row_outer, g.a_row_inner, g.a_mn};
-    p.b = OperandMap{g.b_col_base, g.b_col_inner, g.b_row_outer, g.b_row_inner, g.b_mn};
+    p.a = OperandMap{g.a_col_base, g.a_col_inner, g.a_row_outer, g.a_row_inner, g.a_mn, g.a_conv, g.conv_h, g.conv_w,
+                     g.conv_c, g.conv_taps};
+    p.b = OperandMap{g.b_col_base, g.b_col_inner, g.b_row_outer, g.b_row_inner, g.b_mn, g.b_conv, g.conv_h, g.conv_w,
+                     g.conv_c, g.conv_taps};
     const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
-    gemm_split_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, p);
+    gemm_split_kernel<BN><<<grid, kThreads, kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, p);
     return dsb::check_launch("gemm_split");
+}
+
+int launch(const dsb_gemm_args& g, cudaStream_t stream) {
+    DSB_REQUIRE(g.a_hi && g.b_hi && g.c, "gemm: null pointer");
+    DSB_REQUIRE(g.terms == 1 || g.terms == 3, "gemm: terms must be 1 or 3");
+    DSB_REQUIRE(g.terms == 1 || (g.a_lo && g.b_lo), "gemm: terms=3 needs the lo halves");
+    DSB_REQUIRE(!g.c_hi == !g.c_lo, "gemm: c_hi and c_lo go together");
+    const int bn = g.bn ? g.bn : (g.n % 128 == 0 ? 128 : 64);
+    DSB_REQUIRE(bn == 64 || bn == 128, "gemm: bn must be 64 or 128");
+    return bn == 128 ? launch_bn<128>(g, stream) : launch_bn<64>(g, stream);
 }
 
 }  // namespace

@@ -51,7 +51,10 @@ class GemmArgs(ctypes.Structure):
                 ('m', _i64), ('n', _c.c_int32), ('k', _c.c_int32),
                 ('batch', _c.c_int32), ('inner', _c.c_int32), ('splits', _c.c_int32),
                 ('c_row_outer', _c.c_int32), ('c_row_inner', _c.c_int32), ('c_row_split', _c.c_int32),
-                ('c_col_base', _c.c_int32), ('c_col_inner', _c.c_int32)]
+                ('c_col_base', _c.c_int32), ('c_col_inner', _c.c_int32),
+                ('residual', _vp), ('bn', _c.c_int32),
+                ('a_conv', _c.c_int32), ('b_conv', _c.c_int32), ('conv_h', _c.c_int32), ('conv_w', _c.c_int32),
+                ('conv_c', _c.c_int32), ('conv_taps', _c.c_int32), ('conv_imgs', _i64)]
 
 
 _SIGNATURES['dsb_gemm_ex'] = (_i, [ctypes.POINTER(GemmArgs), _vp])
@@ -106,8 +109,9 @@ def gemm_ex(**kw):
         setattr(g, k, v if v is not None else None)
     for name in ('a', 'b'):
         t = kw[name + '_hi']
-        setattr(g, name + '_rows', t.shape[0])
-        setattr(g, name + '_cols', t.shape[1])
+        if t.dim() == 2:
+            setattr(g, name + '_rows', t.shape[0])
+            setattr(g, name + '_cols', t.shape[1])
     g.c_rows, g.c_cols = kw['c'].shape
     rc = lib.dsb_gemm_ex(ctypes.byref(g), _stream())
     if rc != 0:

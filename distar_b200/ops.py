@@ -414,6 +414,104 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
 
 
 # ------------------------------------------------------------------------------------------------
+# implicit-GEMM convolutions on NHWC activations (spatial ResNet K7, location head K14)
+# ------------------------------------------------------------------------------------------------
+def _pad_to(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+def _conv_weight_matrix(weight: torch.Tensor, cin_pad: int, cout_pad: int) -> torch.Tensor:
+    """[Cout, Cin, kh, kw] -> [cout_pad, kh*kw*cin_pad] with the reduction index ordered (ky, kx, cin)."""
+    Cout, Cin, kh, kw = weight.shape
+    w = weight.permute(0, 2, 3, 1)
+    w = F.pad(w, (0, cin_pad - Cin, 0, 0, 0, 0, 0, cout_pad - Cout))
+    return w.reshape(cout_pad, kh * kw * cin_pad).contiguous()
+
+
+class _ConvNHWC(torch.autograd.Function):
+    """y = act(conv(x, w) + b [+ residual]) for 3x3 (pad 1) and 1x1 kernels, NHWC, channels padded to 64.
+
+    Forward, input gradient (same kernel with flipped / transposed weights) and weight gradient (activation read
+    tap-shifted as an MN-major operand, split-K over pixels) all run on the tcgen05 GEMM: the im2col matrix is never
+    materialised, halos come from TMA zero fill."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, relu, terms):
+        N, H, W, C = x.shape
+        Cout, Cin, kh, kw = weight.shape
+        taps = kh * kw
+        cout_pad = _pad_to(Cout, 64)
+        wm = _conv_weight_matrix(weight, C, cout_pad)
+        x_hi, x_lo = split_bf16(x)
+        w_hi, w_lo = split_bf16(wm)
+        b = F.pad(bias, (0, cout_pad - Cout)).contiguous() if bias is not None else None
+        y = torch.empty((N * H * W, cout_pad), dtype=torch.float32, device=x.device)
+        res = residual.reshape(N * H * W, cout_pad).contiguous() if residual is not None else None
+        _gemm_ex(a_hi=x_hi, a_lo=x_lo, b_hi=w_hi, b_lo=w_lo, bias=b, residual=res, alpha=1.0, relu=1 if relu else 0,
+                 terms=terms, c=y, m=N * H * W, n=cout_pad, k=taps * C, batch=1, inner=1, splits=1,
+                 a_conv=1, conv_h=H, conv_w=W, conv_c=C, conv_taps=taps, conv_imgs=N)
+        ctx.save_for_backward(x_hi, x_lo, wm, y if relu else None)
+        ctx.meta = (N, H, W, C, Cout, Cin, kh, kw, cout_pad, relu, terms, bias is not None, residual is not None)
+        return y.view(N, H, W, cout_pad)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x_hi, x_lo, wm, y = ctx.saved_tensors
+        N, H, W, C, Cout, Cin, kh, kw, cout_pad, relu, terms, has_bias, has_res = ctx.meta
+        taps = kh * kw
+        g = gy.reshape(N * H * W, cout_pad)
+        if relu:
+            g = g * (y > 0)
+        g = g.contiguous()
+        g_hi, g_lo = split_bf16(g)
+        gx = gw = gb = gres = None
+        if has_res:
+            gres = g.view(N, H, W, cout_pad)
+        if ctx.needs_input_grad[0]:
+            # dX = conv(dY, W') with W'[cin, (ky,kx,cout)] = W[cout, cin, kh-1-ky, kw-1-kx]
+            w4 = wm.view(cout_pad, kh, kw, C).flip(1, 2).permute(3, 1, 2, 0).reshape(C, taps * cout_pad).contiguous()
+            wt_hi, wt_lo = split_bf16(w4)
+            gx = torch.empty((N * H * W, C), dtype=torch.float32, device=g.device)
+            _gemm_ex(a_hi=g_hi.view(N, H, W, cout_pad), a_lo=g_lo.view(N, H, W, cout_pad), b_hi=wt_hi, b_lo=wt_lo,
+                     alpha=1.0, terms=terms, c=gx, m=N * H * W, n=C, k=taps * cout_pad, batch=1, inner=1, splits=1,
+                     a_conv=1, conv_h=H, conv_w=W, conv_c=cout_pad, conv_taps=taps, conv_imgs=N)
+            gx = gx.view(N, H, W, C)
+        if ctx.needs_input_grad[1]:
+            pix = N * H * W
+            m_pad = _pad_to(cout_pad, 128)
+            n = taps * C
+            bn = 128 if n % 128 == 0 else 64
+            splits = _pick_splits((m_pad // 128) * (n // bn), pix)
+            part = torch.empty((splits * m_pad, n), dtype=torch.float32, device=g.device)
+            _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=x_hi, b_lo=x_lo, a_mn=1, b_mn=1, b_conv=1, alpha=1.0, terms=terms, c=part,
+                     m=cout_pad, n=n, k=pix, batch=1, inner=1, splits=splits, c_row_split=m_pad, bn=bn,
+                     conv_h=H, conv_w=W, conv_c=C, conv_taps=taps, conv_imgs=N)
+            gwm = part.view(splits, m_pad, n).sum(0)[:Cout]
+            gw = gwm.view(Cout, kh, kw, C)[..., :Cin].permute(0, 3, 1, 2).contiguous()
+        if has_bias and ctx.needs_input_grad[2]:
+            gb = g.sum(0)[:Cout]
+        return gx, gw, gb, gres, None, None
+
+
+def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = False,
+              residual: Optional[torch.Tensor] = None, terms: int = 3) -> torch.Tensor:
+    """conv2d_block (ctools/torch_utils/network/nn_module.py:119-174) on an NHWC activation [N,H,W,C] whose channel
+    count is a multiple of 64 (zero padded); weight is the reference's [Cout, Cin<=C, k, k] (k = 1 or 3, padding k//2).
+    Returns [N,H,W,pad64(Cout)] (padded output channels are exactly 0)."""
+    N, H, W, C = x.shape
+    kh = weight.shape[2]
+    if _use_kernel(x):
+        assert C % 64 == 0 and W <= 64 and 64 % W == 0 and H % max(1, 128 // W) == 0, (x.shape, weight.shape)
+        return _ConvNHWC.apply(x.contiguous(), weight, bias, residual, relu, terms)
+    Cout, Cin = weight.shape[:2]
+    y = F.conv2d(x[..., :Cin].permute(0, 3, 1, 2), weight, bias, padding=kh // 2).permute(0, 2, 3, 1)
+    y = F.pad(y, (0, _pad_to(Cout, 64) - Cout))
+    if residual is not None:
+        y = y + residual
+    return torch.relu(y) if relu else y
+
+
+# ------------------------------------------------------------------------------------------------
 # bilinear x2 up-sampling (location head decoder, K14)
 # ------------------------------------------------------------------------------------------------
 class _Upsample2x(torch.autograd.Function):

@@ -98,7 +98,13 @@ int dsb_gemm_bf16_split(const void* a_hi, const void* a_lo, const void* w_hi, co
  * c_col_base + c_col_inner*bi + [0, n) of the fp32 tensor c [c_rows, c_cols].
  * Examples: S = Q K^T for (obs, head): A = B = the QKV activation, a_col_base 0 / b_col_base 256, col_inner 128,
  * row_outer 512; O = P V: B = QKV with b_mn = 1; dW = dY^T X: both MN-major, splits > 1 over the token dimension.
- * Requirements: n % 128 == 0, k % (64*splits) == 0, m % 128 == 0 unless batch == splits == 1. */
+ * Implicit-GEMM convolution (3x3 pad 1 or 1x1 over NHWC bf16 pairs, conv2d_block nn_module.py:119-174):
+ *   a_conv = 1: A is the activation [conv_imgs, conv_h, conv_w, conv_c]; row i = output pixel, k = (tap, channel);
+ *               the 3x3 halo is TMA zero fill.  B = weights [n = Cout, k = taps*C] (K-major), m = imgs*H*W.
+ *   b_conv = 1: weight gradient: A = dY [pixels, Cout] (a_mn = 1), B = the activation read tap-shifted (b_mn = 1),
+ *               n = taps*C, k = imgs*H*W pixels (split-K).
+ * residual (optional fp32, same layout as c) is added before the ReLU.  bn: output tile width 64 or 128 (0 = auto).
+ * Requirements: n % bn == 0, k % (64*splits) == 0, m % 128 == 0 when batch > 1, c_row_split % 128 == 0 when splits > 1. */
 typedef struct dsb_gemm_args {
     const void *a_hi, *a_lo, *b_hi, *b_lo;   /* bf16 tensors (lo may be NULL when terms == 1) */
     int64_t a_rows, a_cols, b_rows, b_cols;  /* their full 2-D shapes (cols contiguous) */
@@ -115,6 +121,10 @@ typedef struct dsb_gemm_args {
     int32_t n, k;
     int32_t batch, inner, splits;
     int32_t c_row_outer, c_row_inner, c_row_split, c_col_base, c_col_inner;
+    const float* residual;
+    int32_t bn;
+    int32_t a_conv, b_conv, conv_h, conv_w, conv_c, conv_taps;
+    int64_t conv_imgs;
 } dsb_gemm_args;
 int dsb_gemm_ex(const dsb_gemm_args* args, dsb_stream_t stream);
 

@@ -77,7 +77,78 @@ __global__ void upsample2x_bwd_kernel(const float* __restrict__ gout, float* __r
     gin[i] = acc;
 }
 
+// NHWC variants (channels innermost): same taps, consecutive threads walk the channel axis -> fully coalesced.
+__global__ void upsample2x_nhwc_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t total, int H,
+                                           int W, int C) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int OW = 2 * W, OH = 2 * H;
+    const int c = (int)(i % C);
+    const int ox = (int)((i / C) % OW);
+    const int oy = (int)((i / ((int64_t)C * OW)) % OH);
+    const int64_t n = i / ((int64_t)C * OW * OH);
+    const Tap ty = tap_of(oy, H), tx = tap_of(ox, W);
+    const float* p = in + n * H * W * C + c;
+    const float a = __ldg(p + ((int64_t)ty.i0 * W + tx.i0) * C), b = __ldg(p + ((int64_t)ty.i0 * W + tx.i1) * C);
+    const float cc = __ldg(p + ((int64_t)ty.i1 * W + tx.i0) * C), d = __ldg(p + ((int64_t)ty.i1 * W + tx.i1) * C);
+    out[i] = ty.l0 * (tx.l0 * a + tx.l1 * b) + ty.l1 * (tx.l0 * cc + tx.l1 * d);
+}
+
+__global__ void upsample2x_nhwc_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int64_t total, int H,
+                                           int W, int C) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    const int ix = (int)((i / C) % W);
+    const int iy = (int)((i / ((int64_t)C * W)) % H);
+    const int64_t n = i / ((int64_t)C * W * H);
+    const int OW = 2 * W, OH = 2 * H;
+    const float* g = gout + n * OH * OW * C + c;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int oy = 2 * iy - 1 + a;
+        if (oy < 0 || oy >= OH) continue;
+        const Tap ty = tap_of(oy, H);
+        const float wy = (ty.i0 == iy ? ty.l0 : 0.f) + (ty.i1 == iy ? ty.l1 : 0.f);
+        if (wy == 0.f) continue;
+        float row = 0.f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int ox = 2 * ix - 1 + b;
+            if (ox < 0 || ox >= OW) continue;
+            const Tap tx = tap_of(ox, W);
+            const float wx = (tx.i0 == ix ? tx.l0 : 0.f) + (tx.i1 == ix ? tx.l1 : 0.f);
+            if (wx != 0.f) row += wx * __ldg(g + ((int64_t)oy * OW + ox) * C);
+        }
+        acc += wy * row;
+    }
+    gin[i] = acc;
+}
+
 }  // namespace
+
+extern "C" int dsb_upsample_bilinear2x_nhwc_fwd(const float* in, float* out, int64_t N, int H, int W, int C,
+                                                dsb_stream_t stream) {
+    DSB_REQUIRE(in && out && N >= 0 && H > 0 && W > 0 && C > 0, "upsample_bilinear2x_nhwc_fwd: bad argument");
+    const int64_t total = N * 4 * H * W * C;
+    if (total == 0) return DSB_OK;
+    const int64_t blocks = (total + 255) / 256;
+    DSB_REQUIRE(blocks < (1ll << 31), "upsample_bilinear2x_nhwc_fwd: too large");
+    upsample2x_nhwc_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, total, H, W, C);
+    return dsb::check_launch("upsample_bilinear2x_nhwc_fwd");
+}
+
+extern "C" int dsb_upsample_bilinear2x_nhwc_bwd(const float* grad_out, float* grad_in, int64_t N, int H, int W, int C,
+                                                dsb_stream_t stream) {
+    DSB_REQUIRE(grad_out && grad_in && N >= 0 && H > 0 && W > 0 && C > 0, "upsample_bilinear2x_nhwc_bwd: bad argument");
+    const int64_t total = N * H * W * C;
+    if (total == 0) return DSB_OK;
+    const int64_t blocks = (total + 255) / 256;
+    DSB_REQUIRE(blocks < (1ll << 31), "upsample_bilinear2x_nhwc_bwd: too large");
+    upsample2x_nhwc_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(grad_out, grad_in, total, H, W, C);
+    return dsb::check_launch("upsample_bilinear2x_nhwc_bwd");
+}
 
 extern "C" int dsb_upsample_bilinear2x_fwd(const float* in, float* out, int64_t NC, int H, int W, dsb_stream_t stream) {
     DSB_REQUIRE(in && out && NC >= 0 && H > 0 && W > 0, "upsample_bilinear2x_fwd: bad argument");

@@ -27,6 +27,8 @@ _SIGNATURES = {
     'dsb_split_bf16': (_i, [_vp, _vp, _vp, _i64, _vp]),
     'dsb_upsample_bilinear2x_fwd': (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     'dsb_upsample_bilinear2x_bwd': (_i, [_vp, _vp, _i64, _i, _i, _vp]),
+    'dsb_upsample_bilinear2x_nhwc_fwd': (_i, [_vp, _vp, _i64, _i, _i, _i, _vp]),
+    'dsb_upsample_bilinear2x_nhwc_bwd': (_i, [_vp, _vp, _i64, _i, _i, _i, _vp]),
     'dsb_gemm_bf16_split': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     'dsb_attn_softmax_fwd': (_i, [_vp, _vp, _i, _vp, _vp, _i64, _i, _vp]),
     'dsb_attn_softmax_bwd': (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i64, _i, _vp]),

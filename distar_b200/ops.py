@@ -532,6 +532,31 @@ class _Upsample2x(torch.autograd.Function):
         return gin
 
 
+class _Upsample2xNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        N, H, W, C = x.shape
+        x = x.contiguous()
+        out = torch.empty((N, 2 * H, 2 * W, C), dtype=torch.float32, device=x.device)
+        lib.call('dsb_upsample_bilinear2x_nhwc_fwd', x, out, N, H, W, C)
+        ctx.shape = (N, H, W, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        N, H, W, C = ctx.shape
+        gin = torch.empty((N, H, W, C), dtype=torch.float32, device=g.device)
+        lib.call('dsb_upsample_bilinear2x_nhwc_bwd', g.contiguous(), gin, N, H, W, C)
+        return gin
+
+
+def upsample_bilinear2x_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """bilinear x2 (align_corners=False) on a channels-last activation [N,H,W,C]."""
+    if _use_kernel(x):
+        return _Upsample2xNHWC.apply(x.float())
+    return F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2., mode='bilinear').permute(0, 2, 3, 1).contiguous()
+
+
 def upsample_bilinear2x(x: torch.Tensor) -> torch.Tensor:
     """F.interpolate(x, scale_factor=2., mode='bilinear') (align_corners=False) on [N,C,H,W] fp32."""
     if _use_kernel(x):

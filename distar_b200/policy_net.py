@@ -201,16 +201,29 @@ class Net:
             p.scatter_(1, sp[name].long(), 1.0)
             planes.append(p.view(N, 1, H, W))
         planes.append(scatter_map)
-        x = self.conv(pre + 'project', torch.cat(planes, dim=1), 0, relu=True)
-        skips = []
+        x = self.conv(pre + 'project', torch.cat(planes, dim=1), 0, relu=True)          # [N,32,H,W] (library 1x1)
+        skips = [x, None, None]               # the 128^2 / 64^2 / 32^2 skips are never read downstream (unet off)
+        # from here on: channels-last, channels padded to 64, every 3x3 conv an implicit GEMM on the tensor cores
+        x = F.pad(F.max_pool2d(x, 2, 2).permute(0, 2, 3, 1), (0, 32)).contiguous()
         for i in range(3):
-            skips.append(x)
-            x = self.conv(pre + 'downsample.%d' % i, F.max_pool2d(x, 2, 2), 1, relu=True)
+            if i > 0:
+                x = self.pool_nhwc(x)
+            x = self.conv_nhwc(pre + 'downsample.%d' % i, x, relu=True)
         for i in range(4):
             skips.append(x)
-            r = self.conv(pre + 'res.%d.conv2' % i, self.conv(pre + 'res.%d.conv1' % i, x, 1, relu=True), 1)
-            x = torch.relu(r + x)
-        return self.fc(pre + 'fc', x.reshape(N, -1), relu=True), skips
+            r = self.conv_nhwc(pre + 'res.%d.conv1' % i, x, relu=True)
+            x = self.conv_nhwc(pre + 'res.%d.conv2' % i, r, relu=True, residual=x)      # relu(conv2(r) + x)
+        h8, w8, c = x.shape[1:]
+        w = self.P[pre + 'fc.0.weight']
+        w = w.view(w.shape[0], c, h8, w8).permute(0, 2, 3, 1).reshape(w.shape[0], -1)    # (c,y,x) -> (y,x,c) columns
+        return ops.linear(x.reshape(N, -1), w, self.P[pre + 'fc.0.bias'], True, self.terms), skips
+
+    def conv_nhwc(self, name: str, x: Tensor, relu: bool = False, residual: Optional[Tensor] = None) -> Tensor:
+        return ops.conv_nhwc(x, self.P[name + '.0.weight'], self.P[name + '.0.bias'], relu, residual, self.terms)
+
+    @staticmethod
+    def pool_nhwc(x: Tensor) -> Tensor:
+        return F.max_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).contiguous()
 
     def encoder(self, spatial_info, entity_info, scalar_info, entity_num):
         """model/encoder.py:28-45."""
@@ -384,22 +397,30 @@ class Net:
         return logits, target_unit
 
     def location_head(self, emb, map_skip, location=None):
-        """action_arg_head.py:417-450 (K14)."""
+        """action_arg_head.py:417-450 (K14).  map_skip[3..6] are channels-last [P,16,16,128]."""
         pre = 'policy.location_head.'
+        P_ = self.P
         N = emb.shape[0]
-        h8, w8 = map_skip[-1].shape[2:]
-        x = self.fc(pre + 'project_embed', emb, relu=True).reshape(N, 4, h8, w8)
-        x = self.conv(pre + 'conv1', torch.relu(torch.cat([x, map_skip[-1]], dim=1)), 0, relu=True)
+        h8, w8 = map_skip[-1].shape[1:3]
+        x4 = self.fc(pre + 'project_embed', emb, relu=True).reshape(N, 4, h8, w8).permute(0, 2, 3, 1)   # [N,16,16,4]
+        # conv1 (1x1 over cat[x4, skip]) = W[:, :4] . relu(x4)  +  W[:, 4:] . relu(skip): the 4-channel part is a tiny
+        # matmul handed to the 128-channel implicit GEMM as its residual
+        w1 = P_[pre + 'conv1.0.weight']
+        small = torch.matmul(torch.relu(x4), w1[:, :4, 0, 0].t())
+        x = ops.conv_nhwc(torch.relu(map_skip[-1]), w1[:, 4:], P_[pre + 'conv1.0.bias'], True, small, self.terms)
         for i in range(4):
             x = x + map_skip[len(map_skip) - i - 1]
-            rp = pre + 'res.%d.' % i
-            r = self.conv(rp + 'conv2', self.conv(rp + 'conv1', x, 1, relu=True), 1)
+            rp = pre + 'res.%d.' % i                                   # GatedResBlock, module_utils.py:224-231
+            r = self.conv_nhwc(rp + 'conv2', self.conv_nhwc(rp + 'conv1', x, relu=True))
             g = x
             for j in range(4):
-                g = self.conv(rp + 'GateWeightG.%d' % j, g, 0, relu=(j < 3))
-            x = torch.relu(torch.tanh(r * torch.sigmoid(g)) * self.P[rp + 'UpdateSP'] + x)
-        for i in range(3):
-            x = self.conv(pre + 'upsample.%d' % i, ops.upsample_bilinear2x(x), 1, relu=(i < 2))
+                g = self.conv_nhwc(rp + 'GateWeightG.%d' % j, g, relu=(j < 3))
+            x = torch.relu(torch.tanh(r * torch.sigmoid(g)) * P_[rp + 'UpdateSP'] + x)
+        x = self.conv_nhwc(pre + 'upsample.0', ops.upsample_bilinear2x_nhwc(x), relu=True)            # [N,32,32,64]
+        x = self.conv_nhwc(pre + 'upsample.1', ops.upsample_bilinear2x_nhwc(x), relu=True)            # [N,64,64,64] (32 real)
+        x = ops.upsample_bilinear2x_nhwc(x[..., :32].contiguous())                                    # [N,128,128,32]
+        # last conv has ONE output channel (9.4 MFLOP/row): library conv on the channels-last view
+        x = F.conv2d(x.permute(0, 3, 1, 2), P_[pre + 'upsample.2.0.weight'], P_[pre + 'upsample.2.0.bias'], padding=1)
         logits = x.reshape(N, -1) / self.T
         if location is None:
             location = self.sample(logits)

@@ -76,6 +76,10 @@ int dsb_sample_categorical(const float* logits, const float* q, int64_t* index, 
  * in [NC, H, W] f32 -> out [NC, 2H, 2W]; backward is a deterministic gather (no atomics). */
 int dsb_upsample_bilinear2x_fwd(const float* in, float* out, int64_t NC, int H, int W, dsb_stream_t stream);
 int dsb_upsample_bilinear2x_bwd(const float* grad_out, float* grad_in, int64_t NC, int H, int W, dsb_stream_t stream);
+/* channels-last variants: in [N, H, W, C] -> out [N, 2H, 2W, C] */
+int dsb_upsample_bilinear2x_nhwc_fwd(const float* in, float* out, int64_t N, int H, int W, int C, dsb_stream_t stream);
+int dsb_upsample_bilinear2x_nhwc_bwd(const float* grad_out, float* grad_in, int64_t N, int H, int W, int C,
+                                     dsb_stream_t stream);
 
 /* ---- fp32 -> (hi, lo) bf16 split used by the split-precision tensor-core GEMM ---- */
 int dsb_split_bf16(const float* x, void* hi, void* lo, int64_t n, dsb_stream_t stream);

@@ -39,7 +39,7 @@ act, sunum = synth_actions(P, enp.cpu(), torch.Generator().manual_seed(0), 12)
 su = act['selected_units'].to(dev); sunum = sunum.to(dev)
 timeit('selected_units_train[1024]', lambda: net.selected_units_train(embd, ee_p, enp, sunum, su))
 timeit('target_unit_head[1024]', lambda: net.target_unit_head(embd, ee_p, enp, at % 512))
-ms = [None] * 3 + [torch.randn(P, 128, 16, 16, device=dev) for _ in range(4)]
+ms = [None] * 3 + [torch.randn(P, 16, 16, 128, device=dev) for _ in range(4)]
 timeit('location_head[1024]', lambda: net.location_head(embd, ms, at))
 lo2 = torch.randn(4224, 384, device=dev)
 timeit('value_baseline[4224]', lambda: net.value_baseline('winloss', lo2))

@@ -111,7 +111,7 @@ def test_categorical_stats_fwd_bwd(rows, C, masked):
     assert torch.allclose(logp.cpu(), r_logp.detach(), rtol=1e-5, atol=1e-5)
     assert torch.allclose(ent.cpu(), r_ent.detach(), rtol=1e-4, atol=1e-5)
     assert torch.allclose(kl.cpu(), r_kl.detach(), rtol=1e-4, atol=2e-5)
-    assert torch.allclose(zd.grad.cpu(), zr.grad, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(zd.grad.cpu(), zr.grad, rtol=1e-4, atol=5e-5)   # __expf vs the host libm of whatever CPU runs the reference
 
 
 @pytest.mark.parametrize('rows,C', [(64, 327), (64, 2), (32, 513), (16, 16384), (128, 128), (7, 512)])
@@ -166,6 +166,21 @@ def test_upsample_bilinear2x_fwd_bwd(N, C, H, W):
     ref.backward(go)
     xd = x.to(DEV).requires_grad_(True)
     out = ops.upsample_bilinear2x(xd)
+    out.backward(go.to(DEV))
+    assert torch.allclose(out.cpu(), ref.detach(), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(xd.grad.cpu(), xr.grad, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('N,H,W,C', [(3, 16, 16, 128), (2, 32, 32, 64), (1, 64, 64, 32), (2, 3, 5, 7)])
+def test_upsample_bilinear2x_nhwc_fwd_bwd(N, H, W, C):
+    g = torch.Generator().manual_seed(H * W + C)
+    x = torch.randn(N, H, W, C, generator=g)
+    go = torch.randn(N, 2 * H, 2 * W, C, generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref = torch.nn.functional.interpolate(xr.permute(0, 3, 1, 2), scale_factor=2., mode='bilinear').permute(0, 2, 3, 1)
+    ref.backward(go)
+    xd = x.to(DEV).requires_grad_(True)
+    out = ops.upsample_bilinear2x_nhwc(xd)
     out.backward(go.to(DEV))
     assert torch.allclose(out.cpu(), ref.detach(), rtol=1e-6, atol=1e-6)
     assert torch.allclose(xd.grad.cpu(), xr.grad, rtol=1e-5, atol=1e-5)

@@ -32,6 +32,12 @@ _SIGNATURES = {
     'dsb_gemm_bf16_split': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     'dsb_attn_softmax_fwd': (_i, [_vp, _vp, _i, _vp, _vp, _i64, _i, _vp]),
     'dsb_attn_softmax_bwd': (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i64, _i, _vp]),
+    'dsb_layernorm_supported': (_i, [_i]),
+    'dsb_layernorm_fwd': (_i, [_vp] * 9 + [_i64, _i, _f, _vp]),
+    'dsb_layernorm_bwd_blocks': (_i, [_i64]),
+    'dsb_layernorm_bwd': (_i, [_vp] * 7 + [_i64, _i, _vp]),
+    'dsb_lstm_cell_fwd': (_i, [_vp] * 13 + [_i, _i, _f, _vp]),
+    'dsb_lstm_cell_bwd': (_i, [_vp] * 18 + [_i, _i, _vp]),
     'dsb_sumsq_partials': (_i, []),
     'dsb_grad_norm': (_i, [_vp, _i64, _vp, _vp, _vp]),
     'dsb_adam_step': (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp]),

@@ -207,8 +207,17 @@ def sample_categorical(logits: torch.Tensor, generator: Optional[torch.Generator
 # ------------------------------------------------------------------------------------------------
 # split-precision tcgen05 linear (K2/K3 workhorse)
 # ------------------------------------------------------------------------------------------------
+def attach_split(t: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor) -> torch.Tensor:
+    """Remember the bf16 (hi, lo) pair a producer kernel already wrote for `t` so the consuming GEMM skips its split."""
+    t._dsb_split = (hi, lo)
+    return t
+
+
 def split_bf16(x: torch.Tensor):
     """fp32 -> (hi, lo) bf16 with hi + lo == x to ~2^-17 relative."""
+    cached = getattr(x, '_dsb_split', None)
+    if cached is not None and cached[0].shape == x.shape:
+        return cached
     x = x.contiguous()
     if _use_kernel(x):
         hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
@@ -283,17 +292,28 @@ class _SplitLinear(torch.autograd.Function):
     (dY^T . X, split-K over tokens) all on the tcgen05 kernel with 3-term split products."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, relu, terms):
+    def forward(ctx, x, weight, bias, relu, terms, x_hi=None, x_lo=None, emit_split=False):
         x2 = x.reshape(-1, x.shape[-1])
-        a_hi, a_lo = split_bf16(x2)
+        if x_hi is not None:
+            a_hi, a_lo = x_hi.reshape(x2.shape), x_lo.reshape(x2.shape)
+        else:
+            a_hi, a_lo = split_bf16(x2)
         w_hi, w_lo = split_bf16(weight)
-        y = gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu, terms)
+        oshape = (*x.shape[:-1], weight.shape[0])
+        if emit_split:
+            y, y_hi, y_lo = gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu, terms, want_split=True)
+        else:
+            y = gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu, terms)
         ctx.save_for_backward(a_hi, a_lo, w_hi, w_lo, y if relu else None)
         ctx.relu, ctx.terms, ctx.has_bias, ctx.xshape = relu, terms, bias is not None, x.shape
-        return y.view(*x.shape[:-1], weight.shape[0])
+        if emit_split:
+            y_hi, y_lo = y_hi.view(oshape), y_lo.view(oshape)
+            ctx.mark_non_differentiable(y_hi, y_lo)
+            return y.view(oshape), y_hi, y_lo
+        return y.view(oshape), None, None
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, _ghi=None, _glo=None):
         a_hi, a_lo, w_hi, w_lo, y = ctx.saved_tensors
         gy2 = gy.reshape(-1, gy.shape[-1])
         if ctx.relu:
@@ -321,7 +341,7 @@ class _SplitLinear(torch.autograd.Function):
                 gw = gy2.t() @ (a_hi.float() + a_lo.float())
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gy2.sum(0)
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None, None, None
 
 
 class _EntityAttention(torch.autograd.Function):
@@ -402,15 +422,122 @@ def entity_attention(qkv: torch.Tensor, entity_num: torch.Tensor, heads: int, hd
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = False,
-           terms: int = 3) -> torch.Tensor:
+           terms: int = 3, emit_split: bool = False) -> torch.Tensor:
     """fc_block forward (ctools/torch_utils/network/nn_module.py:231-270): tcgen05 split GEMM when the shape
     tiles (N % 128 == 0, K % 64 == 0), plain library matmul for the odd small layers."""
     N, K = weight.shape
     if gemm_eligible(N, K) and (x.is_cuda or _HOST_LOGIC_TESTING) and x.numel() // K >= 1:
-        return _SplitLinear.apply(x, weight, bias, relu, terms)
+        sp = getattr(x, '_dsb_split', None)
+        if sp is None or sp[0].shape != x.shape:
+            sp = (None, None)
+        emit = emit_split and x.is_cuda
+        y, y_hi, y_lo = _SplitLinear.apply(x, weight, bias, relu, terms, sp[0], sp[1], emit)
+        return attach_split(y, y_hi, y_lo) if emit else y
     _use_kernel(x)
     y = F.linear(x, weight, bias)
     return torch.relu(y) if relu else y
+
+
+# ------------------------------------------------------------------------------------------------
+# fused (residual +) LayerNorm and the LayerNorm-LSTM cell
+# ------------------------------------------------------------------------------------------------
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, want_split):
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D).contiguous()
+        rows = x2.shape[0]
+        dev = x.device
+        r2 = residual.reshape(-1, D).contiguous() if residual is not None else None
+        xin = torch.empty_like(x2) if r2 is not None else x2
+        y = torch.empty_like(x2)
+        stats = torch.empty((rows, 2), dtype=torch.float32, device=dev)
+        hi = torch.empty((rows, D), dtype=torch.bfloat16, device=dev) if want_split else None
+        lo = torch.empty((rows, D), dtype=torch.bfloat16, device=dev) if want_split else None
+        lib.call('dsb_layernorm_fwd', x2, r2, weight, bias, xin if r2 is not None else None, y, hi, lo, stats, rows, D, 1e-5)
+        ctx.save_for_backward(xin, weight, stats)
+        ctx.has_res = residual is not None
+        ctx.shape = x.shape
+        y = y.view(x.shape)
+        if want_split:
+            hi, lo = hi.view(x.shape), lo.view(x.shape)
+            ctx.mark_non_differentiable(hi, lo)
+            return y, hi, lo
+        return y, None, None
+
+    @staticmethod
+    def backward(ctx, gy, _ghi, _glo):
+        xin, weight, stats = ctx.saved_tensors
+        rows, D = xin.shape
+        gy2 = gy.reshape(rows, D).contiguous()
+        blocks = lib.load().dsb_layernorm_bwd_blocks(rows)
+        gx = torch.empty_like(xin)
+        pg = torch.empty((blocks, D), dtype=torch.float32, device=gy.device)
+        pb = torch.empty((blocks, D), dtype=torch.float32, device=gy.device)
+        lib.call('dsb_layernorm_bwd', gy2, xin, weight, stats, gx, pg, pb, rows, D)
+        gx = gx.view(ctx.shape)
+        return gx, (gx if ctx.has_res else None), pg.sum(0), pb.sum(0), None
+
+
+def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, residual: Optional[torch.Tensor] = None,
+               want_split: bool = False) -> torch.Tensor:
+    """nn.LayerNorm(x + residual) in one kernel; with want_split the bf16 (hi, lo) pair of the result is produced in
+    the same pass and remembered for the next tensor-core GEMM (ops.attach_split)."""
+    D = x.shape[-1]
+    if _use_kernel(x) and lib.load().dsb_layernorm_supported(D):
+        y, hi, lo = _LayerNorm.apply(x.float(), residual, weight, bias, want_split)
+        return attach_split(y, hi, lo) if want_split else y
+    s = x if residual is None else x + residual
+    return F.layer_norm(s, (D,), weight, bias, 1e-5)
+
+
+class _LstmCell(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ig, hg, c_in, gam_h, bet_h, gam_c, bet_c):
+        B, G = ig.shape
+        H = G // 4
+        dev = ig.device
+        ig, hg, c_in = ig.contiguous(), hg.contiguous(), c_in.contiguous()
+        h = torch.empty((B, H), dtype=torch.float32, device=dev)
+        c = torch.empty_like(h)
+        gates = torch.empty((B, G), dtype=torch.float32, device=dev)
+        pre_c = torch.empty_like(h)
+        st_h = torch.empty((B, 2), dtype=torch.float32, device=dev)
+        st_c = torch.empty((B, 2), dtype=torch.float32, device=dev)
+        lib.call('dsb_lstm_cell_fwd', ig, hg, c_in, gam_h, bet_h, gam_c, bet_c, h, c, gates, st_h, pre_c, st_c, B, H, 1e-5)
+        ctx.save_for_backward(gates, hg, st_h, c_in, pre_c, st_c, gam_h, gam_c, bet_c)
+        return h, c
+
+    @staticmethod
+    def backward(ctx, gh, gc):
+        gates, hg, st_h, c_in, pre_c, st_c, gam_h, gam_c, bet_c = ctx.saved_tensors
+        B, G = gates.shape
+        H = G // 4
+        dev = gates.device
+        gh = gh.contiguous() if gh is not None else torch.zeros((B, H), dtype=torch.float32, device=dev)
+        gc = gc.contiguous() if gc is not None else None
+        d_ig = torch.empty_like(gates)
+        d_hg = torch.empty_like(gates)
+        d_cin = torch.empty((B, H), dtype=torch.float32, device=dev)
+        dgh = torch.zeros(G, dtype=torch.float32, device=dev)
+        dbh = torch.zeros(G, dtype=torch.float32, device=dev)
+        dgc = torch.zeros(H, dtype=torch.float32, device=dev)
+        dbc = torch.zeros(H, dtype=torch.float32, device=dev)
+        lib.call('dsb_lstm_cell_bwd', gh, gc, gates, hg, st_h, c_in, pre_c, st_c, gam_h, gam_c, bet_c, d_ig, d_hg, d_cin,
+                 dgh, dbh, dgc, dbc, B, H)
+        return d_ig, d_hg, d_cin, dgh, dbh, dgc, dbc
+
+
+def lstm_cell(ig, hg, c_in, gam_h, bet_h, gam_c, bet_c):
+    """LayerNormLSTMCell (model/lstm.py:138-153) after the two matmuls, fused: returns (h', c')."""
+    H = c_in.shape[-1]
+    if _use_kernel(ig) and H in (128, 384):
+        return _LstmCell.apply(ig, hg, c_in, gam_h, bet_h, gam_c, bet_c)
+    G = 4 * H
+    gates = ig + F.layer_norm(hg, (G,), gam_h, bet_h, 1e-5)
+    i, f, g, o = gates.chunk(4, 1)
+    c2 = F.layer_norm(torch.sigmoid(f) * c_in + torch.sigmoid(i) * torch.tanh(g), (H,), gam_c, bet_c, 1e-5)
+    return torch.sigmoid(o) * torch.tanh(c2), c2
 
 
 # ------------------------------------------------------------------------------------------------
@@ -436,7 +563,7 @@ class _ConvNHWC(torch.autograd.Function):
     materialised, halos come from TMA zero fill."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, relu, terms):
+    def forward(ctx, x, weight, bias, residual, relu, terms, emit_split=False):
         N, H, W, C = x.shape
         Cout, Cin, kh, kw = weight.shape
         taps = kh * kw
@@ -446,16 +573,22 @@ class _ConvNHWC(torch.autograd.Function):
         w_hi, w_lo = split_bf16(wm)
         b = F.pad(bias, (0, cout_pad - Cout)).contiguous() if bias is not None else None
         y = torch.empty((N * H * W, cout_pad), dtype=torch.float32, device=x.device)
+        y_hi = torch.empty((N * H * W, cout_pad), dtype=torch.bfloat16, device=x.device) if emit_split else None
+        y_lo = torch.empty((N * H * W, cout_pad), dtype=torch.bfloat16, device=x.device) if emit_split else None
         res = residual.reshape(N * H * W, cout_pad).contiguous() if residual is not None else None
         _gemm_ex(a_hi=x_hi, a_lo=x_lo, b_hi=w_hi, b_lo=w_lo, bias=b, residual=res, alpha=1.0, relu=1 if relu else 0,
-                 terms=terms, c=y, m=N * H * W, n=cout_pad, k=taps * C, batch=1, inner=1, splits=1,
+                 terms=terms, c=y, c_hi=y_hi, c_lo=y_lo, m=N * H * W, n=cout_pad, k=taps * C, batch=1, inner=1, splits=1,
                  a_conv=1, conv_h=H, conv_w=W, conv_c=C, conv_taps=taps, conv_imgs=N)
         ctx.save_for_backward(x_hi, x_lo, wm, y if relu else None)
         ctx.meta = (N, H, W, C, Cout, Cin, kh, kw, cout_pad, relu, terms, bias is not None, residual is not None)
-        return y.view(N, H, W, cout_pad)
+        if emit_split:
+            y_hi, y_lo = y_hi.view(N, H, W, cout_pad), y_lo.view(N, H, W, cout_pad)
+            ctx.mark_non_differentiable(y_hi, y_lo)
+            return y.view(N, H, W, cout_pad), y_hi, y_lo
+        return y.view(N, H, W, cout_pad), None, None
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, _ghi=None, _glo=None):
         x_hi, x_lo, wm, y = ctx.saved_tensors
         N, H, W, C, Cout, Cin, kh, kw, cout_pad, relu, terms, has_bias, has_res = ctx.meta
         taps = kh * kw
@@ -490,11 +623,11 @@ class _ConvNHWC(torch.autograd.Function):
             gw = gwm.view(Cout, kh, kw, C)[..., :Cin].permute(0, 3, 1, 2).contiguous()
         if has_bias and ctx.needs_input_grad[2]:
             gb = g.sum(0)[:Cout]
-        return gx, gw, gb, gres, None, None
+        return gx, gw, gb, gres, None, None, None
 
 
 def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = False,
-              residual: Optional[torch.Tensor] = None, terms: int = 3) -> torch.Tensor:
+              residual: Optional[torch.Tensor] = None, terms: int = 3, emit_split: bool = False) -> torch.Tensor:
     """conv2d_block (ctools/torch_utils/network/nn_module.py:119-174) on an NHWC activation [N,H,W,C] whose channel
     count is a multiple of 64 (zero padded); weight is the reference's [Cout, Cin<=C, k, k] (k = 1 or 3, padding k//2).
     Returns [N,H,W,pad64(Cout)] (padded output channels are exactly 0)."""
@@ -502,7 +635,8 @@ def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
     kh = weight.shape[2]
     if _use_kernel(x):
         assert C % 64 == 0 and W <= 64 and 64 % W == 0 and H % max(1, 128 // W) == 0, (x.shape, weight.shape)
-        return _ConvNHWC.apply(x.contiguous(), weight, bias, residual, relu, terms)
+        y, y_hi, y_lo = _ConvNHWC.apply(x.contiguous(), weight, bias, residual, relu, terms, emit_split)
+        return attach_split(y, y_hi, y_lo) if emit_split else y
     Cout, Cin = weight.shape[:2]
     y = F.conv2d(x[..., :Cin].permute(0, 3, 1, 2), weight, bias, padding=kh // 2).permute(0, 2, 3, 1)
     y = F.pad(y, (0, _pad_to(Cout, 64) - Cout))

@@ -75,15 +75,17 @@ class Net:
         set_library_precision()
 
     # -------------------------------------------------------------------------------------- primitives
-    def fc(self, name: str, x: Tensor, relu: bool = False) -> Tensor:
-        return ops.linear(x, self.P[name + '.0.weight'], self.P[name + '.0.bias'], relu, self.terms)
+    def fc(self, name: str, x: Tensor, relu: bool = False, split: bool = False) -> Tensor:
+        """fc_block; split=True makes the GEMM epilogue also write the bf16 pair its consumer GEMM will read."""
+        return ops.linear(x, self.P[name + '.0.weight'], self.P[name + '.0.bias'], relu, self.terms, split)
 
     def conv(self, name: str, x: Tensor, pad: int, relu: bool = False) -> Tensor:
         y = F.conv2d(x, self.P[name + '.0.weight'], self.P[name + '.0.bias'], padding=pad)
         return torch.relu(y) if relu else y
 
-    def ln(self, name: str, x: Tensor) -> Tensor:
-        return F.layer_norm(x, (x.shape[-1],), self.P[name + '.weight'], self.P[name + '.bias'], 1e-5)
+    def ln(self, name: str, x: Tensor, residual: Optional[Tensor] = None, split: bool = False) -> Tensor:
+        """LayerNorm(x [+ residual]); split=True also emits the bf16 pair for the GEMM that consumes the result."""
+        return ops.layer_norm(x, self.P[name + '.weight'], self.P[name + '.bias'], residual, split)
 
     def sample(self, logits: Tensor) -> Tensor:
         return ops.sample_categorical(logits, rng=self.rng)[0]
@@ -181,9 +183,9 @@ class Net:
             lp = '%stransformer.layers.%d' % (pre, i)
             qkv = self.fc(lp + '.attention.attention_pre', x)
             a = self.fc(lp + '.attention.project', ops.entity_attention(qkv, entity_num, 2, 128))
-            x = self.ln(lp + '.layernorm1', x + a)
-            m = self.fc(lp + '.mlp.1', self.fc(lp + '.mlp.0', x, relu=True), relu=True)
-            x = self.ln(lp + '.layernorm2', x + m)
+            x = self.ln(lp + '.layernorm1', x, residual=a, split=True)
+            m = self.fc(lp + '.mlp.1', self.fc(lp + '.mlp.0', x, relu=True, split=True), relu=True)
+            x = self.ln(lp + '.layernorm2', x, residual=m, split=(i < 2))
         x = torch.relu(x)
         entity_embeddings = self.fc(pre + 'entity_fc', x, relu=True)
         pooled = (x * mask.unsqueeze(2)).sum(dim=1) / entity_num.unsqueeze(-1)
@@ -211,15 +213,16 @@ class Net:
             x = self.conv_nhwc(pre + 'downsample.%d' % i, x, relu=True)
         for i in range(4):
             skips.append(x)
-            r = self.conv_nhwc(pre + 'res.%d.conv1' % i, x, relu=True)
-            x = self.conv_nhwc(pre + 'res.%d.conv2' % i, r, relu=True, residual=x)      # relu(conv2(r) + x)
+            r = self.conv_nhwc(pre + 'res.%d.conv1' % i, x, relu=True, split=True)
+            x = self.conv_nhwc(pre + 'res.%d.conv2' % i, r, relu=True, residual=x, split=(i < 3))   # relu(conv2(r) + x)
         h8, w8, c = x.shape[1:]
         w = self.P[pre + 'fc.0.weight']
         w = w.view(w.shape[0], c, h8, w8).permute(0, 2, 3, 1).reshape(w.shape[0], -1)    # (c,y,x) -> (y,x,c) columns
         return ops.linear(x.reshape(N, -1), w, self.P[pre + 'fc.0.bias'], True, self.terms), skips
 
-    def conv_nhwc(self, name: str, x: Tensor, relu: bool = False, residual: Optional[Tensor] = None) -> Tensor:
-        return ops.conv_nhwc(x, self.P[name + '.0.weight'], self.P[name + '.0.bias'], relu, residual, self.terms)
+    def conv_nhwc(self, name: str, x: Tensor, relu: bool = False, residual: Optional[Tensor] = None,
+                  split: bool = False) -> Tensor:
+        return ops.conv_nhwc(x, self.P[name + '.0.weight'], self.P[name + '.0.bias'], relu, residual, self.terms, split)
 
     @staticmethod
     def pool_nhwc(x: Tensor) -> Tensor:
@@ -238,10 +241,9 @@ class Net:
     # -------------------------------------------------------------------------------------- LSTM
     def lstm_cell(self, pre: str, ig: Tensor, h: Tensor, c: Tensor):
         """LayerNormLSTMCell with the input half (LN_i(x W_ih^T)) precomputed: lstm.py:138-153."""
-        hg = self.ln(pre + '.layernorm_h', h @ self.P[pre + '.weight_hh'].t())
-        i, f, g, o = (ig + hg).chunk(4, 1)
-        c2 = self.ln(pre + '.layernorm_c', torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g))
-        return torch.sigmoid(o) * torch.tanh(c2), c2
+        P = self.P
+        return ops.lstm_cell(ig, h @ P[pre + '.weight_hh'].t(), c, P[pre + '.layernorm_h.weight'],
+                             P[pre + '.layernorm_h.bias'], P[pre + '.layernorm_c.weight'], P[pre + '.layernorm_c.bias'])
 
     def lstm(self, pre: str, x: Tensor, state: List[Tuple[Tensor, Tensor]], layers: int):
         """StackedLSTM over [L,B,D] (lstm.py:161-167,223-234).  The input projection of a whole layer is one
@@ -411,10 +413,10 @@ class Net:
         for i in range(4):
             x = x + map_skip[len(map_skip) - i - 1]
             rp = pre + 'res.%d.' % i                                   # GatedResBlock, module_utils.py:224-231
-            r = self.conv_nhwc(rp + 'conv2', self.conv_nhwc(rp + 'conv1', x, relu=True))
+            r = self.conv_nhwc(rp + 'conv2', self.conv_nhwc(rp + 'conv1', x, relu=True, split=True))
             g = x
             for j in range(4):
-                g = self.conv_nhwc(rp + 'GateWeightG.%d' % j, g, relu=(j < 3))
+                g = self.conv_nhwc(rp + 'GateWeightG.%d' % j, g, relu=(j < 3), split=(j < 3))
             x = torch.relu(torch.tanh(r * torch.sigmoid(g)) * P_[rp + 'UpdateSP'] + x)
         x = self.conv_nhwc(pre + 'upsample.0', ops.upsample_bilinear2x_nhwc(x), relu=True)            # [N,32,32,64]
         x = self.conv_nhwc(pre + 'upsample.1', ops.upsample_bilinear2x_nhwc(x), relu=True)            # [N,64,64,64] (32 real)
@@ -431,8 +433,8 @@ class Net:
         pre = 'value_networks.%s.' % name
         x = self.fc(pre + 'project', x, relu=True)
         for i in range(16):
-            r = self.fc(pre + 'res.%d.fc2' % i, self.fc(pre + 'res.%d.fc1' % i, x, relu=True))
-            x = self.ln(pre + 'res.%d.norm' % i, r + x)
+            r = self.fc(pre + 'res.%d.fc2' % i, self.fc(pre + 'res.%d.fc1' % i, x, relu=True, split=True))
+            x = self.ln(pre + 'res.%d.norm' % i, r, residual=x, split=True)
         v = F.linear(x, self.P[pre + 'value_fc.0.weight'], self.P[pre + 'value_fc.0.bias']).squeeze(1)
         if BASELINE_ATAN[name]:
             v = (2.0 / math.pi) * torch.atan((math.pi / 2.0) * v)

@@ -141,6 +141,31 @@ int dsb_attn_softmax_fwd(const float* scores, const int64_t* entity_num, int row
 int dsb_attn_softmax_bwd(const void* p_hi, const void* p_lo, const float* dp, const int64_t* entity_num,
                          int rows_per_obs, void* ds_hi, void* ds_lo, int64_t rows, int S, dsb_stream_t stream);
 
+/* ---- fused (residual +) LayerNorm  (module_utils.py:130-139; res_block.py:68-141; lstm.py:142-143) ----
+ * y[r] = LN(x[r] (+ residual[r])) * gamma + beta over D = 128/256/384/512/1536 features, eps as nn.LayerNorm.
+ * sum_out (optional, only with residual) receives x + residual (the LayerNorm input the backward needs);
+ * y_hi / y_lo (optional) receive the bf16 split of y for a following tensor-core GEMM; stats [rows, 2] = (mean, rstd).
+ * Backward: gx = dL/d(LN input); pgamma / pbeta are per-block partial sums [dsb_layernorm_bwd_blocks(rows), D]. */
+int dsb_layernorm_supported(int D);
+int dsb_layernorm_fwd(const float* x, const float* residual, const float* gamma, const float* beta, float* sum_out,
+                      float* y, void* y_hi, void* y_lo, float* stats, int64_t rows, int D, float eps, dsb_stream_t stream);
+int dsb_layernorm_bwd_blocks(int64_t rows);
+int dsb_layernorm_bwd(const float* gy, const float* xin, const float* gamma, const float* stats, float* gx, float* pgamma,
+                      float* pbeta, int64_t rows, int D, dsb_stream_t stream);
+
+/* ---- fused LayerNorm-LSTM cell  (LayerNormLSTMCell.forward, model/lstm.py:138-153, after the two matmuls) ----
+ * ig [B,4H] = LN_i(x W_ih^T), hg [B,4H] = h W_hh^T (raw), c_in [B,H]; gate order in/forget/cell/out.
+ * forward saves gates (pre-activation), stats_h, pre_c, stats_c for the backward; the backward returns d_ig, d_hg
+ * (wrt the raw recurrent product), d_cin and ACCUMULATES the LayerNorm parameter gradients into dgamma_h / dbeta_h
+ * [4H] and dgamma_c / dbeta_c [H] (caller zero-initialises).  H = 128 or 384. */
+int dsb_lstm_cell_fwd(const float* ig, const float* hg, const float* c_in, const float* gamma_h, const float* beta_h,
+                      const float* gamma_c, const float* beta_c, float* h_out, float* c_out, float* gates, float* stats_h,
+                      float* pre_c, float* stats_c, int B, int H, float eps, dsb_stream_t stream);
+int dsb_lstm_cell_bwd(const float* gh, const float* gcy, const float* gates, const float* hg, const float* stats_h,
+                      const float* c_in, const float* pre_c, const float* stats_c, const float* gamma_h,
+                      const float* gamma_c, const float* beta_c, float* d_ig, float* d_hg, float* d_cin, float* dgamma_h,
+                      float* dbeta_h, float* dgamma_c, float* dbeta_c, int B, int H, dsb_stream_t stream);
+
 /* ---- fused grad-norm -> clip -> Adam over the flat arena  (rl_learner.py:73-80,125,132; grad_clip.py:141-144) ----
  * step 1: dsb_sumsq partial sums of grad^2 into `partial` [>= dsb_sumsq_partials()] then a finishing reduction
  *         into norm_out[0] = sqrt(sum) (all on device, no host sync).

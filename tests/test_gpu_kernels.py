@@ -184,3 +184,51 @@ def test_upsample_bilinear2x_nhwc_fwd_bwd(N, H, W, C):
     out.backward(go.to(DEV))
     assert torch.allclose(out.cpu(), ref.detach(), rtol=1e-6, atol=1e-6)
     assert torch.allclose(xd.grad.cpu(), xr.grad, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('rows,D,res', [(1000, 256, True), (37, 256, False), (4224, 1536, False), (300, 384, True), (64, 128, True)])
+def test_layernorm_fwd_bwd(rows, D, res):
+    g = torch.Generator().manual_seed(rows + D)
+    x = torch.randn(rows, D, generator=g) * 3 + 1
+    r = torch.randn(rows, D, generator=g) if res else None
+    w = torch.randn(D, generator=g)
+    b = torch.randn(D, generator=g)
+    go = torch.randn(rows, D, generator=g)
+    xr, wr, br = [t.double().clone().requires_grad_(True) for t in (x, w, b)]
+    rr = r.double().clone().requires_grad_(True) if res else None
+    ref = torch.nn.functional.layer_norm(xr + rr if res else xr, (D,), wr, br, 1e-5)
+    ref.backward(go.double())
+    xd, wd, bd = [t.to(DEV).requires_grad_(True) for t in (x, w, b)]
+    rd = r.to(DEV).requires_grad_(True) if res else None
+    y = ops.layer_norm(xd, wd, bd, rd, want_split=True)
+    hi, lo = y._dsb_split
+    y.backward(go.to(DEV))
+    assert (y.double().cpu() - ref.detach()).abs().max().item() <= 1e-5 * ref.abs().max().item()
+    assert (hi.float() + lo.float() - y).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    for got, want, n in [(xd.grad, xr.grad, 'dx'), (wd.grad, wr.grad, 'dw'), (bd.grad, br.grad, 'db')] + \
+            ([(rd.grad, rr.grad, 'dres')] if res else []):
+        assert (got.double().cpu() - want).abs().max().item() <= 2e-5 * want.abs().max().item(), n
+
+
+@pytest.mark.parametrize('B,H', [(128, 384), (5, 384), (64, 128)])
+def test_lstm_cell_fwd_bwd(B, H):
+    g = torch.Generator().manual_seed(B + H)
+    ts = [torch.randn(B, 4 * H, generator=g), torch.randn(B, 4 * H, generator=g) * 5, torch.randn(B, H, generator=g),
+          torch.randn(4 * H, generator=g), torch.randn(4 * H, generator=g), torch.randn(H, generator=g), torch.randn(H, generator=g)]
+    gh, gc = torch.randn(B, H, generator=g), torch.randn(B, H, generator=g)
+    refs = [t.double().clone().requires_grad_(True) for t in ts]
+    ig, hg, c, wh, bh, wc, bc = refs
+    F = torch.nn.functional
+    gates = ig + F.layer_norm(hg, (4 * H,), wh, bh, 1e-5)
+    i, f, gg, o = gates.chunk(4, 1)
+    c2 = F.layer_norm(torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg), (H,), wc, bc, 1e-5)
+    h2 = torch.sigmoid(o) * torch.tanh(c2)
+    (h2 * gh.double()).sum().backward(retain_graph=True)
+    (c2 * gc.double()).sum().backward()
+    devs = [t.to(DEV).requires_grad_(True) for t in ts]
+    hd, cd = ops.lstm_cell(*devs)
+    ((hd * gh.to(DEV)).sum() + (cd * gc.to(DEV)).sum()).backward()
+    assert (hd.double().cpu() - h2.detach()).abs().max().item() <= 2e-5
+    assert (cd.double().cpu() - c2.detach()).abs().max().item() <= 2e-5 * c2.abs().max().item()
+    for got, want in zip(devs, refs):
+        assert (got.grad.double().cpu() - want.grad).abs().max().item() <= 1e-4 * want.grad.abs().max().item()

@@ -108,3 +108,24 @@ def test_rl_step_matches_oracle(sd, monkeypatch):
             assert (p.grad - g).abs().max().item() <= 2e-3 * max(g.abs().max().item(), 1e-3 * gmax), n
     # the arena gradient is what the all-reduce / optimiser see
     assert m.flat_grad.abs().sum() > 0
+
+
+def test_sl_loss_matches_oracle(sd):
+    from distar_b200.sl_loss import SupervisedLoss
+    m = _model(sd)
+    B, T = 2, 2
+    en = torch.tensor([512, 100, 256, 64])
+    obs = synth_obs(B * T, seed=31, entity_num=en, hidden=False)
+    g = torch.Generator().manual_seed(2)
+    act, num = synth_actions(B * T, en, g, max_su=5)
+    hidden = [(torch.randn(B, 384, generator=g), torch.randn(B, 384, generator=g)) for _ in range(3)]
+    amask = {k: (torch.rand(B * T, generator=g) < 0.7).float() for k in O.HEADS}
+    with torch.no_grad():
+        ol, _, _ = O.sl_train(sd, **tree_clone(obs), selected_units_num=num.clone(), traj_lens=[T] * B,
+                              hidden_state=tree_clone(hidden), action_info=tree_clone(act))
+        ml, ma, _ = m.sl_train(**tree_clone(obs), selected_units_num=num.clone(), traj_lens=[T] * B,
+                               hidden_state=tree_clone(hidden), action_info=tree_clone(act))
+    want = O.sl_loss(ol, act, amask, num)
+    got = SupervisedLoss({'learner': {'su_mask': False}}).compute_loss(ml, act, amask, num, en, ma)
+    for k, v in want.items():
+        assert abs(got[k].item() - v.item()) <= 1e-3 * max(1.0, abs(v.item())), k

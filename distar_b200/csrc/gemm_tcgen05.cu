@@ -79,6 +79,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                  ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// split-K accumulation: the copy engine adds the fp32 box into global memory (no partial buffers, no reduce pass)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -154,7 +160,7 @@ struct GemmParams {
     float alpha;
     int64_t M;               // valid rows per batch
     int64_t ldc;             // row stride (elements) of c_hi / c_lo
-    int N, terms, relu;
+    int N, terms, relu, accumulate;
     int num_m, num_n, num_k; // tiles per (batch, split); k blocks per split
     int batch, inner, splits;
     int c_row_outer, c_row_inner, c_row_split, c_col_base, c_col_inner;
@@ -379,7 +385,10 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) tma_store_2d(&map_c, buf, c_col0 + c0, c_row0);
+                if (lane == 0) {
+                    if (p.accumulate) tma_reduce_add_2d(&map_c, buf, c_col0 + c0, c_row0);
+                    else tma_store_2d(&map_c, buf, c_col0 + c0, c_row0);
+                }
                 if (p.c_hi && row_ok) {
                     const int64_t off = (int64_t)(c_row0 + lane) * p.ldc + c_col0 + c0;
                     uint4* dh = reinterpret_cast<uint4*>(p.c_hi + off);
@@ -477,7 +486,7 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
                 "gemm: need n %% %d == 0 and k %% (%d*splits) == 0 (m=%lld n=%d k=%d splits=%d)", BN, BK, (long long)g.m,
                 g.n, g.k, splits);
     DSB_REQUIRE(batch == 1 || g.m % BM == 0, "gemm: batched problems need m %% %d == 0", BM);
-    DSB_REQUIRE(splits == 1 || g.c_row_split % BM == 0, "gemm: split-K needs c_row_split %% %d == 0", BM);
+    DSB_REQUIRE(splits == 1 || g.c_accumulate || g.c_row_split % BM == 0, "gemm: split-K needs c_row_split %% %d == 0", BM);
     DSB_REQUIRE(splits == 1 || (!g.bias && !g.relu && !g.residual), "gemm: split-K partial sums take no bias / ReLU / residual");
     DSB_REQUIRE(g.c_cols % 4 == 0, "gemm: C row pitch must be a 16-byte multiple");
     if (g.m == 0) return DSB_OK;
@@ -532,6 +541,7 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
     GemmParams p;
     p.bias = g.bias; p.residual = g.residual; p.c_hi = (__nv_bfloat16*)g.c_hi; p.c_lo = (__nv_bfloat16*)g.c_lo;
     p.alpha = g.alpha; p.M = g.m; p.ldc = g.c_cols; p.N = g.n; p.terms = g.terms; p.relu = g.relu;
+    p.accumulate = g.c_accumulate;
     p.num_m = num_m; p.num_n = num_n; p.num_k = g.k / (BK * splits);
     p.batch = batch; p.inner = inner; p.splits = splits;
     p.c_row_outer = g.c_row_outer; p.c_row_inner = g.c_row_inner; p.c_row_split = g.c_row_split;

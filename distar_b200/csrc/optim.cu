@@ -140,3 +140,52 @@ extern "C" int dsb_split_bf16(const float* x, void* hi, void* lo, int64_t n, dsb
     split_kernel<<<grid_for(n, 8), kThreads, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
     return dsb::check_launch("split_bf16");
 }
+
+// ---- ReLU backward fused with the bf16 split and the bias gradient -------------------------------------------------
+// g = gy * (y > 0);  writes the (hi, lo) pair the dX / dW tensor-core GEMMs read, optionally g itself, and per-block
+// partial column sums (bias gradient) — replaces a compare, a multiply, a split and a column reduction.
+namespace {
+constexpr int kRbRows = 32;
+__global__ void relu_bwd_split_kernel(const float* __restrict__ gy, const float* __restrict__ y, float* __restrict__ g_out,
+                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                      float* __restrict__ colsum, int64_t rows, int N) {
+    const int64_t r0 = (int64_t)blockIdx.x * kRbRows;
+    for (int c = threadIdx.x * 4; c < N; c += blockDim.x * 4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t r = r0; r < r0 + kRbRows && r < rows; ++r) {
+            const int64_t off = r * N + c;
+            float4 g = *reinterpret_cast<const float4*>(gy + off);
+            if (y) {
+                const float4 yy = *reinterpret_cast<const float4*>(y + off);
+                g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f;
+                g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
+            }
+            if (g_out) *reinterpret_cast<float4*>(g_out + off) = g;
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(g.x, g.y), h1 = __floats2bfloat162_rn(g.z, g.w);
+            const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+            const __nv_bfloat162 l0 = __floats2bfloat162_rn(g.x - f0.x, g.y - f0.y);
+            const __nv_bfloat162 l1 = __floats2bfloat162_rn(g.z - f1.x, g.w - f1.y);
+            *reinterpret_cast<uint2*>(hi + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+            *reinterpret_cast<uint2*>(lo + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+            acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+        }
+        if (colsum) *reinterpret_cast<float4*>(colsum + (int64_t)blockIdx.x * N + c) = acc;
+    }
+}
+}  // namespace
+
+extern "C" int dsb_relu_bwd_split_blocks(int64_t rows) { return (int)((rows + kRbRows - 1) / kRbRows); }
+
+extern "C" int dsb_relu_bwd_split(const float* gy, const float* y, float* g_out, void* hi, void* lo, float* colsum,
+                                  int64_t rows, int N, dsb_stream_t stream) {
+    DSB_REQUIRE(gy && hi && lo && rows >= 0 && N > 0 && N % 4 == 0, "relu_bwd_split: bad argument (N %% 4 == 0 required)");
+    if (rows == 0) return DSB_OK;
+    const int64_t blocks = (rows + kRbRows - 1) / kRbRows;
+    DSB_REQUIRE(blocks < (1ll << 31), "relu_bwd_split: too many rows");
+    int threads = N / 4;
+    if (threads > 256) threads = 256;
+    if (threads < 32) threads = 32;
+    relu_bwd_split_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        gy, y, g_out, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, colsum, rows, N);
+    return dsb::check_launch("relu_bwd_split");
+}

@@ -38,6 +38,8 @@ _SIGNATURES = {
     'dsb_layernorm_bwd': (_i, [_vp] * 7 + [_i64, _i, _vp]),
     'dsb_lstm_cell_fwd': (_i, [_vp] * 13 + [_i, _i, _f, _vp]),
     'dsb_lstm_cell_bwd': (_i, [_vp] * 18 + [_i, _i, _vp]),
+    'dsb_relu_bwd_split_blocks': (_i, [_i64]),
+    'dsb_relu_bwd_split': (_i, [_vp] * 6 + [_i64, _i, _vp]),
     'dsb_sumsq_partials': (_i, []),
     'dsb_grad_norm': (_i, [_vp, _i64, _vp, _vp, _vp]),
     'dsb_adam_step': (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp]),
@@ -62,7 +64,7 @@ class GemmArgs(ctypes.Structure):
                 ('c_col_base', _c.c_int32), ('c_col_inner', _c.c_int32),
                 ('residual', _vp), ('bn', _c.c_int32),
                 ('a_conv', _c.c_int32), ('b_conv', _c.c_int32), ('conv_h', _c.c_int32), ('conv_w', _c.c_int32),
-                ('conv_c', _c.c_int32), ('conv_taps', _c.c_int32), ('conv_imgs', _i64)]
+                ('conv_c', _c.c_int32), ('conv_taps', _c.c_int32), ('conv_imgs', _i64), ('c_accumulate', _c.c_int32)]
 
 
 _SIGNATURES['dsb_gemm_ex'] = (_i, [ctypes.POINTER(GemmArgs), _vp])

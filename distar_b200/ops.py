@@ -266,6 +266,19 @@ def _gemm_ex(**kw) -> None:
     lib.gemm_ex(**kw)
 
 
+def relu_bwd_split(gy2: torch.Tensor, y: Optional[torch.Tensor], need_bias: bool, need_g: bool = False):
+    """(g_hi, g_lo, bias_grad or None, g or None) with g = gy * (y > 0): one pass instead of compare + mul + split + sum."""
+    rows, N = gy2.shape
+    dev = gy2.device
+    hi = torch.empty((rows, N), dtype=torch.bfloat16, device=dev)
+    lo = torch.empty((rows, N), dtype=torch.bfloat16, device=dev)
+    g = torch.empty((rows, N), dtype=torch.float32, device=dev) if need_g else None
+    blocks = lib.load().dsb_relu_bwd_split_blocks(rows)
+    cs = torch.empty((blocks, N), dtype=torch.float32, device=dev) if need_bias else None
+    lib.call('dsb_relu_bwd_split', gy2, y, g, hi, lo, cs, rows, N)
+    return hi, lo, (cs.sum(0) if need_bias else None), g
+
+
 def _pick_splits(tiles: int, k: int) -> int:
     """split-K factor for a reduction of length k (tokens) over `tiles` output tiles: fill ~148 SMs, keep >= 512 k per
     split, and k % (64 * splits) == 0."""
@@ -281,10 +294,11 @@ def weight_grad(g_hi, g_lo, x_hi, x_lo, terms: int = 3) -> torch.Tensor:
     M, N = g_hi.shape
     K = x_hi.shape[1]
     splits = _pick_splits((N // 128) * (K // 128), M)
-    part = torch.empty((splits * N, K), dtype=torch.float32, device=g_hi.device)
-    _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=x_hi, b_lo=x_lo, a_mn=1, b_mn=1, alpha=1.0, terms=terms, c=part, m=N, n=K, k=M,
-             batch=1, inner=1, splits=splits, c_row_split=N)
-    return part.view(splits, N, K).sum(0) if splits > 1 else part
+    gw = torch.zeros((N, K), dtype=torch.float32, device=g_hi.device) if splits > 1 else \
+        torch.empty((N, K), dtype=torch.float32, device=g_hi.device)
+    _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=x_hi, b_lo=x_lo, a_mn=1, b_mn=1, alpha=1.0, terms=terms, c=gw, m=N, n=K, k=M,
+             batch=1, inner=1, splits=splits, c_row_split=0, c_accumulate=1 if splits > 1 else 0)
+    return gw
 
 
 class _SplitLinear(torch.autograd.Function):
@@ -315,32 +329,33 @@ class _SplitLinear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy, _ghi=None, _glo=None):
         a_hi, a_lo, w_hi, w_lo, y = ctx.saved_tensors
-        gy2 = gy.reshape(-1, gy.shape[-1])
-        if ctx.relu:
-            gy2 = gy2 * (y > 0)
-        gy2 = gy2.contiguous()
+        gy2 = gy.reshape(-1, gy.shape[-1]).contiguous()
         M, N = gy2.shape
         K = a_hi.shape[1]
         on_gpu = gy2.is_cuda
         gx = gw = gb = None
-        g_hi = g_lo = None
-        if on_gpu and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
-            g_hi, g_lo = split_bf16(gy2)
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if on_gpu and N % 4 == 0:
+            g_hi, g_lo, gb, g = relu_bwd_split(gy2, y if ctx.relu else None, want_b, need_g=False)
+        else:
+            g = gy2 * (y > 0) if ctx.relu else gy2
+            g_hi, g_lo = split_bf16(g) if on_gpu else (None, None)
+            gb = g.sum(0) if want_b else None
         if ctx.needs_input_grad[0]:
             if on_gpu and K % 128 == 0 and N % 64 == 0:
                 gx = torch.empty((M, K), dtype=torch.float32, device=gy2.device)
                 _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=w_hi, b_lo=w_lo, b_mn=1, alpha=1.0, terms=ctx.terms, c=gx, m=M, n=K,
                          k=N, batch=1, inner=1, splits=1)
             else:
-                gx = gy2 @ (w_hi.float() + w_lo.float())
+                gfull = g if g is not None else (g_hi.float() + g_lo.float())
+                gx = gfull @ (w_hi.float() + w_lo.float())
             gx = gx.view(ctx.xshape)
         if ctx.needs_input_grad[1]:
             if on_gpu and N % 128 == 0 and K % 128 == 0 and M % 64 == 0 and M >= 128:
                 gw = weight_grad(g_hi, g_lo, a_hi, a_lo, ctx.terms)
             else:
-                gw = gy2.t() @ (a_hi.float() + a_lo.float())
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy2.sum(0)
+                gfull = g if g is not None else (g_hi.float() + g_lo.float())
+                gw = gfull.t() @ (a_hi.float() + a_lo.float())
         return gx, gw, gb, None, None, None, None, None
 
 
@@ -592,19 +607,17 @@ class _ConvNHWC(torch.autograd.Function):
         x_hi, x_lo, wm, y = ctx.saved_tensors
         N, H, W, C, Cout, Cin, kh, kw, cout_pad, relu, terms, has_bias, has_res = ctx.meta
         taps = kh * kw
-        g = gy.reshape(N * H * W, cout_pad)
-        if relu:
-            g = g * (y > 0)
-        g = g.contiguous()
-        g_hi, g_lo = split_bf16(g)
+        gy2 = gy.reshape(N * H * W, cout_pad).contiguous()
+        want_b = has_bias and ctx.needs_input_grad[2]
+        g_hi, g_lo, gb_full, g = relu_bwd_split(gy2, y if relu else None, want_b, need_g=has_res and relu)
         gx = gw = gb = gres = None
         if has_res:
-            gres = g.view(N, H, W, cout_pad)
+            gres = (g if relu else gy2).view(N, H, W, cout_pad)
         if ctx.needs_input_grad[0]:
             # dX = conv(dY, W') with W'[cin, (ky,kx,cout)] = W[cout, cin, kh-1-ky, kw-1-kx]
             w4 = wm.view(cout_pad, kh, kw, C).flip(1, 2).permute(3, 1, 2, 0).reshape(C, taps * cout_pad).contiguous()
             wt_hi, wt_lo = split_bf16(w4)
-            gx = torch.empty((N * H * W, C), dtype=torch.float32, device=g.device)
+            gx = torch.empty((N * H * W, C), dtype=torch.float32, device=gy2.device)
             _gemm_ex(a_hi=g_hi.view(N, H, W, cout_pad), a_lo=g_lo.view(N, H, W, cout_pad), b_hi=wt_hi, b_lo=wt_lo,
                      alpha=1.0, terms=terms, c=gx, m=N * H * W, n=C, k=taps * cout_pad, batch=1, inner=1, splits=1,
                      a_conv=1, conv_h=H, conv_w=W, conv_c=cout_pad, conv_taps=taps, conv_imgs=N)
@@ -615,14 +628,14 @@ class _ConvNHWC(torch.autograd.Function):
             n = taps * C
             bn = 128 if n % 128 == 0 else 64
             splits = _pick_splits((m_pad // 128) * (n // bn), pix)
-            part = torch.empty((splits * m_pad, n), dtype=torch.float32, device=g.device)
+            part = torch.zeros((m_pad, n), dtype=torch.float32, device=gy2.device)
             _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=x_hi, b_lo=x_lo, a_mn=1, b_mn=1, b_conv=1, alpha=1.0, terms=terms, c=part,
-                     m=cout_pad, n=n, k=pix, batch=1, inner=1, splits=splits, c_row_split=m_pad, bn=bn,
+                     m=cout_pad, n=n, k=pix, batch=1, inner=1, splits=splits, c_row_split=0, c_accumulate=1, bn=bn,
                      conv_h=H, conv_w=W, conv_c=C, conv_taps=taps, conv_imgs=N)
-            gwm = part.view(splits, m_pad, n).sum(0)[:Cout]
+            gwm = part[:Cout]
             gw = gwm.view(Cout, kh, kw, C)[..., :Cin].permute(0, 3, 1, 2).contiguous()
-        if has_bias and ctx.needs_input_grad[2]:
-            gb = g.sum(0)[:Cout]
+        if want_b:
+            gb = gb_full[:Cout]
         return gx, gw, gb, gres, None, None, None
 
 

@@ -84,6 +84,13 @@ int dsb_upsample_bilinear2x_nhwc_bwd(const float* grad_out, float* grad_in, int6
 /* ---- fp32 -> (hi, lo) bf16 split used by the split-precision tensor-core GEMM ---- */
 int dsb_split_bf16(const float* x, void* hi, void* lo, int64_t n, dsb_stream_t stream);
 
+/* ---- ReLU backward + bf16 split + bias gradient in one pass ----
+ * g = gy * (y > 0) (y NULL: g = gy); hi/lo receive the split of g, g_out (optional) g itself, colsum (optional)
+ * per-block partial column sums [dsb_relu_bwd_split_blocks(rows), N] whose sum over blocks is the bias gradient. */
+int dsb_relu_bwd_split_blocks(int64_t rows);
+int dsb_relu_bwd_split(const float* gy, const float* y, float* g_out, void* hi, void* lo, float* colsum, int64_t rows,
+                       int N, dsb_stream_t stream);
+
 /* ---- tcgen05 GEMM family  (fc_block nn_module.py:231-270; attention module_utils.py:88-111; their backward) ----
  * dsb_gemm_bf16_split:  C[M,N] = act( A[M,K] . W[N,K]^T + bias[N] ),  A and W as bf16 (hi, lo) pairs, K contiguous,
  * K % 64 == 0, N % 128 == 0, M arbitrary.  terms = 1: hi*hi only (plain bf16); terms = 3: hi*hi + hi*lo + lo*hi
@@ -129,6 +136,7 @@ typedef struct dsb_gemm_args {
     int32_t bn;
     int32_t a_conv, b_conv, conv_h, conv_w, conv_c, conv_taps;
     int64_t conv_imgs;
+    int32_t c_accumulate;   /* != 0: C += result (TMA reduce-add; use with splits > 1 and c_row_split = 0 on a zeroed C) */
 } dsb_gemm_args;
 int dsb_gemm_ex(const dsb_gemm_args* args, dsb_stream_t stream);
 

@@ -36,10 +36,14 @@ def parse():
     ap.add_argument('--unroll', type=int, default=32, help='unroll length (BASELINE: 32)')
     ap.add_argument('--encoder-chunk', type=int, default=264)
     ap.add_argument('--terms', type=int, default=3, help='tensor-core products per GEMM: 3 = fp32-class (parity), 1 = bf16')
+    ap.add_argument('--no-checkpoint', action='store_true', help='keep encoder activations instead of recomputing them')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--cpu-batch', type=int, default=4)
     ap.add_argument('--cpu-unroll', type=int, default=8)
+    ap.add_argument('--cpu-threads', type=int, default=0,
+                    help='threads for the CPU arm (0 = min(16, usable cores): the tiny-op-bound reference path gets '
+                         'SLOWER beyond that: 128 threads measured 40x slower than 8 on the GPU box)')
     return ap.parse_args()
 
 
@@ -83,6 +87,17 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- CPU reference arm
+def usable_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_threads(args):
+    return args.cpu_threads if args.cpu_threads > 0 else min(16, usable_cores())
+
+
 def cpu_reference_rate(batch, unroll, repeats=2, threads=None):
     """The reference's CPU PyTorch path, as restated by the oracle (kind 'port'): rl_learner_forward + loss +
     backward on a bounded sample.  Returns (frames/s, seconds per step, cores)."""
@@ -90,7 +105,7 @@ def cpu_reference_rate(batch, unroll, repeats=2, threads=None):
     import alphastar_ref as O
     from distar_b200.params import init_state_dict
     from distar_b200.synth import synth_rl_batch, tree_clone
-    cores = threads or os.cpu_count()
+    cores = threads or min(16, usable_cores())
     torch.set_num_threads(cores)
     sd = init_state_dict(seed=0)
     P = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
@@ -115,7 +130,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     times = []
-    cores = os.cpu_count()
+    cores = cpu_threads(args)
     # each "step" is one bounded sample (cpu_batch x cpu_unroll frames)
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import alphastar_ref as O
@@ -238,7 +253,8 @@ def run_b200(args, rank, world, local_rank):
         dist.init_process_group('nccl')
     B, T = args.batch, args.unroll
     cfg = {'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': ['winloss']}}
-    model = Model(cfg, use_value_network=True, seed=0, gemm_terms=args.terms, encoder_chunk=args.encoder_chunk).cuda()
+    model = Model(cfg, use_value_network=True, seed=0, gemm_terms=args.terms, encoder_chunk=args.encoder_chunk,
+                  checkpoint_encoder=not args.no_checkpoint).cuda()
     learner = RLLearner(model, 'MP0', None, lr=1e-5, max_norm=1.0)
     host = synth_rl_batch(B, T, seed=1000 * rank)
     host = tree_map(lambda t: t.pin_memory(), host)
@@ -291,7 +307,11 @@ def run_b200(args, rank, world, local_rank):
         ms_e2e = timed(step_e2e, args.steps)
         e2e = {'value': world * B * T / (ms_e2e / 1e3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d,
                'd2h_bytes_per_step': 4 + 4 * 45, 'ms_per_step': ms_e2e}
+    if world > 1:
+        dist.barrier()
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     peaks = load_peaks()
     roofs = kernel_rooflines(dev, peaks)
@@ -311,11 +331,13 @@ def run_b200(args, rank, world, local_rank):
         'rooflines': roofs,
     }
     if not args.no_cpu_baseline:
-        v, sec, cores = cpu_reference_rate(args.cpu_batch, args.cpu_unroll)
+        v, sec, cores = cpu_reference_rate(args.cpu_batch, args.cpu_unroll, threads=cpu_threads(args))
         line['cpu_baseline'] = {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
                                 'sample': 'oracle port, rl_learner_forward+loss+backward, B=%d x T=%d frames, best of 2 '
                                           '(%.1f s/step)' % (args.cpu_batch, args.cpu_unroll, sec)}
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

@@ -162,17 +162,18 @@ class Model(nn.Module):
         if not chunk or N <= chunk:
             return net.encoder(spatial_info, entity_info, scalar_info, entity_num)
 
-        def run(sp, en, sc, num):
-            li, ctx, bf, ee, ms = net.encoder(sp, en, sc, num)
-            return (li, ctx, bf, ee) + tuple(ms[3:])          # only the 16x16 skips leave the encoder
+        ckpt = self.checkpoint_encoder and torch.is_grad_enabled()
+
+        def entity_fn(en, num):
+            if ckpt:      # recompute only the entity transformer (~34 MB of saved activations per observation) in backward
+                return torch_checkpoint(net.entity_encoder, en, num, use_reentrant=False)
+            return net.entity_encoder(en, num)
 
         outs = []
         for s0 in range(0, N, chunk):
-            args = tree_map(lambda t: t[s0:s0 + chunk], (spatial_info, entity_info, scalar_info, entity_num))
-            if self.checkpoint_encoder and torch.is_grad_enabled():
-                outs.append(torch_checkpoint(run, *args, use_reentrant=False))
-            else:
-                outs.append(run(*args))
+            sp, en, sc, num = tree_map(lambda t: t[s0:s0 + chunk], (spatial_info, entity_info, scalar_info, entity_num))
+            li, ctx, bf, ee, ms = net.encoder(sp, en, sc, num, entity_fn=entity_fn)
+            outs.append((li, ctx, bf, ee) + tuple(ms[3:]))        # only the 16x16 skips leave the encoder
         cat = [torch.cat([o[i] for o in outs], dim=0) for i in range(len(outs[0]))]
         return cat[0], cat[1], cat[2], cat[3], [None, None, None] + cat[4:]
 

@@ -228,10 +228,12 @@ class Net:
     def pool_nhwc(x: Tensor) -> Tensor:
         return F.max_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).contiguous()
 
-    def encoder(self, spatial_info, entity_info, scalar_info, entity_num):
-        """model/encoder.py:28-45."""
+    def encoder(self, spatial_info, entity_info, scalar_info, entity_num, entity_fn=None):
+        """model/encoder.py:28-45.  entity_fn lets the caller wrap the entity transformer (the activation-memory hog)
+        in activation checkpointing while the rest of the encoder keeps its activations."""
         embedded_scalar, scalar_context, baseline_feature = self.scalar_encoder(scalar_info)
-        entity_embeddings, embedded_entity, mask = self.entity_encoder(entity_info, entity_num)
+        run_entity = entity_fn or self.entity_encoder
+        entity_embeddings, embedded_entity, _mask = run_entity(entity_info, entity_num)
         project = self.fc('encoder.scatter_project', entity_embeddings, relu=True)
         scatter_map = ops.scatter_connection(project, entity_info['x'], entity_info['y'], entity_num, self.H, self.W)
         embedded_spatial, map_skip = self.spatial_encoder(spatial_info, scatter_map)

@@ -25,6 +25,8 @@ _SIGNATURES = {
     'dsb_categorical_stats_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
     'dsb_sample_categorical': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     'dsb_split_bf16': (_i, [_vp, _vp, _vp, _i64, _vp]),
+    'dsb_upshift9_fwd': (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp]),
+    'dsb_upshift9_bwd': (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     'dsb_upsample_bilinear2x_fwd': (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     'dsb_upsample_bilinear2x_bwd': (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     'dsb_upsample_bilinear2x_nhwc_fwd': (_i, [_vp, _vp, _i64, _i, _i, _i, _vp]),

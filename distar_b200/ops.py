@@ -704,6 +704,44 @@ def upsample_bilinear2x_nhwc(x: torch.Tensor) -> torch.Tensor:
     return F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2., mode='bilinear').permute(0, 2, 3, 1).contiguous()
 
 
+class _UpShift9(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, bias):
+        N, H, W, _ = z.shape
+        z = z.contiguous()
+        out = torch.empty((N, 2 * H, 2 * W), dtype=torch.float32, device=z.device)
+        lib.call('dsb_upshift9_fwd', z, bias, out, N, H, W)
+        ctx.shape = (N, H, W)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        N, H, W = ctx.shape
+        g = g.contiguous()
+        gz = torch.empty((N, H, W, 9), dtype=torch.float32, device=g.device)
+        lib.call('dsb_upshift9_bwd', g, gz, N, H, W)
+        return gz, (g.sum().reshape(1) if ctx.has_bias else None)
+
+
+def upsample_conv3x3_single(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """conv2d(F.interpolate(x, 2, 'bilinear'), weight[1,C,3,3], bias, padding=1) for a channels-last x [N,H,W,Cpad>=C]
+    -> [N, 2H, 2W].  Up-sampling commutes with the channel contraction, so the 3x3 taps are applied as nine shifted
+    up-samplings of a 9-channel low-resolution projection z = x . w (see csrc/upsample.cu)."""
+    C = weight.shape[1]
+    wm = weight[0].reshape(C, 9)
+    if x.shape[-1] > C:
+        wm = F.pad(wm, (0, 0, 0, x.shape[-1] - C))
+    z = torch.matmul(x, wm)                                   # [N,H,W,9]  (small library GEMM, N = 9)
+    if _use_kernel(x):
+        return _UpShift9.apply(z, bias)
+    up = F.interpolate(z.permute(0, 3, 1, 2), scale_factor=2., mode='bilinear')          # [N,9,2H,2W]
+    up = F.pad(up, (1, 1, 1, 1))
+    H2, W2 = up.shape[2] - 2, up.shape[3] - 2
+    out = sum(up[:, t, t // 3:t // 3 + H2, t % 3:t % 3 + W2] for t in range(9))
+    return out + bias if bias is not None else out
+
+
 def upsample_bilinear2x(x: torch.Tensor) -> torch.Tensor:
     """F.interpolate(x, scale_factor=2., mode='bilinear') (align_corners=False) on [N,C,H,W] fp32."""
     if _use_kernel(x):

@@ -422,9 +422,8 @@ class Net:
             x = torch.relu(torch.tanh(r * torch.sigmoid(g)) * P_[rp + 'UpdateSP'] + x)
         x = self.conv_nhwc(pre + 'upsample.0', ops.upsample_bilinear2x_nhwc(x), relu=True)            # [N,32,32,64]
         x = self.conv_nhwc(pre + 'upsample.1', ops.upsample_bilinear2x_nhwc(x), relu=True)            # [N,64,64,64] (32 real)
-        x = ops.upsample_bilinear2x_nhwc(x[..., :32].contiguous())                                    # [N,128,128,32]
-        # last conv has ONE output channel (9.4 MFLOP/row): library conv on the channels-last view
-        x = F.conv2d(x.permute(0, 3, 1, 2), P_[pre + 'upsample.2.0.weight'], P_[pre + 'upsample.2.0.bias'], padding=1)
+        # last stage (32 -> 1 channel at 128x128): up-sampling commutes with the channel contraction
+        x = ops.upsample_conv3x3_single(x, P_[pre + 'upsample.2.0.weight'], P_[pre + 'upsample.2.0.bias'])
         logits = x.reshape(N, -1) / self.T
         if location is None:
             location = self.sample(logits)

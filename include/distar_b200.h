@@ -81,6 +81,12 @@ int dsb_upsample_bilinear2x_nhwc_fwd(const float* in, float* out, int64_t N, int
 int dsb_upsample_bilinear2x_nhwc_bwd(const float* grad_out, float* grad_in, int64_t N, int H, int W, int C,
                                      dsb_stream_t stream);
 
+/* ---- location-head tail: conv3x3(upsample2x(x), one output channel)  (head/action_arg_head.py:436-443) ----
+ * second half of the factorisation out = b + sum_tap shift_tap(upsample2x(z_tap)), z = x . w[C,9] at low resolution:
+ * z [N, H, W, 9] -> out [N, 2H, 2W] (bias: 1 float, may be NULL); backward gz [N, H, W, 9] from grad_out. */
+int dsb_upshift9_fwd(const float* z, const float* bias, float* out, int64_t N, int H, int W, dsb_stream_t stream);
+int dsb_upshift9_bwd(const float* grad_out, float* grad_z, int64_t N, int H, int W, dsb_stream_t stream);
+
 /* ---- fp32 -> (hi, lo) bf16 split used by the split-precision tensor-core GEMM ---- */
 int dsb_split_bf16(const float* x, void* hi, void* lo, int64_t n, dsb_stream_t stream);
 

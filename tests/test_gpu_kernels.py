@@ -232,3 +232,25 @@ def test_lstm_cell_fwd_bwd(B, H):
     assert (cd.double().cpu() - c2.detach()).abs().max().item() <= 2e-5 * c2.abs().max().item()
     for got, want in zip(devs, refs):
         assert (got.grad.double().cpu() - want.grad).abs().max().item() <= 1e-4 * want.grad.abs().max().item()
+
+
+@pytest.mark.parametrize('N,H,W,C,Cpad', [(2, 64, 64, 32, 64), (3, 8, 8, 32, 32), (1, 5, 7, 3, 8)])
+def test_upsample_conv3x3_single_fwd_bwd(N, H, W, C, Cpad):
+    g = torch.Generator().manual_seed(H + W + C)
+    x = torch.zeros(N, H, W, Cpad)
+    x[..., :C] = torch.randn(N, H, W, C, generator=g)
+    w = torch.randn(1, C, 3, 3, generator=g) / 3
+    b = torch.randn(1, generator=g)
+    go = torch.randn(N, 2 * H, 2 * W, generator=g)
+    F = torch.nn.functional
+    xr, wr, br = [t.double().clone().requires_grad_(True) for t in (x, w, b)]
+    up = F.interpolate(xr[..., :C].permute(0, 3, 1, 2), scale_factor=2., mode='bilinear')
+    ref = F.conv2d(up, wr, br, padding=1)[:, 0]
+    ref.backward(go.double())
+    xd, wd, bd = [t.to(DEV).requires_grad_(True) for t in (x, w, b)]
+    out = ops.upsample_conv3x3_single(xd, wd, bd)
+    out.backward(go.to(DEV))
+    assert (out.double().cpu() - ref.detach()).abs().max().item() <= 1e-5 * ref.abs().max().item()
+    for got, want, n in [(xd.grad[..., :C], xr.grad[..., :C], 'dx'), (wd.grad, wr.grad, 'dw')]:
+        assert (got.double().cpu() - want).abs().max().item() <= 1e-4 * want.abs().max().item(), n
+    assert abs(bd.grad.item() - br.grad.item()) <= 1e-5 * go.abs().sum().item()

@@ -20,6 +20,8 @@ _SIGNATURES = {
     'dsb_launch_count': (_i64, []),
     'dsb_scatter_connection_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'dsb_scatter_connection_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'dsb_spatial_stem_fwd': (_i, [_vp] * 11 + [_i] * 5 + [_vp]),
+    'dsb_spatial_stem_bwd': (_i, [_vp] * 9 + [_i] + [_vp] * 3 + [_i] * 4 + [_vp]),
     'dsb_return_scan': (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'dsb_categorical_stats_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
     'dsb_categorical_stats_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
@@ -128,6 +130,12 @@ def gemm_ex(**kw):
     rc = lib.dsb_gemm_ex(ctypes.byref(g), _stream())
     if rc != 0:
         raise DsbError('dsb_gemm_ex failed (%d): %s' % (rc, lib.dsb_last_error().decode()))
+
+
+def ptr_array(tensors):
+    """host array of device pointers (kept alive by the caller holding the returned object and the tensors)"""
+    arr = (_vp * len(tensors))(*[_ptr(t) for t in tensors])
+    return arr
 
 
 def call(name: str, *args):

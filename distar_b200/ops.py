@@ -76,6 +76,72 @@ def scatter_connection(project: torch.Tensor, ex: torch.Tensor, ey: torch.Tensor
 
 
 # ------------------------------------------------------------------------------------------------
+# fused spatial stem: scatter + plane expansion + 1x1 conv + ReLU + 2x2 max-pool (K6/K7 first stage)
+# ------------------------------------------------------------------------------------------------
+STEM_PLANES = ['height_map', 'visibility_map', 'creep', 'player_relative', 'alerts', 'pathable', 'buildable']
+STEM_EFFECTS = ['effect_PsiStorm', 'effect_NukeDot', 'effect_LiberatorDefenderZone', 'effect_BlindingCloud',
+                'effect_CorrosiveBile', 'effect_LurkerSpines']
+
+
+class _SpatialStem(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, project, weight, bias, ex, ey, entity_num, out_c, *maps):
+        planes, effects = list(maps[:7]), list(maps[7:13])
+        N, H, W = planes[0].shape
+        E = project.shape[1]
+        dev = project.device
+        project = project.contiguous()
+        w2 = weight.reshape(32, 56).contiguous()
+        out = torch.empty((N, H // 2, W // 2, out_c), dtype=torch.float32, device=dev)
+        hi = torch.empty(out.shape, dtype=torch.bfloat16, device=dev)
+        lo = torch.empty(out.shape, dtype=torch.bfloat16, device=dev)
+        pa, ea = lib.ptr_array(planes), lib.ptr_array(effects)
+        lib.call('dsb_spatial_stem_fwd', pa, ea, project, ex, ey, entity_num, w2, bias, out, hi, lo, out_c, N, E, H, W)
+        ctx.save_for_backward(project, w2, bias, ex, ey, entity_num, *planes, *effects)
+        ctx.dims = (N, E, H, W, out_c, tuple(weight.shape))
+        ctx.mark_non_differentiable(hi, lo)
+        return out, hi, lo
+
+    @staticmethod
+    def backward(ctx, gout, _ghi, _glo):
+        project, w2, bias, ex, ey, entity_num = ctx.saved_tensors[:6]
+        planes, effects = list(ctx.saved_tensors[6:13]), list(ctx.saved_tensors[13:19])
+        N, E, H, W, out_c, wshape = ctx.dims
+        dev = gout.device
+        gw = torch.zeros((32, 56), dtype=torch.float32, device=dev)
+        gb = torch.zeros(32, dtype=torch.float32, device=dev)
+        gp = torch.zeros((N, E, 32), dtype=torch.float32, device=dev)
+        pa, ea = lib.ptr_array(planes), lib.ptr_array(effects)
+        lib.call('dsb_spatial_stem_bwd', pa, ea, project, ex, ey, entity_num, w2, bias, gout.contiguous(), out_c, gw, gb, gp,
+                 N, E, H, W)
+        return (gp, gw.view(wshape), gb, None, None, None, None) + (None,) * 13
+
+
+def spatial_stem(spatial_info, project, ex, ey, entity_num, weight, bias, out_c: int = 64):
+    """relu(project_conv(cat[planes, effects, scatter_connection(project)])) max-pooled 2x2, channels-last
+    [N, H/2, W/2, out_c] (first 32 channels real), with the bf16 split attached for the following 3x3 conv."""
+    planes = [spatial_info[k].contiguous() for k in STEM_PLANES]
+    effects = [spatial_info[k].contiguous() for k in STEM_EFFECTS]
+    if _use_kernel(project):
+        out, hi, lo = _SpatialStem.apply(project, weight, bias, ex.contiguous(), ey.contiguous(),
+                                         entity_num.to(torch.int64).contiguous(), out_c, *planes, *effects)
+        return attach_split(out, hi, lo)
+    N, H, W = planes[0].shape
+    scatter_map = scatter_connection(project, ex, ey, entity_num, H, W)
+    chans = [planes[0].float().unsqueeze(1) / 256]
+    for p, n in zip(planes[1:], (4, 2, 5, 2, 2, 2)):
+        chans.append(F.one_hot(p.long(), n).permute(0, 3, 1, 2).float())
+    for e in effects:
+        m = torch.zeros(N, H * W, device=project.device)
+        m.scatter_(1, e.long(), 1.0)
+        chans.append(m.view(N, 1, H, W))
+    chans.append(scatter_map)
+    x = torch.relu(F.conv2d(torch.cat(chans, dim=1), weight, bias))
+    x = F.max_pool2d(x, 2, 2).permute(0, 2, 3, 1)
+    return F.pad(x, (0, out_c - 32)).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
 # return scans (K18)
 # ------------------------------------------------------------------------------------------------
 def return_scan(reward: torch.Tensor, value: torch.Tensor, rho: torch.Tensor, gamma_td: torch.Tensor,

@@ -191,22 +191,15 @@ class Net:
         pooled = (x * mask.unsqueeze(2)).sum(dim=1) / entity_num.unsqueeze(-1)
         return entity_embeddings, self.fc(pre + 'embed_fc', pooled, relu=True), mask
 
-    def spatial_encoder(self, sp: Dict[str, Tensor], scatter_map: Tensor):
-        """obs_encoder/spatial_encoder.py:51-90 (K7)."""
+    def spatial_encoder(self, sp: Dict[str, Tensor], project: Tensor, ex: Tensor, ey: Tensor, entity_num: Tensor):
+        """obs_encoder/spatial_encoder.py:51-90 (K7) with the entity scatter (K6) fused into its first stage."""
         pre = 'encoder.spatial_encoder.'
-        N, H, W = sp['height_map'].shape
-        planes = [sp['height_map'].float().unsqueeze(1) / 256]
-        for name, n in SPATIAL_ONEHOT:
-            planes.append(F.one_hot(sp[name].long(), n).permute(0, 3, 1, 2).float())
-        for name in SPATIAL_EFFECTS:
-            p = torch.zeros(N, H * W, device=scatter_map.device)
-            p.scatter_(1, sp[name].long(), 1.0)
-            planes.append(p.view(N, 1, H, W))
-        planes.append(scatter_map)
-        x = self.conv(pre + 'project', torch.cat(planes, dim=1), 0, relu=True)          # [N,32,H,W] (library 1x1)
-        skips = [x, None, None]               # the 128^2 / 64^2 / 32^2 skips are never read downstream (unet off)
-        # from here on: channels-last, channels padded to 64, every 3x3 conv an implicit GEMM on the tensor cores
-        x = F.pad(F.max_pool2d(x, 2, 2).permute(0, 2, 3, 1), (0, 32)).contiguous()
+        N = project.shape[0]
+        # stem: scatter + plane expansion + 1x1 project conv + ReLU + first 2x2 max-pool in one kernel; from here on
+        # channels-last, channels padded to 64, every 3x3 conv an implicit GEMM on the tensor cores
+        x = ops.spatial_stem(sp, project, ex, ey, entity_num, self.P[pre + 'project.0.weight'],
+                             self.P[pre + 'project.0.bias'], 64)
+        skips = [None, None, None]            # the 128^2 / 64^2 / 32^2 skips are never read downstream (unet off)
         for i in range(3):
             if i > 0:
                 x = self.pool_nhwc(x)
@@ -235,8 +228,10 @@ class Net:
         run_entity = entity_fn or self.entity_encoder
         entity_embeddings, embedded_entity, _mask = run_entity(entity_info, entity_num)
         project = self.fc('encoder.scatter_project', entity_embeddings, relu=True)
-        scatter_map = ops.scatter_connection(project, entity_info['x'], entity_info['y'], entity_num, self.H, self.W)
-        embedded_spatial, map_skip = self.spatial_encoder(spatial_info, scatter_map)
+        # scatter_connection (ops.scatter_connection, K6) is fused into the spatial stem; the stand-alone operator is
+        # kept for API parity / measurement
+        embedded_spatial, map_skip = self.spatial_encoder(spatial_info, project, entity_info['x'], entity_info['y'],
+                                                          entity_num)
         lstm_input = torch.cat([embedded_scalar, embedded_entity, embedded_spatial], dim=-1)
         return lstm_input, scalar_context, baseline_feature, entity_embeddings, map_skip
 

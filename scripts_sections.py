@@ -25,7 +25,7 @@ ee, emb, mask = timeit('entity_encoder[264]', lambda: net.entity_encoder(en, num
 proj = timeit('scatter_project[264]', lambda: net.fc('encoder.scatter_project', ee, relu=True))
 from distar_b200 import ops
 smap = timeit('scatter_connection[264]', lambda: ops.scatter_connection(proj, en['x'], en['y'], num, 128, 128))
-es, skips = timeit('spatial_encoder[264]', lambda: net.spatial_encoder(sp, smap))
+es, skips = timeit("spatial_encoder[264]", lambda: net.spatial_encoder(sp, proj, en["x"], en["y"], num))
 P = 1024
 x = torch.randn(33, 128, 1536, device=dev)
 st = [(torch.randn(128, 384, device=dev), torch.randn(128, 384, device=dev)) for _ in range(3)]

@@ -254,3 +254,36 @@ def test_upsample_conv3x3_single_fwd_bwd(N, H, W, C, Cpad):
     for got, want, n in [(xd.grad[..., :C], xr.grad[..., :C], 'dx'), (wd.grad, wr.grad, 'dw')]:
         assert (got.double().cpu() - want).abs().max().item() <= 1e-4 * want.abs().max().item(), n
     assert abs(bd.grad.item() - br.grad.item()) <= 1e-5 * go.abs().sum().item()
+
+
+@pytest.mark.parametrize('N,ragged', [(3, True), (2, False)])
+def test_spatial_stem_fwd_bwd(N, ragged):
+    from distar_b200.synth import synth_obs
+    g = torch.Generator().manual_seed(N)
+    en = torch.tensor([512, 77, 300][:N]) if ragged else None
+    obs = synth_obs(N, seed=5 + N, entity_num=en, hidden=False)
+    sp, ent, num = obs['spatial_info'], obs['entity_info'], obs['entity_num']
+    proj = torch.relu(torch.randn(N, 512, 32, generator=g))
+    proj = proj * (torch.arange(512).unsqueeze(0) < num.unsqueeze(1)).unsqueeze(-1)
+    w = torch.randn(32, 56, 1, 1, generator=g) / 4
+    b = torch.randn(32, generator=g) / 4
+    go = torch.randn(N, 64, 64, 64, generator=g)
+    ops.enable_host_logic_testing(True)
+    try:
+        pr, wr, br = [t.clone().requires_grad_(True) for t in (proj, w, b)]
+        ref = ops.spatial_stem(sp, pr, ent['x'], ent['y'], num, wr, br, 64)
+        (ref * go).sum().backward()
+    finally:
+        ops.enable_host_logic_testing(False)
+    to = lambda t: t.to(DEV)
+    pd, wd, bd = [t.to(DEV).requires_grad_(True) for t in (proj, w, b)]
+    out = ops.spatial_stem({k: to(v) for k, v in sp.items()}, pd, to(ent['x']), to(ent['y']), to(num), wd, bd, 64)
+    hi, lo = out._dsb_split
+    (out * go.to(DEV)).sum().backward()
+    scale = ref.abs().max().item()
+    assert (out.cpu() - ref.detach()).abs().max().item() <= 2e-5 * scale
+    assert out[..., 32:].abs().max().item() == 0
+    assert (hi.float() + lo.float() - out).abs().max().item() <= 1e-4 * scale
+    for got, want, n in [(pd.grad, pr.grad, 'dproject'), (wd.grad, wr.grad, 'dw'), (bd.grad, br.grad, 'db')]:
+        err = (got.cpu() - want).abs().max().item()
+        assert err <= 2e-4 * want.abs().max().item(), (n, err, want.abs().max().item())

@@ -20,6 +20,7 @@ _SIGNATURES = {
     'dsb_launch_count': (_i64, []),
     'dsb_scatter_connection_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'dsb_scatter_connection_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'dsb_entity_features': (_i, [_vp] * 5 + [_i, _vp, _vp, _i64, _vp, _vp]),
     'dsb_spatial_stem_fwd': (_i, [_vp] * 11 + [_i] * 5 + [_vp]),
     'dsb_spatial_stem_bwd': (_i, [_vp] * 9 + [_i] + [_vp] * 3 + [_i] * 4 + [_vp]),
     'dsb_return_scan': (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -130,6 +131,10 @@ def gemm_ex(**kw):
     rc = lib.dsb_gemm_ex(ctypes.byref(g), _stream())
     if rc != 0:
         raise DsbError('dsb_gemm_ex failed (%d): %s' % (rc, lib.dsb_last_error().decode()))
+
+
+def int_array(values):
+    return (_c.c_int * len(values))(*values)
 
 
 def ptr_array(tensors):

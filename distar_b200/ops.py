@@ -76,6 +76,48 @@ def scatter_connection(project: torch.Tensor, ex: torch.Tensor, ey: torch.Tensor
 
 
 # ------------------------------------------------------------------------------------------------
+# entity feature expansion (K1)
+# ------------------------------------------------------------------------------------------------
+_DTYPE_CODE = {torch.uint8: 0, torch.int16: 1, torch.int8: 2, torch.float16: 3}
+
+
+def entity_features_split(entity_info: dict, fields, check_negative: bool = True):
+    """fields: [(name, kind 'o'|'b'|'u', width)] in concat order.  Returns the [N, E, 1024] bf16 (hi, lo) feature pair the
+    embedding GEMM consumes, built straight from the wire-format fields (no fp32 concat).  None on unsupported dtypes."""
+    first = entity_info[fields[0][0]]
+    if not first.is_cuda:
+        return None
+    tensors, kinds, offs, vocabs, dts = [], [], [], [], []
+    off = 0
+    for name, kind, w in fields:
+        t = entity_info[name]
+        if t.dtype not in _DTYPE_CODE:
+            return None
+        tensors.append(t.contiguous())
+        kinds.append({'o': 0, 'b': 1, 'u': 2}[kind])
+        offs.append(off)
+        vocabs.append(w)
+        dts.append(_DTYPE_CODE[t.dtype])
+        off += w
+    N, E = first.shape
+    hi = torch.empty((N, E, 1024), dtype=torch.bfloat16, device=first.device)
+    lo = torch.empty((N, E, 1024), dtype=torch.bfloat16, device=first.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=first.device)
+    lib.call('dsb_entity_features', lib.ptr_array(tensors), lib.int_array(kinds), lib.int_array(offs),
+             lib.int_array(vocabs), lib.int_array(dts), len(fields), hi, lo, N * E, flag)
+    if check_negative and int(flag.item()) != 0:          # entity_encoder.py:69-72 raises on negative ids
+        raise RuntimeError('negative categorical id in an entity field')
+    return hi, lo
+
+
+def linear_presplit(x_hi: torch.Tensor, x_lo: torch.Tensor, weight: torch.Tensor, bias, relu: bool, terms: int = 3,
+                    emit_split: bool = False) -> torch.Tensor:
+    """fc_block on an input that only exists as a bf16 (hi, lo) pair (no gradient flows to it)."""
+    y, y_hi, y_lo = _SplitLinear.apply(x_hi, weight, bias, relu, terms, x_hi, x_lo, emit_split)
+    return attach_split(y, y_hi, y_lo) if emit_split else y
+
+
+# ------------------------------------------------------------------------------------------------
 # fused spatial stem: scatter + plane expansion + 1x1 conv + ReLU + 2x2 max-pool (K6/K7 first stage)
 # ------------------------------------------------------------------------------------------------
 STEM_PLANES = ['height_map', 'visibility_map', 'creep', 'player_relative', 'alerts', 'pathable', 'buildable']

@@ -169,16 +169,20 @@ class Net:
     def entity_encoder(self, e: Dict[str, Tensor], entity_num: Tensor):
         """obs_encoder/entity_encoder.py:59-96 (K1-K4)."""
         P, pre = self.P, 'encoder.entity_encoder.'
-        for name, kind, w in ENTITY_FIELDS:
-            if kind == 'o' and e[name].dtype in (torch.int8, torch.int16, torch.int32, torch.int64):
-                if bool((e[name] < 0).any()):
-                    raise RuntimeError('negative categorical id in entity field %s' % name)
-        feats = self.entity_features(e)
-        E = feats.shape[1]
-        mask = torch.arange(E, device=feats.device).unsqueeze(0) < entity_num.unsqueeze(1)
         w = P[pre + 'transformer.embedding.0.weight']
-        w_pad = F.pad(w, (0, feats.shape[-1] - w.shape[1]))
-        x = ops.linear(feats, w_pad, P[pre + 'transformer.embedding.0.bias'], True, self.terms)
+        w_pad = F.pad(w, (0, 1024 - w.shape[1]))
+        E = entity_info_E = e['x'].shape[1]
+        mask = torch.arange(E, device=e['x'].device).unsqueeze(0) < entity_num.unsqueeze(1)
+        split = ops.entity_features_split(e, ENTITY_FIELDS)
+        if split is not None:       # K1: features expanded straight into the GEMM's bf16 operand pair
+            x = ops.linear_presplit(split[0], split[1], w_pad, P[pre + 'transformer.embedding.0.bias'], True, self.terms,
+                                    emit_split=True)
+        else:
+            for name, kind, wd in ENTITY_FIELDS:
+                if kind == 'o' and e[name].dtype in (torch.int8, torch.int16, torch.int32, torch.int64):
+                    if bool((e[name] < 0).any()):
+                        raise RuntimeError('negative categorical id in entity field %s' % name)
+            x = ops.linear(self.entity_features(e), w_pad, P[pre + 'transformer.embedding.0.bias'], True, self.terms)
         for i in range(3):
             lp = '%stransformer.layers.%d' % (pre, i)
             qkv = self.fc(lp + '.attention.attention_pre', x)

@@ -42,6 +42,14 @@ int dsb_scatter_connection_fwd(const float* project, const uint8_t* ex, const ui
 int dsb_scatter_connection_bwd(const float* grad_out, const uint8_t* ex, const uint8_t* ey, const int64_t* entity_num,
                                float* grad_project, int N, int E, int H, int W, dsb_stream_t stream);
 
+/* ---- entity feature expansion  (EntityEncoder.forward one-hot / binary / unsqueeze + cat, entity_encoder.py:59-78) ----
+ * fields: host array of 36 device pointers (one per entity field, [tokens] each) with host tables kind (0 one-hot,
+ * 1 11-bit binary MSB first, 2 scalar), offset (first column), vocab, dtype (0 u8, 1 i16, 2 i8, 3 f16).
+ * Writes the 1024-wide (997 + zero padding) feature rows as the bf16 (hi, lo) pair of the embedding GEMM.
+ * error_flag (device int, zeroed by the caller) is set to 1 if a one-hot id is negative (reference raises). */
+int dsb_entity_features(const void* const* fields, const int* kind, const int* offset, const int* vocab, const int* dtype,
+                        int num_fields, void* hi, void* lo, int64_t tokens, int* error_flag, dsb_stream_t stream);
+
 /* ---- fused spatial-encoder stem  (scatter_connection + plane expansion spatial_encoder.py:51-71 + project conv :72
  *      + first max_pool2d :75-79) ----
  * planes: host array of 7 device pointers (height_map, visibility_map, creep, player_relative, alerts, pathable,

@@ -287,3 +287,21 @@ def test_spatial_stem_fwd_bwd(N, ragged):
     for got, want, n in [(pd.grad, pr.grad, 'dproject'), (wd.grad, wr.grad, 'dw'), (bd.grad, br.grad, 'db')]:
         err = (got.cpu() - want).abs().max().item()
         assert err <= 2e-4 * want.abs().max().item(), (n, err, want.abs().max().item())
+
+
+def test_entity_features_kernel_matches_reference_expansion():
+    from distar_b200.policy_net import ENTITY_FIELDS, Net
+    from distar_b200.synth import synth_obs
+    obs = synth_obs(3, seed=9, hidden=False)
+    ent = {k: v.clone() for k, v in obs['entity_info'].items()}
+    ent['unit_type'][0, :5] = 300          # >= vocab: clamped like the reference
+    ent['x'][1, :4] = 255
+    ref = Net({}, 128, 128).entity_features(ent)                         # torch expansion on the CPU (pure function)
+    hi, lo = ops.entity_features_split({k: v.to(DEV) for k, v in ent.items()}, ENTITY_FIELDS)
+    got = hi.float() + lo.float()
+    assert got.shape == (3, 512, 1024)
+    assert (got.cpu() - ref).abs().max().item() <= 1e-6
+    assert torch.equal(hi[..., 997:].cpu().float(), torch.zeros(3, 512, 27))
+    ent['last_selected_units'][0, 0] = -1
+    with pytest.raises(RuntimeError):
+        ops.entity_features_split({k: v.to(DEV) for k, v in ent.items()}, ENTITY_FIELDS)

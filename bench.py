@@ -37,6 +37,8 @@ def parse():
     ap.add_argument('--encoder-chunk', type=int, default=264)
     ap.add_argument('--terms', type=int, default=3, help='tensor-core products per GEMM: 3 = fp32-class (parity), 1 = bf16')
     ap.add_argument('--no-checkpoint', action='store_true', help='keep encoder activations instead of recomputing them')
+    ap.add_argument('--keep-chunks', type=int, default=8,
+                    help='number of encoder chunks whose entity-transformer activations are kept (not recomputed)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--cpu-batch', type=int, default=4)
@@ -203,29 +205,36 @@ def kernel_rooflines(dev, peaks):
                                  'frac': ach / peaks['hbm_gbs'], 'traffic': None, 'us_per_launch': dt * 1e6,
                                  'shape': 'N=%d obs, 512 entities, 32ch, 128x128' % N,
                                  'peak_source': peaks['source']}
-    # entity-transformer MLP GEMM: [M,256] x [1024,256]^T, M = 256 obs * 512 tokens, 3-term split
-    M, K, Nn = 256 * 512, 256, 1024
+    # entity-transformer MLP GEMM: [M,256] x [1024,256]^T, M = 1024 obs * 512 tokens, 3-term split
+    M, K, Nn = 1024 * 512, 256, 1024          # 1024 obs: large enough that the launch is not host-bound
     a = torch.randn(M, K, device=dev)
     w = torch.randn(Nn, K, device=dev) / 16
     b = torch.randn(Nn, device=dev)
     a_hi, a_lo = ops.split_bf16(a)
     w_hi, w_lo = ops.split_bf16(w)
-    for terms in (3, 1):
+    from distar_b200 import lib as _lib
+    c = torch.empty(M, Nn, device=dev)
+    for terms, bn in ((3, 0), (3, 128), (1, 0)):
+        def run():
+            _lib.gemm_ex(a_hi=a_hi, a_lo=a_lo, b_hi=w_hi, b_lo=w_lo, bias=b, alpha=1.0, relu=1, terms=terms, c=c, m=M, n=Nn,
+                         k=K, batch=1, inner=1, splits=1, bn=bn)
         for _ in range(3):
-            ops.gemm_split(a_hi, a_lo, w_hi, w_lo, b, True, terms)
+            run()
         torch.cuda.synchronize()
         s.record()
         for _ in range(reps):
-            ops.gemm_split(a_hi, a_lo, w_hi, w_lo, b, True, terms)
+            run()
         e.record()
         torch.cuda.synchronize()
         dt = s.elapsed_time(e) / reps / 1e3
         flops = 2.0 * M * K * Nn * terms
         ach = flops / dt / 1e12
-        out['entity_mlp_gemm_terms%d' % terms] = {
+        key = 'entity_mlp_gemm_terms%d' % terms + ('_bn%d' % bn if bn else '')
+        out[key] = {
             'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
             'frac': ach / peaks['bf16_tflops'], 'traffic': None, 'us_per_launch': dt * 1e6,
-            'shape': 'M=%d K=%d N=%d, %d bf16 MMA terms (tensor-core flops counted)' % (M, K, Nn, terms),
+            'shape': 'M=%d K=%d N=%d, %d bf16 MMA terms (tensor-core flops counted), tile 128x%s' % (
+                M, K, Nn, terms, bn if bn else 'auto(256)'),
             'peak_source': peaks['source']}
     return out
 
@@ -254,7 +263,7 @@ def run_b200(args, rank, world, local_rank):
     B, T = args.batch, args.unroll
     cfg = {'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': ['winloss']}}
     model = Model(cfg, use_value_network=True, seed=0, gemm_terms=args.terms, encoder_chunk=args.encoder_chunk,
-                  checkpoint_encoder=not args.no_checkpoint).cuda()
+                  checkpoint_encoder=not args.no_checkpoint, keep_chunks=args.keep_chunks).cuda()
     learner = RLLearner(model, 'MP0', None, lr=1e-5, max_norm=1.0)
     host = synth_rl_batch(B, T, seed=1000 * rank)
     host = tree_map(lambda t: t.pin_memory(), host)
@@ -325,8 +334,10 @@ def run_b200(args, rank, world, local_rank):
                                'clip + Adam), BASELINE configs[3] per rank',
                    'batch_per_gpu': B, 'unroll': T, 'entities': 512, 'spatial': '128x128', 'global_batch': world * B,
                    'parallelism': 'dp%d' % world, 'encoder_chunk': args.encoder_chunk,
+                   'entity_chunks_recomputed_in_backward': max(0, -(-(T + 1) * B // args.encoder_chunk) - args.keep_chunks),
                    'l2': 'inputs and activations (GBs per step) far exceed the 126 MB L2; no flush needed'},
         'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches),
+        'peak_hbm_gib': round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
         'roofline': roofs['entity_mlp_gemm_terms3'] if args.terms == 3 else roofs['entity_mlp_gemm_terms1'],
         'rooflines': roofs,
     }

@@ -30,14 +30,18 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 64;                        // BN (64 or 128) is a template parameter
-constexpr int kStages = 3;
+constexpr int BM = 128, BK = 64;                        // BN (64, 128 or 256) is a template parameter
 constexpr int kAccStages = 2;
 constexpr int kTileBytes = BM * BK * 2;                 // 16 KiB: one 128x64 bf16 operand tile (B tiles use BN*128 B of it)
-constexpr int kStageBytes = 4 * kTileBytes;             // A_hi, A_lo, B_hi, B_lo
 constexpr int kStoreBufBytes = 32 * 128;                // one 32-row x 32-col fp32 staging box (128 B rows, SWIZZLE_128B)
 constexpr int kStoreBytes = 4 * 2 * kStoreBufBytes;     // 4 epilogue warps x double buffer
-constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+// per-BN shared-memory plan: stage = A_hi | A_lo | B_hi | B_lo; B slots are 16 KiB (BN <= 128) or 32 KiB (BN = 256)
+template <int BN> struct Plan {
+    static constexpr int kBSlot = BN > 128 ? BN * 128 : kTileBytes;
+    static constexpr int kStageBytes = 2 * kTileBytes + 2 * kBSlot;
+    static constexpr int kStages = BN > 128 ? 2 : 3;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 constexpr int kThreads = 192;
 constexpr int UMMA_K = 16;
 
@@ -235,6 +239,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024 B alignment
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int kStages = Plan<BN>::kStages, kStageBytes = Plan<BN>::kStageBytes, kBSlot = Plan<BN>::kBSlot;
     unsigned char* store_bufs = smem + kStages * kStageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(store_bufs + kStoreBytes);
     uint64_t* full = bars;                       // [kStages]
@@ -288,7 +293,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     load_operand(&map_b_hi, &full[stage], st + 2 * kTileBytes, p.b, t, t.n0, kg, BN);
                     if (three) {
                         load_operand(&map_a_lo, &full[stage], st + kTileBytes, p.a, t, t.m0, kg, BM);
-                        load_operand(&map_b_lo, &full[stage], st + 3 * kTileBytes, p.b, t, t.n0, kg, BN);
+                        load_operand(&map_b_lo, &full[stage], st + 2 * kTileBytes + kBSlot, p.b, t, t.n0, kg, BN);
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -316,7 +321,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 if (elect_one()) {
                     const uint32_t sa = smem_u32(smem + stage * kStageBytes);
                     const uint64_t a_hi = make_desc(sa, a_mn), a_lo = make_desc(sa + kTileBytes, a_mn);
-                    const uint64_t b_hi = make_desc(sa + 2 * kTileBytes, b_mn), b_lo = make_desc(sa + 3 * kTileBytes, b_mn);
+                    const uint64_t b_hi = make_desc(sa + 2 * kTileBytes, b_mn), b_lo = make_desc(sa + 2 * kTileBytes + kBSlot, b_mn);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t ao = a_step * k, bo = b_step * k;
@@ -531,7 +536,8 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
     static bool configured = false;
     static int num_sms = 0;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_split_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(gemm_split_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Plan<BN>::kSmemBytes);
         if (e != cudaSuccess) { dsb::set_error("gemm smem attr: %s", cudaGetErrorString(e)); return DSB_ERR_CUDA; }
         int dev = 0;
         cudaGetDevice(&dev);
@@ -551,7 +557,7 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
     p.b = OperandMap{g.b_col_base, g.b_col_inner, g.b_row_outer, g.b_row_inner, g.b_mn, g.b_conv, g.conv_h, g.conv_w,
                      g.conv_c, g.conv_taps};
     const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
-    gemm_split_kernel<BN><<<grid, kThreads, kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, p);
+    gemm_split_kernel<BN><<<grid, kThreads, Plan<BN>::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, p);
     return dsb::check_launch("gemm_split");
 }
 
@@ -560,8 +566,16 @@ int launch(const dsb_gemm_args& g, cudaStream_t stream) {
     DSB_REQUIRE(g.terms == 1 || g.terms == 3, "gemm: terms must be 1 or 3");
     DSB_REQUIRE(g.terms == 1 || (g.a_lo && g.b_lo), "gemm: terms=3 needs the lo halves");
     DSB_REQUIRE(!g.c_hi == !g.c_lo, "gemm: c_hi and c_lo go together");
-    const int bn = g.bn ? g.bn : (g.n % 128 == 0 ? 128 : 64);
-    DSB_REQUIRE(bn == 64 || bn == 128, "gemm: bn must be 64 or 128");
+    int bn = g.bn;
+    if (!bn) {
+        // wide tiles halve the A-operand traffic per flop (the kernel is L2->smem bound at 128x128: ncu shows 8.6 GB of
+        // operand traffic for a 0.5 GB A matrix); use them when the problem still fills the machine
+        const int64_t batch = g.batch > 0 ? g.batch : 1, splits = g.splits > 0 ? g.splits : 1;
+        const int64_t tiles256 = (g.n % 256 == 0) ? batch * splits * ((g.m + BM - 1) / BM) * (g.n / 256) : 0;
+        bn = tiles256 >= 148 ? 256 : (g.n % 128 == 0 ? 128 : 64);
+    }
+    DSB_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: bn must be 64, 128 or 256");
+    if (bn == 256) return launch_bn<256>(g, stream);
     return bn == 128 ? launch_bn<128>(g, stream) : launch_bn<64>(g, stream);
 }
 

@@ -51,7 +51,7 @@ def _to_cfg(d):
 class Model(nn.Module):
     def __init__(self, cfg={}, use_value_network=False, temperature=None, seed: Optional[int] = None,
                  gemm_terms: int = 3, sample_rng: str = 'cuda', encoder_chunk: int = 0,
-                 checkpoint_encoder: bool = True):
+                 checkpoint_encoder: bool = True, keep_chunks: int = 0):
         super().__init__()
         sx = int(_cfg_get(cfg, 'model.spatial_x', 160))
         sy = int(_cfg_get(cfg, 'model.spatial_y', 152))
@@ -66,6 +66,7 @@ class Model(nn.Module):
         # observation rows are independent in the encoder: process them in chunks (and, while training,
         # recompute each chunk's activations in backward) so B=128 x T=32 fits one GPU's HBM.
         self.encoder_chunk, self.checkpoint_encoder = encoder_chunk, checkpoint_encoder
+        self.keep_chunks = keep_chunks          # the first `keep_chunks` chunks keep their activations (HBM permitting)
         # attributes callers read (agent.py:107-108,148)
         self.cfg = _to_cfg({'encoder': {'core_lstm': {'num_layers': 3, 'hidden_size': 384, 'input_size': 1536}},
                             'temperature': self.temperature, 'spatial_x': sx, 'spatial_y': sy,
@@ -164,13 +165,18 @@ class Model(nn.Module):
 
         ckpt = self.checkpoint_encoder and torch.is_grad_enabled()
 
+        state = {'i': 0}
+
         def entity_fn(en, num):
-            if ckpt:      # recompute only the entity transformer (~34 MB of saved activations per observation) in backward
+            # recompute only the entity transformer (~34 MB of saved activations per observation) in backward, and only
+            # for the chunks that do not fit the HBM budget
+            if ckpt and state['i'] > self.keep_chunks:
                 return torch_checkpoint(net.entity_encoder, en, num, use_reentrant=False)
             return net.entity_encoder(en, num)
 
         outs = []
         for s0 in range(0, N, chunk):
+            state['i'] += 1
             sp, en, sc, num = tree_map(lambda t: t[s0:s0 + chunk], (spatial_info, entity_info, scalar_info, entity_num))
             li, ctx, bf, ee, ms = net.encoder(sp, en, sc, num, entity_fn=entity_fn)
             outs.append((li, ctx, bf, ee) + tuple(ms[3:]))        # only the 16x16 skips leave the encoder

@@ -205,37 +205,46 @@ def kernel_rooflines(dev, peaks):
                                  'frac': ach / peaks['hbm_gbs'], 'traffic': None, 'us_per_launch': dt * 1e6,
                                  'shape': 'N=%d obs, 512 entities, 32ch, 128x128' % N,
                                  'peak_source': peaks['source']}
-    # entity-transformer MLP GEMM: [M,256] x [1024,256]^T, M = 1024 obs * 512 tokens, 3-term split
-    M, K, Nn = 1024 * 512, 256, 1024          # 1024 obs: large enough that the launch is not host-bound
-    a = torch.randn(M, K, device=dev)
-    w = torch.randn(Nn, K, device=dev) / 16
-    b = torch.randn(Nn, device=dev)
-    a_hi, a_lo = ops.split_bf16(a)
-    w_hi, w_lo = ops.split_bf16(w)
+    # entity-transformer MLP GEMM: [M,256] x [1024,256]^T with 3-term split, at the shape the learner step launches
+    # (M = encoder_chunk 264 obs x 512 tokens) and at 4x that.  The launches are replayed from a CUDA graph so the
+    # (Python + tensor-map encode) host time of a launch cannot pad the device-side duration.
     from distar_b200 import lib as _lib
-    c = torch.empty(M, Nn, device=dev)
-    for terms, bn in ((3, 0), (3, 128), (1, 0)):
-        def run():
-            _lib.gemm_ex(a_hi=a_hi, a_lo=a_lo, b_hi=w_hi, b_lo=w_lo, bias=b, alpha=1.0, relu=1, terms=terms, c=c, m=M, n=Nn,
-                         k=K, batch=1, inner=1, splits=1, bn=bn)
-        for _ in range(3):
-            run()
-        torch.cuda.synchronize()
-        s.record()
-        for _ in range(reps):
-            run()
-        e.record()
-        torch.cuda.synchronize()
-        dt = s.elapsed_time(e) / reps / 1e3
-        flops = 2.0 * M * K * Nn * terms
-        ach = flops / dt / 1e12
-        key = 'entity_mlp_gemm_terms%d' % terms + ('_bn%d' % bn if bn else '')
-        out[key] = {
-            'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-            'frac': ach / peaks['bf16_tflops'], 'traffic': None, 'us_per_launch': dt * 1e6,
-            'shape': 'M=%d K=%d N=%d, %d bf16 MMA terms (tensor-core flops counted), tile 128x%s' % (
-                M, K, Nn, terms, bn if bn else 'auto(256)'),
-            'peak_source': peaks['source']}
+    K, Nn = 256, 1024
+    for M, tag in ((264 * 512, ''), (1024 * 512, '_M524288')):
+        a = torch.randn(M, K, device=dev)
+        w = torch.randn(Nn, K, device=dev) / 16
+        b = torch.randn(Nn, device=dev)
+        a_hi, a_lo = ops.split_bf16(a)
+        w_hi, w_lo = ops.split_bf16(w)
+        c = torch.empty(M, Nn, device=dev)
+        for terms, bn in ((3, 0), (3, 128), (1, 0)):
+            def run():
+                _lib.gemm_ex(a_hi=a_hi, a_lo=a_lo, b_hi=w_hi, b_lo=w_lo, bias=b, alpha=1.0, relu=1, terms=terms, c=c, m=M,
+                             n=Nn, k=K, batch=1, inner=1, splits=1, bn=bn)
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for _ in range(reps):
+                    run()
+            graph.replay()
+            torch.cuda.synchronize()
+            s.record()
+            graph.replay()
+            e.record()
+            torch.cuda.synchronize()
+            dt = s.elapsed_time(e) / reps / 1e3
+            flops = 2.0 * M * K * Nn * terms
+            ach = flops / dt / 1e12
+            key = 'entity_mlp_gemm_terms%d' % terms + ('_bn%d' % bn if bn else '') + tag
+            out[key] = {
+                'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
+                'frac': ach / peaks['bf16_tflops'], 'traffic': None, 'us_per_launch': dt * 1e6,
+                'shape': 'M=%d K=%d N=%d, %d bf16 MMA terms (tensor-core flops counted), tile 128x%s' % (
+                    M, K, Nn, terms, bn if bn else 'auto(256)'),
+                'peak_source': peaks['source']}
+        del a, a_hi, a_lo, c
     return out
 
 

@@ -368,15 +368,32 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 }
+                // The epilogue is issue-bound (one warp per scheduler owns a 32 x BN slab), so keep it at ~2 instructions
+                // per element: bias comes in as 8 broadcast 16-byte loads, alpha/bias fold into one FFMA, ReLU is an
+                // FMNMX against 0 or -inf, and the residual path is a separate warp-uniform branch.
                 float v[32];
+                if (p.bias) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + t.n0 + c0);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(r[j]) * p.alpha;
-                    if (p.bias) x += __ldg(p.bias + t.n0 + c0 + j);
-                    if (p.residual && row_ok) x += __ldg(p.residual + (int64_t)(c_row0 + lane) * p.ldc + c_col0 + c0 + j);
-                    if (p.relu) x = fmaxf(x, 0.f);
-                    v[j] = x;
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 bb = __ldg(b4 + j);
+                        v[4 * j] = bb.x; v[4 * j + 1] = bb.y; v[4 * j + 2] = bb.z; v[4 * j + 3] = bb.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
                 }
+                if (p.residual && row_ok) {
+                    const float4* r4 = reinterpret_cast<const float4*>(p.residual + (int64_t)(c_row0 + lane) * p.ldc + c_col0 + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 rr = __ldg(r4 + j);
+                        v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
+                    }
+                }
+                const float floor_v = p.relu ? 0.f : -3.402823466e38f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(fmaf(__uint_as_float(r[j]), p.alpha, v[j]), floor_v);
                 unsigned char* buf = my_bufs + (chunk_no & 1) * kStoreBufBytes;
                 // the TMA store that last read this buffer (two chunks ago) must have finished reading it
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");

@@ -27,6 +27,7 @@ constexpr int kEffLen = 100;
 
 __device__ __constant__ int kPlaneBase[kPlanes] = {0, 1, 5, 7, 12, 14, 16};
 __device__ __constant__ int kPlaneVocab[kPlanes] = {0, 4, 2, 5, 2, 2, 2};
+__host__ __device__ constexpr int vocab_c(int k) { return k == 1 ? 4 : (k == 3 ? 5 : (k == 0 ? 0 : 2)); }   // compile-time vocab
 
 struct StemArgs {
     const uint8_t* planes[kPlanes];     // each [N, H, W]
@@ -195,6 +196,9 @@ stem_bwd_kernel(const StemArgs a, const float* __restrict__ gout, int out_c, flo
     for (int i = threadIdx.x; i < (kIC + 1) * kOC; i += kThreads) gw[i] = 0.f;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int PW = W / 2, PH = a.H / 2;
+    float racc[25];
+#pragma unroll
+    for (int i = 0; i < 25; ++i) racc[i] = 0.f;
     for (int tile = blockIdx.x; tile < a.N * bands; tile += gridDim.x) {
         const int n = tile / bands, y0 = (tile - n * bands) * kRows;
         const int len = build_pre_tile(a, s, n, y0);
@@ -215,20 +219,24 @@ stem_bwd_kernel(const StemArgs a, const float* __restrict__ gout, int out_c, flo
             for (int k = 0; k < 4; ++k) s.pre[cand[k] * kOC + lane] = (k == bi) ? g : 0.f;
         }
         __syncthreads();
-        // parameter gradients of the dense part (per-warp walk, shared-memory atomics across warps)
+        // parameter gradients of the dense part: 25 register accumulators per lane (bias, height, 17 one-hot columns,
+        // 6 effect planes) selected with predicated adds — no atomics in the per-pixel loop
         for (int p = warp; p < npix; p += kWarps) {
             const float d = s.pre[p * kOC + lane];
             if (__ballot_sync(0xffffffffu, d != 0.f) == 0u) continue;
-            atomicAdd(&gw[kIC * kOC + lane], d);                                             // bias
-            atomicAdd(&gw[lane], d * ((float)s.pl[p] * (1.0f / 256.0f)));
+            racc[0] += d;
+            racc[1] += d * ((float)s.pl[p] * (1.0f / 256.0f));
+            int slot = 2;
 #pragma unroll
             for (int k = 1; k < kPlanes; ++k) {
-                const int idx = min((int)s.pl[k * npix + p], kPlaneVocab[k] - 1);
-                atomicAdd(&gw[(kPlaneBase[k] + idx) * kOC + lane], d);
+                const int idx = min((int)s.pl[k * npix + p], vocab_c(k) - 1);
+#pragma unroll
+                for (int v = 0; v < vocab_c(k); ++v) racc[slot + v] += (idx == v) ? d : 0.f;
+                slot += vocab_c(k);
             }
 #pragma unroll
             for (int j = 0; j < kEffects; ++j)
-                if ((s.eff[j * (npix / 32) + (p >> 5)] >> (p & 31)) & 1u) atomicAdd(&gw[(18 + j) * kOC + lane], d);
+                racc[19 + j] += ((s.eff[j * (npix / 32) + (p >> 5)] >> (p & 31)) & 1u) ? d : 0.f;
         }
         // entities: d_project[e, c] = sum_o W[o, 24+c] dpre[pix, o];  dW[o, 24+c] += dpre[pix, o] * project[e, c]
         const float* prow = a.project + (size_t)n * a.E * kOC;
@@ -249,6 +257,12 @@ stem_bwd_kernel(const StemArgs a, const float* __restrict__ gout, int out_c, flo
         }
         __syncthreads();
     }
+    // fold the register accumulators: slot 0 = bias, 1 = height (column 0), 2..18 = one-hot columns 1..17, 19..24 = effects
+    atomicAdd(&gw[kIC * kOC + lane], racc[0]);
+    atomicAdd(&gw[lane], racc[1]);
+#pragma unroll
+    for (int i = 2; i < 25; ++i) atomicAdd(&gw[(i - 1) * kOC + lane], racc[i]);
+    __syncthreads();
     for (int i = threadIdx.x; i < kIC * kOC; i += kThreads) {
         const int k = i / kOC, o = i - k * kOC;
         atomicAdd(&gweight[o * kIC + k], gw[i]);

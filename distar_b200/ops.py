@@ -141,6 +141,7 @@ class _SpatialStem(torch.autograd.Function):
         lib.call('dsb_spatial_stem_fwd', pa, ea, project, ex, ey, entity_num, w2, bias, out, hi, lo, out_c, N, E, H, W)
         ctx.save_for_backward(project, w2, bias, ex, ey, entity_num, *planes, *effects)
         ctx.dims = (N, E, H, W, out_c, tuple(weight.shape))
+        ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(hi, lo)
         return out, hi, lo
 
@@ -149,6 +150,8 @@ class _SpatialStem(torch.autograd.Function):
         project, w2, bias, ex, ey, entity_num = ctx.saved_tensors[:6]
         planes, effects = list(ctx.saved_tensors[6:13]), list(ctx.saved_tensors[13:19])
         N, E, H, W, out_c, wshape = ctx.dims
+        if gout is None:
+            return (None,) * 20
         dev = gout.device
         gw = torch.zeros((32, 56), dtype=torch.float32, device=dev)
         gb = torch.zeros(32, dtype=torch.float32, device=dev)
@@ -422,6 +425,7 @@ class _SplitLinear(torch.autograd.Function):
             a_hi, a_lo = split_bf16(x2)
         w_hi, w_lo = split_bf16(weight)
         oshape = (*x.shape[:-1], weight.shape[0])
+        ctx.set_materialize_grads(False)      # no zero-filled bf16 'gradients' for the (hi, lo) side outputs
         if emit_split:
             y, y_hi, y_lo = gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu, terms, want_split=True)
         else:
@@ -437,6 +441,8 @@ class _SplitLinear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy, _ghi=None, _glo=None):
         a_hi, a_lo, w_hi, w_lo, y = ctx.saved_tensors
+        if gy is None:
+            return (None,) * 8
         gy2 = gy.reshape(-1, gy.shape[-1]).contiguous()
         M, N = gy2.shape
         K = a_hi.shape[1]
@@ -579,6 +585,7 @@ class _LayerNorm(torch.autograd.Function):
         lo = torch.empty((rows, D), dtype=torch.bfloat16, device=dev) if want_split else None
         lib.call('dsb_layernorm_fwd', x2, r2, weight, bias, xin if r2 is not None else None, y, hi, lo, stats, rows, D, 1e-5)
         ctx.save_for_backward(xin, weight, stats)
+        ctx.set_materialize_grads(False)
         ctx.has_res = residual is not None
         ctx.shape = x.shape
         y = y.view(x.shape)
@@ -591,6 +598,8 @@ class _LayerNorm(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy, _ghi, _glo):
         xin, weight, stats = ctx.saved_tensors
+        if gy is None:
+            return (None,) * 5
         rows, D = xin.shape
         gy2 = gy.reshape(rows, D).contiguous()
         blocks = lib.load().dsb_layernorm_bwd_blocks(rows)
@@ -702,6 +711,7 @@ class _ConvNHWC(torch.autograd.Function):
         _gemm_ex(a_hi=x_hi, a_lo=x_lo, b_hi=w_hi, b_lo=w_lo, bias=b, residual=res, alpha=1.0, relu=1 if relu else 0,
                  terms=terms, c=y, c_hi=y_hi, c_lo=y_lo, m=N * H * W, n=cout_pad, k=taps * C, batch=1, inner=1, splits=1,
                  a_conv=1, conv_h=H, conv_w=W, conv_c=C, conv_taps=taps, conv_imgs=N)
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(x_hi, x_lo, wm, y if relu else None)
         ctx.meta = (N, H, W, C, Cout, Cin, kh, kw, cout_pad, relu, terms, bias is not None, residual is not None)
         if emit_split:
@@ -714,6 +724,8 @@ class _ConvNHWC(torch.autograd.Function):
     def backward(ctx, gy, _ghi=None, _glo=None):
         x_hi, x_lo, wm, y = ctx.saved_tensors
         N, H, W, C, Cout, Cin, kh, kw, cout_pad, relu, terms, has_bias, has_res = ctx.meta
+        if gy is None:
+            return (None,) * 7
         taps = kh * kw
         gy2 = gy.reshape(N * H * W, cout_pad).contiguous()
         want_b = has_bias and ctx.needs_input_grad[2]

@@ -302,9 +302,24 @@ def run_b200(args, rank, world, local_rank):
         learner._train(resident)
 
     last_loss = [None]
+    copy_stream = torch.cuda.Stream(device=dev)
+    staged = {}
+
+    def prefetch():
+        """host -> device copy of the NEXT step's batch from pinned memory on a side stream (what the reference's
+        `use_async_cuda` dataloader does, rl_dataloader.py:113-127); every step pays for exactly one such copy."""
+        with torch.cuda.stream(copy_stream):
+            staged['data'] = tree_map(lambda t: t.to(dev, non_blocking=True), host)
+            staged['event'] = torch.cuda.Event()
+            staged['event'].record(copy_stream)
 
     def step_e2e():
-        data = tree_map(lambda t: t.to(dev, non_blocking=True), host)
+        if 'data' not in staged:
+            prefetch()
+        torch.cuda.current_stream().wait_event(staged['event'])
+        data = staged.pop('data')
+        tree_map(lambda t: t.record_stream(torch.cuda.current_stream()) or t, data)
+        prefetch()                                          # overlaps with this step's compute
         info = learner._train(data)
         last_loss[0] = info['total_loss'].item()           # device -> host read of the step result
 

@@ -34,7 +34,7 @@ constexpr int BM = 128, BK = 64;                        // BN (64, 128 or 256) i
 constexpr int kAccStages = 2;
 constexpr int kTileBytes = BM * BK * 2;                 // 16 KiB: one 128x64 bf16 operand tile (B tiles use BN*128 B of it)
 constexpr int kStoreBufBytes = 32 * 128;                // one 32-row x 32-col fp32 staging box (128 B rows, SWIZZLE_128B)
-constexpr int kStoreBytes = 4 * 2 * kStoreBufBytes;     // 4 epilogue warps x double buffer
+constexpr int kStoreBytes = 8 * kStoreBufBytes;         // 8 epilogue warps x one staging box each
 // per-BN shared-memory plan: stage = A_hi | A_lo | B_hi | B_lo; B slots are 16 KiB (BN <= 128) or 32 KiB (BN = 256)
 template <int BN> struct Plan {
     static constexpr int kBSlot = BN > 128 ? BN * 128 : kTileBytes;
@@ -42,7 +42,8 @@ template <int BN> struct Plan {
     static constexpr int kStages = BN > 128 ? 2 : 3;
     static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                            // two epilogue warps per scheduler: the epilogue is issue-bound
+constexpr int kThreads = (2 + kEpiWarps) * 32;          // 320
 constexpr int UMMA_K = 16;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -263,7 +264,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
         }
         for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // TMEM allocation is warp-collective; the same warp deallocates at the end
@@ -346,9 +347,9 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         // TMEM -> registers -> (alpha, +bias, ReLU) -> swizzled smem box -> TMA store: every global write is a full,
         // coalesced 128 B line issued by the copy engine; the staging box is double buffered per warp.
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
-        unsigned char* my_bufs = store_bufs + (warp - 2) * 2 * kStoreBufBytes;
+        const int half = (warp - 2) >> 2;          // warps 2..5 take the left half of the tile's columns, 6..9 the right
+        unsigned char* my_buf = store_bufs + (warp - 2) * kStoreBufBytes;
         int it = 0;
-        uint32_t chunk_no = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -360,10 +361,10 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             const int c_row0 = t.bo * p.c_row_outer + t.bi * p.c_row_inner + t.s * p.c_row_split + t.m0 + q * 32;
             const int c_col0 = p.c_col_base + t.bi * p.c_col_inner + t.n0;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_no) {
+            for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
-                if (c0 == BN - 32) {               // accumulator fully read: hand TMEM back to the MMA warp early
+                if (c0 == (half + 1) * (BN / 2) - 32) {   // this warp's share fully read: hand TMEM back to the MMA warp early
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -394,9 +395,10 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 const float floor_v = p.relu ? 0.f : -3.402823466e38f;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(fmaf(__uint_as_float(r[j]), p.alpha, v[j]), floor_v);
-                unsigned char* buf = my_bufs + (chunk_no & 1) * kStoreBufBytes;
-                // the TMA store that last read this buffer (two chunks ago) must have finished reading it
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                unsigned char* buf = my_buf;
+                // the TMA store that last read this staging box must have finished reading it (the sibling warp on this
+                // scheduler keeps issuing meanwhile)
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncwarp();
                 const uint32_t rowbase = smem_u32(buf) + lane * 128;
 #pragma unroll

@@ -146,16 +146,26 @@ extern "C" int dsb_split_bf16(const float* x, void* hi, void* lo, int64_t n, dsb
 // partial column sums (bias gradient) — replaces a compare, a multiply, a split and a column reduction.
 namespace {
 constexpr int kRbRows = 32;
-__global__ void relu_bwd_split_kernel(const float* __restrict__ gy, const float* __restrict__ y, float* __restrict__ g_out,
+template <bool kMaskBf16>
+__global__ void relu_bwd_split_kernel(const float* __restrict__ gy, const void* __restrict__ yv, float* __restrict__ g_out,
                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                       float* __restrict__ colsum, int64_t rows, int N) {
+    const float* y = kMaskBf16 ? nullptr : reinterpret_cast<const float*>(yv);
+    const __nv_bfloat16* yb = kMaskBf16 ? reinterpret_cast<const __nv_bfloat16*>(yv) : nullptr;
     const int64_t r0 = (int64_t)blockIdx.x * kRbRows;
     for (int c = threadIdx.x * 4; c < N; c += blockDim.x * 4) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int64_t r = r0; r < r0 + kRbRows && r < rows; ++r) {
             const int64_t off = r * N + c;
             float4 g = *reinterpret_cast<const float4*>(gy + off);
-            if (y) {
+            if (kMaskBf16) {
+                // the ReLU output only survives as the hi half of its bf16 pair: bf16 rounding keeps sign and zero
+                const uint2 m = *reinterpret_cast<const uint2*>(yb + off);
+                g.x = ((m.x & 0xFFFFu) != 0u && !(m.x & 0x8000u)) ? g.x : 0.f;
+                g.y = ((m.x >> 16) != 0u && !(m.x & 0x80000000u)) ? g.y : 0.f;
+                g.z = ((m.y & 0xFFFFu) != 0u && !(m.y & 0x8000u)) ? g.z : 0.f;
+                g.w = ((m.y >> 16) != 0u && !(m.y & 0x80000000u)) ? g.w : 0.f;
+            } else if (y) {
                 const float4 yy = *reinterpret_cast<const float4*>(y + off);
                 g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f;
                 g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
@@ -176,8 +186,8 @@ __global__ void relu_bwd_split_kernel(const float* __restrict__ gy, const float*
 
 extern "C" int dsb_relu_bwd_split_blocks(int64_t rows) { return (int)((rows + kRbRows - 1) / kRbRows); }
 
-extern "C" int dsb_relu_bwd_split(const float* gy, const float* y, float* g_out, void* hi, void* lo, float* colsum,
-                                  int64_t rows, int N, dsb_stream_t stream) {
+extern "C" int dsb_relu_bwd_split(const float* gy, const void* y, int y_is_bf16, float* g_out, void* hi, void* lo,
+                                  float* colsum, int64_t rows, int N, dsb_stream_t stream) {
     DSB_REQUIRE(gy && hi && lo && rows >= 0 && N > 0 && N % 4 == 0, "relu_bwd_split: bad argument (N %% 4 == 0 required)");
     if (rows == 0) return DSB_OK;
     const int64_t blocks = (rows + kRbRows - 1) / kRbRows;
@@ -185,7 +195,11 @@ extern "C" int dsb_relu_bwd_split(const float* gy, const float* y, float* g_out,
     int threads = N / 4;
     if (threads > 256) threads = 256;
     if (threads < 32) threads = 32;
-    relu_bwd_split_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-        gy, y, g_out, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, colsum, rows, N);
+    if (y && y_is_bf16)
+        relu_bwd_split_kernel<true><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+            gy, y, g_out, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, colsum, rows, N);
+    else
+        relu_bwd_split_kernel<false><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+            gy, y, g_out, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, colsum, rows, N);
     return dsb::check_launch("relu_bwd_split");
 }

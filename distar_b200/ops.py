@@ -386,7 +386,7 @@ def relu_bwd_split(gy2: torch.Tensor, y: Optional[torch.Tensor], need_bias: bool
     g = torch.empty((rows, N), dtype=torch.float32, device=dev) if need_g else None
     blocks = lib.load().dsb_relu_bwd_split_blocks(rows)
     cs = torch.empty((blocks, N), dtype=torch.float32, device=dev) if need_bias else None
-    lib.call('dsb_relu_bwd_split', gy2, y, g, hi, lo, cs, rows, N)
+    lib.call('dsb_relu_bwd_split', gy2, y, 1 if (y is not None and y.dtype == torch.bfloat16) else 0, g, hi, lo, cs, rows, N)
     return hi, lo, (cs.sum(0) if need_bias else None), g
 
 
@@ -430,7 +430,9 @@ class _SplitLinear(torch.autograd.Function):
             y, y_hi, y_lo = gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu, terms, want_split=True)
         else:
             y = gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu, terms)
-        ctx.save_for_backward(a_hi, a_lo, w_hi, w_lo, y if relu else None)
+        # the ReLU mask only needs the sign: when the bf16 pair is emitted (and kept by the consumer anyway) save its hi
+        # half instead of the fp32 output
+        ctx.save_for_backward(a_hi, a_lo, w_hi, w_lo, (y_hi if emit_split else y) if relu else None)
         ctx.relu, ctx.terms, ctx.has_bias, ctx.xshape = relu, terms, bias is not None, x.shape
         if emit_split:
             y_hi, y_lo = y_hi.view(oshape), y_lo.view(oshape)
@@ -452,7 +454,7 @@ class _SplitLinear(torch.autograd.Function):
         if on_gpu and N % 4 == 0:
             g_hi, g_lo, gb, g = relu_bwd_split(gy2, y if ctx.relu else None, want_b, need_g=False)
         else:
-            g = gy2 * (y > 0) if ctx.relu else gy2
+            g = gy2 * (y.reshape(gy2.shape) > 0) if ctx.relu else gy2
             g_hi, g_lo = split_bf16(g) if on_gpu else (None, None)
             gb = g.sum(0) if want_b else None
         if ctx.needs_input_grad[0]:
@@ -712,7 +714,7 @@ class _ConvNHWC(torch.autograd.Function):
                  terms=terms, c=y, c_hi=y_hi, c_lo=y_lo, m=N * H * W, n=cout_pad, k=taps * C, batch=1, inner=1, splits=1,
                  a_conv=1, conv_h=H, conv_w=W, conv_c=C, conv_taps=taps, conv_imgs=N)
         ctx.set_materialize_grads(False)
-        ctx.save_for_backward(x_hi, x_lo, wm, y if relu else None)
+        ctx.save_for_backward(x_hi, x_lo, wm, (y_hi if emit_split else y) if relu else None)
         ctx.meta = (N, H, W, C, Cout, Cin, kh, kw, cout_pad, relu, terms, bias is not None, residual is not None)
         if emit_split:
             y_hi, y_lo = y_hi.view(N, H, W, cout_pad), y_lo.view(N, H, W, cout_pad)

@@ -116,11 +116,11 @@ int dsb_upshift9_bwd(const float* grad_out, float* grad_z, int64_t N, int H, int
 int dsb_split_bf16(const float* x, void* hi, void* lo, int64_t n, dsb_stream_t stream);
 
 /* ---- ReLU backward + bf16 split + bias gradient in one pass ----
- * g = gy * (y > 0) (y NULL: g = gy); hi/lo receive the split of g, g_out (optional) g itself, colsum (optional)
+ * g = gy * (y > 0) (y NULL: g = gy; y may be fp32 or, with y_is_bf16, the bf16 hi half of the ReLU output); hi/lo receive the split of g, g_out (optional) g itself, colsum (optional)
  * per-block partial column sums [dsb_relu_bwd_split_blocks(rows), N] whose sum over blocks is the bias gradient. */
 int dsb_relu_bwd_split_blocks(int64_t rows);
-int dsb_relu_bwd_split(const float* gy, const float* y, float* g_out, void* hi, void* lo, float* colsum, int64_t rows,
-                       int N, dsb_stream_t stream);
+int dsb_relu_bwd_split(const float* gy, const void* y, int y_is_bf16, float* g_out, void* hi, void* lo, float* colsum,
+                       int64_t rows, int N, dsb_stream_t stream);
 
 /* ---- tcgen05 GEMM family  (fc_block nn_module.py:231-270; attention module_utils.py:88-111; their backward) ----
  * dsb_gemm_bf16_split:  C[M,N] = act( A[M,K] . W[N,K]^T + bias[N] ),  A and W as bf16 (hi, lo) pairs, K contiguous,

@@ -123,3 +123,28 @@ def test_sl_forward_matches_oracle(model, sd):
                                   hidden_state=to_dev(hidden), action_info=to_dev(act))
     for k in O.HEADS:
         close(ml[k], ol[k], 'sl_logit/' + k)
+
+
+def test_sl_loss_on_gpu_matches_oracle(model, sd):
+    from distar_b200.sl_loss import SupervisedLoss
+    from distar_b200.synth import synth_obs, synth_actions
+    B, T = 2, 2
+    en = torch.tensor([512, 100, 256, 64])
+    obs = synth_obs(B * T, seed=31, entity_num=en, hidden=False)
+    g = torch.Generator().manual_seed(2)
+    act, num = synth_actions(B * T, en, g, max_su=5)
+    hidden = [(torch.randn(B, 384, generator=g), torch.randn(B, 384, generator=g)) for _ in range(3)]
+    amask = {k: (torch.rand(B * T, generator=g) < 0.7).float() for k in O.HEADS}
+    with torch.no_grad():
+        ol, _, _ = O.sl_train(sd, **tree_clone(obs), selected_units_num=num.clone(), traj_lens=[T] * B,
+                              hidden_state=tree_clone(hidden), action_info=tree_clone(act))
+    want = O.sl_loss(ol, act, amask, num)
+    model.zero_grad()
+    ml, ma, _ = model.sl_train(**to_dev(obs), selected_units_num=num.to(DEV), traj_lens=[T] * B,
+                               hidden_state=to_dev(hidden), action_info=to_dev(act))
+    got = SupervisedLoss({'learner': {'su_mask': False}}).compute_loss(ml, to_dev(act), to_dev(amask), num.to(DEV),
+                                                                      en.to(DEV), ma)
+    got['total_loss'].backward()
+    for k, v in want.items():
+        assert abs(got[k].item() - v.item()) <= 1e-3 * max(1.0, abs(v.item())), k
+    assert float(model.flat_grad.abs().sum()) > 0

@@ -346,6 +346,20 @@ def run_b200(args, rank, world, local_rank):
         if world > 1:
             dist.destroy_process_group()
         return
+    # secondary figure (BASELINE configs[1]): actor-side inference, batch 32, forward + sampling, per GPU
+    from distar_b200.synth import synth_obs
+    obs = tree_map(lambda t: t.to(dev), synth_obs(32, seed=7))
+    with torch.no_grad():
+        for _ in range(2):
+            model.compute_logp_action(**obs)
+        torch.cuda.synchronize()
+        i0, i1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        i0.record()
+        for _ in range(5):
+            model.compute_logp_action(**obs)
+        i1.record()
+        torch.cuda.synchronize()
+    infer_ms = i0.elapsed_time(i1) / 5
     peaks = load_peaks()
     roofs = kernel_rooflines(dev, peaks)
     line = {
@@ -362,6 +376,8 @@ def run_b200(args, rank, world, local_rank):
                    'l2': 'inputs and activations (GBs per step) far exceed the 126 MB L2; no flush needed'},
         'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches),
         'peak_hbm_gib': round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+        'inference': {'workload': 'compute_logp_action, batch 32 (forward + sampling), 1 GPU', 'ms_per_call': infer_ms,
+                      'obs_per_s': 32 / (infer_ms / 1e3)},
         'roofline': roofs['entity_mlp_gemm_terms3'] if args.terms == 3 else roofs['entity_mlp_gemm_terms1'],
         'rooflines': roofs,
     }

@@ -40,8 +40,6 @@ entity_features_kernel(const FieldTable t, __nv_bfloat16* __restrict__ hi, __nv_
     const float v0 = load_field(t, lane, tok);
     const float v1 = (lane + 32 < kFields) ? load_field(t, lane + 32, tok) : 0.f;
     uint32_t mask = 0u;
-    float sval = 0.f;      // scalar feature value if one of this lane's columns is a scalar field
-    int scol = -1;
     bool bad = false;
 #pragma unroll
     for (int f = 0; f < kFields; ++f) {
@@ -60,9 +58,7 @@ entity_features_kernel(const FieldTable t, __nv_bfloat16* __restrict__ hi, __nv_
                 const int col = off + b;
                 if ((col >> 5) == lane && ((id >> (10 - b)) & 1)) mask |= 1u << (col & 31);
             }
-        } else {
-            if ((off >> 5) == lane) { scol = off & 31; sval = v; }    // at most one scalar per 32 columns? no: handled below
-        }
+        }   // scalar fields are resolved per column below
     }
     if (bad && lane == 0) atomicExch(error_flag, 1);
     // build the 32 columns; scalar fields may share a lane (e.g. columns 274..277), so resolve them per column
@@ -73,7 +69,6 @@ entity_features_kernel(const FieldTable t, __nv_bfloat16* __restrict__ hi, __nv_
 #pragma unroll
     for (int c = 0; c < 32; ++c)
         if ((mask >> c) & 1u) h[c >> 1] |= one << ((c & 1) * 16);
-    (void)scol; (void)sval;
 #pragma unroll
     for (int f = 0; f < kFields; ++f) {
         if (t.kind[f] != 2) continue;

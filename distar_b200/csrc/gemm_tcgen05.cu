@@ -79,6 +79,31 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// multicast variants: the box lands at the same CTA-relative smem offset in every CTA of `mask` and completes tx bytes on
+// the mbarrier at the same offset there
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                               int c3, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
@@ -137,6 +162,10 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -172,15 +201,20 @@ struct GemmParams {
     OperandMap a, b;
 };
 
-struct TileCoord { int b, s, m0, n0, bo, bi; };
+struct TileCoord { int b, s, m0, n0, bo, bi, valid; };
 
-template <int BN>
-__device__ __forceinline__ TileCoord decode_tile(int tile, const GemmParams& p) {
+// MC = 1: `tile` enumerates output tiles.  MC = 2 (cluster of two CTAs sharing every B tile by TMA multicast): `tile`
+// enumerates PAIRS of vertically adjacent tiles; CTA `rank` owns m tile 2*pair_m + rank (possibly past the end).
+template <int BN, int MC>
+__device__ __forceinline__ TileCoord decode_tile(int tile, const GemmParams& p, int rank) {
     TileCoord t;
     const int n_i = tile % p.num_n;
     int r = tile / p.num_n;
-    const int m_i = r % p.num_m;
-    r /= p.num_m;
+    const int num_mu = (MC == 1) ? p.num_m : (p.num_m + 1) / 2;
+    int m_i = r % num_mu;
+    r /= num_mu;
+    if (MC == 2) m_i = 2 * m_i + rank;
+    t.valid = m_i < p.num_m;
     t.s = r % p.splits;
     t.b = r / p.splits;
     t.m0 = m_i * BM;
@@ -195,14 +229,19 @@ __device__ __forceinline__ void tap_offset(int tap, int taps, int& dy, int& dx) 
 }
 
 // mn0 = first row (A) / column (B) of the output tile this operand tile feeds, kg = first reduction index, width = 128
-// for A, BN for B.
+// for A, BN for B.  mc_rank >= 0: this is the B operand of a 2-CTA cluster: load only this CTA's half of the tile and
+// multicast it to both CTAs (the other half arrives from the sibling).
 __device__ __forceinline__ void load_operand(const CUtensorMap* map, uint64_t* bar, unsigned char* dst,
-                                             const OperandMap& o, const TileCoord& t, int mn0, int kg, int width) {
+                                             const OperandMap& o, const TileCoord& t, int mn0, int kg, int width,
+                                             int mc_rank = -1) {
+    const bool mc = mc_rank >= 0;
+    const int halves = width / 64;
+    const int h_lo = mc ? mc_rank * (halves / 2) : 0, h_hi = mc ? (mc_rank + 1) * (halves / 2) : halves;
     if (o.conv) {
         const int cblocks = o.C / 64;
         if (!o.mn_major) {
             // forward / input-gradient convolution: rows = 128 consecutive output pixels (whole image rows),
-            // reduction index = (tap, channel)
+            // reduction index = (tap, channel)   (A operand only: never multicast)
             const int pix0 = mn0, hw = o.H * o.W;
             const int img = pix0 / hw, y0 = (pix0 - img * hw) / o.W;
             const int kb = kg / 64, tap = kb / cblocks, cb = kb - tap * cblocks;
@@ -213,11 +252,12 @@ __device__ __forceinline__ void load_operand(const CUtensorMap* map, uint64_t* b
             // weight-gradient convolution: reduction index = 64 consecutive pixels, columns = (tap, channel)
             const int hw = o.H * o.W;
             const int img = kg / hw, y0 = (kg - img * hw) / o.W;
-            for (int h = 0; h < width / 64; ++h) {
+            for (int h = h_lo; h < h_hi; ++h) {
                 const int col = mn0 + 64 * h, tap = col / o.C, c = col - tap * o.C;
                 int dy, dx;
                 tap_offset(tap, o.taps, dy, dx);
-                tma_load_4d(map, bar, dst + h * (kTileBytes / 2), c, dx, y0 + dy, img);   // box {64 c, W, 64/W, 1}
+                if (mc) tma_load_4d_mc(map, bar, dst + h * (kTileBytes / 2), c, dx, y0 + dy, img, 3);
+                else tma_load_4d(map, bar, dst + h * (kTileBytes / 2), c, dx, y0 + dy, img);   // box {64 c, W, 64/W, 1}
             }
         }
         return;
@@ -225,14 +265,20 @@ __device__ __forceinline__ void load_operand(const CUtensorMap* map, uint64_t* b
     const int col0 = o.col_base + t.bi * o.col_inner;
     const int row0 = o.row_outer * t.bo + o.row_inner * t.bi;
     if (!o.mn_major) {
-        tma_load_2d(map, bar, dst, col0 + kg, row0 + mn0);                      // box {64 k, 128 (or BN) rows}
+        if (mc) {   // box {64 k, width/2 rows}: rows [rank*width/2, +width/2) of the tile, 128 B per row
+            tma_load_2d_mc(map, bar, dst + mc_rank * (width / 2) * 128, col0 + kg, row0 + mn0 + mc_rank * (width / 2), 3);
+        } else {
+            tma_load_2d(map, bar, dst, col0 + kg, row0 + mn0);                  // box {64 k, 128 (or BN) rows}
+        }
     } else {
-        for (int h = 0; h < width / 64; ++h)                                    // box {64 mn, 64 k} per 64-wide half
-            tma_load_2d(map, bar, dst + h * (kTileBytes / 2), col0 + mn0 + 64 * h, row0 + kg);
+        for (int h = h_lo; h < h_hi; ++h) {                                     // box {64 mn, 64 k} per 64-wide half
+            if (mc) tma_load_2d_mc(map, bar, dst + h * (kTileBytes / 2), col0 + mn0 + 64 * h, row0 + kg, 3);
+            else tma_load_2d(map, bar, dst + h * (kTileBytes / 2), col0 + mn0 + 64 * h, row0 + kg);
+        }
     }
 }
 
-template <int BN>
+template <int BN, int MC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -251,7 +297,11 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 
     constexpr int kTmemColsAlloc = kAccStages * BN;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = p.batch * p.splits * p.num_m * p.num_n;
+    const int cta_rank = (MC == 2) ? (int)cluster_ctarank() : 0;
+    // MC = 2: work items are tile pairs, distributed over clusters
+    const int num_tiles = p.batch * p.splits * ((MC == 1) ? p.num_m : (p.num_m + 1) / 2) * p.num_n;
+    const int work_first = (MC == 1) ? (int)blockIdx.x : (int)(blockIdx.x >> 1);
+    const int work_stride = (MC == 1) ? (int)gridDim.x : (int)(gridDim.x >> 1);
     const int num_k = p.num_k;
     const bool three = p.terms == 3;
 
@@ -263,7 +313,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
         }
-        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], MC); }   // MC=2: both CTAs' MMAs release a stage
         for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -274,6 +324,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    if (MC == 2) cluster_sync_all();           // sibling barriers are initialised before any multicast can reach them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_ptr;
 
@@ -283,18 +334,19 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx = (three ? 2 : 1) * (kTileBytes + BN * 128);
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile<BN>(tile, p);
+            for (int tile = work_first; tile < num_tiles; tile += work_stride) {
+                const TileCoord t = decode_tile<BN, MC>(tile, p, cta_rank);
                 for (int kb = 0; kb < num_k; ++kb) {
                     const int kg = (t.s * num_k + kb) * BK;
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char* st = smem + stage * kStageBytes;
                     mbar_expect_tx(&full[stage], tx);
                     load_operand(&map_a_hi, &full[stage], st, p.a, t, t.m0, kg, BM);
-                    load_operand(&map_b_hi, &full[stage], st + 2 * kTileBytes, p.b, t, t.n0, kg, BN);
+                    load_operand(&map_b_hi, &full[stage], st + 2 * kTileBytes, p.b, t, t.n0, kg, BN, MC == 2 ? cta_rank : -1);
                     if (three) {
                         load_operand(&map_a_lo, &full[stage], st + kTileBytes, p.a, t, t.m0, kg, BM);
-                        load_operand(&map_b_lo, &full[stage], st + 2 * kTileBytes + kBSlot, p.b, t, t.n0, kg, BN);
+                        load_operand(&map_b_lo, &full[stage], st + 2 * kTileBytes + kBSlot, p.b, t, t.n0, kg, BN,
+                                     MC == 2 ? cta_rank : -1);
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -310,7 +362,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         // descriptor start-address step (>>4) per UMMA_K: 32 B inside the swizzle row (K-major) or 16 k-rows (MN-major)
         const uint64_t a_step = a_mn ? (uint64_t)((UMMA_K * 128) >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
         const uint64_t b_step = b_mn ? (uint64_t)((UMMA_K * 128) >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = work_first; tile < num_tiles; tile += work_stride, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -335,7 +387,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                             umma(d_tmem, a_hi + ao, b_hi + bo, idesc, first);
                         }
                     }
-                    umma_commit(&empty[stage]);                         // frees this smem stage when the MMAs retire
+                    if (MC == 2) umma_commit_mc(&empty[stage], 3);     // the stage is shared: tell both producers
+                    else umma_commit(&empty[stage]);                    // frees this smem stage when the MMAs retire
                     if (kb == num_k - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
                 }
                 __syncwarp();
@@ -350,14 +403,14 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         const int half = (warp - 2) >> 2;          // warps 2..5 take the left half of the tile's columns, 6..9 the right
         unsigned char* my_buf = store_bufs + (warp - 2) * kStoreBufBytes;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = work_first; tile < num_tiles; tile += work_stride, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const TileCoord t = decode_tile<BN>(tile, p);
+            const TileCoord t = decode_tile<BN, MC>(tile, p, cta_rank);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const int row_in_batch = t.m0 + q * 32 + lane;
-            const bool row_ok = row_in_batch < p.M;
+            const bool row_ok = t.valid && row_in_batch < p.M;
             const int c_row0 = t.bo * p.c_row_outer + t.bi * p.c_row_inner + t.s * p.c_row_split + t.m0 + q * 32;
             const int c_col0 = p.c_col_base + t.bi * p.c_col_inner + t.n0;
 #pragma unroll 1
@@ -409,7 +462,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) {
+                if (lane == 0 && t.valid) {
                     if (p.accumulate) tma_reduce_add_2d(&map_c, buf, c_col0 + c0, c_row0);
                     else tma_store_2d(&map_c, buf, c_col0 + c0, c_row0);
                 }
@@ -441,6 +494,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 
     tc_fence_before();
     __syncthreads();
+    if (MC == 2) cluster_sync_all();           // no CTA exits while a sibling may still multicast into it
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemColsAlloc) : "memory");
@@ -503,7 +557,7 @@ int make_map_nhwc(CUtensorMap* map, const void* base, int64_t imgs, int H, int W
     return DSB_OK;
 }
 
-template <int BN>
+template <int BN, int MC>
 int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
     const int batch = g.batch > 0 ? g.batch : 1, splits = g.splits > 0 ? g.splits : 1, inner = g.inner > 0 ? g.inner : 1;
     DSB_REQUIRE(g.m >= 0 && g.n > 0 && g.k > 0 && g.n % BN == 0 && g.k % (BK * splits) == 0,
@@ -547,7 +601,7 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
         if ((rc = make_map_nhwc(&mb_lo, b_lo, g.conv_imgs, g.conv_h, g.conv_w, g.conv_c, 64 / g.conv_w))) return rc;
     } else {
         DSB_REQUIRE(g.b_cols % 8 == 0, "gemm: B row pitch must be a 16-byte multiple");
-        const int b_br = g.b_mn ? 64 : BN;
+        const int b_br = g.b_mn ? 64 : BN / MC;     // MC = 2: each CTA loads (and multicasts) half of the B rows
         if ((rc = make_map(&mb_hi, g.b_hi, g.b_rows, g.b_cols, 2, b_br, 64))) return rc;
         if ((rc = make_map(&mb_lo, b_lo, g.b_rows, g.b_cols, 2, b_br, 64))) return rc;
     }
@@ -555,7 +609,7 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
     static bool configured = false;
     static int num_sms = 0;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_split_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_split_kernel<BN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Plan<BN>::kSmemBytes);
         if (e != cudaSuccess) { dsb::set_error("gemm smem attr: %s", cudaGetErrorString(e)); return DSB_ERR_CUDA; }
         int dev = 0;
@@ -575,8 +629,26 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
                      g.conv_c, g.conv_taps};
     p.b = OperandMap{g.b_col_base, g.b_col_inner, g.b_row_outer, g.b_row_inner, g.b_mn, g.b_conv, g.conv_h, g.conv_w,
                      g.conv_c, g.conv_taps};
-    const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
-    gemm_split_kernel<BN><<<grid, kThreads, Plan<BN>::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, p);
+    if (MC == 1) {
+        const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
+        gemm_split_kernel<BN, 1><<<grid, kThreads, Plan<BN>::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, p);
+    } else {
+        // clusters of two CTAs; each cluster walks pairs of vertically adjacent tiles
+        const int64_t pairs = (int64_t)batch * splits * ((num_m + 1) / 2) * num_n;
+        const int clusters = (int)(pairs < num_sms / 2 ? pairs : num_sms / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = Plan<BN>::kSmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_split_kernel<BN, 2>, ma_hi, ma_lo, mb_hi, mb_lo, mc, p);
+        if (e != cudaSuccess) { dsb::set_error("gemm cluster launch: %s", cudaGetErrorString(e)); return DSB_ERR_CUDA; }
+    }
     return dsb::check_launch("gemm_split");
 }
 
@@ -594,8 +666,21 @@ int launch(const dsb_gemm_args& g, cudaStream_t stream) {
         bn = tiles256 >= 148 ? 256 : (g.n % 128 == 0 ? 128 : 64);
     }
     DSB_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: bn must be 64, 128 or 256");
-    if (bn == 256) return launch_bn<256>(g, stream);
-    return bn == 128 ? launch_bn<128>(g, stream) : launch_bn<64>(g, stream);
+    // 2-CTA clusters halve the B-operand traffic out of L2 (each CTA fetches half of every B tile and multicasts it).
+    // Measured (M=135168, K=256, N=1024): +5 % for 1-term products, nothing for 3-term ones — those are bound by
+    // shared-memory bandwidth (MMA operand reads + TMA writes ~158 B/clk/SM against 128), which multicast does not
+    // reduce; that needs cta_group::2 MMAs (next round).  Auto-select only where it pays.
+    int mcast = g.mc;
+    if (!mcast) {
+        const int64_t batch = g.batch > 0 ? g.batch : 1, splits = g.splits > 0 ? g.splits : 1;
+        const int64_t num_m = (g.m + BM - 1) / BM;
+        const int64_t pairs = batch * splits * ((num_m + 1) / 2) * (g.n / bn);
+        mcast = (g.terms == 1 && bn >= 128 && num_m >= 2 && pairs >= 74) ? 2 : 1;
+    }
+    DSB_REQUIRE(mcast == 1 || (mcast == 2 && bn >= 128), "gemm: mc must be 1 or 2 (2 needs bn >= 128)");
+    if (mcast == 2) return bn == 256 ? launch_bn<256, 2>(g, stream) : launch_bn<128, 2>(g, stream);
+    if (bn == 256) return launch_bn<256, 1>(g, stream);
+    return bn == 128 ? launch_bn<128, 1>(g, stream) : launch_bn<64, 1>(g, stream);
 }
 
 }  // namespace

@@ -12,7 +12,6 @@
 namespace {
 
 constexpr int kC = 32;        // scatter_dim (actor_critic_default_config.yaml: encoder.scatter.output_dim)
-constexpr int kThreadsDefault = 512;
 constexpr int kPad = 4;       // channel stride = npix + 4 floats: keeps 16 B alignment, 4-way (not 32-way) bank conflicts
 
 // Forward, v2.  The map is >= 97 % zeros (<= 512 entities on 16384 pixels), so the shared-memory tile is never
@@ -152,7 +151,6 @@ extern "C" int dsb_scatter_connection_fwd(const float* project, const uint8_t* e
     DSB_REQUIRE(project && ex && ey && out, "scatter_connection_fwd: null pointer");
     DSB_REQUIRE(N >= 0 && E > 0 && E <= 65535 && H > 0 && W > 0, "scatter_connection_fwd: bad shape");
     if (N == 0) return DSB_OK;
-    constexpr int ROWS = 4;
     DSB_REQUIRE(H % 8 == 0 && W % 4 == 0 && 8 * W <= 65535, "scatter_connection_fwd: need H %% 8 == 0 and W %% 4 == 0");
     DSB_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "scatter_connection_fwd: out must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;

@@ -69,7 +69,7 @@ class GemmArgs(ctypes.Structure):
                 ('c_col_base', _c.c_int32), ('c_col_inner', _c.c_int32),
                 ('residual', _vp), ('bn', _c.c_int32),
                 ('a_conv', _c.c_int32), ('b_conv', _c.c_int32), ('conv_h', _c.c_int32), ('conv_w', _c.c_int32),
-                ('conv_c', _c.c_int32), ('conv_taps', _c.c_int32), ('conv_imgs', _i64), ('c_accumulate', _c.c_int32)]
+                ('conv_c', _c.c_int32), ('conv_taps', _c.c_int32), ('conv_imgs', _i64), ('c_accumulate', _c.c_int32), ('mc', _c.c_int32)]
 
 
 _SIGNATURES['dsb_gemm_ex'] = (_i, [ctypes.POINTER(GemmArgs), _vp])

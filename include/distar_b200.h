@@ -168,6 +168,7 @@ typedef struct dsb_gemm_args {
     int32_t a_conv, b_conv, conv_h, conv_w, conv_c, conv_taps;
     int64_t conv_imgs;
     int32_t c_accumulate;   /* != 0: C += result (TMA reduce-add; use with splits > 1 and c_row_split = 0 on a zeroed C) */
+    int32_t mc;             /* 0 auto, 1 single CTAs, 2 clusters of two CTAs sharing B tiles by TMA multicast */
 } dsb_gemm_args;
 int dsb_gemm_ex(const dsb_gemm_args* args, dsb_stream_t stream);
 

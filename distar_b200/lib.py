@@ -26,6 +26,7 @@ _SIGNATURES = {
     'dsb_return_scan': (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'dsb_categorical_stats_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
     'dsb_categorical_stats_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    'dsb_su_sample_step': (_i, [_vp] * 17 + [_i, _i, _i, _f, _vp]),
     'dsb_sample_categorical': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     'dsb_split_bf16': (_i, [_vp, _vp, _vp, _i64, _vp]),
     'dsb_upshift9_fwd': (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp]),

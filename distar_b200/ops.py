@@ -316,6 +316,60 @@ def sample_categorical(logits: torch.Tensor, generator: Optional[torch.Generator
 
 
 # ------------------------------------------------------------------------------------------------
+# selected-units pointer network, sampling path (K12)
+# ------------------------------------------------------------------------------------------------
+def su_sample(weights16, emb0, key, valid_mask, entity_num, su_mask, temperature: float, rng: str = 'cuda',
+              max_steps: int = 64):
+    """The sampling loop of SelectedUnitsHead._query (action_arg_head.py:262-314) with ONE kernel per step.
+
+    key [N,S,32] (end token at slot entity_num), valid_mask [N,S] bool (slots < entity_num + 1), su_mask [N] bool (rows
+    whose action type takes a unit selection).  rng='cpu' draws every step's Exp(1) variates from the CPU generator in the
+    reference's order and checks the all-ended condition after every step (so the stream is consumed identically);
+    rng='cuda' draws on device and polls the exit condition every 8 steps (extra steps do not change any output).
+    Returns (logits [N,steps,S], units [N,steps], ae [N,1024], selected_units_num [N])."""
+    N, S, _ = key.shape
+    dev = key.device
+    rows = torch.arange(N, device=dev)
+    mask = valid_mask.clone()
+    mask[rows, entity_num] = False                       # end flag is not available at the first selection
+    mask = mask.to(torch.uint8).contiguous()
+    ae = emb0.detach().clone().contiguous()
+    emb0c = emb0.detach().contiguous()
+    h = torch.zeros((N, 32), dtype=torch.float32, device=dev)
+    c = torch.zeros((N, 32), dtype=torch.float32, device=dev)
+    ksum = torch.zeros((N, 32), dtype=torch.float32, device=dev)
+    count = torch.zeros(N, dtype=torch.int32, device=dev)
+    end_flag = (~su_mask).to(torch.uint8).contiguous()
+    num = torch.where(su_mask, torch.full((N,), max_steps, dtype=torch.int64, device=dev),
+                      torch.zeros(N, dtype=torch.int64, device=dev)).contiguous()
+    logits = torch.empty((max_steps, N, S), dtype=torch.float32, device=dev)
+    results = torch.empty((max_steps, N), dtype=torch.int64, device=dev)
+    ended = torch.ones(max_steps, dtype=torch.int32, device=dev)
+    en = entity_num.to(torch.int64).contiguous()
+    keyc = key.detach().contiguous()
+    keep = [w.detach().contiguous() for w in weights16]      # keep the contiguous copies alive during the launches
+    warr = lib.ptr_array(keep)
+    steps = max_steps
+    for i in range(max_steps):
+        if rng == 'cpu':
+            q = torch.empty((N, S), dtype=torch.float32).exponential_(1).to(dev)
+        else:
+            q = torch.empty((N, S), dtype=torch.float32, device=dev).exponential_(1)
+        lib.call('dsb_su_sample_step', warr, emb0c, ae, keyc, h, c, mask, ksum, count, end_flag, num, en,
+                 results[i - 1] if i > 0 else None, q, logits[i], results[i], ended[i:i + 1], N, S, i, float(temperature))
+        if rng == 'cpu':
+            if int(ended[i].item()) != 0:
+                steps = i + 1
+                break
+        elif (i & 7) == 7 or i == max_steps - 1:
+            flags = ended[:i + 1].tolist()
+            if 1 in flags:
+                steps = flags.index(1) + 1
+                break
+    return logits[:steps].transpose(0, 1).contiguous(), results[:steps].transpose(0, 1).contiguous(), ae, num
+
+
+# ------------------------------------------------------------------------------------------------
 # split-precision tcgen05 linear (K2/K3 workhorse)
 # ------------------------------------------------------------------------------------------------
 def attach_split(t: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor) -> torch.Tensor:

@@ -355,6 +355,17 @@ class Net:
         dev = emb0.device
         rows = torch.arange(N, device=dev)
         key, valid, slot = self.su_keys(entity_embeddings, entity_num)
+        if emb0.is_cuda:
+            # K12: one fused kernel per step (query MLP + LN-LSTM + dot/mask/sample + bookkeeping + embedding MLP)
+            P, cp = self.P, pre + 'lstm.layers.0.cell'
+            w16 = [P[pre + 'query_fc1.0.weight'], P[pre + 'query_fc1.0.bias'], P[pre + 'query_fc2.0.weight'],
+                   P[pre + 'query_fc2.0.bias'], P[cp + '.weight_ih'], P[cp + '.weight_hh'],
+                   P[cp + '.layernorm_i.weight'], P[cp + '.layernorm_i.bias'], P[cp + '.layernorm_h.weight'],
+                   P[cp + '.layernorm_h.bias'], P[cp + '.layernorm_c.weight'], P[cp + '.layernorm_c.bias'],
+                   P[pre + 'embed_fc1.0.weight'], P[pre + 'embed_fc1.0.bias'], P[pre + 'embed_fc2.0.weight'],
+                   P[pre + 'embed_fc2.0.bias']]
+            logits, units, ae, num = ops.su_sample(w16, emb0, key, valid, entity_num, su_mask, self.T, self.rng)
+            return logits, units, ae, num, torch.zeros(N, MAX_ENTITY_NUM + 1, device=dev)
         step_mask = valid & (slot != entity_num.unsqueeze(1))
         num = torch.full((N,), MAX_SELECTED_UNITS_NUM, dtype=torch.long, device=dev)
         num[~su_mask] = 0

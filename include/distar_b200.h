@@ -90,6 +90,19 @@ int dsb_categorical_stats_bwd(const float* logits, const float* teacher, const i
                               const float* entropy, const float* lse_t, const float* g_logp, const float* g_ent,
                               const float* g_kl, float* grad_logits, int64_t rows, int C, dsb_stream_t stream);
 
+/* ---- selected-units pointer network: one sampling step  (SelectedUnitsHead._query loop body, action_arg_head.py:267-306) ----
+ * weights16: host array of 16 device pointers in this order: query_fc1 W,b; query_fc2 W,b; lstm W_ih, W_hh;
+ * layernorm_i w,b; layernorm_h w,b; layernorm_c w,b; embed_fc1 W,b; embed_fc2 W,b.
+ * Per row n (one CTA): query MLP, LN-LSTM(32) cell, logits over the S = E+1 key slots (slot entity_num = end token),
+ * mask / temperature / softmax / argmax(p/q), end_flag + selected_units_num bookkeeping, running mean of the selected
+ * keys and the embedding MLP -> ae = emb0 + embedding.  State tensors are updated in place: ae [N,1024], h/c [N,32],
+ * mask u8 [N,S], ksum [N,32], count i32 [N], end_flag u8 [N], num i64 [N].  prev = previous step's result (step > 0).
+ * q [N,S]: Exp(1) draws of this step.  all_ended (device int, preset to 1) is cleared by any row still selecting. */
+int dsb_su_sample_step(const void* const* weights16, const float* emb0, float* ae, const float* key, float* h, float* c,
+                       uint8_t* mask, float* ksum, int* count, uint8_t* end_flag, int64_t* num, const int64_t* entity_num,
+                       const int64_t* prev, const float* q, float* logits_out, int64_t* result, int* all_ended, int N,
+                       int S, int step, float temperature, dsb_stream_t stream);
+
 /* ---- masked categorical sampling  (torch.multinomial(softmax(x),1) sites: head/action_type_head.py:57-58,
  *      head/action_arg_head.py:46-47,79-80,147-148,361-362,448-449) ----
  * index[r] = argmax_j softmax(logits[r])_j / q[r,j]  (first max wins), q ~ Exp(1) supplied by the caller so the

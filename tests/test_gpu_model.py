@@ -148,3 +148,27 @@ def test_sl_loss_on_gpu_matches_oracle(model, sd):
     for k, v in want.items():
         assert abs(got[k].item() - v.item()) <= 1e-3 * max(1.0, abs(v.item())), k
     assert float(model.flat_grad.abs().sum()) > 0
+
+
+def test_pointer_sampling_device_rng_is_consistent(sd):
+    """rng='cuda' polls the all-ended flag every 8 steps; the truncated outputs must still have the reference's shape
+    (steps = the step at which the last row picked the end token) and consistent bookkeeping."""
+    cfg = {'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': list(G.BASELINES)}}
+    m = Model(cfg, use_value_network=True, seed=0, sample_rng='cuda')
+    m.load_state_dict(sd)
+    m = m.cuda()
+    torch.manual_seed(5)
+    case = to_dev(G.infer_case())
+    with torch.no_grad():
+        o = m.compute_logp_action(**case)
+    su = o['action_info']['selected_units']
+    num = o['selected_units_num']
+    en = case['entity_num']
+    assert su.shape[1] == o['logit']['selected_units'].shape[1]
+    assert su.shape[1] == max(int(num.max().item()), 1) or int(num.max().item()) == 0
+    for n in range(su.shape[0]):
+        k = int(num[n].item())
+        if 0 < k <= su.shape[1] and (su[n] == en[n]).any():
+            assert int(su[n, k - 1].item()) == int(en[n].item())          # the end token closes the selection
+            picked = su[n, :k - 1].tolist()
+            assert len(set(picked)) == len(picked) and all(p < int(en[n].item()) for p in picked)

@@ -195,6 +195,7 @@ struct GemmParams {
     int64_t M;               // valid rows per batch
     int64_t ldc;             // row stride (elements) of c_hi / c_lo
     int N, terms, relu, accumulate;
+    int store_c;             // 0: only the bf16 (hi, lo) pair is written (no fp32 C)
     int num_m, num_n, num_k; // tiles per (batch, split); k blocks per split
     int batch, inner, splits;
     int c_row_outer, c_row_inner, c_row_split, c_col_base, c_col_inner;
@@ -282,7 +283,8 @@ template <int BN, int MC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                  const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
+                  const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c_hi,
+                  const __grid_constant__ CUtensorMap map_c_lo, const GemmParams p) {
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024 B alignment
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -449,41 +451,55 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(fmaf(__uint_as_float(r[j]), p.alpha, v[j]), floor_v);
                 unsigned char* buf = my_buf;
-                // the TMA store that last read this staging box must have finished reading it (the sibling warp on this
-                // scheduler keeps issuing meanwhile)
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncwarp();
-                const uint32_t rowbase = smem_u32(buf) + lane * 128;
+                if (p.store_c) {
+                    // the TMA store that last read this staging box must have finished reading it (the sibling warp on
+                    // this scheduler keeps issuing meanwhile)
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                    const uint32_t rowbase = smem_u32(buf) + lane * 128;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t addr = rowbase + (uint32_t)((j ^ (lane & 7)) << 4);
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * j]), "f"(v[4 * j + 1]),
-                                 "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t addr = rowbase + (uint32_t)((j ^ (lane & 7)) << 4);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                                     "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0 && t.valid) {
+                        if (p.accumulate) tma_reduce_add_2d(&map_c, buf, c_col0 + c0, c_row0);
+                        else tma_store_2d(&map_c, buf, c_col0 + c0, c_row0);
+                    }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0 && t.valid) {
-                    if (p.accumulate) tma_reduce_add_2d(&map_c, buf, c_col0 + c0, c_row0);
-                    else tma_store_2d(&map_c, buf, c_col0 + c0, c_row0);
-                }
-                if (p.c_hi && row_ok) {
-                    const int64_t off = (int64_t)(c_row0 + lane) * p.ldc + c_col0 + c0;
-                    uint4* dh = reinterpret_cast<uint4*>(p.c_hi + off);
-                    uint4* dl = reinterpret_cast<uint4*>(p.c_lo + off);
+                if (p.c_hi) {
+                    // bf16 (hi, lo) pair of the same 32 x 32 block: two 2 KiB SWIZZLE_64B boxes in the same staging slot,
+                    // written by the copy engine as full lines (the consumer GEMM reads them straight back through TMA)
+                    uint32_t h[16], l[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const float x0 = v[2 * e], x1 = v[2 * e + 1];
+                        const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+                        const float2 hf = __bfloat1622float2(hh);
+                        const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+                        h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                        l[e] = *reinterpret_cast<const uint32_t*>(&ll);
+                    }
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                    const uint32_t rowbase = smem_u32(buf) + lane * 64;
+                    const uint32_t sw = (uint32_t)((lane >> 1) & 3);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        uint32_t h[4], l[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float x0 = v[8 * j + 2 * e], x1 = v[8 * j + 2 * e + 1];
-                            const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
-                            const float2 hf = __bfloat1622float2(hh);
-                            const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
-                            h[e] = *reinterpret_cast<const uint32_t*>(&hh);
-                            l[e] = *reinterpret_cast<const uint32_t*>(&ll);
-                        }
-                        dh[j] = make_uint4(h[0], h[1], h[2], h[3]);
-                        dl[j] = make_uint4(l[0], l[1], l[2], l[3]);
+                        const uint32_t addr = rowbase + ((j ^ sw) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h[4 * j]), "r"(h[4 * j + 1]),
+                                     "r"(h[4 * j + 2]), "r"(h[4 * j + 3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + 2048), "r"(l[4 * j]),
+                                     "r"(l[4 * j + 1]), "r"(l[4 * j + 2]), "r"(l[4 * j + 3]) : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0 && t.valid) {
+                        tma_store_2d(&map_c_hi, buf, c_col0 + c0, c_row0);
+                        tma_store_2d(&map_c_lo, buf + 2048, c_col0 + c0, c_row0);
                     }
                 }
             }
@@ -518,7 +534,8 @@ EncodeTiledFn get_encode() {
 }
 
 // 2-D row-major [rows, cols] tensor of `esize`-byte elements, box = [box_rows, box_cols], 128 B swizzle
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int esize, int box_rows, int box_cols) {
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int esize, int box_rows, int box_cols,
+             CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { dsb::set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return DSB_ERR_CUDA; }
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -526,8 +543,7 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int
     const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                      esize == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -571,7 +587,7 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
     const int num_m = (int)((g.m + BM - 1) / BM), num_n = g.n / BN;
     const int64_t tiles = (int64_t)batch * splits * num_m * num_n;
     DSB_REQUIRE(tiles < (1ll << 31), "gemm: too many tiles");
-    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mc;
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mc, mc_hi, mc_lo;
     int rc;
     const void* a_lo = g.terms == 3 ? g.a_lo : g.a_hi;
     const void* b_lo = g.terms == 3 ? g.b_lo : g.b_hi;
@@ -605,7 +621,17 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
         if ((rc = make_map(&mb_hi, g.b_hi, g.b_rows, g.b_cols, 2, b_br, 64))) return rc;
         if ((rc = make_map(&mb_lo, b_lo, g.b_rows, g.b_cols, 2, b_br, 64))) return rc;
     }
-    if ((rc = make_map(&mc, g.c, g.c_rows, g.c_cols, 4, 32, 32))) return rc;
+    if (g.c_hi) {
+        DSB_REQUIRE(g.c_cols % 8 == 0, "gemm: (hi, lo) output row pitch must be a 16-byte multiple");
+        if ((rc = make_map(&mc_hi, g.c_hi, g.c_rows, g.c_cols, 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+        if ((rc = make_map(&mc_lo, g.c_lo, g.c_rows, g.c_cols, 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    }
+    if (g.c) {
+        if ((rc = make_map(&mc, g.c, g.c_rows, g.c_cols, 4, 32, 32))) return rc;
+    } else {
+        mc = mc_hi;                           // never dereferenced (store_c = 0)
+    }
+    if (!g.c_hi) mc_hi = mc_lo = mc;
     static bool configured = false;
     static int num_sms = 0;
     if (!configured) {
@@ -620,7 +646,7 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
     GemmParams p;
     p.bias = g.bias; p.residual = g.residual; p.c_hi = (__nv_bfloat16*)g.c_hi; p.c_lo = (__nv_bfloat16*)g.c_lo;
     p.alpha = g.alpha; p.M = g.m; p.ldc = g.c_cols; p.N = g.n; p.terms = g.terms; p.relu = g.relu;
-    p.accumulate = g.c_accumulate;
+    p.accumulate = g.c_accumulate; p.store_c = g.c != nullptr;
     p.num_m = num_m; p.num_n = num_n; p.num_k = g.k / (BK * splits);
     p.batch = batch; p.inner = inner; p.splits = splits;
     p.c_row_outer = g.c_row_outer; p.c_row_inner = g.c_row_inner; p.c_row_split = g.c_row_split;
@@ -631,7 +657,7 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
                      g.conv_c, g.conv_taps};
     if (MC == 1) {
         const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
-        gemm_split_kernel<BN, 1><<<grid, kThreads, Plan<BN>::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, p);
+        gemm_split_kernel<BN, 1><<<grid, kThreads, Plan<BN>::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, mc_hi, mc_lo, p);
     } else {
         // clusters of two CTAs; each cluster walks pairs of vertically adjacent tiles
         const int64_t pairs = (int64_t)batch * splits * ((num_m + 1) / 2) * num_n;
@@ -646,14 +672,15 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_split_kernel<BN, 2>, ma_hi, ma_lo, mb_hi, mb_lo, mc, p);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_split_kernel<BN, 2>, ma_hi, ma_lo, mb_hi, mb_lo, mc, mc_hi, mc_lo, p);
         if (e != cudaSuccess) { dsb::set_error("gemm cluster launch: %s", cudaGetErrorString(e)); return DSB_ERR_CUDA; }
     }
     return dsb::check_launch("gemm_split");
 }
 
 int launch(const dsb_gemm_args& g, cudaStream_t stream) {
-    DSB_REQUIRE(g.a_hi && g.b_hi && g.c, "gemm: null pointer");
+    DSB_REQUIRE(g.a_hi && g.b_hi && (g.c || g.c_hi), "gemm: null pointer");
+    DSB_REQUIRE(g.c || (!g.c_accumulate && (g.splits <= 1)), "gemm: pair-only output takes no split-K / accumulate");
     DSB_REQUIRE(g.terms == 1 || g.terms == 3, "gemm: terms must be 1 or 3");
     DSB_REQUIRE(g.terms == 1 || (g.a_lo && g.b_lo), "gemm: terms=3 needs the lo halves");
     DSB_REQUIRE(!g.c_hi == !g.c_lo, "gemm: c_hi and c_lo go together");

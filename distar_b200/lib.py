@@ -128,7 +128,7 @@ def gemm_ex(**kw):
         if t.dim() == 2:
             setattr(g, name + '_rows', t.shape[0])
             setattr(g, name + '_cols', t.shape[1])
-    g.c_rows, g.c_cols = kw['c'].shape
+    g.c_rows, g.c_cols = (kw['c'] if kw.get('c') is not None else kw['c_hi']).shape
     rc = lib.dsb_gemm_ex(ctypes.byref(g), _stream())
     if rc != 0:
         raise DsbError('dsb_gemm_ex failed (%d): %s' % (rc, lib.dsb_last_error().decode()))

@@ -378,6 +378,18 @@ def attach_split(t: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor) -> torch.T
     return t
 
 
+_PLACEHOLDER = {}
+
+
+def pair_only_placeholder(shape, device) -> torch.Tensor:
+    """Stand-in for the fp32 output of a GEMM launched with emit_split='only': a stride-0 view of one NaN, so it costs no
+    memory or bandwidth and anything that wrongly reads it (instead of the attached bf16 pair) poisons the result loudly."""
+    t = _PLACEHOLDER.get(device)
+    if t is None:
+        t = _PLACEHOLDER[device] = torch.full((), float('nan'), dtype=torch.float32, device=device)
+    return t.expand(shape)
+
+
 def split_bf16(x: torch.Tensor):
     """fp32 -> (hi, lo) bf16 with hi + lo == x to ~2^-17 relative."""
     cached = getattr(x, '_dsb_split', None)
@@ -408,10 +420,12 @@ def gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu: bool, terms: int = 3, want_sp
     N = w_hi.shape[0]
     assert w_hi.shape[1] == K and gemm_eligible(N, K), (M, N, K)
     if _use_kernel(a_hi):
-        c = torch.empty((M, N), dtype=torch.float32, device=a_hi.device)
+        c = torch.empty((M, N), dtype=torch.float32, device=a_hi.device) if want_split != 'only' else None
         c_hi = torch.empty((M, N), dtype=torch.bfloat16, device=a_hi.device) if want_split else None
         c_lo = torch.empty((M, N), dtype=torch.bfloat16, device=a_hi.device) if want_split else None
         lib.call('dsb_gemm_bf16_split', a_hi, a_lo, w_hi, w_lo, bias, c, c_hi, c_lo, M, N, K, terms, 1 if relu else 0)
+        if c is None:
+            c = pair_only_placeholder((M, N), a_hi.device)
         return (c, c_hi, c_lo) if want_split else c
     if terms == 3:
         c = (a_hi.float() + a_lo.float()) @ (w_hi.float() + w_lo.float()).t()
@@ -481,7 +495,7 @@ class _SplitLinear(torch.autograd.Function):
         oshape = (*x.shape[:-1], weight.shape[0])
         ctx.set_materialize_grads(False)      # no zero-filled bf16 'gradients' for the (hi, lo) side outputs
         if emit_split:
-            y, y_hi, y_lo = gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu, terms, want_split=True)
+            y, y_hi, y_lo = gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu, terms, want_split=emit_split)
         else:
             y = gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu, terms)
         # the ReLU mask only needs the sign: when the bf16 pair is emitted (and kept by the consumer anyway) save its hi
@@ -760,13 +774,16 @@ class _ConvNHWC(torch.autograd.Function):
         x_hi, x_lo = split_bf16(x)
         w_hi, w_lo = split_bf16(wm)
         b = F.pad(bias, (0, cout_pad - Cout)).contiguous() if bias is not None else None
-        y = torch.empty((N * H * W, cout_pad), dtype=torch.float32, device=x.device)
+        pair_only = emit_split == 'only'
+        y = torch.empty((N * H * W, cout_pad), dtype=torch.float32, device=x.device) if not pair_only else None
         y_hi = torch.empty((N * H * W, cout_pad), dtype=torch.bfloat16, device=x.device) if emit_split else None
         y_lo = torch.empty((N * H * W, cout_pad), dtype=torch.bfloat16, device=x.device) if emit_split else None
         res = residual.reshape(N * H * W, cout_pad).contiguous() if residual is not None else None
         _gemm_ex(a_hi=x_hi, a_lo=x_lo, b_hi=w_hi, b_lo=w_lo, bias=b, residual=res, alpha=1.0, relu=1 if relu else 0,
                  terms=terms, c=y, c_hi=y_hi, c_lo=y_lo, m=N * H * W, n=cout_pad, k=taps * C, batch=1, inner=1, splits=1,
                  a_conv=1, conv_h=H, conv_w=W, conv_c=C, conv_taps=taps, conv_imgs=N)
+        if pair_only:
+            y = pair_only_placeholder((N * H * W, cout_pad), x.device)
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(x_hi, x_lo, wm, (y_hi if emit_split else y) if relu else None)
         ctx.meta = (N, H, W, C, Cout, Cin, kh, kw, cout_pad, relu, terms, bias is not None, residual is not None)
@@ -824,7 +841,9 @@ def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
     kh = weight.shape[2]
     if _use_kernel(x):
         assert C % 64 == 0 and W <= 64 and 64 % W == 0 and H % max(1, 128 // W) == 0, (x.shape, weight.shape)
-        y, y_hi, y_lo = _ConvNHWC.apply(x.contiguous(), weight, bias, residual, relu, terms, emit_split)
+        if getattr(x, '_dsb_split', None) is None:
+            x = x.contiguous()
+        y, y_hi, y_lo = _ConvNHWC.apply(x, weight, bias, residual, relu, terms, emit_split)
         return attach_split(y, y_hi, y_lo) if emit_split else y
     Cout, Cin = weight.shape[:2]
     y = F.conv2d(x[..., :Cin].permute(0, 3, 1, 2), weight, bias, padding=kh // 2).permute(0, 2, 3, 1)

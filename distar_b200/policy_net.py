@@ -76,7 +76,8 @@ class Net:
 
     # -------------------------------------------------------------------------------------- primitives
     def fc(self, name: str, x: Tensor, relu: bool = False, split: bool = False) -> Tensor:
-        """fc_block; split=True makes the GEMM epilogue also write the bf16 pair its consumer GEMM will read."""
+        """fc_block; split=True makes the GEMM epilogue also write the bf16 pair its consumer GEMM will read, split='only'
+        writes nothing but the pair (the consumer must be another tcgen05 GEMM; the fp32 result is a NaN placeholder)."""
         return ops.linear(x, self.P[name + '.0.weight'], self.P[name + '.0.bias'], relu, self.terms, split)
 
     def conv(self, name: str, x: Tensor, pad: int, relu: bool = False) -> Tensor:
@@ -188,7 +189,7 @@ class Net:
             qkv = self.fc(lp + '.attention.attention_pre', x)
             a = self.fc(lp + '.attention.project', ops.entity_attention(qkv, entity_num, 2, 128))
             x = self.ln(lp + '.layernorm1', x, residual=a, split=True)
-            m = self.fc(lp + '.mlp.1', self.fc(lp + '.mlp.0', x, relu=True, split=True), relu=True)
+            m = self.fc(lp + '.mlp.1', self.fc(lp + '.mlp.0', x, relu=True, split='only'), relu=True)
             x = self.ln(lp + '.layernorm2', x, residual=m, split=(i < 2))
         x = torch.relu(x)
         entity_embeddings = self.fc(pre + 'entity_fc', x, relu=True)
@@ -210,7 +211,7 @@ class Net:
             x = self.conv_nhwc(pre + 'downsample.%d' % i, x, relu=True)
         for i in range(4):
             skips.append(x)
-            r = self.conv_nhwc(pre + 'res.%d.conv1' % i, x, relu=True, split=True)
+            r = self.conv_nhwc(pre + 'res.%d.conv1' % i, x, relu=True, split='only')
             x = self.conv_nhwc(pre + 'res.%d.conv2' % i, r, relu=True, residual=x, split=(i < 3))   # relu(conv2(r) + x)
         h8, w8, c = x.shape[1:]
         w = self.P[pre + 'fc.0.weight']
@@ -425,10 +426,10 @@ class Net:
         for i in range(4):
             x = x + map_skip[len(map_skip) - i - 1]
             rp = pre + 'res.%d.' % i                                   # GatedResBlock, module_utils.py:224-231
-            r = self.conv_nhwc(rp + 'conv2', self.conv_nhwc(rp + 'conv1', x, relu=True, split=True))
+            r = self.conv_nhwc(rp + 'conv2', self.conv_nhwc(rp + 'conv1', x, relu=True, split='only'))
             g = x
             for j in range(4):
-                g = self.conv_nhwc(rp + 'GateWeightG.%d' % j, g, relu=(j < 3), split=(j < 3))
+                g = self.conv_nhwc(rp + 'GateWeightG.%d' % j, g, relu=(j < 3), split=('only' if j < 3 else False))
             x = torch.relu(torch.tanh(r * torch.sigmoid(g)) * P_[rp + 'UpdateSP'] + x)
         x = self.conv_nhwc(pre + 'upsample.0', ops.upsample_bilinear2x_nhwc(x), relu=True)            # [N,32,32,64]
         x = self.conv_nhwc(pre + 'upsample.1', ops.upsample_bilinear2x_nhwc(x), relu=True)            # [N,64,64,64] (32 real)
@@ -444,7 +445,7 @@ class Net:
         pre = 'value_networks.%s.' % name
         x = self.fc(pre + 'project', x, relu=True)
         for i in range(16):
-            r = self.fc(pre + 'res.%d.fc2' % i, self.fc(pre + 'res.%d.fc1' % i, x, relu=True, split=True))
+            r = self.fc(pre + 'res.%d.fc2' % i, self.fc(pre + 'res.%d.fc1' % i, x, relu=True, split='only'))
             x = self.ln(pre + 'res.%d.norm' % i, r, residual=x, split=True)
         v = F.linear(x, self.P[pre + 'value_fc.0.weight'], self.P[pre + 'value_fc.0.bias']).squeeze(1)
         if BASELINE_ATAN[name]:

@@ -8,7 +8,7 @@ from distar_b200.model import Model
 from distar_b200.synth import synth_rl_batch, tree_map
 B, T = int(sys.argv[1]), int(sys.argv[2]); chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 264
 dev = torch.device('cuda', 0)
-model = Model({'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': ['winloss']}}, use_value_network=True, seed=0, encoder_chunk=chunk).cuda()
+model = Model({'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': ['winloss']}}, use_value_network=True, seed=0, encoder_chunk=chunk, checkpoint_encoder=True, keep_chunks=int(os.environ.get('KEEP', 11))).cuda()
 learner = RLLearner(model)
 data = tree_map(lambda t: t.to(dev), synth_rl_batch(B, T, seed=0))
 learner._train(data); torch.cuda.synchronize()
@@ -20,5 +20,5 @@ for ev in prof.events():
         agg[ev.name[:110]][0] += 1; agg[ev.name[:110]][1] += ev.device_time
 tot = sum(v[1] for v in agg.values())
 print('total device us', tot, 'kernels', sum(v[0] for v in agg.values()))
-for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:45]:
+for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:70]:
     print('%10.0f us %5.1f%% n=%6d %s' % (t, 100 * t / tot, n, k))

@@ -29,6 +29,12 @@ def test_gemm_against_fp64(M, N, K, terms):
     c2, h, l = ops.gemm_split(a_hi, a_lo, w_hi, w_lo, b.to(DEV), relu=True, terms=terms, want_split=True)
     assert torch.equal(c2, torch.relu(c))
     assert (h.float() + l.float() - c2).abs().max().item() <= 1e-4 * max(scale, 1.0)
+    # the pair must be exactly the split of the fp32 result, with or without the fp32 store
+    eh, el = ops.split_bf16(c2.clone())
+    assert torch.equal(h, eh) and torch.equal(l, el)
+    c3, h3, l3 = ops.gemm_split(a_hi, a_lo, w_hi, w_lo, b.to(DEV), relu=True, terms=terms, want_split='only')
+    assert torch.equal(h3, eh) and torch.equal(l3, el)
+    assert c3.shape == c2.shape and bool(torch.isnan(c3).all())       # placeholder, never to be read
 
 
 def test_linear_autograd_through_gemm():

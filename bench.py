@@ -37,7 +37,7 @@ def parse():
     ap.add_argument('--encoder-chunk', type=int, default=264)
     ap.add_argument('--terms', type=int, default=3, help='tensor-core products per GEMM: 3 = fp32-class (parity), 1 = bf16')
     ap.add_argument('--no-checkpoint', action='store_true', help='keep encoder activations instead of recomputing them')
-    ap.add_argument('--keep-chunks', type=int, default=11,
+    ap.add_argument('--keep-chunks', type=int, default=12,
                     help='number of encoder chunks whose entity-transformer activations are kept (not recomputed)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -178,6 +178,12 @@ def tree_bytes(tree):
     return n[0]
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the two kernels BASELINE.json names, from the committed
+# `ncu --set full --clock-control none` captures of exactly these launches (profiles/r01_summary.md)
+NCU_SOURCE = 'profiles/r01_ncu_raw_{scatter,gemm}_final.csv'
+NCU_DRAM_BYTES = {'scatter_connection': 70.4e6 + 2155e6, 'entity_mlp_gemm_terms3': 139.5e6 + 493.7e6}
+
+
 def kernel_rooflines(dev, peaks):
     """Stand-alone CUDA-event timings of the two kernels BASELINE.json names, at the bench shapes."""
     from distar_b200 import ops
@@ -202,7 +208,9 @@ def kernel_rooflines(dev, peaks):
     bytes_per_obs = 32 * 128 * 128 * 4 + E * 32 * 4 + E * 2
     ach = N * bytes_per_obs / dt / 1e9
     out['scatter_connection'] = {'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                                 'frac': ach / peaks['hbm_gbs'], 'traffic': None, 'us_per_launch': dt * 1e6,
+                                 'frac': ach / peaks['hbm_gbs'], 'traffic': NCU_DRAM_BYTES['scatter_connection'],
+                                 'traffic_source': NCU_SOURCE, 'algorithmic_bytes': N * bytes_per_obs,
+                                 'us_per_launch': dt * 1e6,
                                  'shape': 'N=%d obs, 512 entities, 32ch, 128x128' % N,
                                  'peak_source': peaks['source']}
     # entity-transformer MLP GEMM: [M,256] x [1024,256]^T with 3-term split, at the shape the learner step launches
@@ -240,7 +248,7 @@ def kernel_rooflines(dev, peaks):
             key = 'entity_mlp_gemm_terms%d' % terms + ('_bn%d' % bn if bn else '') + tag
             out[key] = {
                 'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-                'frac': ach / peaks['bf16_tflops'], 'traffic': None, 'us_per_launch': dt * 1e6,
+                'frac': ach / peaks['bf16_tflops'], 'traffic': NCU_DRAM_BYTES.get(key), 'us_per_launch': dt * 1e6,
                 'shape': 'M=%d K=%d N=%d, %d bf16 MMA terms (tensor-core flops counted), tile 128x%s' % (
                     M, K, Nn, terms, bn if bn else 'auto(256)'),
                 'peak_source': peaks['source']}

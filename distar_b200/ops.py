@@ -549,14 +549,15 @@ class _EntityAttention(torch.autograd.Function):
     QKV activation by coordinates (no split / permute / contiguous copies) plus two row-softmax kernels."""
 
     @staticmethod
-    def forward(ctx, qkv, entity_num, heads, hd):
+    def forward(ctx, qkv, entity_num, heads, hd, q_hi=None, q_lo=None):
         NS, W3 = qkv.shape
         S = 512 if NS % 512 == 0 else None
         n_obs = entity_num.shape[0]
         S = NS // n_obs
         H, D = heads, hd
         dev = qkv.device
-        q_hi, q_lo = split_bf16(qkv)
+        if q_hi is None:                       # otherwise the producer GEMM already wrote the pair (qkv may be a placeholder)
+            q_hi, q_lo = split_bf16(qkv)
         scores = torch.empty((n_obs * H * S, S), dtype=torch.float32, device=dev)
         _gemm_ex(a_hi=q_hi, a_lo=q_lo, b_hi=q_hi, b_lo=q_lo, alpha=1.0 / math.sqrt(D), terms=3, c=scores, m=S, n=S, k=D,
                  batch=n_obs * H, inner=H, splits=1, a_col_base=0, a_col_inner=D, a_row_outer=S,
@@ -565,16 +566,20 @@ class _EntityAttention(torch.autograd.Function):
         p_lo = torch.empty_like(p_hi)
         lib.call('dsb_attn_softmax_fwd', scores, entity_num, H * S, p_hi, p_lo, n_obs * H * S, S)
         del scores
-        out = torch.empty((NS, H * D), dtype=torch.float32, device=dev)
-        _gemm_ex(a_hi=p_hi, a_lo=p_lo, b_hi=q_hi, b_lo=q_lo, b_mn=1, alpha=1.0, terms=3, c=out, m=S, n=D, k=S,
-                 batch=n_obs * H, inner=H, splits=1, a_row_outer=H * S, a_row_inner=S,
+        # the context only feeds the projection GEMM: write it as a bf16 pair, no fp32 copy
+        o_hi = torch.empty((NS, H * D), dtype=torch.bfloat16, device=dev)
+        o_lo = torch.empty_like(o_hi)
+        _gemm_ex(a_hi=p_hi, a_lo=p_lo, b_hi=q_hi, b_lo=q_lo, b_mn=1, alpha=1.0, terms=3, c=None, c_hi=o_hi, c_lo=o_lo, m=S,
+                 n=D, k=S, batch=n_obs * H, inner=H, splits=1, a_row_outer=H * S, a_row_inner=S,
                  b_col_base=2 * H * D, b_col_inner=D, b_row_outer=S, c_row_outer=S, c_col_inner=D)
         ctx.save_for_backward(q_hi, q_lo, p_hi, p_lo, entity_num)
         ctx.dims = (n_obs, S, H, D)
-        return out
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(o_hi, o_lo)
+        return pair_only_placeholder((NS, H * D), dev), o_hi, o_lo
 
     @staticmethod
-    def backward(ctx, g_out):
+    def backward(ctx, g_out, _ghi=None, _glo=None):
         q_hi, q_lo, p_hi, p_lo, entity_num = ctx.saved_tensors
         n_obs, S, H, D = ctx.dims
         dev = g_out.device
@@ -603,15 +608,24 @@ class _EntityAttention(torch.autograd.Function):
         _gemm_ex(a_hi=ds_hi, a_lo=ds_lo, b_hi=q_hi, b_lo=q_lo, a_mn=1, b_mn=1, alpha=alpha, c=dqkv, m=S, n=D, k=S,
                  a_row_outer=H * S, a_row_inner=S, b_col_base=0, b_col_inner=D, b_row_outer=S,
                  c_row_outer=S, c_col_base=H * D, c_col_inner=D, **common)
-        return dqkv, None, None, None
+        return dqkv, None, None, None, None, None
 
 
 def entity_attention(qkv: torch.Tensor, entity_num: torch.Tensor, heads: int, hd: int) -> torch.Tensor:
-    """qkv [N, S, 3*heads*hd] (q | k | v, each head-major) -> context [N, S, heads*hd]; keys >= entity_num masked."""
+    """qkv [N, S, 3*heads*hd] (q | k | v, each head-major) -> context [N, S, heads*hd]; keys >= entity_num masked.
+    On the GPU the context is returned as a pair-only tensor (fp32 placeholder + attached bf16 (hi, lo) pair, see
+    pair_only_placeholder): its one consumer is the projection GEMM."""
     N, S, W3 = qkv.shape
     if _use_kernel(qkv) and S % 128 == 0 and hd % 128 == 0:
-        out = _EntityAttention.apply(qkv.reshape(N * S, W3).contiguous(), entity_num.to(torch.int64).contiguous(), heads, hd)
-        return out.view(N, S, heads * hd)
+        sp = getattr(qkv, '_dsb_split', None)
+        if sp is not None and sp[0].shape == qkv.shape:
+            out, o_hi, o_lo = _EntityAttention.apply(qkv.reshape(N * S, W3), entity_num.to(torch.int64).contiguous(), heads,
+                                                     hd, sp[0].reshape(N * S, W3), sp[1].reshape(N * S, W3))
+        else:
+            out, o_hi, o_lo = _EntityAttention.apply(qkv.reshape(N * S, W3).contiguous(),
+                                                     entity_num.to(torch.int64).contiguous(), heads, hd)
+        shape = (N, S, heads * hd)
+        return attach_split(out.view(shape), o_hi.view(shape), o_lo.view(shape))
     q, k, v = qkv.view(N, S, 3, heads, hd).permute(2, 0, 3, 1, 4)
     score = torch.matmul(q, k.transpose(2, 3)) / math.sqrt(hd)
     if entity_num is not None:

@@ -186,7 +186,7 @@ class Net:
             x = ops.linear(self.entity_features(e), w_pad, P[pre + 'transformer.embedding.0.bias'], True, self.terms)
         for i in range(3):
             lp = '%stransformer.layers.%d' % (pre, i)
-            qkv = self.fc(lp + '.attention.attention_pre', x)
+            qkv = self.fc(lp + '.attention.attention_pre', x, split='only')
             a = self.fc(lp + '.attention.project', ops.entity_attention(qkv, entity_num, 2, 128))
             x = self.ln(lp + '.layernorm1', x, residual=a, split=True)
             m = self.fc(lp + '.mlp.1', self.fc(lp + '.mlp.0', x, relu=True, split='only'), relu=True)

@@ -144,62 +144,102 @@ extern "C" int dsb_split_bf16(const float* x, void* hi, void* lo, int64_t n, dsb
 // ---- ReLU backward fused with the bf16 split and the bias gradient -------------------------------------------------
 // g = gy * (y > 0);  writes the (hi, lo) pair the dX / dW tensor-core GEMMs read, optionally g itself, and per-block
 // partial column sums (bias gradient) — replaces a compare, a multiply, a split and a column reduction.
+// Thread layout: min(N/4, 256) column threads (one float4 column group each) x as many row groups as fit in the block, so
+// narrow activations (64 / 128 channels of the conv layers) still fill the block; rows are walked grid-stride with four
+// independent 16-byte loads in flight per thread; the grid is capped so the partial-sum matrix stays tiny.
 namespace {
-constexpr int kRbRows = 32;
+constexpr int kRbThreads = 256;
+constexpr int kRbMaxBlocks = 148 * 8;
+constexpr int kRbRowsPerGroup = 8;            // rows one row group handles per grid-stride step
+
 template <bool kMaskBf16>
-__global__ void relu_bwd_split_kernel(const float* __restrict__ gy, const void* __restrict__ yv, float* __restrict__ g_out,
-                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                      float* __restrict__ colsum, int64_t rows, int N) {
+__global__ void __launch_bounds__(kRbThreads)
+relu_bwd_split_kernel(const float* __restrict__ gy, const void* __restrict__ yv, float* __restrict__ g_out,
+                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ colsum,
+                      int64_t rows, int N) {
+    __shared__ float4 part[kRbThreads];
     const float* y = kMaskBf16 ? nullptr : reinterpret_cast<const float*>(yv);
     const __nv_bfloat16* yb = kMaskBf16 ? reinterpret_cast<const __nv_bfloat16*>(yv) : nullptr;
-    const int64_t r0 = (int64_t)blockIdx.x * kRbRows;
-    for (int c = threadIdx.x * 4; c < N; c += blockDim.x * 4) {
+    const int quads = N / 4;
+    const int cthreads = quads < kRbThreads ? quads : kRbThreads;
+    const int rgroups = kRbThreads / cthreads;
+    const int ct = threadIdx.x % cthreads, rg = threadIdx.x / cthreads;
+    const bool active = rg < rgroups;
+    const int64_t rows_per_step = (int64_t)rgroups * kRbRowsPerGroup;
+    for (int c = ct * 4; c < N; c += cthreads * 4) {           // uniform trip count over the block (ct < cthreads)
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int64_t r = r0; r < r0 + kRbRows && r < rows; ++r) {
-            const int64_t off = r * N + c;
-            float4 g = *reinterpret_cast<const float4*>(gy + off);
-            if (kMaskBf16) {
-                // the ReLU output only survives as the hi half of its bf16 pair: bf16 rounding keeps sign and zero
-                const uint2 m = *reinterpret_cast<const uint2*>(yb + off);
-                g.x = ((m.x & 0xFFFFu) != 0u && !(m.x & 0x8000u)) ? g.x : 0.f;
-                g.y = ((m.x >> 16) != 0u && !(m.x & 0x80000000u)) ? g.y : 0.f;
-                g.z = ((m.y & 0xFFFFu) != 0u && !(m.y & 0x8000u)) ? g.z : 0.f;
-                g.w = ((m.y >> 16) != 0u && !(m.y & 0x80000000u)) ? g.w : 0.f;
-            } else if (y) {
-                const float4 yy = *reinterpret_cast<const float4*>(y + off);
-                g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f;
-                g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
+        if (active) {
+            for (int64_t r0 = (int64_t)blockIdx.x * rows_per_step; r0 < rows; r0 += (int64_t)gridDim.x * rows_per_step) {
+#pragma unroll 4
+                for (int i = 0; i < kRbRowsPerGroup; ++i) {
+                    const int64_t r = r0 + (int64_t)i * rgroups + rg;
+                    if (r >= rows) break;
+                    const int64_t off = r * N + c;
+                    float4 g = __ldcs(reinterpret_cast<const float4*>(gy + off));
+                    if (kMaskBf16) {
+                        // the ReLU output only survives as the hi half of its bf16 pair: bf16 rounding keeps sign and zero
+                        const uint2 m = *reinterpret_cast<const uint2*>(yb + off);
+                        g.x = ((m.x & 0xFFFFu) != 0u && !(m.x & 0x8000u)) ? g.x : 0.f;
+                        g.y = ((m.x >> 16) != 0u && !(m.x & 0x80000000u)) ? g.y : 0.f;
+                        g.z = ((m.y & 0xFFFFu) != 0u && !(m.y & 0x8000u)) ? g.z : 0.f;
+                        g.w = ((m.y >> 16) != 0u && !(m.y & 0x80000000u)) ? g.w : 0.f;
+                    } else if (y) {
+                        const float4 yy = *reinterpret_cast<const float4*>(y + off);
+                        g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f;
+                        g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
+                    }
+                    if (g_out) *reinterpret_cast<float4*>(g_out + off) = g;
+                    if (hi) {
+                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(g.x, g.y), h1 = __floats2bfloat162_rn(g.z, g.w);
+                        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+                        const __nv_bfloat162 l0 = __floats2bfloat162_rn(g.x - f0.x, g.y - f0.y);
+                        const __nv_bfloat162 l1 = __floats2bfloat162_rn(g.z - f1.x, g.w - f1.y);
+                        *reinterpret_cast<uint2*>(hi + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+                        *reinterpret_cast<uint2*>(lo + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+                    }
+                    acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+                }
             }
-            if (g_out) *reinterpret_cast<float4*>(g_out + off) = g;
-            const __nv_bfloat162 h0 = __floats2bfloat162_rn(g.x, g.y), h1 = __floats2bfloat162_rn(g.z, g.w);
-            const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-            const __nv_bfloat162 l0 = __floats2bfloat162_rn(g.x - f0.x, g.y - f0.y);
-            const __nv_bfloat162 l1 = __floats2bfloat162_rn(g.z - f1.x, g.w - f1.y);
-            *reinterpret_cast<uint2*>(hi + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-            *reinterpret_cast<uint2*>(lo + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
-            acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
         }
-        if (colsum) *reinterpret_cast<float4*>(colsum + (int64_t)blockIdx.x * N + c) = acc;
+        if (colsum) {                                          // warp-uniform: colsum is a kernel argument
+            if (rgroups > 1) {
+                part[threadIdx.x] = acc;
+                __syncthreads();
+                if (rg == 0) {
+                    for (int j = 1; j < rgroups; ++j) {
+                        const float4 o = part[j * cthreads + ct];
+                        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+                    }
+                }
+                __syncthreads();
+            }
+            if (rg == 0) *reinterpret_cast<float4*>(colsum + (int64_t)blockIdx.x * N + c) = acc;
+        }
     }
+}
+
+inline int64_t rb_blocks(int64_t rows, int N) {
+    const int quads = N / 4;
+    const int cthreads = quads < kRbThreads ? quads : kRbThreads;
+    const int64_t rows_per_step = (int64_t)(kRbThreads / cthreads) * kRbRowsPerGroup;
+    const int64_t b = (rows + rows_per_step - 1) / rows_per_step;
+    return b < kRbMaxBlocks ? (b > 0 ? b : 1) : kRbMaxBlocks;
 }
 }  // namespace
 
-extern "C" int dsb_relu_bwd_split_blocks(int64_t rows) { return (int)((rows + kRbRows - 1) / kRbRows); }
+extern "C" int dsb_relu_bwd_split_blocks(int64_t rows, int N) { return (int)rb_blocks(rows, N > 0 ? N : 4); }
 
 extern "C" int dsb_relu_bwd_split(const float* gy, const void* y, int y_is_bf16, float* g_out, void* hi, void* lo,
                                   float* colsum, int64_t rows, int N, dsb_stream_t stream) {
-    DSB_REQUIRE(gy && hi && lo && rows >= 0 && N > 0 && N % 4 == 0, "relu_bwd_split: bad argument (N %% 4 == 0 required)");
+    DSB_REQUIRE(gy && (!hi == !lo) && (hi || g_out || colsum) && rows >= 0 && N > 0 && N % 4 == 0,
+                "relu_bwd_split: bad argument (N %% 4 == 0 required)");
     if (rows == 0) return DSB_OK;
-    const int64_t blocks = (rows + kRbRows - 1) / kRbRows;
-    DSB_REQUIRE(blocks < (1ll << 31), "relu_bwd_split: too many rows");
-    int threads = N / 4;
-    if (threads > 256) threads = 256;
-    if (threads < 32) threads = 32;
+    const unsigned blocks = (unsigned)rb_blocks(rows, N);
     if (y && y_is_bf16)
-        relu_bwd_split_kernel<true><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        relu_bwd_split_kernel<true><<<blocks, kRbThreads, 0, (cudaStream_t)stream>>>(
             gy, y, g_out, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, colsum, rows, N);
     else
-        relu_bwd_split_kernel<false><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        relu_bwd_split_kernel<false><<<blocks, kRbThreads, 0, (cudaStream_t)stream>>>(
             gy, y, g_out, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, colsum, rows, N);
     return dsb::check_launch("relu_bwd_split");
 }

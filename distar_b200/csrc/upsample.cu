@@ -237,7 +237,216 @@ __global__ void upshift9_bwd_kernel(const float* __restrict__ gout, float* __res
     gz[i] = acc;
 }
 
+
+// ---- location-head up-sampling stages with C output channels: y = act(conv3x3(upsample2x(x), w) + b) --------------------
+// (head/action_arg_head.py:436-443, `upsample` stages 0 and 1).  Same factorisation as upshift9, generalised to C output
+// channels: z[p, tap, co] = sum_ci w[co, ci, tap] x[p, ci] is ONE low-resolution GEMM on the tensor cores (K = Cin,
+// N = 9*C), and y(o) = b + sum_tap up(z[., tap, .])(o + tap - 1) is this kernel.  Against convolving the up-sampled image
+// it needs 4x fewer tensor-core flops and never materialises (or keeps for backward) the 4x larger up-sampled activation.
+// One thread owns a low-resolution cell (iy, ix) x 4 channels = a 2x2 block of outputs, so the 3x3 low-resolution
+// neighbourhood of every tap is loaded once for four outputs (81 16-byte loads instead of 144).
+struct AxisW { float w[4][3]; };   // [u - (2i - 1)][low-res neighbour j = row - (i - 1)] bilinear weight (0 outside the image)
+
+__device__ __forceinline__ AxisW axis_weights(int i, int size) {
+    AxisW a;
+#pragma unroll
+    for (int ui = 0; ui < 4; ++ui) {
+        a.w[ui][0] = a.w[ui][1] = a.w[ui][2] = 0.f;
+        const int u = 2 * i - 1 + ui;
+        if (u < 0 || u >= 2 * size) continue;               // the conv's zero padding
+        const Tap t = tap_of(u, size);
+        const int j0 = t.i0 - (i - 1), j1 = t.i1 - (i - 1);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) a.w[ui][j] += (j == j0 ? t.l0 : 0.f) + (j == j1 ? t.l1 : 0.f);
+    }
+    return a;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+upconv_fwd_kernel(const float* __restrict__ z, int ldz, const float* __restrict__ bias, int relu, float* __restrict__ out,
+                  __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int ldo, int H, int W) {
+    constexpr int Q = C / 4, TW = 8, TH = 512 / (Q * TW);         // 8x8 cells (C = 32) or 4x8 (C = 64) per block
+    const int tiles_x = W / TW, tiles_y = H / TH;
+    const int tile = blockIdx.x % (tiles_x * tiles_y);
+    const int64_t n = blockIdx.x / (tiles_x * tiles_y);
+    const int ty0 = (tile / tiles_x) * TH, tx0 = (tile % tiles_x) * TW;
+    const float* zn = z + n * H * W * (int64_t)ldz;
+    for (int idx = threadIdx.x; idx < TH * TW * Q; idx += 256) {
+        const int q = idx % Q, cell = idx / Q;
+        const int iy = ty0 + cell / TW, ix = tx0 + cell % TW;
+        const AxisW wy = axis_weights(iy, H), wx = axis_weights(ix, W);
+        float4 acc[2][2];
+        const float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = b4;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int dy = t / 3, dx = t % 3;                       // tap offset + 1
+            float4 R[2][3];                                         // R[b][j] = sum_k wx[b + dx][k] * Z[j][k]
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                R[0][j] = R[1][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int ry = iy - 1 + j;
+                if (ry < 0 || ry >= H) continue;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int rx = ix - 1 + k;
+                    if (rx < 0 || rx >= W) continue;
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(zn + ((int64_t)ry * W + rx) * ldz + t * C) + q);
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        const float w = wx.w[b + dx][k];
+                        R[b][j].x += w * v.x; R[b][j].y += w * v.y; R[b][j].z += w * v.z; R[b][j].w += w * v.w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const float w = wy.w[a + dy][j];
+                        acc[a][b].x += w * R[b][j].x; acc[a][b].y += w * R[b][j].y;
+                        acc[a][b].z += w * R[b][j].z; acc[a][b].w += w * R[b][j].w;
+                    }
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                float4 v = acc[a][b];
+                if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                const int64_t off = ((n * 2 * H + 2 * iy + a) * (int64_t)(2 * W) + 2 * ix + b) * ldo + 4 * q;
+                if (out) *reinterpret_cast<float4*>(out + off) = v;
+                if (out_hi) {
+                    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+                    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+                    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y);
+                    const __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+                    *reinterpret_cast<uint2*>(out_hi + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+                    *reinterpret_cast<uint2*>(out_lo + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+                }
+            }
+    }
+}
+
+// Transpose of the above: gz[cell, tap, c] = sum over the (<= 4x4) up-sampled positions u that read cell with bilinear weight
+// w(u):  w(u) * g[u - tap offset, c],  g = dL/dy already ReLU-masked.  One thread owns (cell, 4 channels) and all nine taps:
+// the 6x6 window of g it needs is streamed row by row (36 16-byte loads for 9 outputs).  gz is written as the bf16
+// (hi, lo) pair the dX / dW tensor-core GEMMs read; columns [9C, ldz) are zero filled.
+template <int C>
+__global__ void __launch_bounds__(256)
+upconv_bwd_kernel(const float* __restrict__ g, int ldg, __nv_bfloat16* __restrict__ gz_hi, __nv_bfloat16* __restrict__ gz_lo,
+                  int ldz, int H, int W) {
+    constexpr int Q = C / 4, TW = 8, TH = 512 / (Q * TW);
+    const int tiles_x = W / TW, tiles_y = H / TH;
+    const int tile = blockIdx.x % (tiles_x * tiles_y);
+    const int64_t n = blockIdx.x / (tiles_x * tiles_y);
+    const int ty0 = (tile / tiles_x) * TH, tx0 = (tile % tiles_x) * TW;
+    const int OH = 2 * H, OW = 2 * W;
+    const float* gn = g + n * OH * OW * (int64_t)ldg;
+    for (int idx = threadIdx.x; idx < TH * TW * Q; idx += 256) {
+        const int q = idx % Q, cell = idx / Q;
+        const int iy = ty0 + cell / TW, ix = tx0 + cell % TW;
+        // weight of up-sampled position u = 2i - 1 + ui on this cell (0 when u is outside the image)
+        float wy[4], wx[4];
+#pragma unroll
+        for (int ui = 0; ui < 4; ++ui) {
+            const int uy = 2 * iy - 1 + ui, ux = 2 * ix - 1 + ui;
+            wy[ui] = wx[ui] = 0.f;
+            if (uy >= 0 && uy < OH) { const Tap t = tap_of(uy, H); wy[ui] = (t.i0 == iy ? t.l0 : 0.f) + (t.i1 == iy ? t.l1 : 0.f); }
+            if (ux >= 0 && ux < OW) { const Tap t = tap_of(ux, W); wx[ui] = (t.i0 == ix ? t.l0 : 0.f) + (t.i1 == ix ? t.l1 : 0.f); }
+        }
+        float4 acc[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // output pixel o = u - d, d in {-1,0,1}: o ranges over 2i - 2 .. 2i + 3 (index oi = o - (2i - 2) in 0..5); the pair
+        // (ui, d) that meets o satisfies ui = oi - 1 + d  (d = tap offset)
+#pragma unroll
+        for (int oi = 0; oi < 6; ++oi) {
+            const int oy = 2 * iy - 2 + oi;
+            if (oy < 0 || oy >= OH) continue;
+            float4 T[3];                                 // T[dx + 1] = sum_ui wx[ui] * g[oy, ux - dx]
+            T[0] = T[1] = T[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int oj = 0; oj < 6; ++oj) {
+                const int ox = 2 * ix - 2 + oj;
+                if (ox < 0 || ox >= OW) continue;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(gn + ((int64_t)oy * OW + ox) * ldg) + q);
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const int ui = oj - 1 + (d - 1);     // ux = ox + dx
+                    if (ui < 0 || ui > 3) continue;
+                    const float w = wx[ui];
+                    T[d].x += w * v.x; T[d].y += w * v.y; T[d].z += w * v.z; T[d].w += w * v.w;
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const int ui = oi - 1 + (d - 1);
+                if (ui < 0 || ui > 3) continue;
+                const float w = wy[ui];
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    float4& a = acc[d * 3 + e];
+                    a.x += w * T[e].x; a.y += w * T[e].y; a.z += w * T[e].z; a.w += w * T[e].w;
+                }
+            }
+        }
+        const int64_t row = ((n * H + iy) * (int64_t)W + ix) * ldz;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const float4 v = acc[t];
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+            const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+            const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y);
+            const __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+            const int64_t off = row + t * C + 4 * q;
+            *reinterpret_cast<uint2*>(gz_hi + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+            *reinterpret_cast<uint2*>(gz_lo + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+        }
+        for (int c = 9 * C + 4 * q; c < ldz; c += C) {
+            *reinterpret_cast<uint2*>(gz_hi + row + c) = make_uint2(0u, 0u);
+            *reinterpret_cast<uint2*>(gz_lo + row + c) = make_uint2(0u, 0u);
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int dsb_upconv_fwd(const float* z, int ldz, const float* bias, int relu, float* out, void* out_hi, void* out_lo,
+                              int ldo, int64_t N, int H, int W, int C, dsb_stream_t stream) {
+    DSB_REQUIRE(z && (out || out_hi) && (!out_hi == !out_lo) && N >= 0 && (C == 32 || C == 64) && ldz >= 9 * C && ldz % 4 == 0 &&
+                ldo >= C && ldo % 4 == 0 && W % 8 == 0 && H % 8 == 0, "upconv_fwd: bad argument (C in {32,64}, H, W %% 8 == 0)");
+    if (N == 0) return DSB_OK;
+    const int64_t blocks = N * (W / 8) * (H / (C == 32 ? 8 : 4));
+    DSB_REQUIRE(blocks < (1ll << 31), "upconv_fwd: too large");
+    if (C == 32)
+        upconv_fwd_kernel<32><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(z, ldz, bias, relu, out, (__nv_bfloat16*)out_hi,
+                                                                                  (__nv_bfloat16*)out_lo, ldo, H, W);
+    else
+        upconv_fwd_kernel<64><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(z, ldz, bias, relu, out, (__nv_bfloat16*)out_hi,
+                                                                                  (__nv_bfloat16*)out_lo, ldo, H, W);
+    return dsb::check_launch("upconv_fwd");
+}
+
+extern "C" int dsb_upconv_bwd(const float* g, int ldg, void* gz_hi, void* gz_lo, int ldz, int64_t N, int H, int W, int C,
+                              dsb_stream_t stream) {
+    DSB_REQUIRE(g && gz_hi && gz_lo && N >= 0 && (C == 32 || C == 64) && ldz >= 9 * C && ldz % 4 == 0 && (ldz - 9 * C) % C == 0 &&
+                ldg >= C && ldg % 4 == 0 && W % 8 == 0 && H % 8 == 0, "upconv_bwd: bad argument");
+    if (N == 0) return DSB_OK;
+    const int64_t blocks = N * (W / 8) * (H / (C == 32 ? 8 : 4));
+    DSB_REQUIRE(blocks < (1ll << 31), "upconv_bwd: too large");
+    if (C == 32)
+        upconv_bwd_kernel<32><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, ldg, (__nv_bfloat16*)gz_hi,
+                                                                                  (__nv_bfloat16*)gz_lo, ldz, H, W);
+    else
+        upconv_bwd_kernel<64><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, ldg, (__nv_bfloat16*)gz_hi,
+                                                                                  (__nv_bfloat16*)gz_lo, ldz, H, W);
+    return dsb::check_launch("upconv_bwd");
+}
+
 
 extern "C" int dsb_upshift9_fwd(const float* z, const float* bias, float* out, int64_t N, int H, int W, dsb_stream_t stream) {
     DSB_REQUIRE(z && out && N >= 0 && H > 0 && W > 0, "upshift9_fwd: bad argument");

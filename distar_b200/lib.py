@@ -44,7 +44,9 @@ _SIGNATURES = {
     'dsb_layernorm_bwd': (_i, [_vp] * 7 + [_i64, _i, _vp]),
     'dsb_lstm_cell_fwd': (_i, [_vp] * 13 + [_i, _i, _f, _vp]),
     'dsb_lstm_cell_bwd': (_i, [_vp] * 18 + [_i, _i, _vp]),
-    'dsb_relu_bwd_split_blocks': (_i, [_i64]),
+    'dsb_upconv_fwd': (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp]),
+    'dsb_upconv_bwd': (_i, [_vp, _i, _vp, _vp, _i, _i64, _i, _i, _i, _vp]),
+    'dsb_relu_bwd_split_blocks': (_i, [_i64, _i]),
     'dsb_relu_bwd_split': (_i, [_vp, _vp, _i] + [_vp] * 4 + [_i64, _i, _vp]),
     'dsb_sumsq_partials': (_i, []),
     'dsb_grad_norm': (_i, [_vp, _i64, _vp, _vp, _vp]),

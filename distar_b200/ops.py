@@ -445,14 +445,15 @@ def _gemm_ex(**kw) -> None:
     lib.gemm_ex(**kw)
 
 
-def relu_bwd_split(gy2: torch.Tensor, y: Optional[torch.Tensor], need_bias: bool, need_g: bool = False):
+def relu_bwd_split(gy2: torch.Tensor, y: Optional[torch.Tensor], need_bias: bool, need_g: bool = False,
+                   need_split: bool = True):
     """(g_hi, g_lo, bias_grad or None, g or None) with g = gy * (y > 0): one pass instead of compare + mul + split + sum."""
     rows, N = gy2.shape
     dev = gy2.device
-    hi = torch.empty((rows, N), dtype=torch.bfloat16, device=dev)
-    lo = torch.empty((rows, N), dtype=torch.bfloat16, device=dev)
+    hi = torch.empty((rows, N), dtype=torch.bfloat16, device=dev) if need_split else None
+    lo = torch.empty((rows, N), dtype=torch.bfloat16, device=dev) if need_split else None
     g = torch.empty((rows, N), dtype=torch.float32, device=dev) if need_g else None
-    blocks = lib.load().dsb_relu_bwd_split_blocks(rows)
+    blocks = lib.load().dsb_relu_bwd_split_blocks(rows, N)
     cs = torch.empty((blocks, N), dtype=torch.float32, device=dev) if need_bias else None
     lib.call('dsb_relu_bwd_split', gy2, y, 1 if (y is not None and y.dtype == torch.bfloat16) else 0, g, hi, lo, cs, rows, N)
     return hi, lo, (cs.sum(0) if need_bias else None), g
@@ -949,6 +950,93 @@ def upsample_conv3x3_single(x: torch.Tensor, weight: torch.Tensor, bias: Optiona
     H2, W2 = up.shape[2] - 2, up.shape[3] - 2
     out = sum(up[:, t, t // 3:t // 3 + H2, t % 3:t % 3 + W2] for t in range(9))
     return out + bias if bias is not None else out
+
+
+class _UpConv(torch.autograd.Function):
+    """y = act(conv3x3(upsample_bilinear2x(x), w) + b), channels-last, through the low-resolution factorisation
+    z = x . w (tensor-core GEMM, N = 9*C) followed by nine shifted up-samplings (csrc/upsample.cu: dsb_upconv_*)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu, pair_only, x_hi=None, x_lo=None):
+        N, H, W, Cp = x.shape
+        C, Cin = weight.shape[:2]
+        M = N * H * W
+        ldz = _pad_to(9 * C, 64)
+        dev = x.device
+        wz = torch.zeros((_pad_to(ldz, 128), Cp), dtype=torch.float32, device=dev)
+        wz[:9 * C, :Cin] = weight.permute(2, 3, 0, 1).reshape(9 * C, Cin)          # row = tap * C + co
+        if x_hi is None:
+            x_hi, x_lo = split_bf16(x.reshape(M, Cp).contiguous())
+        x_hi, x_lo = x_hi.reshape(M, Cp), x_lo.reshape(M, Cp)
+        w_hi, w_lo = split_bf16(wz)
+        z = torch.empty((M, ldz), dtype=torch.float32, device=dev)
+        _gemm_ex(a_hi=x_hi, a_lo=x_lo, b_hi=w_hi, b_lo=w_lo, alpha=1.0, terms=3, c=z, m=M, n=ldz, k=Cp, batch=1, inner=1,
+                 splits=1, bn=64)
+        oshape = (N, 2 * H, 2 * W, C)
+        y = None if pair_only else torch.empty(oshape, dtype=torch.float32, device=dev)
+        y_hi = torch.empty(oshape, dtype=torch.bfloat16, device=dev) if pair_only else None
+        y_lo = torch.empty(oshape, dtype=torch.bfloat16, device=dev) if pair_only else None
+        lib.call('dsb_upconv_fwd', z, ldz, bias, 1 if relu else 0, y, y_hi, y_lo, C, N, H, W, C)
+        del z
+        ctx.save_for_backward(x_hi, x_lo, w_hi, w_lo, (y_hi if pair_only else y) if relu else None)
+        ctx.meta = (N, H, W, Cp, C, Cin, ldz, relu, bias is not None)
+        ctx.set_materialize_grads(False)
+        if pair_only:
+            ctx.mark_non_differentiable(y_hi, y_lo)
+            return pair_only_placeholder(oshape, dev), y_hi, y_lo
+        return y, None, None
+
+    @staticmethod
+    def backward(ctx, gy, _ghi=None, _glo=None):
+        x_hi, x_lo, w_hi, w_lo, mask = ctx.saved_tensors
+        N, H, W, Cp, C, Cin, ldz, relu, has_bias = ctx.meta
+        if gy is None:
+            return (None,) * 7
+        M = N * H * W
+        dev = gy.device
+        gy2 = gy.reshape(4 * M, C).contiguous()
+        want_b = has_bias and ctx.needs_input_grad[2]
+        if relu or want_b:
+            _, _, gb, g = relu_bwd_split(gy2, mask.reshape(4 * M, C) if relu else None, want_b, need_g=relu, need_split=False)
+            g = g if relu else gy2
+        else:
+            g, gb = gy2, None
+        gz_hi = torch.empty((M, ldz), dtype=torch.bfloat16, device=dev)
+        gz_lo = torch.empty((M, ldz), dtype=torch.bfloat16, device=dev)
+        lib.call('dsb_upconv_bwd', g, C, gz_hi, gz_lo, ldz, N, H, W, C)
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty((M, Cp), dtype=torch.float32, device=dev)
+            _gemm_ex(a_hi=gz_hi, a_lo=gz_lo, b_hi=w_hi, b_lo=w_lo, b_mn=1, alpha=1.0, terms=3, c=gx, m=M, n=Cp, k=ldz,
+                     batch=1, inner=1, splits=1, bn=64 if Cp % 128 else 128)
+            gx = gx.view(N, H, W, Cp)
+        if ctx.needs_input_grad[1]:
+            rows = w_hi.shape[0]                                    # ldz padded to a whole 128-row tile
+            bn = 64 if Cp % 128 else 128
+            splits = _pick_splits((rows // 128) * (Cp // bn), M)
+            gwz = torch.zeros((rows, Cp), dtype=torch.float32, device=dev)
+            _gemm_ex(a_hi=gz_hi, a_lo=gz_lo, b_hi=x_hi, b_lo=x_lo, a_mn=1, b_mn=1, alpha=1.0, terms=3, c=gwz, m=ldz, n=Cp, k=M,
+                     batch=1, inner=1, splits=splits, c_row_split=0, c_accumulate=1, bn=bn)
+            gw = gwz[:9 * C, :Cin].reshape(3, 3, C, Cin).permute(2, 3, 0, 1).contiguous()
+        return gx, gw, gb, None, None, None, None
+
+
+def upsample_conv3x3(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = True,
+                     pair_only: bool = False) -> torch.Tensor:
+    """conv2d_block(F.interpolate(x, 2, 'bilinear'), weight[C,Cin,3,3], bias, padding=1, activation) on a channels-last x
+    [N,H,W,Cpad>=Cin] -> [N,2H,2W,C] (exactly C channels; C in {32, 64} on the GPU).  With pair_only the result exists only
+    as the bf16 (hi, lo) pair the next tensor-core GEMM reads (see pair_only_placeholder)."""
+    C, Cin = weight.shape[:2]
+    if _use_kernel(x):
+        assert C in (32, 64) and x.shape[-1] % 64 == 0 and x.shape[1] % 8 == 0 and x.shape[2] % 8 == 0, (x.shape, weight.shape)
+        sp = getattr(x, '_dsb_split', None)
+        if sp is None or sp[0].shape != x.shape:
+            sp = (None, None)
+        y, y_hi, y_lo = _UpConv.apply(x, weight, bias, relu, pair_only, sp[0], sp[1])
+        return attach_split(y, y_hi, y_lo) if pair_only else y
+    up = F.interpolate(x[..., :Cin].permute(0, 3, 1, 2), scale_factor=2., mode='bilinear')
+    y = F.conv2d(up, weight, bias, padding=1).permute(0, 2, 3, 1)
+    return torch.relu(y) if relu else y
 
 
 def upsample_bilinear2x(x: torch.Tensor) -> torch.Tensor:

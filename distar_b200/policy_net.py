@@ -431,8 +431,10 @@ class Net:
             for j in range(4):
                 g = self.conv_nhwc(rp + 'GateWeightG.%d' % j, g, relu=(j < 3), split=('only' if j < 3 else False))
             x = torch.relu(torch.tanh(r * torch.sigmoid(g)) * P_[rp + 'UpdateSP'] + x)
-        x = self.conv_nhwc(pre + 'upsample.0', ops.upsample_bilinear2x_nhwc(x), relu=True)            # [N,32,32,64]
-        x = self.conv_nhwc(pre + 'upsample.1', ops.upsample_bilinear2x_nhwc(x), relu=True)            # [N,64,64,64] (32 real)
+        # up-sampling stages: the 3x3 taps are applied as nine shifted up-samplings of a low-resolution projection
+        x = ops.upsample_conv3x3(x, P_[pre + 'upsample.0.0.weight'], P_[pre + 'upsample.0.0.bias'], True,
+                                 pair_only=True)                                                       # [N,32,32,64]
+        x = ops.upsample_conv3x3(x, P_[pre + 'upsample.1.0.weight'], P_[pre + 'upsample.1.0.bias'], True)   # [N,64,64,32]
         # last stage (32 -> 1 channel at 128x128): up-sampling commutes with the channel contraction
         x = ops.upsample_conv3x3_single(x, P_[pre + 'upsample.2.0.weight'], P_[pre + 'upsample.2.0.bias'])
         logits = x.reshape(N, -1) / self.T

@@ -125,13 +125,24 @@ int dsb_upsample_bilinear2x_nhwc_bwd(const float* grad_out, float* grad_in, int6
 int dsb_upshift9_fwd(const float* z, const float* bias, float* out, int64_t N, int H, int W, dsb_stream_t stream);
 int dsb_upshift9_bwd(const float* grad_out, float* grad_z, int64_t N, int H, int W, dsb_stream_t stream);
 
+/* ---- location-head up-sampling stages: y = act(conv3x3(upsample_bilinear2x(x), w[C,Cin,3,3]) + b), C in {32, 64} ----
+ * (head/action_arg_head.py:436-443).  z [N*H*W, ldz] holds the low-resolution projection z[p, tap*C + co] =
+ * sum_ci w[co,ci,tap] x[p,ci] (one tensor-core GEMM); dsb_upconv_fwd applies the nine shifted bilinear up-samplings, bias
+ * and ReLU and writes y [N,2H,2W,ldo] as fp32 and/or a bf16 (hi, lo) pair.  dsb_upconv_bwd is its transpose: from the
+ * (ReLU-masked) g = dL/dy [N,2H,2W,ldg] it writes dL/dz as the (hi, lo) pair [N*H*W, ldz] (pad columns zeroed). */
+int dsb_upconv_fwd(const float* z, int ldz, const float* bias, int relu, float* out, void* out_hi, void* out_lo, int ldo,
+                   int64_t N, int H, int W, int C, dsb_stream_t stream);
+int dsb_upconv_bwd(const float* g, int ldg, void* gz_hi, void* gz_lo, int ldz, int64_t N, int H, int W, int C,
+                   dsb_stream_t stream);
+
 /* ---- fp32 -> (hi, lo) bf16 split used by the split-precision tensor-core GEMM ---- */
 int dsb_split_bf16(const float* x, void* hi, void* lo, int64_t n, dsb_stream_t stream);
 
 /* ---- ReLU backward + bf16 split + bias gradient in one pass ----
  * g = gy * (y > 0) (y NULL: g = gy; y may be fp32 or, with y_is_bf16, the bf16 hi half of the ReLU output); hi/lo receive the split of g, g_out (optional) g itself, colsum (optional)
- * per-block partial column sums [dsb_relu_bwd_split_blocks(rows), N] whose sum over blocks is the bias gradient. */
-int dsb_relu_bwd_split_blocks(int64_t rows);
+ * per-block partial column sums [dsb_relu_bwd_split_blocks(rows, N), N] whose sum over blocks is the bias gradient.
+ * hi/lo (together) and g_out may each be NULL when that output is not wanted. */
+int dsb_relu_bwd_split_blocks(int64_t rows, int N);
 int dsb_relu_bwd_split(const float* gy, const void* y, int y_is_bf16, float* g_out, void* hi, void* lo, float* colsum,
                        int64_t rows, int N, dsb_stream_t stream);
 

@@ -305,3 +305,25 @@ def test_entity_features_kernel_matches_reference_expansion():
     ent['last_selected_units'][0, 0] = -1
     with pytest.raises(RuntimeError):
         ops.entity_features_split({k: v.to(DEV) for k, v in ent.items()}, ENTITY_FIELDS)
+
+
+@pytest.mark.parametrize('rows,N,bf16_mask', [(1000, 64, False), (4097, 128, True), (300, 1024, True), (77, 320, False),
+                                              (100000, 64, True)])
+def test_relu_bwd_split_layouts(rows, N, bf16_mask):
+    """column-thread x row-group layouts of the ReLU-backward pass (narrow conv activations up to the 1024-wide MLP)."""
+    g = torch.Generator().manual_seed(rows + N)
+    gy = torch.randn(rows, N, generator=g)
+    y = torch.relu(torch.randn(rows, N, generator=g))
+    want = gy * (y > 0)
+    yd = y.to(DEV)
+    mask = yd.to(torch.bfloat16) if bf16_mask else yd
+    if bf16_mask:                                  # bf16 rounding keeps sign and zero; tiny positives may round to > 0 only
+        want = gy * (mask.float().cpu() > 0)
+    hi, lo, gb, gout = ops.relu_bwd_split(gy.to(DEV), mask, True, need_g=True)
+    assert torch.equal(gout.cpu(), want)
+    eh, el = ops.split_bf16(want.to(DEV))
+    assert torch.equal(hi, eh) and torch.equal(lo, el)
+    ref = want.double().sum(0)
+    assert (gb.double().cpu() - ref).abs().max().item() <= 1e-5 * max(1.0, want.abs().sum(0).max().item())
+    _, _, gb2, g2 = ops.relu_bwd_split(gy.to(DEV), mask, True, need_g=True, need_split=False)
+    assert torch.equal(g2.cpu(), want) and torch.allclose(gb2, gb)

@@ -76,7 +76,7 @@ template <int VEC>
 __global__ void __launch_bounds__(kWarps * 32)
 ln_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ xin, const float* __restrict__ gamma,
               const float* __restrict__ stats, float* __restrict__ gx, float* __restrict__ pgamma,
-              float* __restrict__ pbeta, int64_t rows, int rows_per_block) {
+              float* __restrict__ pbeta, int64_t rows, int rows_per_block, int atomic) {
     constexpr int D = 128 * VEC;
     __shared__ float sg[kWarps][D];
     __shared__ float sb[kWarps][D];
@@ -125,8 +125,13 @@ ln_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ xin, const
         float a = 0.f, b = 0.f;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) { a += sg[w][c]; b += sb[w][c]; }
-        pgamma[(int64_t)blockIdx.x * D + c] = a;
-        pbeta[(int64_t)blockIdx.x * D + c] = b;
+        if (atomic) {                 // pgamma / pbeta are the parameters' gradients themselves ([D])
+            atomicAdd(pgamma + c, a);
+            atomicAdd(pbeta + c, b);
+        } else {
+            pgamma[(int64_t)blockIdx.x * D + c] = a;
+            pbeta[(int64_t)blockIdx.x * D + c] = b;
+        }
     }
 }
 
@@ -341,8 +346,8 @@ int launch_ln_fwd(const float* x, const float* res, const float* gamma, const fl
 }
 template <int VEC>
 int launch_ln_bwd(const float* gy, const float* xin, const float* gamma, const float* stats, float* gx, float* pg,
-                  float* pb, int64_t rows, int rows_per_block, int blocks, cudaStream_t s) {
-    ln_bwd_kernel<VEC><<<(unsigned)blocks, kWarps * 32, 0, s>>>(gy, xin, gamma, stats, gx, pg, pb, rows, rows_per_block);
+                  float* pb, int64_t rows, int rows_per_block, int blocks, int atomic, cudaStream_t s) {
+    ln_bwd_kernel<VEC><<<(unsigned)blocks, kWarps * 32, 0, s>>>(gy, xin, gamma, stats, gx, pg, pb, rows, rows_per_block, atomic);
     return dsb::check_launch("layernorm_bwd");
 }
 
@@ -375,18 +380,18 @@ extern "C" int dsb_layernorm_bwd_blocks(int64_t rows) {
 }
 
 extern "C" int dsb_layernorm_bwd(const float* gy, const float* xin, const float* gamma, const float* stats, float* gx,
-                                 float* pgamma, float* pbeta, int64_t rows, int D, dsb_stream_t stream) {
+                                 float* pgamma, float* pbeta, int atomic, int64_t rows, int D, dsb_stream_t stream) {
     DSB_REQUIRE(gy && xin && gamma && stats && gx && pgamma && pbeta && rows > 0, "layernorm_bwd: bad argument");
     DSB_REQUIRE(dsb_layernorm_supported(D), "layernorm_bwd: unsupported width %d", D);
     const int blocks = dsb_layernorm_bwd_blocks(rows);
     const int rpb = (int)((rows + blocks - 1) / blocks);
     cudaStream_t s = (cudaStream_t)stream;
     switch (D / 128) {
-        case 1: return launch_ln_bwd<1>(gy, xin, gamma, stats, gx, pgamma, pbeta, rows, rpb, blocks, s);
-        case 2: return launch_ln_bwd<2>(gy, xin, gamma, stats, gx, pgamma, pbeta, rows, rpb, blocks, s);
-        case 3: return launch_ln_bwd<3>(gy, xin, gamma, stats, gx, pgamma, pbeta, rows, rpb, blocks, s);
-        case 4: return launch_ln_bwd<4>(gy, xin, gamma, stats, gx, pgamma, pbeta, rows, rpb, blocks, s);
-        default: return launch_ln_bwd<12>(gy, xin, gamma, stats, gx, pgamma, pbeta, rows, rpb, blocks, s);
+        case 1: return launch_ln_bwd<1>(gy, xin, gamma, stats, gx, pgamma, pbeta, rows, rpb, blocks, atomic, s);
+        case 2: return launch_ln_bwd<2>(gy, xin, gamma, stats, gx, pgamma, pbeta, rows, rpb, blocks, atomic, s);
+        case 3: return launch_ln_bwd<3>(gy, xin, gamma, stats, gx, pgamma, pbeta, rows, rpb, blocks, atomic, s);
+        case 4: return launch_ln_bwd<4>(gy, xin, gamma, stats, gx, pgamma, pbeta, rows, rpb, blocks, atomic, s);
+        default: return launch_ln_bwd<12>(gy, xin, gamma, stats, gx, pgamma, pbeta, rows, rpb, blocks, atomic, s);
     }
 }
 

@@ -156,7 +156,7 @@ template <bool kMaskBf16>
 __global__ void __launch_bounds__(kRbThreads)
 relu_bwd_split_kernel(const float* __restrict__ gy, const void* __restrict__ yv, float* __restrict__ g_out,
                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ colsum,
-                      int64_t rows, int N) {
+                      int colsum_atomic, int64_t rows, int N) {
     __shared__ float4 part[kRbThreads];
     const float* y = kMaskBf16 ? nullptr : reinterpret_cast<const float*>(yv);
     const __nv_bfloat16* yb = kMaskBf16 ? reinterpret_cast<const __nv_bfloat16*>(yv) : nullptr;
@@ -213,33 +213,42 @@ relu_bwd_split_kernel(const float* __restrict__ gy, const void* __restrict__ yv,
                 }
                 __syncthreads();
             }
-            if (rg == 0) *reinterpret_cast<float4*>(colsum + (int64_t)blockIdx.x * N + c) = acc;
+            if (rg == 0) {
+                if (colsum_atomic) {            // accumulate straight into the bias gradient [N] (<= kRbMaxBlocks adds per column)
+                    atomicAdd(reinterpret_cast<float4*>(colsum + c), acc);      // one 16-byte RED (sm_90+)
+                } else {
+                    *reinterpret_cast<float4*>(colsum + (int64_t)blockIdx.x * N + c) = acc;
+                }
+            }
         }
     }
 }
 
-inline int64_t rb_blocks(int64_t rows, int N) {
+constexpr int kRbMaxBlocksAtomic = 148 * 4;   // every block ends with N/4 vector REDs onto the same N floats: keep them few
+
+inline int64_t rb_blocks(int64_t rows, int N, bool atomic = false) {
     const int quads = N / 4;
     const int cthreads = quads < kRbThreads ? quads : kRbThreads;
     const int64_t rows_per_step = (int64_t)(kRbThreads / cthreads) * kRbRowsPerGroup;
     const int64_t b = (rows + rows_per_step - 1) / rows_per_step;
-    return b < kRbMaxBlocks ? (b > 0 ? b : 1) : kRbMaxBlocks;
+    const int64_t cap = atomic ? kRbMaxBlocksAtomic : kRbMaxBlocks;
+    return b < cap ? (b > 0 ? b : 1) : cap;
 }
 }  // namespace
 
 extern "C" int dsb_relu_bwd_split_blocks(int64_t rows, int N) { return (int)rb_blocks(rows, N > 0 ? N : 4); }
 
 extern "C" int dsb_relu_bwd_split(const float* gy, const void* y, int y_is_bf16, float* g_out, void* hi, void* lo,
-                                  float* colsum, int64_t rows, int N, dsb_stream_t stream) {
+                                  float* colsum, int colsum_atomic, int64_t rows, int N, dsb_stream_t stream) {
     DSB_REQUIRE(gy && (!hi == !lo) && (hi || g_out || colsum) && rows >= 0 && N > 0 && N % 4 == 0,
                 "relu_bwd_split: bad argument (N %% 4 == 0 required)");
     if (rows == 0) return DSB_OK;
-    const unsigned blocks = (unsigned)rb_blocks(rows, N);
+    const unsigned blocks = (unsigned)rb_blocks(rows, N, colsum && colsum_atomic);
     if (y && y_is_bf16)
         relu_bwd_split_kernel<true><<<blocks, kRbThreads, 0, (cudaStream_t)stream>>>(
-            gy, y, g_out, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, colsum, rows, N);
+            gy, y, g_out, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, colsum, colsum_atomic, rows, N);
     else
         relu_bwd_split_kernel<false><<<blocks, kRbThreads, 0, (cudaStream_t)stream>>>(
-            gy, y, g_out, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, colsum, rows, N);
+            gy, y, g_out, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, colsum, colsum_atomic, rows, N);
     return dsb::check_launch("relu_bwd_split");
 }

@@ -34,6 +34,9 @@ class RLLearner:
         loss = log_vars['total_loss']
         self.model.zero_grad()
         loss.backward()
+        # the forward pass only records invalid inputs (negative entity ids) in a device flag; raise here, after the whole
+        # forward + backward has been queued and before any weight is touched
+        self.model.raise_on_bad_input()
         if self._distributed:
             self._model.sync_gradients()
         gradient = self._optimizer.step(grad_scale=1.0 / self.world)

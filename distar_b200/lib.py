@@ -41,13 +41,13 @@ _SIGNATURES = {
     'dsb_layernorm_supported': (_i, [_i]),
     'dsb_layernorm_fwd': (_i, [_vp] * 9 + [_i64, _i, _f, _vp]),
     'dsb_layernorm_bwd_blocks': (_i, [_i64]),
-    'dsb_layernorm_bwd': (_i, [_vp] * 7 + [_i64, _i, _vp]),
+    'dsb_layernorm_bwd': (_i, [_vp] * 7 + [_i, _i64, _i, _vp]),
     'dsb_lstm_cell_fwd': (_i, [_vp] * 13 + [_i, _i, _f, _vp]),
     'dsb_lstm_cell_bwd': (_i, [_vp] * 18 + [_i, _i, _vp]),
     'dsb_upconv_fwd': (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp]),
     'dsb_upconv_bwd': (_i, [_vp, _i, _vp, _vp, _i, _i64, _i, _i, _i, _vp]),
     'dsb_relu_bwd_split_blocks': (_i, [_i64, _i]),
-    'dsb_relu_bwd_split': (_i, [_vp, _vp, _i] + [_vp] * 4 + [_i64, _i, _vp]),
+    'dsb_relu_bwd_split': (_i, [_vp, _vp, _i] + [_vp] * 4 + [_i, _i64, _i, _vp]),
     'dsb_sumsq_partials': (_i, []),
     'dsb_grad_norm': (_i, [_vp, _i64, _vp, _vp, _vp]),
     'dsb_adam_step': (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp]),
@@ -112,25 +112,27 @@ def _ptr(t):
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    # raw handle of torch's current stream; torch.cuda.current_stream() builds a Stream object (~15 us per call, which
+    # adds up over the ~4000 launches of a learner step)
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 def gemm_ex(**kw):
     """dsb_gemm_ex with tensors given by keyword (a_hi, a_lo, b_hi, b_lo, bias, c, c_hi, c_lo) plus the integer fields."""
-    lib = load()
-    g = GemmArgs()
-    keep = []
+    lib = _lib or load()
+    fields = {}
     for k, v in kw.items():
-        if isinstance(v, torch.Tensor):
-            keep.append(v)
-            v = _ptr(v)
-        setattr(g, k, v if v is not None else None)
-    for name in ('a', 'b'):
-        t = kw[name + '_hi']
-        if t.dim() == 2:
-            setattr(g, name + '_rows', t.shape[0])
-            setattr(g, name + '_cols', t.shape[1])
-    g.c_rows, g.c_cols = (kw['c'] if kw.get('c') is not None else kw['c_hi']).shape
+        if v is None:
+            continue
+        fields[k] = _ptr(v) if isinstance(v, torch.Tensor) else v
+    a, b = kw['a_hi'], kw['b_hi']
+    if a.dim() == 2:
+        fields['a_rows'], fields['a_cols'] = a.shape
+    if b.dim() == 2:
+        fields['b_rows'], fields['b_cols'] = b.shape
+    c = kw.get('c')
+    fields['c_rows'], fields['c_cols'] = (c if c is not None else kw['c_hi']).shape
+    g = GemmArgs(**fields)
     rc = lib.dsb_gemm_ex(ctypes.byref(g), _stream())
     if rc != 0:
         raise DsbError('dsb_gemm_ex failed (%d): %s' % (rc, lib.dsb_last_error().decode()))
@@ -147,7 +149,7 @@ def ptr_array(tensors):
 
 
 def call(name: str, *args):
-    lib = load()
+    lib = _lib or load()
     conv = [(_ptr(a) if isinstance(a, torch.Tensor) else a) for a in args]
     rc = getattr(lib, name)(*conv, _stream())
     if rc != 0:

@@ -48,6 +48,20 @@ def _to_cfg(d):
     return _Cfg({k: _to_cfg(v) for k, v in d.items()}) if isinstance(d, dict) else d
 
 
+def _async_scalar(t: torch.Tensor):
+    """Start a device->host copy of a 0-d tensor now; the returned thunk waits for that copy only (an event recorded
+    right behind it), not for whatever was queued on the stream afterwards."""
+    host = torch.empty(1, dtype=t.dtype, pin_memory=True)
+    host.copy_(t.detach().reshape(1), non_blocking=True)
+    event = torch.cuda.Event()
+    event.record()
+
+    def value():
+        event.synchronize()
+        return host[0].item()
+    return value
+
+
 class Model(nn.Module):
     def __init__(self, cfg={}, use_value_network=False, temperature=None, seed: Optional[int] = None,
                  gemm_terms: int = 3, sample_rng: str = 'cuda', encoder_chunk: int = 0,
@@ -155,7 +169,22 @@ class Model(nn.Module):
 
     # ---------------------------------------------------------------- compute
     def _net(self) -> Net:
-        return Net(self._params, self.spatial_x, self.spatial_y, self.temperature, self.gemm_terms, self.sample_rng)
+        net = Net(self._params, self.spatial_x, self.spatial_y, self.temperature, self.gemm_terms, self.sample_rng)
+        if self.flat_param.is_cuda:
+            if getattr(self, '_bad_input_flag', None) is None or self._bad_input_flag.device != self.flat_param.device:
+                self._bad_input_flag = torch.zeros(1, dtype=torch.int32, device=self.flat_param.device)
+            net.bad_input_flag = self._bad_input_flag
+        self._last_net = net
+        return net
+
+    def raise_on_bad_input(self) -> None:
+        """Raise the error the reference raises inside the forward pass for a negative categorical entity id
+        (entity_encoder.py:69-72).  compute_logp_action / compute_teacher_logit / sl_train call this before returning;
+        rl_learner_forward leaves it to the caller (RLLearner._train checks after backward, before the optimiser step)
+        because reading the flag is a host<->device synchronisation."""
+        net = getattr(self, '_last_net', None)
+        if net is not None:
+            net.raise_on_bad_input()
 
     def _encode(self, net: Net, spatial_info, entity_info, scalar_info, entity_num):
         N = entity_num.shape[0]
@@ -199,6 +228,7 @@ class Model(nn.Module):
         logp = {}
         for k, a in action.items():
             logp[k] = torch.log_softmax(logit[k], dim=-1).gather(-1, a.unsqueeze(-1)).squeeze(-1)
+        net.raise_on_bad_input()
         return {'action_info': action, 'action_logp': logp, 'selected_units_num': su_num, 'entity_num': entity_num,
                 'hidden_state': out_state, 'logit': logit, 'extra_units': extra}
 
@@ -211,6 +241,7 @@ class Model(nn.Module):
         lstm_out, out_state = net.lstm('core_lstm', lstm_input.unsqueeze(0), hidden_state, 3)
         _a, su_num, logit = net.policy_train(lstm_out.squeeze(0), entity_embeddings, map_skip, scalar_context,
                                              entity_num, action_info, selected_units_num)
+        net.raise_on_bad_input()
         return {'logit': logit, 'hidden_state': out_state, 'entity_num': entity_num, 'selected_units_num': su_num}
 
     def rl_learner_forward(self, spatial_info, entity_info, scalar_info, entity_num, hidden_state, action_info,
@@ -221,13 +252,18 @@ class Model(nn.Module):
         B, T = batch_size, unroll_len
         flat_action = {k: v.flatten(0, 1) for k, v in action_info.items()}
         flat_su_num = selected_units_num.flatten(0, 1)
+        # the pointer head loops max(selected_units_num) times: fetch that number with a copy queued BEFORE the encoder so
+        # that reading it later waits for nothing (a plain .max().item() there would drain ~200 ms of queued kernels and
+        # expose the launch latency of everything after it)
+        su_steps = _async_scalar(flat_su_num.max()) if flat_su_num.is_cuda else None
         lstm_input, scalar_context, baseline_feature, entity_embeddings, map_skip = self._encode(
             net, spatial_info, entity_info, scalar_info, entity_num)
         state0 = [(h.view(-1, B, h.shape[-1])[0], c.view(-1, B, c.shape[-1])[0]) for h, c in hidden_state]
         lstm_out, _ = net.lstm('core_lstm', lstm_input.view(-1, B, lstm_input.shape[-1]), state0, 3)
         lstm_out = lstm_out.reshape(-1, lstm_out.shape[-1])
         _a, _n, logits = net.policy_train(lstm_out[:-B], entity_embeddings[:-B], [(m[:-B] if m is not None else None) for m in map_skip],
-                                          scalar_context[:-B], entity_num[:-B], flat_action, flat_su_num)
+                                          scalar_context[:-B], entity_num[:-B], flat_action, flat_su_num,
+                                          su_steps=su_steps() if su_steps is not None else None)
         critic_input = lstm_out.detach() if self.only_update_baseline else lstm_out
         values = {k: net.value_baseline(k, critic_input).view(T + 1, B) for k in self.baselines}
         logits = {k: v.view(T, B, *v.shape[1:]) for k, v in logits.items()}
@@ -250,4 +286,5 @@ class Model(nn.Module):
         lstm_out = lstm_out.permute(1, 0, 2).reshape(-1, lstm_out.shape[-1])
         action, su_num, logits = net.policy_train(lstm_out, entity_embeddings, map_skip, scalar_context, entity_num,
                                                   action_info, selected_units_num)
+        net.raise_on_bad_input()
         return logits, action, out_state

@@ -81,9 +81,11 @@ def scatter_connection(project: torch.Tensor, ex: torch.Tensor, ey: torch.Tensor
 _DTYPE_CODE = {torch.uint8: 0, torch.int16: 1, torch.int8: 2, torch.float16: 3}
 
 
-def entity_features_split(entity_info: dict, fields, check_negative: bool = True):
+def entity_features_split(entity_info: dict, fields, check_negative: bool = True, flag: Optional[torch.Tensor] = None):
     """fields: [(name, kind 'o'|'b'|'u', width)] in concat order.  Returns the [N, E, 1024] bf16 (hi, lo) feature pair the
-    embedding GEMM consumes, built straight from the wire-format fields (no fp32 concat).  None on unsupported dtypes."""
+    embedding GEMM consumes, built straight from the wire-format fields (no fp32 concat).  None on unsupported dtypes.
+    With ``flag`` (device int32[1]) the negative-id error is only recorded there and the caller raises later: reading it
+    here would stall the host once per encoder chunk and drain the launch queue."""
     first = entity_info[fields[0][0]]
     if not first.is_cuda:
         return None
@@ -102,10 +104,12 @@ def entity_features_split(entity_info: dict, fields, check_negative: bool = True
     N, E = first.shape
     hi = torch.empty((N, E, 1024), dtype=torch.bfloat16, device=first.device)
     lo = torch.empty((N, E, 1024), dtype=torch.bfloat16, device=first.device)
-    flag = torch.zeros(1, dtype=torch.int32, device=first.device)
+    deferred = flag is not None
+    if flag is None:
+        flag = torch.zeros(1, dtype=torch.int32, device=first.device)
     lib.call('dsb_entity_features', lib.ptr_array(tensors), lib.int_array(kinds), lib.int_array(offs),
              lib.int_array(vocabs), lib.int_array(dts), len(fields), hi, lo, N * E, flag)
-    if check_negative and int(flag.item()) != 0:          # entity_encoder.py:69-72 raises on negative ids
+    if check_negative and not deferred and int(flag.item()) != 0:          # entity_encoder.py:69-72 raises on negative ids
         raise RuntimeError('negative categorical id in an entity field')
     return hi, lo
 
@@ -446,17 +450,37 @@ def _gemm_ex(**kw) -> None:
 
 
 def relu_bwd_split(gy2: torch.Tensor, y: Optional[torch.Tensor], need_bias: bool, need_g: bool = False,
-                   need_split: bool = True):
-    """(g_hi, g_lo, bias_grad or None, g or None) with g = gy * (y > 0): one pass instead of compare + mul + split + sum."""
+                   need_split: bool = True, bias_grad_out: Optional[torch.Tensor] = None):
+    """(g_hi, g_lo, bias_grad or None, g or None) with g = gy * (y > 0): one pass instead of compare + mul + split + sum.
+    With ``bias_grad_out`` ([N] fp32, e.g. the bias parameter's .grad) the column sums are added into it by the kernel and
+    no bias gradient is returned."""
     rows, N = gy2.shape
     dev = gy2.device
     hi = torch.empty((rows, N), dtype=torch.bfloat16, device=dev) if need_split else None
     lo = torch.empty((rows, N), dtype=torch.bfloat16, device=dev) if need_split else None
     g = torch.empty((rows, N), dtype=torch.float32, device=dev) if need_g else None
+    is_bf16 = 1 if (y is not None and y.dtype == torch.bfloat16) else 0
+    if bias_grad_out is not None:
+        assert bias_grad_out.numel() == N and bias_grad_out.is_contiguous()
+        lib.call('dsb_relu_bwd_split', gy2, y, is_bf16, g, hi, lo, bias_grad_out, 1, rows, N)
+        return hi, lo, None, g
     blocks = lib.load().dsb_relu_bwd_split_blocks(rows, N)
     cs = torch.empty((blocks, N), dtype=torch.float32, device=dev) if need_bias else None
-    lib.call('dsb_relu_bwd_split', gy2, y, 1 if (y is not None and y.dtype == torch.bfloat16) else 0, g, hi, lo, cs, rows, N)
+    lib.call('dsb_relu_bwd_split', gy2, y, is_bf16, g, hi, lo, cs, 0, rows, N)
     return hi, lo, (cs.sum(0) if need_bias else None), g
+
+
+# Parameters of the Model live in one flat arena and their .grad is a view of the flat gradient arena (model.py).  When a
+# Function's weight / bias is such a leaf, its backward adds the gradient straight into .grad (TMA reduce-add in the dW GEMM
+# epilogue, atomics for the bias column sums) and hands autograd None: no zero-filled temporary, no AccumulateGrad add
+# kernel per parameter per encoder chunk.
+def _grad_slot(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if p is None or not p.is_leaf or not p.is_cuda:
+        return None
+    g = p.grad
+    if g is None or g.shape != p.shape or g.dtype != torch.float32 or not g.is_contiguous() or g.data_ptr() % 16 != 0:
+        return None
+    return g
 
 
 def _pick_splits(tiles: int, k: int) -> int:
@@ -468,12 +492,17 @@ def _pick_splits(tiles: int, k: int) -> int:
     return s
 
 
-def weight_grad(g_hi, g_lo, x_hi, x_lo, terms: int = 3) -> torch.Tensor:
+def weight_grad(g_hi, g_lo, x_hi, x_lo, terms: int = 3, accumulate_into: Optional[torch.Tensor] = None):
     """dW[N,K] = dY^T X with both operands read in place (MN-major: the reduction runs over rows = tokens), split-K over
-    tokens on the tensor cores, partial tiles summed afterwards."""
+    tokens on the tensor cores, partial tiles summed by the copy engine (TMA reduce-add).  With ``accumulate_into`` the
+    result is added to that [N,K] tensor (the parameter's .grad) and None is returned."""
     M, N = g_hi.shape
     K = x_hi.shape[1]
     splits = _pick_splits((N // 128) * (K // 128), M)
+    if accumulate_into is not None:
+        _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=x_hi, b_lo=x_lo, a_mn=1, b_mn=1, alpha=1.0, terms=terms, c=accumulate_into, m=N,
+                 n=K, k=M, batch=1, inner=1, splits=splits, c_row_split=0, c_accumulate=1)
+        return None
     gw = torch.zeros((N, K), dtype=torch.float32, device=g_hi.device) if splits > 1 else \
         torch.empty((N, K), dtype=torch.float32, device=g_hi.device)
     _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=x_hi, b_lo=x_lo, a_mn=1, b_mn=1, alpha=1.0, terms=terms, c=gw, m=N, n=K, k=M,
@@ -503,6 +532,7 @@ class _SplitLinear(torch.autograd.Function):
         # half instead of the fp32 output
         ctx.save_for_backward(a_hi, a_lo, w_hi, w_lo, (y_hi if emit_split else y) if relu else None)
         ctx.relu, ctx.terms, ctx.has_bias, ctx.xshape = relu, terms, bias is not None, x.shape
+        ctx.weight_ref, ctx.bias_ref = weight, bias
         if emit_split:
             y_hi, y_lo = y_hi.view(oshape), y_lo.view(oshape)
             ctx.mark_non_differentiable(y_hi, y_lo)
@@ -521,7 +551,8 @@ class _SplitLinear(torch.autograd.Function):
         gx = gw = gb = None
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if on_gpu and N % 4 == 0:
-            g_hi, g_lo, gb, g = relu_bwd_split(gy2, y if ctx.relu else None, want_b, need_g=False)
+            g_hi, g_lo, gb, g = relu_bwd_split(gy2, y if ctx.relu else None, want_b, need_g=False,
+                                               bias_grad_out=_grad_slot(ctx.bias_ref) if want_b else None)
         else:
             g = gy2 * (y.reshape(gy2.shape) > 0) if ctx.relu else gy2
             g_hi, g_lo = split_bf16(g) if on_gpu else (None, None)
@@ -537,7 +568,7 @@ class _SplitLinear(torch.autograd.Function):
             gx = gx.view(ctx.xshape)
         if ctx.needs_input_grad[1]:
             if on_gpu and N % 128 == 0 and K % 128 == 0 and M % 64 == 0 and M >= 128:
-                gw = weight_grad(g_hi, g_lo, a_hi, a_lo, ctx.terms)
+                gw = weight_grad(g_hi, g_lo, a_hi, a_lo, ctx.terms, accumulate_into=_grad_slot(ctx.weight_ref))
             else:
                 gfull = g if g is not None else (g_hi.float() + g_lo.float())
                 gw = gfull.t() @ (a_hi.float() + a_lo.float())
@@ -671,6 +702,7 @@ class _LayerNorm(torch.autograd.Function):
         lib.call('dsb_layernorm_fwd', x2, r2, weight, bias, xin if r2 is not None else None, y, hi, lo, stats, rows, D, 1e-5)
         ctx.save_for_backward(xin, weight, stats)
         ctx.set_materialize_grads(False)
+        ctx.weight_ref, ctx.bias_ref = weight, bias
         ctx.has_res = residual is not None
         ctx.shape = x.shape
         y = y.view(x.shape)
@@ -687,11 +719,16 @@ class _LayerNorm(torch.autograd.Function):
             return (None,) * 5
         rows, D = xin.shape
         gy2 = gy.reshape(rows, D).contiguous()
-        blocks = lib.load().dsb_layernorm_bwd_blocks(rows)
         gx = torch.empty_like(xin)
+        gw_slot, gb_slot = _grad_slot(ctx.weight_ref), _grad_slot(ctx.bias_ref)
+        if gw_slot is not None and gb_slot is not None and ctx.needs_input_grad[2] and ctx.needs_input_grad[3]:
+            lib.call('dsb_layernorm_bwd', gy2, xin, weight, stats, gx, gw_slot, gb_slot, 1, rows, D)
+            gx = gx.view(ctx.shape)
+            return gx, (gx if ctx.has_res else None), None, None, None
+        blocks = lib.load().dsb_layernorm_bwd_blocks(rows)
         pg = torch.empty((blocks, D), dtype=torch.float32, device=gy.device)
         pb = torch.empty((blocks, D), dtype=torch.float32, device=gy.device)
-        lib.call('dsb_layernorm_bwd', gy2, xin, weight, stats, gx, pg, pb, rows, D)
+        lib.call('dsb_layernorm_bwd', gy2, xin, weight, stats, gx, pg, pb, 0, rows, D)
         gx = gx.view(ctx.shape)
         return gx, (gx if ctx.has_res else None), pg.sum(0), pb.sum(0), None
 
@@ -802,6 +839,7 @@ class _ConvNHWC(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(x_hi, x_lo, wm, (y_hi if emit_split else y) if relu else None)
         ctx.meta = (N, H, W, C, Cout, Cin, kh, kw, cout_pad, relu, terms, bias is not None, residual is not None)
+        ctx.bias_ref = bias
         if emit_split:
             y_hi, y_lo = y_hi.view(N, H, W, cout_pad), y_lo.view(N, H, W, cout_pad)
             ctx.mark_non_differentiable(y_hi, y_lo)
@@ -817,7 +855,9 @@ class _ConvNHWC(torch.autograd.Function):
         taps = kh * kw
         gy2 = gy.reshape(N * H * W, cout_pad).contiguous()
         want_b = has_bias and ctx.needs_input_grad[2]
-        g_hi, g_lo, gb_full, g = relu_bwd_split(gy2, y if relu else None, want_b, need_g=has_res and relu)
+        b_slot = _grad_slot(ctx.bias_ref) if (want_b and Cout == cout_pad) else None
+        g_hi, g_lo, gb_full, g = relu_bwd_split(gy2, y if relu else None, want_b, need_g=has_res and relu,
+                                                bias_grad_out=b_slot)
         gx = gw = gb = gres = None
         if has_res:
             gres = (g if relu else gy2).view(N, H, W, cout_pad)
@@ -842,7 +882,7 @@ class _ConvNHWC(torch.autograd.Function):
                      conv_h=H, conv_w=W, conv_c=C, conv_taps=taps, conv_imgs=N)
             gwm = part[:Cout]
             gw = gwm.view(Cout, kh, kw, C)[..., :Cin].permute(0, 3, 1, 2).contiguous()
-        if want_b:
+        if want_b and gb_full is not None:
             gb = gb_full[:Cout]
         return gx, gw, gb, gres, None, None, None
 

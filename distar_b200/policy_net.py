@@ -72,7 +72,15 @@ class Net:
     def __init__(self, P: Dict[str, Tensor], spatial_x: int, spatial_y: int, temperature: float = 1.0,
                  terms: int = 3, rng: str = 'cuda'):
         self.P, self.W, self.H, self.T, self.terms, self.rng = P, spatial_x, spatial_y, temperature, terms, rng
+        self.bad_input_flag: Optional[Tensor] = None      # device int32[1]: set by kernels that meet an invalid input
         set_library_precision()
+
+    def raise_on_bad_input(self) -> None:
+        """entity_encoder.py:69-72 raises on a negative categorical id.  The kernels only record it (one device flag for
+        the whole forward) so the check costs a single host read at the end instead of one pipeline drain per chunk."""
+        if self.bad_input_flag is not None and int(self.bad_input_flag.item()) != 0:
+            self.bad_input_flag.zero_()
+            raise RuntimeError('negative categorical id in an entity field')
 
     # -------------------------------------------------------------------------------------- primitives
     def fc(self, name: str, x: Tensor, relu: bool = False, split: bool = False) -> Tensor:
@@ -174,7 +182,9 @@ class Net:
         w_pad = F.pad(w, (0, 1024 - w.shape[1]))
         E = entity_info_E = e['x'].shape[1]
         mask = torch.arange(E, device=e['x'].device).unsqueeze(0) < entity_num.unsqueeze(1)
-        split = ops.entity_features_split(e, ENTITY_FIELDS)
+        if self.bad_input_flag is None and e['x'].is_cuda:
+            self.bad_input_flag = torch.zeros(1, dtype=torch.int32, device=e['x'].device)
+        split = ops.entity_features_split(e, ENTITY_FIELDS, flag=self.bad_input_flag)
         if split is not None:       # K1: features expanded straight into the GEMM's bf16 operand pair
             x = ops.linear_presplit(split[0], split[1], w_pad, P[pre + 'transformer.embedding.0.bias'], True, self.terms,
                                     emit_split=True)
@@ -317,13 +327,18 @@ class Net:
         s = torch.where(normalise, s / cnt, s)
         return self.fc(pre + 'embed_fc2', self.fc(pre + 'embed_fc1', s, relu=True))
 
-    def selected_units_train(self, emb0, entity_embeddings, entity_num, selected_units_num, selected_units):
+    def selected_units_train(self, emb0, entity_embeddings, entity_num, selected_units_num, selected_units,
+                             steps: Optional[int] = None):
         """Teacher-forced pointer network (action_arg_head.py:168-216) in its step-parallel form
-        (SURVEY.md Appendix B.1): everything but the 32-wide LN-LSTM is computed for all steps at once."""
+        (SURVEY.md Appendix B.1): everything but the 32-wide LN-LSTM is computed for all steps at once.
+
+        The reference loops max(selected_units_num) times.  ``steps`` is that maximum when the caller already has it on the
+        host (the learner fetches it with an asynchronous copy queued before the encoder, so reading it here does not
+        drain the launch queue); otherwise it is read back now."""
         pre = 'policy.selected_units_head.'
         N = emb0.shape[0]
         key, valid, slot = self.su_keys(entity_embeddings, entity_num)
-        S = max(int(selected_units_num.max()), 1)
+        S = max(int(selected_units_num.max()) if steps is None else int(steps), 1)
         su = selected_units[:, :S].long()
         onehot = su.unsqueeze(-1) == slot.unsqueeze(1)                               # [N,S,E+1]
         ended = torch.cummax((su == entity_num.unsqueeze(1)).long(), dim=1)[0].bool()  # end_flag after step i
@@ -469,7 +484,7 @@ class Net:
         return action, su_num, logit, extra
 
     def policy_train(self, lstm_out, entity_embeddings, map_skip, scalar_context, entity_num, action_info,
-                     selected_units_num):
+                     selected_units_num, su_steps: Optional[int] = None):
         """model/policy.py:50-73."""
         logit, action = {}, {}
         logit['action_type'], action['action_type'], emb = self.action_type_head(
@@ -479,7 +494,7 @@ class Net:
         logit['queued'], action['queued'], emb = self.arg_head('policy.queued_head.', emb, 2, True,
                                                                action_info['queued'])
         logit['selected_units'], emb, su_num = self.selected_units_train(
-            emb, entity_embeddings, entity_num, selected_units_num, action_info['selected_units'])
+            emb, entity_embeddings, entity_num, selected_units_num, action_info['selected_units'], su_steps)
         action['selected_units'] = None   # the reference returns None here (action_arg_head.py:166,314)
         logit['target_unit'], action['target_unit'] = self.target_unit_head(
             emb, entity_embeddings, entity_num, action_info['target_unit'])

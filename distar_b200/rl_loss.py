@@ -59,6 +59,64 @@ def _merge(a, b):
     return out
 
 
+class LazyScalars(dict):
+    """dict of logged scalars whose values are still on their way from the device.
+
+    The reference returns ``.item()`` floats (rl_loss.py:40-47 / as_rl_utils); fetching them synchronises host and
+    device.  Here all of them travel in one asynchronous copy into pinned memory and turn into floats the first time any
+    of them is read (tensor entries such as ``total_loss`` are stored directly and never wait)."""
+
+    def __init__(self, keys, stacked: torch.Tensor):
+        super().__init__()
+        self._pending_keys = list(keys)
+        if stacked.is_cuda:
+            self._host = torch.empty(stacked.shape, dtype=stacked.dtype, pin_memory=True)
+            self._host.copy_(stacked, non_blocking=True)
+            self._event = torch.cuda.Event()
+            self._event.record()
+        else:
+            self._host, self._event = stacked, None
+
+    def _settle(self):
+        if self._pending_keys is not None:
+            if self._event is not None:
+                self._event.synchronize()
+            keys, self._pending_keys = self._pending_keys, None
+            for k, v in zip(keys, self._host.tolist()):
+                dict.setdefault(self, k, v)
+
+    def __getitem__(self, k):
+        if not dict.__contains__(self, k):
+            self._settle()
+        return dict.__getitem__(self, k)
+
+    def __contains__(self, k):
+        return dict.__contains__(self, k) or (self._pending_keys is not None and k in self._pending_keys)
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+    def keys(self):
+        self._settle()
+        return dict.keys(self)
+
+    def items(self):
+        self._settle()
+        return dict.items(self)
+
+    def values(self):
+        self._settle()
+        return dict.values(self)
+
+    def __iter__(self):
+        self._settle()
+        return dict.__iter__(self)
+
+    def __len__(self):
+        self._settle()
+        return dict.__len__(self)
+
+
 class ReinforcementLoss:
     def __init__(self, learner_cfg: dict = None, player_id: str = 'MP0') -> None:
         self.cfg = _merge(_DEFAULTS, learner_cfg if learner_cfg is not None else USER_LEARNER_CFG)
@@ -118,7 +176,11 @@ class ReinforcementLoss:
             return x if act_mask[h] is None else x * act_mask[h]
 
         # as_rl_utils.py:157-312 — every scan in one launch
-        gam = torch.tensor([float(self.gammas['baseline'][f]) for f in fields], device=keep.device)
+        gkey = (tuple(fields), keep.device)
+        if getattr(self, '_gam_key', None) != gkey:          # cached: building it is a (synchronising) host->device copy
+            self._gam = torch.tensor([float(self.gammas['baseline'][f]) for f in fields], device=keep.device)
+            self._gam_key = gkey
+        gam = self._gam
         vt, up, td = ops.return_scan(torch.stack([reward[f].float() for f in fields]),
                                      torch.stack([values[f] for f in fields]),
                                      torch.stack([rho[h] for h in HEADS]), gam, 0.8)
@@ -189,9 +251,9 @@ class ReinforcementLoss:
             total = total_critic
         else:
             total = total_pg + total_upgo + total_critic + total_ent + total_kl + at_kl
-        # one device->host copy for every logged scalar
+        # one device->host copy for every logged scalar, and it is not waited for here: the values materialise on first
+        # access, so backward can be queued behind the forward pass without draining the launch queue in between
         keys = list(log.keys())
-        vals = torch.stack([log[k].detach().float() for k in keys]).tolist()
-        out = dict(zip(keys, vals))
+        out = LazyScalars(keys, torch.stack([log[k].detach().float() for k in keys]))
         out['total_loss'] = total
         return out

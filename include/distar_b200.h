@@ -141,10 +141,11 @@ int dsb_split_bf16(const float* x, void* hi, void* lo, int64_t n, dsb_stream_t s
 /* ---- ReLU backward + bf16 split + bias gradient in one pass ----
  * g = gy * (y > 0) (y NULL: g = gy; y may be fp32 or, with y_is_bf16, the bf16 hi half of the ReLU output); hi/lo receive the split of g, g_out (optional) g itself, colsum (optional)
  * per-block partial column sums [dsb_relu_bwd_split_blocks(rows, N), N] whose sum over blocks is the bias gradient.
- * hi/lo (together) and g_out may each be NULL when that output is not wanted. */
+ * With colsum_atomic != 0, colsum is instead a [N] vector (the bias gradient itself) that the column sums are atomically
+ * added to.  hi/lo (together) and g_out may each be NULL when that output is not wanted. */
 int dsb_relu_bwd_split_blocks(int64_t rows, int N);
 int dsb_relu_bwd_split(const float* gy, const void* y, int y_is_bf16, float* g_out, void* hi, void* lo, float* colsum,
-                       int64_t rows, int N, dsb_stream_t stream);
+                       int colsum_atomic, int64_t rows, int N, dsb_stream_t stream);
 
 /* ---- tcgen05 GEMM family  (fc_block nn_module.py:231-270; attention module_utils.py:88-111; their backward) ----
  * dsb_gemm_bf16_split:  C[M,N] = act( A[M,K] . W[N,K]^T + bias[N] ),  A and W as bf16 (hi, lo) pairs, K contiguous,
@@ -209,13 +210,14 @@ int dsb_attn_softmax_bwd(const void* p_hi, const void* p_lo, const float* dp, co
  * y[r] = LN(x[r] (+ residual[r])) * gamma + beta over D = 128/256/384/512/1536 features, eps as nn.LayerNorm.
  * sum_out (optional, only with residual) receives x + residual (the LayerNorm input the backward needs);
  * y_hi / y_lo (optional) receive the bf16 split of y for a following tensor-core GEMM; stats [rows, 2] = (mean, rstd).
- * Backward: gx = dL/d(LN input); pgamma / pbeta are per-block partial sums [dsb_layernorm_bwd_blocks(rows), D]. */
+ * Backward: gx = dL/d(LN input); pgamma / pbeta are per-block partial sums [dsb_layernorm_bwd_blocks(rows), D], or with
+ * atomic != 0 the [D] gradients of gamma / beta themselves, which the kernel adds to atomically. */
 int dsb_layernorm_supported(int D);
 int dsb_layernorm_fwd(const float* x, const float* residual, const float* gamma, const float* beta, float* sum_out,
                       float* y, void* y_hi, void* y_lo, float* stats, int64_t rows, int D, float eps, dsb_stream_t stream);
 int dsb_layernorm_bwd_blocks(int64_t rows);
 int dsb_layernorm_bwd(const float* gy, const float* xin, const float* gamma, const float* stats, float* gx, float* pgamma,
-                      float* pbeta, int64_t rows, int D, dsb_stream_t stream);
+                      float* pbeta, int atomic, int64_t rows, int D, dsb_stream_t stream);
 
 /* ---- fused LayerNorm-LSTM cell  (LayerNormLSTMCell.forward, model/lstm.py:138-153, after the two matmuls) ----
  * ig [B,4H] = LN_i(x W_ih^T), hg [B,4H] = h W_hh^T (raw), c_in [B,H]; gate order in/forget/cell/out.

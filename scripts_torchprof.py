@@ -22,3 +22,23 @@ tot = sum(v[1] for v in agg.values())
 print('total device us', tot, 'kernels', sum(v[0] for v in agg.values()))
 for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:70]:
     print('%10.0f us %5.1f%% n=%6d %s' % (t, 100 * t / tot, n, k))
+# ---- where does the GPU idle?  gaps between consecutive kernels, attributed to the kernel that ends the gap
+evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e.time_range.start)
+gap_by = collections.defaultdict(lambda: [0, 0.0])
+end = evs[0].time_range.end
+t_first = evs[0].time_range.start
+timeline = []
+for e in evs[1:]:
+    g = e.time_range.start - end
+    if g > 2:
+        gap_by[e.name[:90]][0] += 1; gap_by[e.name[:90]][1] += g
+        timeline.append((e.time_range.start - t_first, g, e.name[:60]))
+    end = max(end, e.time_range.end)
+print('span us', end - t_first, 'idle us', sum(v[1] for v in gap_by.values()))
+for k, (n, t) in sorted(gap_by.items(), key=lambda x: -x[1][1])[:25]:
+    print('%9.0f us idle before n=%5d %s' % (t, n, k))
+# idle per 20 ms window of the step
+win = collections.defaultdict(float)
+for t, g, _ in timeline:
+    win[int(t // 20000)] += g
+print('idle ms per 20 ms window:', ' '.join('%d:%.1f' % (w, win[w] / 1e3) for w in sorted(win)))

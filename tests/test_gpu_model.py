@@ -172,3 +172,31 @@ def test_pointer_sampling_device_rng_is_consistent(sd):
             assert int(su[n, k - 1].item()) == int(en[n].item())          # the end token closes the selection
             picked = su[n, :k - 1].tolist()
             assert len(set(picked)) == len(picked) and all(p < int(en[n].item()) for p in picked)
+
+
+def test_negative_entity_id_raises(model):
+    """entity_encoder.py:69-72: a negative categorical id is an error.  The sampling / teacher entry points raise before
+    returning; the learner forward records it and RLLearner._train raises before the optimiser step."""
+    from distar_b200.learner import RLLearner
+    case = to_dev(G.infer_case())
+    case['entity_info'] = dict(case['entity_info'])
+    bad = case['entity_info']['unit_type'].clone()
+    bad[0, 0] = -3
+    case['entity_info']['unit_type'] = bad
+    with pytest.raises(RuntimeError, match='negative categorical id'):
+        with torch.no_grad():
+            model.compute_logp_action(**case)
+    data = to_dev(G.rl_case())
+    data['entity_info'] = dict(data['entity_info'])
+    bad = data['entity_info']['unit_type'].clone()
+    bad[1, 2] = -1
+    data['entity_info']['unit_type'] = bad
+    learner = RLLearner(model, 'MP0', None, lr=1e-5, max_norm=1.0, distributed=False)
+    before = model.flat_param.clone()
+    with pytest.raises(RuntimeError, match='negative categorical id'):
+        learner._train(data)
+    assert torch.equal(before, model.flat_param)           # raised before any weight moved
+    # and a clean batch still trains afterwards
+    log = learner._train(to_dev(G.rl_case()))
+    assert abs(float(log['total_loss'])) < 1e6 and log['kl/total'] == log['kl/total']
+    model.load_state_dict(init_state_dict(seed=G.WEIGHT_SEED, baselines=G.BASELINES))

@@ -225,10 +225,10 @@ def kernel_rooflines(dev, peaks):
         a_hi, a_lo = ops.split_bf16(a)
         w_hi, w_lo = ops.split_bf16(w)
         c = torch.empty(M, Nn, device=dev)
-        for terms, bn in ((3, 0), (3, 128), (1, 0)):
+        for terms, bn, mc in ((3, 0, 1), (3, 128, 1), (1, 0, 1), (3, 256, 4), (3, 128, 4), (1, 256, 4)):
             def run():
                 _lib.gemm_ex(a_hi=a_hi, a_lo=a_lo, b_hi=w_hi, b_lo=w_lo, bias=b, alpha=1.0, relu=1, terms=terms, c=c, m=M,
-                             n=Nn, k=K, batch=1, inner=1, splits=1, bn=bn)
+                             n=Nn, k=K, batch=1, inner=1, splits=1, bn=bn, mc=mc)
             for _ in range(3):
                 run()
             torch.cuda.synchronize()
@@ -245,12 +245,12 @@ def kernel_rooflines(dev, peaks):
             dt = s.elapsed_time(e) / reps / 1e3
             flops = 2.0 * M * K * Nn * terms
             ach = flops / dt / 1e12
-            key = 'entity_mlp_gemm_terms%d' % terms + ('_bn%d' % bn if bn else '') + tag
+            key = 'entity_mlp_gemm_terms%d' % terms + ('_bn%d' % bn if bn else '') + ('_pair' if mc == 4 else '') + tag
             out[key] = {
                 'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
                 'frac': ach / peaks['bf16_tflops'], 'traffic': NCU_DRAM_BYTES.get(key), 'us_per_launch': dt * 1e6,
-                'shape': 'M=%d K=%d N=%d, %d bf16 MMA terms (tensor-core flops counted), tile 128x%s' % (
-                    M, K, Nn, terms, bn if bn else 'auto(256)'),
+                'shape': 'M=%d K=%d N=%d, %d bf16 MMA terms (tensor-core flops counted), tile %sx%s' % (
+                    M, K, Nn, terms, '256(CTA pair)' if mc == 4 else '128', bn if bn else 'auto(256)'),
                 'peak_source': peaks['source']}
         del a, a_hi, a_lo, c
     return out

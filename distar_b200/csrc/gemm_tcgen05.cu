@@ -26,6 +26,7 @@
 //   warps 2..5  epilogue     : tcgen05.ld 32x32b -> alpha, +bias, ReLU -> swizzled smem box -> TMA store of fp32 C
 //               (optional bf16 hi/lo split of C for a following GEMM)
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -34,13 +35,19 @@ constexpr int BM = 128, BK = 64;                        // BN (64, 128 or 256) i
 constexpr int kAccStages = 2;
 constexpr int kTileBytes = BM * BK * 2;                 // 16 KiB: one 128x64 bf16 operand tile (B tiles use BN*128 B of it)
 constexpr int kStoreBufBytes = 32 * 128;                // one 32-row x 32-col fp32 staging box (128 B rows, SWIZZLE_128B)
-constexpr int kStoreBytes = 8 * kStoreBufBytes;         // 8 epilogue warps x one staging box each
+constexpr int kStoreBytes = 8 * kStoreBufBytes;         // 8 epilogue warps x one staging box each (x2 in CTA-pair mode)
 // per-BN shared-memory plan: stage = A_hi | A_lo | B_hi | B_lo; B slots are 16 KiB (BN <= 128) or 32 KiB (BN = 256)
-template <int BN> struct Plan {
-    static constexpr int kBSlot = BN > 128 ? BN * 128 : kTileBytes;
+// MC = 4 (CTA pair, cta_group::2 MMAs): each CTA stages only its half of every B tile, which leaves room for a deeper ring.
+// The shared memory that frees goes to a second staging box per epilogue warp: with one box every 32x32 block of the
+// epilogue waits for the previous TMA store to drain (the measured limiter of the single-CTA kernel: the 1-term product is
+// no faster than ~0.7x the 3-term one), with two the store of block i overlaps the conversion of block i+1.
+template <int BN, int MC = 1> struct Plan {
+    static constexpr int kBSlot = MC == 4 ? BN * 64 : (BN > 128 ? BN * 128 : kTileBytes);
     static constexpr int kStageBytes = 2 * kTileBytes + 2 * kBSlot;
-    static constexpr int kStages = BN > 128 ? 2 : 3;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kStages = MC == 4 ? (BN > 128 ? 2 : 3) : (BN > 128 ? 2 : 3);
+    static constexpr int kStoreBufs = MC == 4 ? 2 : 1;
+    static constexpr int kStoreTotal = kStoreBufs * kStoreBytes;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStoreTotal + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 constexpr int kEpiWarps = 8;                            // two epilogue warps per scheduler: the epilogue is issue-bound
 constexpr int kThreads = (2 + kEpiWarps) * 32;          // 320
@@ -95,6 +102,31 @@ __device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* map, uint64_t*
         "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask) : "memory");
 }
+// ---- CTA-pair (cta_group::2) plumbing: barriers live in the leader CTA (rank 0) and are addressed through the cluster
+// window (mapa); loads issued by either CTA complete on the leader's barrier.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_addr, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint32_t bar_addr, void* dst, int c0, int c1, int c2,
+                                                 int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -104,10 +136,14 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1, bool commit = true) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    if (commit) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int kPending>
+__device__ __forceinline__ void tma_store_wait_read() {      // at most kPending store groups may still be reading smem
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
 }
 // split-K accumulation: the copy engine adds the fp32 box into global memory (no partial buffers, no reduce pass)
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
@@ -144,9 +180,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
 }
 // cute::UMMA::InstrDescriptor: c_format F32=1 [4,6), a/b_format BF16=1 [7,10)/[10,13), a_major [15], b_major [16]
 // (0 = K, 1 = MN), n_dim = N>>3 [17,23), m_dim = M>>4 [24,29).
-__device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn, int bn) {
+__device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn, int bn, int m = BM) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-           ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+           ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -157,6 +193,21 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// CTA-pair MMA: one instruction drives the tensor cores of both SMs (M = 256: each CTA's 128 rows of A from its own shared
+// memory, the N columns of B split half / half between the two CTAs' shared memories, accumulators in each CTA's TMEM).
+__device__ __forceinline__ void umma_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {      // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -196,6 +247,7 @@ struct GemmParams {
     int64_t ldc;             // row stride (elements) of c_hi / c_lo
     int N, terms, relu, accumulate;
     int store_c;             // 0: only the bf16 (hi, lo) pair is written (no fp32 C)
+    int debug;               // DEV ONLY (env DSB_GEMM_DEBUG): 1 = skip global stores, 2 = skip MMAs, 4 = skip operand loads
     int num_m, num_n, num_k; // tiles per (batch, split); k blocks per split
     int batch, inner, splits;
     int c_row_outer, c_row_inner, c_row_split, c_col_base, c_col_inner;
@@ -214,7 +266,7 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const GemmParams& p, 
     const int num_mu = (MC == 1) ? p.num_m : (p.num_m + 1) / 2;
     int m_i = r % num_mu;
     r /= num_mu;
-    if (MC == 2) m_i = 2 * m_i + rank;
+    if (MC != 1) m_i = 2 * m_i + rank;
     t.valid = m_i < p.num_m;
     t.s = r % p.splits;
     t.b = r / p.splits;
@@ -232,11 +284,47 @@ __device__ __forceinline__ void tap_offset(int tap, int taps, int& dy, int& dx) 
 // mn0 = first row (A) / column (B) of the output tile this operand tile feeds, kg = first reduction index, width = 128
 // for A, BN for B.  mc_rank >= 0: this is the B operand of a 2-CTA cluster: load only this CTA's half of the tile and
 // multicast it to both CTAs (the other half arrives from the sibling).
+// pair_bar != 0 (CTA pair): every load completes on the leader's barrier `pair_bar` (cluster address); for the B operand
+// (mc_rank >= 0) this CTA loads only its half of the tile, into ITS OWN slot at offset 0.
 __device__ __forceinline__ void load_operand(const CUtensorMap* map, uint64_t* bar, unsigned char* dst,
                                              const OperandMap& o, const TileCoord& t, int mn0, int kg, int width,
-                                             int mc_rank = -1) {
-    const bool mc = mc_rank >= 0;
+                                             int mc_rank = -1, uint32_t pair_bar = 0) {
     const int halves = width / 64;
+    if (pair_bar) {
+        const bool half = mc_rank >= 0;
+        const int h_lo = half ? mc_rank * (halves / 2) : 0, h_hi = half ? (mc_rank + 1) * (halves / 2) : halves;
+        if (o.conv) {
+            const int cblocks = o.C / 64;
+            if (!o.mn_major) {
+                const int pix0 = mn0, hw = o.H * o.W;
+                const int img = pix0 / hw, y0 = (pix0 - img * hw) / o.W;
+                const int kb = kg / 64, tap = kb / cblocks, cb = kb - tap * cblocks;
+                int dy, dx;
+                tap_offset(tap, o.taps, dy, dx);
+                tma_load_4d_pair(map, pair_bar, dst, cb * 64, dx, y0 + dy, img);
+            } else {
+                const int hw = o.H * o.W;
+                const int img = kg / hw, y0 = (kg - img * hw) / o.W;
+                for (int h = h_lo; h < h_hi; ++h) {
+                    const int col = mn0 + 64 * h, tap = col / o.C, c = col - tap * o.C;
+                    int dy, dx;
+                    tap_offset(tap, o.taps, dy, dx);
+                    tma_load_4d_pair(map, pair_bar, dst + (h - h_lo) * (kTileBytes / 2), c, dx, y0 + dy, img);
+                }
+            }
+            return;
+        }
+        const int col0 = o.col_base + t.bi * o.col_inner;
+        const int row0 = o.row_outer * t.bo + o.row_inner * t.bi;
+        if (!o.mn_major) {      // box {64 k, 128 rows (A) or width/2 rows (B half)}
+            tma_load_2d_pair(map, pair_bar, dst, col0 + kg, row0 + mn0 + (half ? mc_rank * (width / 2) : 0));
+        } else {
+            for (int h = h_lo; h < h_hi; ++h)
+                tma_load_2d_pair(map, pair_bar, dst + (h - h_lo) * (kTileBytes / 2), col0 + mn0 + 64 * h, row0 + kg);
+        }
+        return;
+    }
+    const bool mc = mc_rank >= 0;
     const int h_lo = mc ? mc_rank * (halves / 2) : 0, h_hi = mc ? (mc_rank + 1) * (halves / 2) : halves;
     if (o.conv) {
         const int cblocks = o.C / 64;
@@ -288,9 +376,11 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024 B alignment
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr int kStages = Plan<BN>::kStages, kStageBytes = Plan<BN>::kStageBytes, kBSlot = Plan<BN>::kBSlot;
+    constexpr int kStages = Plan<BN, MC>::kStages, kStageBytes = Plan<BN, MC>::kStageBytes, kBSlot = Plan<BN, MC>::kBSlot;
+    constexpr bool kPair = MC == 4;
     unsigned char* store_bufs = smem + kStages * kStageBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(store_bufs + kStoreBytes);
+    constexpr int kStoreBufs = Plan<BN, MC>::kStoreBufs;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(store_bufs + Plan<BN, MC>::kStoreTotal);
     uint64_t* full = bars;                       // [kStages]
     uint64_t* empty = bars + kStages;            // [kStages]
     uint64_t* tmem_full = bars + 2 * kStages;    // [kAccStages]
@@ -299,7 +389,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 
     constexpr int kTmemColsAlloc = kAccStages * BN;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cta_rank = (MC == 2) ? (int)cluster_ctarank() : 0;
+    const int cta_rank = (MC != 1) ? (int)cluster_ctarank() : 0;
     // MC = 2: work items are tile pairs, distributed over clusters
     const int num_tiles = p.batch * p.splits * ((MC == 1) ? p.num_m : (p.num_m + 1) / 2) * p.num_n;
     const int work_first = (MC == 1) ? (int)blockIdx.x : (int)(blockIdx.x >> 1);
@@ -315,18 +405,29 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
         }
-        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], MC); }   // MC=2: both CTAs' MMAs release a stage
-        for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
+        // MC=2: both CTAs' MMAs release a stage.  Pair: the leader's `full` collects one expect_tx arrival per CTA, its
+        // `tmem_empty` the epilogue warps of both CTAs; `empty` / `tmem_full` get one multicast commit each.
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], kPair ? 2 : 1); mbar_init(&empty[i], MC == 2 ? 2 : 1); }
+        for (int i = 0; i < kAccStages; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], kPair ? 2 * kEpiWarps : kEpiWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // TMEM allocation is warp-collective; the same warp deallocates at the end
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_ptr)),
-                     "n"(kTmemColsAlloc) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (kPair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_ptr)),
+                         "n"(kTmemColsAlloc) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_ptr)),
+                         "n"(kTmemColsAlloc) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (MC == 2) cluster_sync_all();           // sibling barriers are initialised before any multicast can reach them
+    if (MC != 1) cluster_sync_all();           // sibling barriers are initialised before any multicast can reach them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_ptr;
 
@@ -335,32 +436,45 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx = (three ? 2 : 1) * (kTileBytes + BN * 128);
+            // bytes THIS CTA contributes to a stage (pair: its A tile + its half of the B tile)
+            const uint32_t tx = (three ? 2 : 1) * (kTileBytes + (kPair ? BN * 64 : BN * 128));
             for (int tile = work_first; tile < num_tiles; tile += work_stride) {
                 const TileCoord t = decode_tile<BN, MC>(tile, p, cta_rank);
                 for (int kb = 0; kb < num_k; ++kb) {
                     const int kg = (t.s * num_k + kb) * BK;
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char* st = smem + stage * kStageBytes;
-                    mbar_expect_tx(&full[stage], tx);
-                    load_operand(&map_a_hi, &full[stage], st, p.a, t, t.m0, kg, BM);
-                    load_operand(&map_b_hi, &full[stage], st + 2 * kTileBytes, p.b, t, t.n0, kg, BN, MC == 2 ? cta_rank : -1);
+                    uint32_t pair_bar = 0;
+                    if (p.debug & 4) {
+                        if (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&full[stage]), 0)); else mbar_arrive(&full[stage]);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
+                    if (kPair) {
+                        pair_bar = mapa_u32(smem_u32(&full[stage]), 0);     // the leader's barrier
+                        mbar_expect_tx_cluster(pair_bar, tx);
+                    } else {
+                        mbar_expect_tx(&full[stage], tx);
+                    }
+                    const int brank = MC != 1 ? cta_rank : -1;
+                    load_operand(&map_a_hi, &full[stage], st, p.a, t, t.m0, kg, BM, -1, pair_bar);
+                    load_operand(&map_b_hi, &full[stage], st + 2 * kTileBytes, p.b, t, t.n0, kg, BN, brank, pair_bar);
                     if (three) {
-                        load_operand(&map_a_lo, &full[stage], st + kTileBytes, p.a, t, t.m0, kg, BM);
-                        load_operand(&map_b_lo, &full[stage], st + 2 * kTileBytes + kBSlot, p.b, t, t.n0, kg, BN,
-                                     MC == 2 ? cta_rank : -1);
+                        load_operand(&map_a_lo, &full[stage], st + kTileBytes, p.a, t, t.m0, kg, BM, -1, pair_bar);
+                        load_operand(&map_b_lo, &full[stage], st + 2 * kTileBytes + kBSlot, p.b, t, t.n0, kg, BN, brank,
+                                     pair_bar);
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 && (!kPair || cta_rank == 0)) {
+        // ===================== MMA issuer (pair: the leader CTA only) =====================
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
         const bool a_mn = p.a.mn_major != 0, b_mn = p.b.mn_major != 0;
-        const uint32_t idesc = make_idesc(a_mn, b_mn, BN);
+        const uint32_t idesc = make_idesc(a_mn, b_mn, BN, kPair ? 2 * BM : BM);
         // descriptor start-address step (>>4) per UMMA_K: 32 B inside the swizzle row (K-major) or 16 k-rows (MN-major)
         const uint64_t a_step = a_mn ? (uint64_t)((UMMA_K * 128) >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
         const uint64_t b_step = b_mn ? (uint64_t)((UMMA_K * 128) >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
@@ -379,9 +493,18 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     const uint64_t b_hi = make_desc(sa + 2 * kTileBytes, b_mn), b_lo = make_desc(sa + 2 * kTileBytes + kBSlot, b_mn);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
+                        if (p.debug & 2) break;
                         const uint64_t ao = a_step * k, bo = b_step * k;
                         const uint32_t first = (kb | k) ? 1u : 0u;
-                        if (three) {
+                        if (kPair) {
+                            if (three) {
+                                umma_pair(d_tmem, a_lo + ao, b_hi + bo, idesc, first);
+                                umma_pair(d_tmem, a_hi + ao, b_lo + bo, idesc, 1u);
+                                umma_pair(d_tmem, a_hi + ao, b_hi + bo, idesc, 1u);
+                            } else {
+                                umma_pair(d_tmem, a_hi + ao, b_hi + bo, idesc, first);
+                            }
+                        } else if (three) {
                             umma(d_tmem, a_lo + ao, b_hi + bo, idesc, first);
                             umma(d_tmem, a_hi + ao, b_lo + bo, idesc, 1u);
                             umma(d_tmem, a_hi + ao, b_hi + bo, idesc, 1u);
@@ -389,21 +512,27 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                             umma(d_tmem, a_hi + ao, b_hi + bo, idesc, first);
                         }
                     }
-                    if (MC == 2) umma_commit_mc(&empty[stage], 3);     // the stage is shared: tell both producers
-                    else umma_commit(&empty[stage]);                    // frees this smem stage when the MMAs retire
-                    if (kb == num_k - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
+                    if (kPair) {
+                        umma_commit_pair(&empty[stage]);                        // both CTAs' producers may refill the stage
+                        if (kb == num_k - 1) umma_commit_pair(&tmem_full[acc]); // both CTAs' epilogues may read their half
+                    } else {
+                        if (MC == 2) umma_commit_mc(&empty[stage], 3);     // the stage is shared: tell both producers
+                        else umma_commit(&empty[stage]);                    // frees this smem stage when the MMAs retire
+                        if (kb == num_k - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
+                    }
                 }
                 __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
-    } else {
-        // ===================== epilogue (warps 2..5) =====================
+    } else if (warp >= 2) {
+        // ===================== epilogue (warps 2..9) =====================
         // TMEM -> registers -> (alpha, +bias, ReLU) -> swizzled smem box -> TMA store: every global write is a full,
         // coalesced 128 B line issued by the copy engine; the staging box is double buffered per warp.
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;          // warps 2..5 take the left half of the tile's columns, 6..9 the right
-        unsigned char* my_buf = store_bufs + (warp - 2) * kStoreBufBytes;
+        unsigned char* my_buf = store_bufs + (warp - 2) * kStoreBufs * kStoreBufBytes;
+        int buf_sel = 0;                           // staging boxes alternate per store group
         int it = 0;
         for (int tile = work_first; tile < num_tiles; tile += work_stride, ++it) {
             const int acc = it & 1;
@@ -422,7 +551,10 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 if (c0 == (half + 1) * (BN / 2) - 32) {   // this warp's share fully read: hand TMEM back to the MMA warp early
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    if (lane == 0) {
+                        if (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));   // the leader's MMA warp waits
+                        else mbar_arrive(&tmem_empty[acc]);
+                    }
                 }
                 // The epilogue is issue-bound (one warp per scheduler owns a 32 x BN slab), so keep it at ~2 instructions
                 // per element: bias comes in as 8 broadcast 16-byte loads, alpha/bias fold into one FFMA, ReLU is an
@@ -450,11 +582,12 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 const float floor_v = p.relu ? 0.f : -3.402823466e38f;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(fmaf(__uint_as_float(r[j]), p.alpha, v[j]), floor_v);
-                unsigned char* buf = my_buf;
                 if (p.store_c) {
+                    unsigned char* buf = my_buf + buf_sel * kStoreBufBytes;
+                    buf_sel = (buf_sel + 1) % kStoreBufs;
                     // the TMA store that last read this staging box must have finished reading it (the sibling warp on
                     // this scheduler keeps issuing meanwhile)
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    if (lane == 0) tma_store_wait_read<kStoreBufs - 1>();
                     __syncwarp();
                     const uint32_t rowbase = smem_u32(buf) + lane * 128;
 #pragma unroll
@@ -465,7 +598,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0 && t.valid) {
+                    if (lane == 0 && t.valid && !(p.debug & 1)) {
                         if (p.accumulate) tma_reduce_add_2d(&map_c, buf, c_col0 + c0, c_row0);
                         else tma_store_2d(&map_c, buf, c_col0 + c0, c_row0);
                     }
@@ -483,7 +616,9 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                         h[e] = *reinterpret_cast<const uint32_t*>(&hh);
                         l[e] = *reinterpret_cast<const uint32_t*>(&ll);
                     }
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    unsigned char* buf = my_buf + buf_sel * kStoreBufBytes;
+                    buf_sel = (buf_sel + 1) % kStoreBufs;
+                    if (lane == 0) tma_store_wait_read<kStoreBufs - 1>();
                     __syncwarp();
                     const uint32_t rowbase = smem_u32(buf) + lane * 64;
                     const uint32_t sw = (uint32_t)((lane >> 1) & 3);
@@ -497,8 +632,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0 && t.valid) {
-                        tma_store_2d(&map_c_hi, buf, c_col0 + c0, c_row0);
+                    if (lane == 0 && t.valid && !(p.debug & 1)) {
+                        tma_store_2d(&map_c_hi, buf, c_col0 + c0, c_row0, false);       // one group for the pair
                         tma_store_2d(&map_c_lo, buf + 2048, c_col0 + c0, c_row0);
                     }
                 }
@@ -510,10 +645,13 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 
     tc_fence_before();
     __syncthreads();
-    if (MC == 2) cluster_sync_all();           // no CTA exits while a sibling may still multicast into it
+    if (MC != 1) cluster_sync_all();           // no CTA exits while a sibling may still multicast into / read from it
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemColsAlloc) : "memory");
+        if (kPair)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemColsAlloc) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemColsAlloc) : "memory");
     }
 }
 
@@ -617,7 +755,7 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
         if ((rc = make_map_nhwc(&mb_lo, b_lo, g.conv_imgs, g.conv_h, g.conv_w, g.conv_c, 64 / g.conv_w))) return rc;
     } else {
         DSB_REQUIRE(g.b_cols % 8 == 0, "gemm: B row pitch must be a 16-byte multiple");
-        const int b_br = g.b_mn ? 64 : BN / MC;     // MC = 2: each CTA loads (and multicasts) half of the B rows
+        const int b_br = g.b_mn ? 64 : (MC == 1 ? BN : BN / 2);     // cluster modes: each CTA loads half of the B rows
         if ((rc = make_map(&mb_hi, g.b_hi, g.b_rows, g.b_cols, 2, b_br, 64))) return rc;
         if ((rc = make_map(&mb_lo, b_lo, g.b_rows, g.b_cols, 2, b_br, 64))) return rc;
     }
@@ -636,7 +774,7 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
     static int num_sms = 0;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_split_kernel<BN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Plan<BN>::kSmemBytes);
+                                             Plan<BN, MC>::kSmemBytes);
         if (e != cudaSuccess) { dsb::set_error("gemm smem attr: %s", cudaGetErrorString(e)); return DSB_ERR_CUDA; }
         int dev = 0;
         cudaGetDevice(&dev);
@@ -647,6 +785,8 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
     p.bias = g.bias; p.residual = g.residual; p.c_hi = (__nv_bfloat16*)g.c_hi; p.c_lo = (__nv_bfloat16*)g.c_lo;
     p.alpha = g.alpha; p.M = g.m; p.ldc = g.c_cols; p.N = g.n; p.terms = g.terms; p.relu = g.relu;
     p.accumulate = g.c_accumulate; p.store_c = g.c != nullptr;
+    static const int debug_bits = getenv("DSB_GEMM_DEBUG") ? atoi(getenv("DSB_GEMM_DEBUG")) : 0;
+    p.debug = debug_bits;
     p.num_m = num_m; p.num_n = num_n; p.num_k = g.k / (BK * splits);
     p.batch = batch; p.inner = inner; p.splits = splits;
     p.c_row_outer = g.c_row_outer; p.c_row_inner = g.c_row_inner; p.c_row_split = g.c_row_split;
@@ -657,7 +797,7 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
                      g.conv_c, g.conv_taps};
     if (MC == 1) {
         const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
-        gemm_split_kernel<BN, 1><<<grid, kThreads, Plan<BN>::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, mc_hi, mc_lo, p);
+        gemm_split_kernel<BN, 1><<<grid, kThreads, Plan<BN, 1>::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, mc_hi, mc_lo, p);
     } else {
         // clusters of two CTAs; each cluster walks pairs of vertically adjacent tiles
         const int64_t pairs = (int64_t)batch * splits * ((num_m + 1) / 2) * num_n;
@@ -665,14 +805,14 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * clusters);
         cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = Plan<BN>::kSmemBytes;
+        cfg.dynamicSmemBytes = Plan<BN, MC>::kSmemBytes;
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_split_kernel<BN, 2>, ma_hi, ma_lo, mb_hi, mb_lo, mc, mc_hi, mc_lo, p);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_split_kernel<BN, MC>, ma_hi, ma_lo, mb_hi, mb_lo, mc, mc_hi, mc_lo, p);
         if (e != cudaSuccess) { dsb::set_error("gemm cluster launch: %s", cudaGetErrorString(e)); return DSB_ERR_CUDA; }
     }
     return dsb::check_launch("gemm_split");
@@ -704,7 +844,8 @@ int launch(const dsb_gemm_args& g, cudaStream_t stream) {
         const int64_t pairs = batch * splits * ((num_m + 1) / 2) * (g.n / bn);
         mcast = (g.terms == 1 && bn >= 128 && num_m >= 2 && pairs >= 74) ? 2 : 1;
     }
-    DSB_REQUIRE(mcast == 1 || (mcast == 2 && bn >= 128), "gemm: mc must be 1 or 2 (2 needs bn >= 128)");
+    DSB_REQUIRE(mcast == 1 || ((mcast == 2 || mcast == 4) && bn >= 128), "gemm: mc must be 1, 2 or 4 (2 and 4 need bn >= 128)");
+    if (mcast == 4) return bn == 256 ? launch_bn<256, 4>(g, stream) : launch_bn<128, 4>(g, stream);
     if (mcast == 2) return bn == 256 ? launch_bn<256, 2>(g, stream) : launch_bn<128, 2>(g, stream);
     if (bn == 256) return launch_bn<256, 1>(g, stream);
     return bn == 128 ? launch_bn<128, 1>(g, stream) : launch_bn<64, 1>(g, stream);

@@ -178,9 +178,11 @@ def test_entity_attention_fwd_bwd(entity_num):
     assert gerr <= 1e-4 * qr.grad.abs().max().item(), ('bwd', gerr, qr.grad.abs().max().item())
 
 
-# ------------------------------------------------------------------------------------------ 2-CTA cluster multicast (mc=2)
-@pytest.mark.parametrize('M,N,K,bn', [(4096, 256, 256, 128), (4224, 1024, 256, 256), (1280, 256, 1024, 256), (3 * 128, 512, 128, 128)])
-def test_gemm_ex_multicast_k_major(M, N, K, bn):
+# ------------------------------------------------------------ 2-CTA clusters: TMA multicast (mc=2), cta_group::2 MMA pair (mc=4)
+@pytest.mark.parametrize('mc', [2, 4])
+@pytest.mark.parametrize('M,N,K,bn', [(4096, 256, 256, 128), (4224, 1024, 256, 256), (1280, 256, 1024, 256), (3 * 128, 512, 128, 128),
+                                      (1000, 512, 192, 256)])
+def test_gemm_ex_multicast_k_major(M, N, K, bn, mc):
     g = torch.Generator().manual_seed(M + N)
     a = torch.randn(M, K, generator=g)
     w = torch.randn(N, K, generator=g) / K ** 0.5
@@ -189,12 +191,20 @@ def test_gemm_ex_multicast_k_major(M, N, K, bn):
     w_hi, w_lo = _split(w)
     c = torch.empty(M, N, device=DEV)
     _lib.gemm_ex(a_hi=a_hi, a_lo=a_lo, b_hi=w_hi, b_lo=w_lo, bias=b.to(DEV), alpha=1.0, terms=3, c=c, m=M, n=N, k=K,
-                 batch=1, inner=1, splits=1, bn=bn, mc=2)
+                 batch=1, inner=1, splits=1, bn=bn, mc=mc)
     torch.cuda.synchronize()
     _check(c, a.double() @ w.double().t() + b.double())
+    # 1-term product and the bf16-pair epilogue through the same cluster mode
+    c_hi = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    c_lo = torch.empty_like(c_hi)
+    _lib.gemm_ex(a_hi=a_hi, a_lo=a_lo, b_hi=w_hi, b_lo=w_lo, bias=b.to(DEV), alpha=1.0, relu=1, terms=3, c=None, c_hi=c_hi,
+                 c_lo=c_lo, m=M, n=N, k=K, batch=1, inner=1, splits=1, bn=bn, mc=mc)
+    eh, el = ops.split_bf16(torch.relu(c))
+    assert torch.equal(c_hi, eh) and torch.equal(c_lo, el)
 
 
-def test_gemm_ex_multicast_mn_major_and_split_k():
+@pytest.mark.parametrize('mc', [2, 4])
+def test_gemm_ex_multicast_mn_major_and_split_k(mc):
     tokens, Nw, Kw, splits = 8192, 768, 256, 8
     g = torch.Generator().manual_seed(3)
     dy = torch.randn(tokens, Nw, generator=g)
@@ -203,12 +213,13 @@ def test_gemm_ex_multicast_mn_major_and_split_k():
     b_hi, b_lo = _split(x)
     gw = torch.zeros(Nw, Kw, device=DEV)
     _lib.gemm_ex(a_hi=a_hi, a_lo=a_lo, b_hi=b_hi, b_lo=b_lo, a_mn=1, b_mn=1, alpha=1.0, terms=3, c=gw, m=Nw, n=Kw,
-                 k=tokens, batch=1, inner=1, splits=splits, c_accumulate=1, mc=2)
+                 k=tokens, batch=1, inner=1, splits=splits, c_accumulate=1, mc=mc)
     torch.cuda.synchronize()
     _check(gw, dy.double().t() @ x.double(), tol=5e-5)
 
 
-def test_gemm_ex_multicast_batched_attention():
+@pytest.mark.parametrize('mc', [2, 4])
+def test_gemm_ex_multicast_batched_attention(mc):
     obs, S, H, D = 5, 512, 2, 128
     g = torch.Generator().manual_seed(4)
     qkv = torch.randn(obs * S, 3 * H * D, generator=g)
@@ -216,7 +227,7 @@ def test_gemm_ex_multicast_batched_attention():
     sc = torch.empty(obs * H * S, S, device=DEV)
     _lib.gemm_ex(a_hi=q_hi, a_lo=q_lo, b_hi=q_hi, b_lo=q_lo, alpha=1.0 / D ** 0.5, terms=3, c=sc, m=S, n=S, k=D,
                  batch=obs * H, inner=H, splits=1, a_col_base=0, a_col_inner=D, a_row_outer=S,
-                 b_col_base=H * D, b_col_inner=D, b_row_outer=S, c_row_outer=H * S, c_row_inner=S, mc=2)
+                 b_col_base=H * D, b_col_inner=D, b_row_outer=S, c_row_outer=H * S, c_row_inner=S, mc=mc)
     torch.cuda.synchronize()
     x = qkv.double().view(obs, S, 3, H, D)
     ref = torch.einsum('oqhd,okhd->ohqk', x[:, :, 0], x[:, :, 1]) / D ** 0.5
@@ -226,6 +237,6 @@ def test_gemm_ex_multicast_batched_attention():
     ctx = torch.empty(obs * S, H * D, device=DEV)
     _lib.gemm_ex(a_hi=p_hi, a_lo=p_lo, b_hi=q_hi, b_lo=q_lo, b_mn=1, alpha=1.0, terms=3, c=ctx, m=S, n=D, k=S,
                  batch=obs * H, inner=H, splits=1, a_row_outer=H * S, a_row_inner=S,
-                 b_col_base=2 * H * D, b_col_inner=D, b_row_outer=S, c_row_outer=S, c_col_inner=D, mc=2)
+                 b_col_base=2 * H * D, b_col_inner=D, b_row_outer=S, c_row_outer=S, c_col_inner=D, mc=mc)
     torch.cuda.synchronize()
     _check(ctx.view(obs, S, H, D), torch.einsum('ohqk,okhd->oqhd', p.double().view(obs, H, S, S), x[:, :, 2]))

@@ -37,7 +37,7 @@ def parse():
     ap.add_argument('--encoder-chunk', type=int, default=264)
     ap.add_argument('--terms', type=int, default=3, help='tensor-core products per GEMM: 3 = fp32-class (parity), 1 = bf16')
     ap.add_argument('--no-checkpoint', action='store_true', help='keep encoder activations instead of recomputing them')
-    ap.add_argument('--keep-chunks', type=int, default=13,
+    ap.add_argument('--keep-chunks', type=int, default=16,
                     help='number of encoder chunks whose entity-transformer activations are kept (not recomputed)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')

@@ -127,6 +127,15 @@ __device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint32_
         "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// L2 prefetch of a box (no shared-memory destination, no barrier): issued one tile ahead for the streamed A operand so the
+// real load later is an L2 hit - the kernel is bound by the latency of its (at most 2-3 stage) operand ring, not by bandwidth
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -247,6 +256,7 @@ struct GemmParams {
     int64_t ldc;             // row stride (elements) of c_hi / c_lo
     int N, terms, relu, accumulate;
     int store_c;             // 0: only the bf16 (hi, lo) pair is written (no fp32 C)
+    int prefetch;            // L2-prefetch the next tile's A operand
     int debug;               // DEV ONLY (env DSB_GEMM_DEBUG): 1 = skip global stores, 2 = skip MMAs, 4 = skip operand loads
     int num_m, num_n, num_k; // tiles per (batch, split); k blocks per split
     int batch, inner, splits;
@@ -367,6 +377,28 @@ __device__ __forceinline__ void load_operand(const CUtensorMap* map, uint64_t* b
     }
 }
 
+// A-operand tile of (t, k block kg) -> L2, same addressing as load_operand's A cases
+__device__ __forceinline__ void prefetch_a(const CUtensorMap* map, const OperandMap& o, const TileCoord& t, int kg) {
+    if (o.conv) {
+        if (o.mn_major) return;
+        const int cblocks = o.C / 64, hw = o.H * o.W;
+        const int img = t.m0 / hw, y0 = (t.m0 - img * hw) / o.W;
+        const int kb = kg / 64, tap = kb / cblocks, cb = kb - tap * cblocks;
+        int dy, dx;
+        tap_offset(tap, o.taps, dy, dx);
+        tma_prefetch_4d(map, cb * 64, dx, y0 + dy, img);
+        return;
+    }
+    const int col0 = o.col_base + t.bi * o.col_inner;
+    const int row0 = o.row_outer * t.bo + o.row_inner * t.bi;
+    if (!o.mn_major) {
+        tma_prefetch_2d(map, col0 + kg, row0 + t.m0);
+    } else {
+        tma_prefetch_2d(map, col0 + t.m0, row0 + kg);
+        tma_prefetch_2d(map, col0 + t.m0 + 64, row0 + kg);
+    }
+}
+
 template <int BN, int MC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -440,8 +472,15 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             const uint32_t tx = (three ? 2 : 1) * (kTileBytes + (kPair ? BN * 64 : BN * 128));
             for (int tile = work_first; tile < num_tiles; tile += work_stride) {
                 const TileCoord t = decode_tile<BN, MC>(tile, p, cta_rank);
+                const bool pf = p.prefetch && tile + work_stride < num_tiles;
+                const TileCoord tn = decode_tile<BN, MC>(pf ? tile + work_stride : tile, p, cta_rank);
                 for (int kb = 0; kb < num_k; ++kb) {
                     const int kg = (t.s * num_k + kb) * BK;
+                    if (pf && (tn.m0 != t.m0 || tn.b != t.b || tn.s != t.s)) {      // next tile's A block -> L2, one tile ahead
+                        const int kgn = (tn.s * num_k + kb) * BK;
+                        prefetch_a(&map_a_hi, p.a, tn, kgn);
+                        if (three) prefetch_a(&map_a_lo, p.a, tn, kgn);
+                    }
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char* st = smem + stage * kStageBytes;
                     uint32_t pair_bar = 0;
@@ -787,6 +826,8 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
     p.accumulate = g.c_accumulate; p.store_c = g.c != nullptr;
     static const int debug_bits = getenv("DSB_GEMM_DEBUG") ? atoi(getenv("DSB_GEMM_DEBUG")) : 0;
     p.debug = debug_bits;
+    static const int no_prefetch = getenv("DSB_GEMM_NO_PREFETCH") ? atoi(getenv("DSB_GEMM_NO_PREFETCH")) : 0;   // DEV ONLY (A/B)
+    p.prefetch = !no_prefetch && g.terms == 1;   // measured: -21 % time for 1-term products, nothing (or worse) for 3-term ones
     p.num_m = num_m; p.num_n = num_n; p.num_k = g.k / (BK * splits);
     p.batch = batch; p.inner = inner; p.splits = splits;
     p.c_row_outer = g.c_row_outer; p.c_row_inner = g.c_row_inner; p.c_row_split = g.c_row_split;

@@ -575,6 +575,65 @@ class _SplitLinear(torch.autograd.Function):
         return gx, gw, gb, None, None, None, None, None
 
 
+class _FFN(torch.autograd.Function):
+    """m = relu(relu(x W1^T + b1) W2^T + b2): the transformer MLP (module_utils.py:130-139) as one node that does NOT keep its
+    hidden activation h [tokens, 4d] for backward - h is the largest tensor a transformer layer saves (as large as the
+    attention probabilities) and costs one 3-term GEMM to rebuild, far cheaper per byte than re-running the whole encoder
+    chunk, which is what running out of HBM otherwise forces (model.py: keep_chunks)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, terms, x_hi, x_lo):
+        K = x.shape[-1]
+        a_hi, a_lo = x_hi.reshape(-1, K), x_lo.reshape(-1, K)
+        w1_hi, w1_lo = split_bf16(w1)
+        w2_hi, w2_lo = split_bf16(w2)
+        _, h_hi, h_lo = gemm_split(a_hi, a_lo, w1_hi, w1_lo, b1, True, terms, want_split='only')
+        m = gemm_split(h_hi, h_lo, w2_hi, w2_lo, b2, True, terms)
+        ctx.save_for_backward(a_hi, a_lo, w1_hi, w1_lo, w2_hi, w2_lo, m)
+        ctx.refs = (w1, b1, w2, b2)
+        ctx.terms, ctx.xshape = terms, x.shape
+        return m.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        a_hi, a_lo, w1_hi, w1_lo, w2_hi, w2_lo, m = ctx.saved_tensors
+        w1, b1, w2, b2 = ctx.refs
+        terms = ctx.terms
+        gy2 = gy.reshape(m.shape).contiguous()
+        M = gy2.shape[0]
+        H, K = w1_hi.shape
+        dev = gy2.device
+        # second layer
+        g2_hi, g2_lo, gb2, _ = relu_bwd_split(gy2, m, ctx.needs_input_grad[4], bias_grad_out=_grad_slot(b2))
+        _, h_hi, h_lo = gemm_split(a_hi, a_lo, w1_hi, w1_lo, b1, True, terms, want_split='only')      # rebuild h
+        gw2 = weight_grad(g2_hi, g2_lo, h_hi, h_lo, terms, accumulate_into=_grad_slot(w2)) if ctx.needs_input_grad[3] else None
+        dh = torch.empty((M, H), dtype=torch.float32, device=dev)
+        _gemm_ex(a_hi=g2_hi, a_lo=g2_lo, b_hi=w2_hi, b_lo=w2_lo, b_mn=1, alpha=1.0, terms=terms, c=dh, m=M, n=H, k=w2_hi.shape[0],
+                 batch=1, inner=1, splits=1)
+        del g2_hi, g2_lo
+        # first layer
+        g1_hi, g1_lo, gb1, _ = relu_bwd_split(dh, h_hi, ctx.needs_input_grad[2], bias_grad_out=_grad_slot(b1))
+        del dh, h_hi, h_lo
+        gw1 = weight_grad(g1_hi, g1_lo, a_hi, a_lo, terms, accumulate_into=_grad_slot(w1)) if ctx.needs_input_grad[1] else None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty((M, K), dtype=torch.float32, device=dev)
+            _gemm_ex(a_hi=g1_hi, a_lo=g1_lo, b_hi=w1_hi, b_lo=w1_lo, b_mn=1, alpha=1.0, terms=terms, c=gx, m=M, n=K, k=H, batch=1,
+                     inner=1, splits=1)
+            gx = gx.view(ctx.xshape)
+        return gx, gw1, gb1, gw2, gb2, None, None, None
+
+
+def ffn(x: torch.Tensor, w1, b1, w2, b2, terms: int = 3) -> torch.Tensor:
+    """relu(fc2(relu(fc1(x)))) of a transformer layer; on the GPU (x carrying its bf16 pair) through _FFN."""
+    sp = getattr(x, '_dsb_split', None)
+    H, K = w1.shape
+    if (x.is_cuda and sp is not None and sp[0].shape == x.shape and gemm_eligible(H, K) and gemm_eligible(w2.shape[0], H)
+            and K % 128 == 0 and w2.shape[0] % 128 == 0 and (x.numel() // K) % 64 == 0 and x.numel() // K >= 128):
+        return _FFN.apply(x, w1, b1, w2, b2, terms, sp[0], sp[1])
+    return linear(linear(x, w1, b1, True, terms, emit_split='only' if x.is_cuda else False), w2, b2, True, terms)
+
+
 class _EntityAttention(torch.autograd.Function):
     """softmax(Q K^T / sqrt(d) + key mask) V for all (observation, head) pairs of the entity transformer
     (model/module_utils.py:95-110), forward and backward, as batched tcgen05 GEMMs that address Q, K, V inside the

@@ -199,7 +199,8 @@ class Net:
             qkv = self.fc(lp + '.attention.attention_pre', x, split='only')
             a = self.fc(lp + '.attention.project', ops.entity_attention(qkv, entity_num, 2, 128))
             x = self.ln(lp + '.layernorm1', x, residual=a, split=True)
-            m = self.fc(lp + '.mlp.1', self.fc(lp + '.mlp.0', x, relu=True, split='only'), relu=True)
+            m = ops.ffn(x, P[lp + '.mlp.0.0.weight'], P[lp + '.mlp.0.0.bias'], P[lp + '.mlp.1.0.weight'],
+                        P[lp + '.mlp.1.0.bias'], self.terms)
             x = self.ln(lp + '.layernorm2', x, residual=m, split=(i < 2))
         x = torch.relu(x)
         entity_embeddings = self.fc(pre + 'entity_fc', x, relu=True)

@@ -9,7 +9,7 @@ from distar_b200.synth import synth_rl_batch, tree_map
 B, T = int(sys.argv[1]), int(sys.argv[2])
 dev = torch.device('cuda', 0)
 model = Model({'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': ['winloss']}}, use_value_network=True, seed=0,
-              encoder_chunk=264, checkpoint_encoder=True, keep_chunks=13).cuda()
+              encoder_chunk=264, checkpoint_encoder=True, keep_chunks=16).cuda()
 learner = RLLearner(model)
 data = tree_map(lambda t: t.to(dev), synth_rl_batch(B, T, seed=0))
 learner._train(data); torch.cuda.synchronize()

@@ -8,7 +8,7 @@ from distar_b200.model import Model
 from distar_b200.synth import synth_rl_batch, tree_map
 B, T = int(sys.argv[1]), int(sys.argv[2]); chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 264
 dev = torch.device('cuda', 0)
-model = Model({'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': ['winloss']}}, use_value_network=True, seed=0, encoder_chunk=chunk, checkpoint_encoder=True, keep_chunks=int(os.environ.get('KEEP', 13))).cuda()
+model = Model({'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': ['winloss']}}, use_value_network=True, seed=0, encoder_chunk=chunk, checkpoint_encoder=True, keep_chunks=int(os.environ.get('KEEP', 16))).cuda()
 learner = RLLearner(model)
 data = tree_map(lambda t: t.to(dev), synth_rl_batch(B, T, seed=0))
 learner._train(data); torch.cuda.synchronize()

@@ -240,3 +240,29 @@ def test_gemm_ex_multicast_batched_attention(mc):
                  b_col_base=2 * H * D, b_col_inner=D, b_row_outer=S, c_row_outer=S, c_col_inner=D, mc=mc)
     torch.cuda.synchronize()
     _check(ctx.view(obs, S, H, D), torch.einsum('ohqk,okhd->oqhd', p.double().view(obs, H, S, S), x[:, :, 2]))
+
+
+def test_ffn_recompute_fwd_bwd():
+    """transformer MLP node that rebuilds its hidden activation in backward (ops._FFN) against fp64 autograd."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 128, 256, generator=g)
+    w1 = torch.randn(1024, 256, generator=g) / 16
+    b1 = torch.randn(1024, generator=g) * 0.1
+    w2 = torch.randn(256, 1024, generator=g) / 32
+    b2 = torch.randn(256, generator=g) * 0.1
+    go = torch.randn(3, 128, 256, generator=g)
+    ref_in = [t.double().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    h = torch.relu(torch.nn.functional.linear(ref_in[0], ref_in[1], ref_in[2]))
+    pre = torch.nn.functional.linear(h, ref_in[3], ref_in[4])
+    go = go * (pre.detach().abs() > 1e-4).float()                   # stay away from the outer ReLU boundary
+    torch.relu(pre).backward(go.double())
+    dev_in = [t.to(DEV).requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    xd = dev_in[0]
+    xs = ops.attach_split(xd, *ops.split_bf16(xd.detach()))
+    y = ops.ffn(xs, *dev_in[1:], 3)
+    assert y.grad_fn is not None and type(y.grad_fn).__name__.startswith('_FFN')
+    y.backward(go.to(DEV))
+    assert (y.detach().double().cpu() - torch.relu(pre).detach()).abs().max().item() <= 3e-5 * pre.abs().max().item()
+    for got, want, n in zip(dev_in, ref_in, ['dx', 'dw1', 'db1', 'dw2', 'db2']):
+        err = (got.grad.double().cpu() - want.grad).abs().max().item()
+        assert err <= 2e-4 * want.grad.abs().max().item(), (n, err, want.grad.abs().max().item())

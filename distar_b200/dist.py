@@ -83,8 +83,10 @@ class DistModule(torch.nn.Module):
             dist.all_reduce(self.module.flat_grad)
 
     def broadcast_params(self):
+        from . import ops
         if get_world_size() > 1:
             dist.broadcast(self.module.flat_param, 0)
             for name, p in self.module.named_parameters():
                 if not p.requires_grad:
                     dist.broadcast(p.data, 0)
+        ops.invalidate_weight_cache()

@@ -18,6 +18,7 @@ import torch.nn.functional as F
 
 from .constants import SELECTED_UNITS_ACTION_MASK
 from .params import init_state_dict
+from . import ops
 from .policy_net import BASELINE_ATAN, HEADS, MAX_SELECTED_UNITS_NUM, Net
 from .spec import BASELINES, is_trainable, param_specs
 from .synth import tree_map
@@ -149,6 +150,7 @@ class Model(nn.Module):
                 p.data = fn(p.data)
         self._bind_grads()
         self._su_mask = fn(self._su_mask)
+        ops.invalidate_weight_cache()
         return self
 
     def zero_grad(self, set_to_none: bool = False):
@@ -163,6 +165,7 @@ class Model(nn.Module):
                     p.data.copy_(state_dict[name].to(p.device))
                 else:
                     missing.append(name)
+        ops.invalidate_weight_cache()
         if strict and (missing or unexpected):
             raise RuntimeError('load_state_dict: missing %s unexpected %s' % (missing[:5], unexpected[:5]))
         return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)

@@ -384,6 +384,38 @@ def attach_split(t: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor) -> torch.T
 
 _PLACEHOLDER = {}
 
+# ---- derived forms of a weight (bf16 pair, conv GEMM matrices) are rebuilt at most once per optimiser step ----------------
+# A learner step calls every encoder layer once per chunk (and again in backward); re-splitting the same unchanged weight
+# each time was ~1000 tiny launches per step.  The cache lives on the parameter object and is keyed by the tensor version
+# (bumped by every in-place torch op: load_state_dict, manual edits) and by WEIGHT_EPOCH, which FlatAdam bumps because its
+# kernel updates the arena behind torch's back.
+WEIGHT_EPOCH = [0]
+
+
+def weight_cached(w: torch.Tensor, key: str, build):
+    if not (w.is_leaf and w.is_cuda):
+        return build()
+    cache = w.__dict__.setdefault('_dsb_wcache', {})
+    stamp = (w._version, WEIGHT_EPOCH[0], w.data_ptr())
+    hit = cache.get(key)
+    if hit is not None and hit[0] == stamp:
+        return hit[1]
+    val = build()
+    cache[key] = (stamp, val)
+    return val
+
+
+def invalidate_weight_cache() -> None:
+    """Call after changing parameter storage through an alias torch's version counter does not see (the flat arena,
+    ``p.data``): Model.load_state_dict / .to() / DistModule.broadcast_params and FlatAdam.step do."""
+    WEIGHT_EPOCH[0] += 1
+
+
+def weight_split(w: torch.Tensor):
+    """bf16 (hi, lo) pair of a parameter, cached per optimiser step."""
+    return weight_cached(w, 'split', lambda: split_bf16(w.detach()))
+
+
 
 def pair_only_placeholder(shape, device) -> torch.Tensor:
     """Stand-in for the fp32 output of a GEMM launched with emit_split='only': a stride-0 view of one NaN, so it costs no
@@ -521,7 +553,7 @@ class _SplitLinear(torch.autograd.Function):
             a_hi, a_lo = x_hi.reshape(x2.shape), x_lo.reshape(x2.shape)
         else:
             a_hi, a_lo = split_bf16(x2)
-        w_hi, w_lo = split_bf16(weight)
+        w_hi, w_lo = weight_split(weight)
         oshape = (*x.shape[:-1], weight.shape[0])
         ctx.set_materialize_grads(False)      # no zero-filled bf16 'gradients' for the (hi, lo) side outputs
         if emit_split:
@@ -585,8 +617,8 @@ class _FFN(torch.autograd.Function):
     def forward(ctx, x, w1, b1, w2, b2, terms, x_hi, x_lo):
         K = x.shape[-1]
         a_hi, a_lo = x_hi.reshape(-1, K), x_lo.reshape(-1, K)
-        w1_hi, w1_lo = split_bf16(w1)
-        w2_hi, w2_lo = split_bf16(w2)
+        w1_hi, w1_lo = weight_split(w1)
+        w2_hi, w2_lo = weight_split(w2)
         _, h_hi, h_lo = gemm_split(a_hi, a_lo, w1_hi, w1_lo, b1, True, terms, want_split='only')
         m = gemm_split(h_hi, h_lo, w2_hi, w2_lo, b2, True, terms)
         ctx.save_for_backward(a_hi, a_lo, w1_hi, w1_lo, w2_hi, w2_lo, m)
@@ -868,6 +900,17 @@ def _conv_weight_matrix(weight: torch.Tensor, cin_pad: int, cout_pad: int) -> to
     return w.reshape(cout_pad, kh * kw * cin_pad).contiguous()
 
 
+def _conv_forward_operands(weight, cin_pad, cout_pad):
+    wm = _conv_weight_matrix(weight.detach(), cin_pad, cout_pad)
+    return (wm,) + tuple(split_bf16(wm))
+
+
+def _conv_dx_operands(wm, cout_pad, kh, kw, C):
+    """W'[cin, (ky,kx,cout)] = W[cout, cin, kh-1-ky, kw-1-kx] as a bf16 pair (the input-gradient convolution's weights)"""
+    w4 = wm.view(cout_pad, kh, kw, C).flip(1, 2).permute(3, 1, 2, 0).reshape(C, kh * kw * cout_pad).contiguous()
+    return split_bf16(w4)
+
+
 class _ConvNHWC(torch.autograd.Function):
     """y = act(conv(x, w) + b [+ residual]) for 3x3 (pad 1) and 1x1 kernels, NHWC, channels padded to 64.
 
@@ -881,9 +924,8 @@ class _ConvNHWC(torch.autograd.Function):
         Cout, Cin, kh, kw = weight.shape
         taps = kh * kw
         cout_pad = _pad_to(Cout, 64)
-        wm = _conv_weight_matrix(weight, C, cout_pad)
+        wm, w_hi, w_lo = weight_cached(weight, 'conv_fwd_%d_%d' % (C, cout_pad), lambda: _conv_forward_operands(weight, C, cout_pad))
         x_hi, x_lo = split_bf16(x)
-        w_hi, w_lo = split_bf16(wm)
         b = F.pad(bias, (0, cout_pad - Cout)).contiguous() if bias is not None else None
         pair_only = emit_split == 'only'
         y = torch.empty((N * H * W, cout_pad), dtype=torch.float32, device=x.device) if not pair_only else None
@@ -898,7 +940,7 @@ class _ConvNHWC(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(x_hi, x_lo, wm, (y_hi if emit_split else y) if relu else None)
         ctx.meta = (N, H, W, C, Cout, Cin, kh, kw, cout_pad, relu, terms, bias is not None, residual is not None)
-        ctx.bias_ref = bias
+        ctx.bias_ref, ctx.weight_ref = bias, weight
         if emit_split:
             y_hi, y_lo = y_hi.view(N, H, W, cout_pad), y_lo.view(N, H, W, cout_pad)
             ctx.mark_non_differentiable(y_hi, y_lo)
@@ -922,8 +964,8 @@ class _ConvNHWC(torch.autograd.Function):
             gres = (g if relu else gy2).view(N, H, W, cout_pad)
         if ctx.needs_input_grad[0]:
             # dX = conv(dY, W') with W'[cin, (ky,kx,cout)] = W[cout, cin, kh-1-ky, kw-1-kx]
-            w4 = wm.view(cout_pad, kh, kw, C).flip(1, 2).permute(3, 1, 2, 0).reshape(C, taps * cout_pad).contiguous()
-            wt_hi, wt_lo = split_bf16(w4)
+            wt_hi, wt_lo = weight_cached(ctx.weight_ref, 'conv_dx_%d_%d' % (C, cout_pad),
+                                         lambda: _conv_dx_operands(wm, cout_pad, kh, kw, C))
             gx = torch.empty((N * H * W, C), dtype=torch.float32, device=gy2.device)
             _gemm_ex(a_hi=g_hi.view(N, H, W, cout_pad), a_lo=g_lo.view(N, H, W, cout_pad), b_hi=wt_hi, b_lo=wt_lo,
                      alpha=1.0, terms=terms, c=gx, m=N * H * W, n=C, k=taps * cout_pad, batch=1, inner=1, splits=1,
@@ -1062,12 +1104,14 @@ class _UpConv(torch.autograd.Function):
         M = N * H * W
         ldz = _pad_to(9 * C, 64)
         dev = x.device
-        wz = torch.zeros((_pad_to(ldz, 128), Cp), dtype=torch.float32, device=dev)
-        wz[:9 * C, :Cin] = weight.permute(2, 3, 0, 1).reshape(9 * C, Cin)          # row = tap * C + co
+        def build():
+            wz = torch.zeros((_pad_to(ldz, 128), Cp), dtype=torch.float32, device=dev)
+            wz[:9 * C, :Cin] = weight.detach().permute(2, 3, 0, 1).reshape(9 * C, Cin)          # row = tap * C + co
+            return split_bf16(wz)
         if x_hi is None:
             x_hi, x_lo = split_bf16(x.reshape(M, Cp).contiguous())
         x_hi, x_lo = x_hi.reshape(M, Cp), x_lo.reshape(M, Cp)
-        w_hi, w_lo = split_bf16(wz)
+        w_hi, w_lo = weight_cached(weight, 'upconv_%d' % Cp, build)
         z = torch.empty((M, ldz), dtype=torch.float32, device=dev)
         _gemm_ex(a_hi=x_hi, a_lo=x_lo, b_hi=w_hi, b_lo=w_lo, alpha=1.0, terms=3, c=z, m=M, n=ldz, k=Cp, batch=1, inner=1,
                  splits=1, bn=64)
@@ -1169,6 +1213,7 @@ class FlatAdam:
 
     def step(self, grad_scale: float = 1.0):
         self.t += 1
+        WEIGHT_EPOCH[0] += 1            # the arena is about to change under every cached weight form
         n = self.param.numel()
         if _use_kernel(self.param):
             if self._partial is None:

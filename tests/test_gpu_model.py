@@ -200,3 +200,25 @@ def test_negative_entity_id_raises(model):
     log = learner._train(to_dev(G.rl_case()))
     assert abs(float(log['total_loss'])) < 1e6 and log['kl/total'] == log['kl/total']
     model.load_state_dict(init_state_dict(seed=G.WEIGHT_SEED, baselines=G.BASELINES))
+
+
+def test_weight_cache_follows_updates(model):
+    """the per-step cache of derived weight forms (bf16 pairs, conv matrices) must refresh after the optimiser kernel
+    (which updates the arena behind torch's version counters), after in-place torch edits and after load_state_dict."""
+    from distar_b200 import ops
+    from distar_b200.learner import RLLearner
+    w = model._params['encoder.entity_encoder.entity_fc.0.weight']
+    h0, l0 = ops.weight_split(w)
+    assert ops.weight_split(w)[0] is h0                                   # cached within a step
+    learner = RLLearner(model, 'MP0', None, lr=1e-3, max_norm=1.0, distributed=False)
+    learner._train(to_dev(G.rl_case()))
+    h1, l1 = ops.weight_split(w)
+    eh, el = ops.split_bf16(w.detach().clone())
+    assert torch.equal(h1, eh) and torch.equal(l1, el) and not torch.equal(h1, h0)
+    with torch.no_grad():
+        w.mul_(0.5)
+    h2, _ = ops.weight_split(w)
+    assert torch.equal(h2, ops.split_bf16(w.detach().clone())[0])
+    model.load_state_dict(init_state_dict(seed=G.WEIGHT_SEED, baselines=G.BASELINES))
+    h3, l3 = ops.weight_split(w)
+    assert torch.equal(h3, h0) and torch.equal(l3, l0)

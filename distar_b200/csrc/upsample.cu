@@ -204,39 +204,54 @@ __global__ void upshift9_fwd_kernel(const float* __restrict__ z, const float* __
 }
 
 // dz[n, iy, ix, tap] = sum over up-sampled positions u that read input (iy, ix):  w_u * dOut[u - (tap offset)]
+// One thread owns a low-resolution pixel and all nine taps: the 6x6 window of dOut they share is read once (36 loads for 9
+// outputs instead of 16 each) and the nine results leave as one contiguous 36-byte run.
 __global__ void upshift9_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gz, int64_t total, int H, int W) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int t = (int)(i % 9);
-    const int ix = (int)((i / 9) % W), iy = (int)((i / (9 * (int64_t)W)) % H);
-    const int64_t n = i / (9 * (int64_t)W * H);
+    const int ix = (int)(i % W), iy = (int)((i / W) % H);
+    const int64_t n = i / ((int64_t)W * H);
     const int OW = 2 * W, OH = 2 * H;
-    const int dy = t / 3 - 1, dx = t % 3 - 1;
     const float* g = gout + n * OH * OW;
-    float acc = 0.f;
+    float wy[4], wx[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int uy = 2 * iy - 1 + a;
-        if (uy < 0 || uy >= OH) continue;
-        const Tap ty = tap_of(uy, H);
-        const float wy = (ty.i0 == iy ? ty.l0 : 0.f) + (ty.i1 == iy ? ty.l1 : 0.f);
-        const int oy = uy - dy;                       // output pixel whose tap (dy,dx) reads up-sampled position uy
-        if (wy == 0.f || oy < 0 || oy >= OH) continue;
-        float row = 0.f;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int ux = 2 * ix - 1 + b;
-            if (ux < 0 || ux >= OW) continue;
-            const Tap tx = tap_of(ux, W);
-            const float wx = (tx.i0 == ix ? tx.l0 : 0.f) + (tx.i1 == ix ? tx.l1 : 0.f);
-            const int ox = ux - dx;
-            if (wx != 0.f && ox >= 0 && ox < OW) row += wx * __ldg(g + (int64_t)oy * OW + ox);
-        }
-        acc += wy * row;
+    for (int ui = 0; ui < 4; ++ui) {
+        const int uy = 2 * iy - 1 + ui, ux = 2 * ix - 1 + ui;
+        wy[ui] = wx[ui] = 0.f;
+        if (uy >= 0 && uy < OH) { const Tap t = tap_of(uy, H); wy[ui] = (t.i0 == iy ? t.l0 : 0.f) + (t.i1 == iy ? t.l1 : 0.f); }
+        if (ux >= 0 && ux < OW) { const Tap t = tap_of(ux, W); wx[ui] = (t.i0 == ix ? t.l0 : 0.f) + (t.i1 == ix ? t.l1 : 0.f); }
     }
-    gz[i] = acc;
+    float acc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+#pragma unroll
+    for (int oi = 0; oi < 6; ++oi) {                 // output row o = 2 iy - 2 + oi meets (ui, d) with ui = oi - 1 + d
+        const int oy = 2 * iy - 2 + oi;
+        if (oy < 0 || oy >= OH) continue;
+        float T[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int oj = 0; oj < 6; ++oj) {
+            const int ox = 2 * ix - 2 + oj;
+            if (ox < 0 || ox >= OW) continue;
+            const float v = __ldg(g + (int64_t)oy * OW + ox);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const int ui = oj - 1 + (d - 1);
+                if (ui >= 0 && ui <= 3) T[d] += wx[ui] * v;
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int ui = oi - 1 + (d - 1);
+            if (ui < 0 || ui > 3) continue;
+#pragma unroll
+            for (int e = 0; e < 3; ++e) acc[d * 3 + e] += wy[ui] * T[e];
+        }
+    }
+    float* out = gz + i * 9;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) out[t] = acc[t];
 }
-
 
 // ---- location-head up-sampling stages with C output channels: y = act(conv3x3(upsample2x(x), w) + b) --------------------
 // (head/action_arg_head.py:436-443, `upsample` stages 0 and 1).  Same factorisation as upshift9, generalised to C output
@@ -460,7 +475,7 @@ extern "C" int dsb_upshift9_fwd(const float* z, const float* bias, float* out, i
 
 extern "C" int dsb_upshift9_bwd(const float* grad_out, float* grad_z, int64_t N, int H, int W, dsb_stream_t stream) {
     DSB_REQUIRE(grad_out && grad_z && N >= 0 && H > 0 && W > 0, "upshift9_bwd: bad argument");
-    const int64_t total = N * H * W * 9;
+    const int64_t total = N * H * W;
     if (total == 0) return DSB_OK;
     const int64_t blocks = (total + 255) / 256;
     DSB_REQUIRE(blocks < (1ll << 31), "upshift9_bwd: too large");

@@ -481,6 +481,27 @@ def _gemm_ex(**kw) -> None:
     lib.gemm_ex(**kw)
 
 
+def _skinny_gemm(a_hi, a_lo, w_hi, w_lo, bias, relu: bool, terms: int):
+    """Few rows, very long reduction (the spatial encoder's fc: 264 x 32768 -> 256 gives 6 output tiles for 148 SMs): split
+    the reduction over CTAs (partials summed by TMA reduce-add) and apply bias / ReLU afterwards.  None when not worth it."""
+    M, K = a_hi.shape
+    N = w_hi.shape[0]
+    if not (a_hi.is_cuda and K >= 4096 and N % 128 == 0 and K % 64 == 0):
+        return None
+    tiles = ((M + 127) // 128) * (N // 128)
+    if tiles > 37:
+        return None
+    splits = _pick_splits(tiles, K)
+    if splits < 2:
+        return None
+    c = torch.zeros((M, N), dtype=torch.float32, device=a_hi.device)
+    _gemm_ex(a_hi=a_hi, a_lo=a_lo, b_hi=w_hi, b_lo=w_lo, alpha=1.0, terms=terms, c=c, m=M, n=N, k=K, batch=1, inner=1,
+             splits=splits, c_row_split=0, c_accumulate=1, bn=128)
+    if bias is not None:
+        c += bias
+    return torch.relu_(c) if relu else c
+
+
 def relu_bwd_split(gy2: torch.Tensor, y: Optional[torch.Tensor], need_bias: bool, need_g: bool = False,
                    need_split: bool = True, bias_grad_out: Optional[torch.Tensor] = None):
     """(g_hi, g_lo, bias_grad or None, g or None) with g = gy * (y > 0): one pass instead of compare + mul + split + sum.
@@ -559,7 +580,9 @@ class _SplitLinear(torch.autograd.Function):
         if emit_split:
             y, y_hi, y_lo = gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu, terms, want_split=emit_split)
         else:
-            y = gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu, terms)
+            y = _skinny_gemm(a_hi, a_lo, w_hi, w_lo, bias, relu, terms)
+            if y is None:
+                y = gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu, terms)
         # the ReLU mask only needs the sign: when the bf16 pair is emitted (and kept by the consumer anyway) save its hi
         # half instead of the fp32 output
         ctx.save_for_backward(a_hi, a_lo, w_hi, w_lo, (y_hi if emit_split else y) if relu else None)

@@ -266,3 +266,24 @@ def test_ffn_recompute_fwd_bwd():
     for got, want, n in zip(dev_in, ref_in, ['dx', 'dw1', 'db1', 'dw2', 'db2']):
         err = (got.grad.double().cpu() - want.grad).abs().max().item()
         assert err <= 2e-4 * want.grad.abs().max().item(), (n, err, want.grad.abs().max().item())
+
+
+def test_linear_skinny_split_k():
+    """few rows x very long reduction (the spatial encoder's fc) goes through split-K + TMA reduce-add"""
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(264, 8192, generator=g)
+    w = torch.randn(256, 8192, generator=g) / 90
+    b = torch.randn(256, generator=g)
+    go = torch.randn(264, 256, generator=g)
+    xr, wr, br = [t.double().requires_grad_(True) for t in (x, w, b)]
+    pre = torch.nn.functional.linear(xr, wr, br)
+    go = go * (pre.detach().abs() > 1e-4).float()              # keep the gradient check away from the ReLU boundary
+    ref = torch.relu(pre)
+    ref.backward(go.double())
+    xd, wd, bd = [t.to(DEV).requires_grad_(True) for t in (x, w, b)]
+    y = ops.linear(xd, wd, bd, relu=True)
+    y.backward(go.to(DEV))
+    _check(y.detach(), ref.detach(), tol=3e-5)
+    for got, want, n in [(xd.grad, xr.grad, 'dx'), (wd.grad, wr.grad, 'dw'), (bd.grad, br.grad, 'db')]:
+        err = (got.double().cpu() - want).abs().max().item()
+        assert err <= 1e-3 * want.abs().max().item(), (n, err)

@@ -255,6 +255,7 @@ struct GemmParams {
     int64_t M;               // valid rows per batch
     int64_t ldc;             // row stride (elements) of c_hi / c_lo
     int N, terms, relu, accumulate;
+    int a_exact, b_exact;    // terms == 3: that operand has no lo half (exactly representable in bf16)
     int store_c;             // 0: only the bf16 (hi, lo) pair is written (no fp32 C)
     int prefetch;            // L2-prefetch the next tile's A operand
     int debug;               // DEV ONLY (env DSB_GEMM_DEBUG): 1 = skip global stores, 2 = skip MMAs, 4 = skip operand loads
@@ -427,16 +428,14 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     const int work_first = (MC == 1) ? (int)blockIdx.x : (int)(blockIdx.x >> 1);
     const int work_stride = (MC == 1) ? (int)gridDim.x : (int)(gridDim.x >> 1);
     const int num_k = p.num_k;
-    const bool three = p.terms == 3;
+    const bool a_lo_on = p.terms == 3 && !p.a_exact, b_lo_on = p.terms == 3 && !p.b_exact;   // which (hi, lo) pairs carry a lo half
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
-        if (three) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
-        }
+        if (a_lo_on) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
+        if (b_lo_on) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
         // MC=2: both CTAs' MMAs release a stage.  Pair: the leader's `full` collects one expect_tx arrival per CTA, its
         // `tmem_empty` the epilogue warps of both CTAs; `empty` / `tmem_full` get one multicast commit each.
         for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], kPair ? 2 : 1); mbar_init(&empty[i], MC == 2 ? 2 : 1); }
@@ -469,7 +468,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             // bytes THIS CTA contributes to a stage (pair: its A tile + its half of the B tile)
-            const uint32_t tx = (three ? 2 : 1) * (kTileBytes + (kPair ? BN * 64 : BN * 128));
+            const uint32_t tx = (a_lo_on ? 2 : 1) * kTileBytes + (b_lo_on ? 2 : 1) * (kPair ? BN * 64 : BN * 128);
             for (int tile = work_first; tile < num_tiles; tile += work_stride) {
                 const TileCoord t = decode_tile<BN, MC>(tile, p, cta_rank);
                 const bool pf = p.prefetch && tile + work_stride < num_tiles;
@@ -479,7 +478,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     if (pf && (tn.m0 != t.m0 || tn.b != t.b || tn.s != t.s)) {      // next tile's A block -> L2, one tile ahead
                         const int kgn = (tn.s * num_k + kb) * BK;
                         prefetch_a(&map_a_hi, p.a, tn, kgn);
-                        if (three) prefetch_a(&map_a_lo, p.a, tn, kgn);
+                        if (a_lo_on) prefetch_a(&map_a_lo, p.a, tn, kgn);
                     }
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char* st = smem + stage * kStageBytes;
@@ -498,11 +497,10 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     const int brank = MC != 1 ? cta_rank : -1;
                     load_operand(&map_a_hi, &full[stage], st, p.a, t, t.m0, kg, BM, -1, pair_bar);
                     load_operand(&map_b_hi, &full[stage], st + 2 * kTileBytes, p.b, t, t.n0, kg, BN, brank, pair_bar);
-                    if (three) {
-                        load_operand(&map_a_lo, &full[stage], st + kTileBytes, p.a, t, t.m0, kg, BM, -1, pair_bar);
+                    if (a_lo_on) load_operand(&map_a_lo, &full[stage], st + kTileBytes, p.a, t, t.m0, kg, BM, -1, pair_bar);
+                    if (b_lo_on)
                         load_operand(&map_b_lo, &full[stage], st + 2 * kTileBytes + kBSlot, p.b, t, t.n0, kg, BN, brank,
                                      pair_bar);
-                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -534,21 +532,15 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         if (p.debug & 2) break;
                         const uint64_t ao = a_step * k, bo = b_step * k;
-                        const uint32_t first = (kb | k) ? 1u : 0u;
+                        uint32_t accum = (kb | k) ? 1u : 0u;        // the tile's first MMA overwrites the accumulator
                         if (kPair) {
-                            if (three) {
-                                umma_pair(d_tmem, a_lo + ao, b_hi + bo, idesc, first);
-                                umma_pair(d_tmem, a_hi + ao, b_lo + bo, idesc, 1u);
-                                umma_pair(d_tmem, a_hi + ao, b_hi + bo, idesc, 1u);
-                            } else {
-                                umma_pair(d_tmem, a_hi + ao, b_hi + bo, idesc, first);
-                            }
-                        } else if (three) {
-                            umma(d_tmem, a_lo + ao, b_hi + bo, idesc, first);
-                            umma(d_tmem, a_hi + ao, b_lo + bo, idesc, 1u);
-                            umma(d_tmem, a_hi + ao, b_hi + bo, idesc, 1u);
+                            if (a_lo_on) { umma_pair(d_tmem, a_lo + ao, b_hi + bo, idesc, accum); accum = 1u; }
+                            if (b_lo_on) { umma_pair(d_tmem, a_hi + ao, b_lo + bo, idesc, accum); accum = 1u; }
+                            umma_pair(d_tmem, a_hi + ao, b_hi + bo, idesc, accum);
                         } else {
-                            umma(d_tmem, a_hi + ao, b_hi + bo, idesc, first);
+                            if (a_lo_on) { umma(d_tmem, a_lo + ao, b_hi + bo, idesc, accum); accum = 1u; }
+                            if (b_lo_on) { umma(d_tmem, a_hi + ao, b_lo + bo, idesc, accum); accum = 1u; }
+                            umma(d_tmem, a_hi + ao, b_hi + bo, idesc, accum);
                         }
                     }
                     if (kPair) {
@@ -766,8 +758,8 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
     DSB_REQUIRE(tiles < (1ll << 31), "gemm: too many tiles");
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mc, mc_hi, mc_lo;
     int rc;
-    const void* a_lo = g.terms == 3 ? g.a_lo : g.a_hi;
-    const void* b_lo = g.terms == 3 ? g.b_lo : g.b_hi;
+    const void* a_lo = (g.terms == 3 && !g.a_exact) ? g.a_lo : g.a_hi;
+    const void* b_lo = (g.terms == 3 && !g.b_exact) ? g.b_lo : g.b_hi;
     if (g.a_conv) {
         DSB_REQUIRE(!g.a_mn && batch == 1 && splits == 1, "gemm: conv A operand is K-major, unbatched");
         DSB_REQUIRE(g.conv_c % 64 == 0 && (g.conv_taps == 1 || g.conv_taps == 9) && g.conv_w <= 128 && 128 % g.conv_w == 0 &&
@@ -824,6 +816,7 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
     p.bias = g.bias; p.residual = g.residual; p.c_hi = (__nv_bfloat16*)g.c_hi; p.c_lo = (__nv_bfloat16*)g.c_lo;
     p.alpha = g.alpha; p.M = g.m; p.ldc = g.c_cols; p.N = g.n; p.terms = g.terms; p.relu = g.relu;
     p.accumulate = g.c_accumulate; p.store_c = g.c != nullptr;
+    p.a_exact = g.a_exact; p.b_exact = g.b_exact;
     static const int debug_bits = getenv("DSB_GEMM_DEBUG") ? atoi(getenv("DSB_GEMM_DEBUG")) : 0;
     p.debug = debug_bits;
     static const int no_prefetch = getenv("DSB_GEMM_NO_PREFETCH") ? atoi(getenv("DSB_GEMM_NO_PREFETCH")) : 0;   // DEV ONLY (A/B)
@@ -863,7 +856,7 @@ int launch(const dsb_gemm_args& g, cudaStream_t stream) {
     DSB_REQUIRE(g.a_hi && g.b_hi && (g.c || g.c_hi), "gemm: null pointer");
     DSB_REQUIRE(g.c || (!g.c_accumulate && (g.splits <= 1)), "gemm: pair-only output takes no split-K / accumulate");
     DSB_REQUIRE(g.terms == 1 || g.terms == 3, "gemm: terms must be 1 or 3");
-    DSB_REQUIRE(g.terms == 1 || (g.a_lo && g.b_lo), "gemm: terms=3 needs the lo halves");
+    DSB_REQUIRE(g.terms == 1 || ((g.a_lo || g.a_exact) && (g.b_lo || g.b_exact)), "gemm: terms=3 needs the lo halves (or a_exact / b_exact)");
     DSB_REQUIRE(!g.c_hi == !g.c_lo, "gemm: c_hi and c_lo go together");
     int bn = g.bn;
     if (!bn) {

@@ -20,7 +20,7 @@ _SIGNATURES = {
     'dsb_launch_count': (_i64, []),
     'dsb_scatter_connection_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'dsb_scatter_connection_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    'dsb_entity_features': (_i, [_vp] * 5 + [_i, _vp, _vp, _i64, _vp, _vp]),
+    'dsb_entity_features': (_i, [_vp] * 5 + [_i, _vp, _vp, _i, _i64, _vp, _vp]),
     'dsb_spatial_stem_fwd': (_i, [_vp] * 11 + [_i] * 5 + [_vp]),
     'dsb_spatial_stem_bwd': (_i, [_vp] * 9 + [_i] + [_vp] * 3 + [_i] * 4 + [_vp]),
     'dsb_return_scan': (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -72,7 +72,8 @@ class GemmArgs(ctypes.Structure):
                 ('c_col_base', _c.c_int32), ('c_col_inner', _c.c_int32),
                 ('residual', _vp), ('bn', _c.c_int32),
                 ('a_conv', _c.c_int32), ('b_conv', _c.c_int32), ('conv_h', _c.c_int32), ('conv_w', _c.c_int32),
-                ('conv_c', _c.c_int32), ('conv_taps', _c.c_int32), ('conv_imgs', _i64), ('c_accumulate', _c.c_int32), ('mc', _c.c_int32)]
+                ('conv_c', _c.c_int32), ('conv_taps', _c.c_int32), ('conv_imgs', _i64), ('c_accumulate', _c.c_int32), ('mc', _c.c_int32),
+                ('a_exact', _c.c_int32), ('b_exact', _c.c_int32)]
 
 
 _SIGNATURES['dsb_gemm_ex'] = (_i, [ctypes.POINTER(GemmArgs), _vp])

@@ -81,11 +81,15 @@ def scatter_connection(project: torch.Tensor, ex: torch.Tensor, ey: torch.Tensor
 _DTYPE_CODE = {torch.uint8: 0, torch.int16: 1, torch.int8: 2, torch.float16: 3}
 
 
-def entity_features_split(entity_info: dict, fields, check_negative: bool = True, flag: Optional[torch.Tensor] = None):
+def entity_features_split(entity_info: dict, fields, check_negative: bool = True, flag: Optional[torch.Tensor] = None,
+                          exact: bool = False):
     """fields: [(name, kind 'o'|'b'|'u', width)] in concat order.  Returns the [N, E, 1024] bf16 (hi, lo) feature pair the
     embedding GEMM consumes, built straight from the wire-format fields (no fp32 concat).  None on unsupported dtypes.
     With ``flag`` (device int32[1]) the negative-id error is only recorded there and the caller raises later: reading it
-    here would stall the host once per encoder chunk and drain the launch queue."""
+    here would stall the host once per encoder chunk and drain the launch queue.
+    ``exact``: one-hot / binary columns are exact in bf16 and the bf16 residuals of the scalar fields are placed in the spare
+    columns [row width, row width + #scalar fields) of the hi tensor, so NO lo tensor exists (returns (hi, None)); the caller
+    must repeat the scalar fields' weight columns there (``entity_exact_weight``) and run the GEMM with a_exact."""
     first = entity_info[fields[0][0]]
     if not first.is_cuda:
         return None
@@ -103,20 +107,33 @@ def entity_features_split(entity_info: dict, fields, check_negative: bool = True
         off += w
     N, E = first.shape
     hi = torch.empty((N, E, 1024), dtype=torch.bfloat16, device=first.device)
-    lo = torch.empty((N, E, 1024), dtype=torch.bfloat16, device=first.device)
+    lo = None if exact else torch.empty((N, E, 1024), dtype=torch.bfloat16, device=first.device)
     deferred = flag is not None
     if flag is None:
         flag = torch.zeros(1, dtype=torch.int32, device=first.device)
     lib.call('dsb_entity_features', lib.ptr_array(tensors), lib.int_array(kinds), lib.int_array(offs),
-             lib.int_array(vocabs), lib.int_array(dts), len(fields), hi, lo, N * E, flag)
+             lib.int_array(vocabs), lib.int_array(dts), len(fields), hi, lo, off if exact else -1, N * E, flag)
     if check_negative and not deferred and int(flag.item()) != 0:          # entity_encoder.py:69-72 raises on negative ids
         raise RuntimeError('negative categorical id in an entity field')
     return hi, lo
 
 
-def linear_presplit(x_hi: torch.Tensor, x_lo: torch.Tensor, weight: torch.Tensor, bias, relu: bool, terms: int = 3,
+def entity_exact_weight(w: torch.Tensor, fields) -> torch.Tensor:
+    """[out, 997] embedding weight -> [out, 1024] for the exact-operand feature rows of entity_features_split(exact=True):
+    the columns of the scalar ('u') fields are repeated after the row (they multiply the bf16 residuals), zeros after."""
+    off, ucols = 0, []
+    for _name, kind, wd in fields:
+        if kind == 'u':
+            ucols.append(off)
+        off += wd
+    idx = torch.tensor(ucols, device=w.device)
+    return torch.cat([w, w.index_select(1, idx), w.new_zeros(w.shape[0], 1024 - off - len(ucols))], dim=1)
+
+
+def linear_presplit(x_hi: torch.Tensor, x_lo: Optional[torch.Tensor], weight: torch.Tensor, bias, relu: bool, terms: int = 3,
                     emit_split: bool = False) -> torch.Tensor:
-    """fc_block on an input that only exists as a bf16 (hi, lo) pair (no gradient flows to it)."""
+    """fc_block on an input that only exists as a bf16 (hi, lo) pair (no gradient flows to it).  x_lo None: the input is
+    exactly representable in bf16 (one product less)."""
     y, y_hi, y_lo = _SplitLinear.apply(x_hi, weight, bias, relu, terms, x_hi, x_lo, emit_split)
     return attach_split(y, y_hi, y_lo) if emit_split else y
 
@@ -451,10 +468,20 @@ def gemm_eligible(N: int, K: int) -> bool:
 
 
 def gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu: bool, terms: int = 3, want_split: bool = False):
-    """C = act(A @ W^T + bias) on the tensor cores; A [M,K], W [N,K] as bf16 (hi, lo) pairs -> fp32 [M,N]."""
+    """C = act(A @ W^T + bias) on the tensor cores; A [M,K], W [N,K] as bf16 (hi, lo) pairs -> fp32 [M,N].
+    a_lo None: A is exact in bf16 (two products instead of three)."""
     M, K = a_hi.shape
     N = w_hi.shape[0]
     assert w_hi.shape[1] == K and gemm_eligible(N, K), (M, N, K)
+    if a_lo is None and a_hi.is_cuda:
+        c = torch.empty((M, N), dtype=torch.float32, device=a_hi.device) if want_split != 'only' else None
+        c_hi = torch.empty((M, N), dtype=torch.bfloat16, device=a_hi.device) if want_split else None
+        c_lo = torch.empty((M, N), dtype=torch.bfloat16, device=a_hi.device) if want_split else None
+        _gemm_ex(a_hi=a_hi, a_lo=None, b_hi=w_hi, b_lo=w_lo, bias=bias, alpha=1.0, relu=1 if relu else 0, terms=terms, c=c,
+                 c_hi=c_hi, c_lo=c_lo, m=M, n=N, k=K, batch=1, inner=1, splits=1, a_exact=1)
+        if c is None:
+            c = pair_only_placeholder((M, N), a_hi.device)
+        return (c, c_hi, c_lo) if want_split else c
     if _use_kernel(a_hi):
         c = torch.empty((M, N), dtype=torch.float32, device=a_hi.device) if want_split != 'only' else None
         c_hi = torch.empty((M, N), dtype=torch.bfloat16, device=a_hi.device) if want_split else None
@@ -464,7 +491,7 @@ def gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu: bool, terms: int = 3, want_sp
             c = pair_only_placeholder((M, N), a_hi.device)
         return (c, c_hi, c_lo) if want_split else c
     if terms == 3:
-        c = (a_hi.float() + a_lo.float()) @ (w_hi.float() + w_lo.float()).t()
+        c = (a_hi.float() + (a_lo.float() if a_lo is not None else 0)) @ (w_hi.float() + w_lo.float()).t()
     else:
         c = a_hi.float() @ w_hi.float().t()
     if bias is not None:
@@ -552,14 +579,15 @@ def weight_grad(g_hi, g_lo, x_hi, x_lo, terms: int = 3, accumulate_into: Optiona
     M, N = g_hi.shape
     K = x_hi.shape[1]
     splits = _pick_splits((N // 128) * (K // 128), M)
+    bx = 1 if x_lo is None else 0                       # the activation is exact in bf16: no dY_hi x X_lo product
     if accumulate_into is not None:
         _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=x_hi, b_lo=x_lo, a_mn=1, b_mn=1, alpha=1.0, terms=terms, c=accumulate_into, m=N,
-                 n=K, k=M, batch=1, inner=1, splits=splits, c_row_split=0, c_accumulate=1)
+                 n=K, k=M, batch=1, inner=1, splits=splits, c_row_split=0, c_accumulate=1, b_exact=bx)
         return None
     gw = torch.zeros((N, K), dtype=torch.float32, device=g_hi.device) if splits > 1 else \
         torch.empty((N, K), dtype=torch.float32, device=g_hi.device)
     _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=x_hi, b_lo=x_lo, a_mn=1, b_mn=1, alpha=1.0, terms=terms, c=gw, m=N, n=K, k=M,
-             batch=1, inner=1, splits=splits, c_row_split=0, c_accumulate=1 if splits > 1 else 0)
+             batch=1, inner=1, splits=splits, c_row_split=0, c_accumulate=1 if splits > 1 else 0, b_exact=bx)
     return gw
 
 
@@ -571,7 +599,7 @@ class _SplitLinear(torch.autograd.Function):
     def forward(ctx, x, weight, bias, relu, terms, x_hi=None, x_lo=None, emit_split=False):
         x2 = x.reshape(-1, x.shape[-1])
         if x_hi is not None:
-            a_hi, a_lo = x_hi.reshape(x2.shape), x_lo.reshape(x2.shape)
+            a_hi, a_lo = x_hi.reshape(x2.shape), (x_lo.reshape(x2.shape) if x_lo is not None else None)
         else:
             a_hi, a_lo = split_bf16(x2)
         w_hi, w_lo = weight_split(weight)
@@ -580,7 +608,7 @@ class _SplitLinear(torch.autograd.Function):
         if emit_split:
             y, y_hi, y_lo = gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu, terms, want_split=emit_split)
         else:
-            y = _skinny_gemm(a_hi, a_lo, w_hi, w_lo, bias, relu, terms)
+            y = _skinny_gemm(a_hi, a_lo, w_hi, w_lo, bias, relu, terms) if a_lo is not None else None
             if y is None:
                 y = gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu, terms)
         # the ReLU mask only needs the sign: when the bf16 pair is emitted (and kept by the consumer anyway) save its hi
@@ -626,7 +654,7 @@ class _SplitLinear(torch.autograd.Function):
                 gw = weight_grad(g_hi, g_lo, a_hi, a_lo, ctx.terms, accumulate_into=_grad_slot(ctx.weight_ref))
             else:
                 gfull = g if g is not None else (g_hi.float() + g_lo.float())
-                gw = gfull.t() @ (a_hi.float() + a_lo.float())
+                gw = gfull.t() @ (a_hi.float() + (a_lo.float() if a_lo is not None else 0))
         return gx, gw, gb, None, None, None, None, None
 
 

@@ -179,21 +179,22 @@ class Net:
         """obs_encoder/entity_encoder.py:59-96 (K1-K4)."""
         P, pre = self.P, 'encoder.entity_encoder.'
         w = P[pre + 'transformer.embedding.0.weight']
-        w_pad = F.pad(w, (0, 1024 - w.shape[1]))
         E = entity_info_E = e['x'].shape[1]
         mask = torch.arange(E, device=e['x'].device).unsqueeze(0) < entity_num.unsqueeze(1)
         if self.bad_input_flag is None and e['x'].is_cuda:
             self.bad_input_flag = torch.zeros(1, dtype=torch.int32, device=e['x'].device)
-        split = ops.entity_features_split(e, ENTITY_FIELDS, flag=self.bad_input_flag)
-        if split is not None:       # K1: features expanded straight into the GEMM's bf16 operand pair
-            x = ops.linear_presplit(split[0], split[1], w_pad, P[pre + 'transformer.embedding.0.bias'], True, self.terms,
+        split = ops.entity_features_split(e, ENTITY_FIELDS, flag=self.bad_input_flag, exact=True)
+        if split is not None:       # K1: features expanded straight into the GEMM's (exact) bf16 operand, no lo half
+            w_x = ops.entity_exact_weight(w, ENTITY_FIELDS)
+            x = ops.linear_presplit(split[0], None, w_x, P[pre + 'transformer.embedding.0.bias'], True, self.terms,
                                     emit_split=True)
         else:
             for name, kind, wd in ENTITY_FIELDS:
                 if kind == 'o' and e[name].dtype in (torch.int8, torch.int16, torch.int32, torch.int64):
                     if bool((e[name] < 0).any()):
                         raise RuntimeError('negative categorical id in entity field %s' % name)
-            x = ops.linear(self.entity_features(e), w_pad, P[pre + 'transformer.embedding.0.bias'], True, self.terms)
+            x = ops.linear(self.entity_features(e), F.pad(w, (0, 1024 - w.shape[1])), P[pre + 'transformer.embedding.0.bias'],
+                           True, self.terms)
         for i in range(3):
             lp = '%stransformer.layers.%d' % (pre, i)
             qkv = self.fc(lp + '.attention.attention_pre', x, split='only')

@@ -46,9 +46,13 @@ int dsb_scatter_connection_bwd(const float* grad_out, const uint8_t* ex, const u
  * fields: host array of 36 device pointers (one per entity field, [tokens] each) with host tables kind (0 one-hot,
  * 1 11-bit binary MSB first, 2 scalar), offset (first column), vocab, dtype (0 u8, 1 i16, 2 i8, 3 f16).
  * Writes the 1024-wide (997 + zero padding) feature rows as the bf16 (hi, lo) pair of the embedding GEMM.
+ * lo_col_base >= 0 selects the exact-operand layout: one-hot / binary columns are exact in bf16, and the bf16 residual of
+ * the j-th scalar field is written to the spare hi column lo_col_base + j (the caller repeats that field's weight column
+ * there), so the row needs no lo tensor (lo may be NULL) and the GEMM one product less (dsb_gemm_args.a_exact).
  * error_flag (device int, zeroed by the caller) is set to 1 if a one-hot id is negative (reference raises). */
 int dsb_entity_features(const void* const* fields, const int* kind, const int* offset, const int* vocab, const int* dtype,
-                        int num_fields, void* hi, void* lo, int64_t tokens, int* error_flag, dsb_stream_t stream);
+                        int num_fields, void* hi, void* lo, int lo_col_base, int64_t tokens, int* error_flag,
+                        dsb_stream_t stream);
 
 /* ---- fused spatial-encoder stem  (scatter_connection + plane expansion spatial_encoder.py:51-71 + project conv :72
  *      + first max_pool2d :75-79) ----
@@ -193,7 +197,11 @@ typedef struct dsb_gemm_args {
     int32_t a_conv, b_conv, conv_h, conv_w, conv_c, conv_taps;
     int64_t conv_imgs;
     int32_t c_accumulate;   /* != 0: C += result (TMA reduce-add; use with splits > 1 and c_row_split = 0 on a zeroed C) */
-    int32_t mc;             /* 0 auto, 1 single CTAs, 2 clusters of two CTAs sharing B tiles by TMA multicast */
+    int32_t mc;             /* 0 auto, 1 single CTAs, 2 clusters of two CTAs sharing B tiles by TMA multicast,
+                               4 CTA pairs issuing cta_group::2 MMAs (M = 256 across two SMs) */
+    int32_t a_exact;        /* terms == 3 only: A is exactly representable in bf16 (a_lo may be NULL): the a_lo x b_hi product
+                               and the a_lo loads are skipped */
+    int32_t b_exact;        /* same for B */
 } dsb_gemm_args;
 int dsb_gemm_ex(const dsb_gemm_args* args, dsb_stream_t stream);
 

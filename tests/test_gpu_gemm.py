@@ -287,3 +287,26 @@ def test_linear_skinny_split_k():
     for got, want, n in [(xd.grad, xr.grad, 'dx'), (wd.grad, wr.grad, 'dw'), (bd.grad, br.grad, 'db')]:
         err = (got.double().cpu() - want).abs().max().item()
         assert err <= 1e-3 * want.abs().max().item(), (n, err)
+
+
+@pytest.mark.parametrize('mc', [1, 4])
+def test_gemm_ex_exact_operands(mc):
+    """a_exact / b_exact: an operand that is exactly representable in bf16 carries no lo half (two products, not three)"""
+    g = torch.Generator().manual_seed(12)
+    M, N, K = 2048, 256, 512
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).float()          # exact in bf16
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    a_hi, a_lo = _split(a)
+    assert not bool(a_lo.float().any())
+    w_hi, w_lo = _split(w)
+    c = torch.empty(M, N, device=DEV)
+    _lib.gemm_ex(a_hi=a_hi, a_lo=None, b_hi=w_hi, b_lo=w_lo, alpha=1.0, terms=3, c=c, m=M, n=N, k=K, batch=1, inner=1, splits=1,
+                 a_exact=1, bn=128, mc=mc)
+    _check(c, a.double() @ w.double().t())
+    # exact B, MN-major operands, split-K accumulate (the weight-gradient form)
+    dy = torch.randn(M, N, generator=g)
+    d_hi, d_lo = _split(dy)
+    gw = torch.zeros(N, K, device=DEV)
+    _lib.gemm_ex(a_hi=d_hi, a_lo=d_lo, b_hi=a_hi, b_lo=None, a_mn=1, b_mn=1, alpha=1.0, terms=3, c=gw, m=N, n=K, k=M, batch=1,
+                 inner=1, splits=4, c_accumulate=1, b_exact=1, bn=128, mc=mc)
+    _check(gw, dy.double().t() @ a.double(), tol=5e-5)

@@ -302,6 +302,18 @@ def test_entity_features_kernel_matches_reference_expansion():
     assert got.shape == (3, 512, 1024)
     assert (got.cpu() - ref).abs().max().item() <= 1e-6
     assert torch.equal(hi[..., 997:].cpu().float(), torch.zeros(3, 512, 27))
+    # exact-operand layout: no lo tensor, scalar-field residuals in the spare columns; x . w is unchanged when the weight
+    # repeats those fields' columns there
+    xh, xl = ops.entity_features_split({k: v.to(DEV) for k, v in ent.items()}, ENTITY_FIELDS, exact=True)
+    assert xl is None and torch.equal(xh[..., :997], hi[..., :997])
+    ucols = [off for off, (n_, kind, wd) in zip(__import__('itertools').accumulate([0] + [f[2] for f in ENTITY_FIELDS[:-1]]),
+                                                 ENTITY_FIELDS) if kind == 'u']
+    assert torch.equal(xh[..., 997:997 + len(ucols)], lo[..., ucols]) and not bool(xh[..., 997 + len(ucols):].any())
+    w = torch.randn(256, 997, generator=torch.Generator().manual_seed(1)).to(DEV)
+    wx = ops.entity_exact_weight(w, ENTITY_FIELDS)
+    want = ref.double() [..., :997] @ w.double().cpu().t()
+    got = xh.double().cpu() @ wx.double().cpu().t()
+    assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
     ent['last_selected_units'][0, 0] = -1
     with pytest.raises(RuntimeError):
         ops.entity_features_split({k: v.to(DEV) for k, v in ent.items()}, ENTITY_FIELDS)

@@ -222,3 +222,42 @@ def test_weight_cache_follows_updates(model):
     model.load_state_dict(init_state_dict(seed=G.WEIGHT_SEED, baselines=G.BASELINES))
     h3, l3 = ops.weight_split(w)
     assert torch.equal(h3, h0) and torch.equal(l3, l0)
+
+
+def test_edge_entity_counts_match_oracle(model, sd):
+    """ragged / extreme entity_num (1 entity, all 512, a handful) and a row without a unit selection, against the oracle."""
+    from distar_b200.synth import synth_obs, synth_actions
+    en = torch.tensor([1, 512, 3, 37])
+    obs = synth_obs(4, seed=77, entity_num=en)
+    g = torch.Generator().manual_seed(8)
+    act, num = synth_actions(4, en, g, max_su=6)
+    num[0] = 0                                           # a single entity cannot carry a selection (needs unit + end token)
+    with torch.no_grad():
+        want = O.compute_teacher_logit(sd, **tree_clone(obs), selected_units_num=num.clone(), action_info=tree_clone(act))
+        got = model.compute_teacher_logit(**to_dev(obs), selected_units_num=num.to(DEV), action_info=to_dev(act))
+    for k in O.HEADS:
+        close(got['logit'][k], want['logit'][k], 'edge/' + k)
+
+
+def test_encoder_chunking_is_invisible(sd):
+    """size-independent property used at the full benchmark size: processing the observation rows in encoder chunks (with
+    or without recomputation in backward) must not change logits, values or gradients beyond fp32 reassociation."""
+    cfg = {'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': list(G.BASELINES)}}
+    data = to_dev(G.rl_case())
+    outs = []
+    for kw in ({}, {'encoder_chunk': 3, 'checkpoint_encoder': True, 'keep_chunks': 1}):
+        m = Model(cfg, use_value_network=True, seed=0, **kw)
+        m.load_state_dict(sd)
+        m = m.cuda()
+        m.zero_grad()
+        out = m.rl_learner_forward(**tree_clone(data))
+        info = ReinforcementLoss(None, 'MP0').compute_loss(out)
+        info['total_loss'].backward()
+        m.raise_on_bad_input()
+        outs.append(({k: v.detach().clone() for k, v in out['target_logit'].items()}, m.flat_grad.clone(),
+                     float(info['total_loss'])))
+    (la, ga, ta), (lb, gb, tb) = outs
+    for k in O.HEADS:
+        close(lb[k], la[k], 'chunked/' + k, rtol=1e-5)
+    assert abs(ta - tb) <= 1e-5 * max(1.0, abs(ta))
+    assert (ga - gb).norm().item() <= 1e-3 * ga.norm().item()      # split-K / accumulation order differ between chunkings

@@ -252,3 +252,103 @@ extern "C" int dsb_relu_bwd_split(const float* gy, const void* y, int y_is_bf16,
             gy, y, g_out, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, colsum, colsum_atomic, rows, N);
     return dsb::check_launch("relu_bwd_split");
 }
+
+
+// ---- GatedResBlock tail (module_utils.py:228-229) in one pass: out = relu(tanh(r * sigmoid(g)) * sp + x) [+ skip] ---------
+// Replaces sigmoid, mul, tanh, mul, add, relu (and the next block's `x + map_skip`) = 7 elementwise launches over a
+// [P,16,16,128] activation each way, and the five intermediates autograd would keep.  The backward recomputes the gate
+// from (r, g, x); the scalar UpdateSP gradient is block-reduced and added atomically.
+namespace {
+constexpr int kGateThreads = 256;
+
+__device__ __forceinline__ float sigmoid_f(float v) { return 1.f / (1.f + __expf(-v)); }
+
+__global__ void __launch_bounds__(kGateThreads)
+gate_fwd_kernel(const float4* __restrict__ r, const float4* __restrict__ g, const float4* __restrict__ x,
+                const float4* __restrict__ skip, const float* __restrict__ sp, float4* __restrict__ out,
+                uint2* __restrict__ out_hi, uint2* __restrict__ out_lo, int64_t n4) {
+    const float s = __ldg(sp);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 rv = __ldcs(r + i), gv = __ldcs(g + i), xv = __ldcs(x + i);
+        float4 o;
+        o.x = fmaxf(tanhf(rv.x * sigmoid_f(gv.x)) * s + xv.x, 0.f);
+        o.y = fmaxf(tanhf(rv.y * sigmoid_f(gv.y)) * s + xv.y, 0.f);
+        o.z = fmaxf(tanhf(rv.z * sigmoid_f(gv.z)) * s + xv.z, 0.f);
+        o.w = fmaxf(tanhf(rv.w * sigmoid_f(gv.w)) * s + xv.w, 0.f);
+        if (skip) { const float4 k = __ldcs(skip + i); o.x += k.x; o.y += k.y; o.z += k.z; o.w += k.w; }
+        out[i] = o;
+        if (out_hi) {
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+            const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+            const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - f0.x, o.y - f0.y);
+            const __nv_bfloat162 l1 = __floats2bfloat162_rn(o.z - f1.x, o.w - f1.y);
+            out_hi[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+            out_lo[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+        }
+    }
+}
+
+__device__ __forceinline__ void gate_bwd_one(float d, float rv, float gv, float xv, float s, float& dr, float& dg, float& dx,
+                                             float& dsp) {
+    const float u = sigmoid_f(gv), t = tanhf(rv * u);
+    const float dy = (t * s + xv > 0.f) ? d : 0.f;
+    dx = dy;
+    dsp += dy * t;
+    const float dz = dy * s * (1.f - t * t);        // d/d(r*u)
+    dr = dz * u;
+    dg = dz * rv * u * (1.f - u);
+}
+
+__global__ void __launch_bounds__(kGateThreads)
+gate_bwd_kernel(const float4* __restrict__ dout, const float4* __restrict__ r, const float4* __restrict__ g,
+                const float4* __restrict__ x, const float* __restrict__ sp, float4* __restrict__ dr, float4* __restrict__ dg,
+                float4* __restrict__ dx, float* __restrict__ dsp, int64_t n4) {
+    __shared__ float red[kGateThreads / 32];
+    const float s = __ldg(sp);
+    float acc = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 d = __ldcs(dout + i), rv = __ldcs(r + i), gv = __ldcs(g + i), xv = __ldcs(x + i);
+        float4 a, b, c;
+        gate_bwd_one(d.x, rv.x, gv.x, xv.x, s, a.x, b.x, c.x, acc);
+        gate_bwd_one(d.y, rv.y, gv.y, xv.y, s, a.y, b.y, c.y, acc);
+        gate_bwd_one(d.z, rv.z, gv.z, xv.z, s, a.z, b.z, c.z, acc);
+        gate_bwd_one(d.w, rv.w, gv.w, xv.w, s, a.w, b.w, c.w, acc);
+        dr[i] = a; dg[i] = b; dx[i] = c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < kGateThreads / 32; ++w) t += red[w];
+        atomicAdd(dsp, t);
+    }
+}
+}  // namespace
+
+extern "C" int dsb_gate_update_fwd(const float* r, const float* g, const float* x, const float* skip, const float* sp, float* out,
+                                   void* out_hi, void* out_lo, int64_t n, dsb_stream_t stream) {
+    DSB_REQUIRE(r && g && x && sp && out && (!out_hi == !out_lo) && n >= 0 && n % 4 == 0, "gate_update_fwd: bad argument (n %% 4 == 0)");
+    if (n == 0) return DSB_OK;
+    const int64_t n4 = n / 4;
+    int64_t blocks = (n4 + kGateThreads - 1) / kGateThreads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    gate_fwd_kernel<<<(unsigned)blocks, kGateThreads, 0, (cudaStream_t)stream>>>(
+        (const float4*)r, (const float4*)g, (const float4*)x, (const float4*)skip, sp, (float4*)out, (uint2*)out_hi, (uint2*)out_lo, n4);
+    return dsb::check_launch("gate_update_fwd");
+}
+
+extern "C" int dsb_gate_update_bwd(const float* grad_out, const float* r, const float* g, const float* x, const float* sp,
+                                   float* grad_r, float* grad_g, float* grad_x, float* grad_sp, int64_t n, dsb_stream_t stream) {
+    DSB_REQUIRE(grad_out && r && g && x && sp && grad_r && grad_g && grad_x && grad_sp && n >= 0 && n % 4 == 0,
+                "gate_update_bwd: bad argument (n %% 4 == 0; grad_sp is accumulated into)");
+    if (n == 0) return DSB_OK;
+    const int64_t n4 = n / 4;
+    int64_t blocks = (n4 + kGateThreads - 1) / kGateThreads;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    gate_bwd_kernel<<<(unsigned)blocks, kGateThreads, 0, (cudaStream_t)stream>>>(
+        (const float4*)grad_out, (const float4*)r, (const float4*)g, (const float4*)x, sp, (float4*)grad_r, (float4*)grad_g,
+        (float4*)grad_x, grad_sp, n4);
+    return dsb::check_launch("gate_update_bwd");
+}

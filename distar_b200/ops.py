@@ -1144,6 +1144,48 @@ def upsample_conv3x3_single(x: torch.Tensor, weight: torch.Tensor, bias: Optiona
     return out + bias if bias is not None else out
 
 
+class _GateUpdate(torch.autograd.Function):
+    """relu(tanh(r * sigmoid(g)) * sp + x) [+ skip] in one kernel each way (csrc/optim.cu: dsb_gate_update_*)."""
+
+    @staticmethod
+    def forward(ctx, r, g, x, sp, skip, want_split):
+        r, g, x = r.contiguous(), g.contiguous(), x.contiguous()
+        out = torch.empty_like(x)
+        hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_split else None
+        lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_split else None
+        lib.call('dsb_gate_update_fwd', r, g, x, skip.contiguous() if skip is not None else None, sp, out, hi, lo, x.numel())
+        ctx.save_for_backward(r, g, x, sp)
+        ctx.sp_ref, ctx.has_skip = sp, skip is not None
+        ctx.set_materialize_grads(False)
+        if want_split:
+            ctx.mark_non_differentiable(hi, lo)
+        return out, hi, lo
+
+    @staticmethod
+    def backward(ctx, gout, _ghi=None, _glo=None):
+        r, g, x, sp = ctx.saved_tensors
+        if gout is None:
+            return (None,) * 6
+        gout = gout.contiguous()
+        dr, dg, dx = torch.empty_like(r), torch.empty_like(g), torch.empty_like(x)
+        slot = _grad_slot(ctx.sp_ref)
+        dsp = slot if slot is not None else torch.zeros(1, dtype=torch.float32, device=x.device)
+        lib.call('dsb_gate_update_bwd', gout, r, g, x, sp, dr, dg, dx, dsp, x.numel())
+        return dr, dg, dx, (None if slot is not None else dsp), (gout if ctx.has_skip else None), None
+
+
+def gate_update(r: torch.Tensor, g: torch.Tensor, x: torch.Tensor, sp: torch.Tensor, skip: Optional[torch.Tensor] = None,
+                want_split: bool = True) -> torch.Tensor:
+    """GatedResBlock tail (module_utils.py:228-229): relu(tanh(r * sigmoid(g)) * sp + x), plus ``skip`` (the `x +
+    map_skip` that opens the next block of the location head) when given.  With want_split the bf16 pair of the result
+    is attached for the convolutions that read it."""
+    if _use_kernel(x) and x.numel() % 4 == 0:
+        out, hi, lo = _GateUpdate.apply(r, g, x, sp, skip, want_split)
+        return attach_split(out, hi, lo) if want_split else out
+    out = torch.relu(torch.tanh(r * torch.sigmoid(g)) * sp + x)
+    return out + skip if skip is not None else out
+
+
 class _UpConv(torch.autograd.Function):
     """y = act(conv3x3(upsample_bilinear2x(x), w) + b), channels-last, through the low-resolution factorisation
     z = x . w (tensor-core GEMM, N = 9*C) followed by nine shifted up-samplings (csrc/upsample.cu: dsb_upconv_*)."""

@@ -440,14 +440,17 @@ class Net:
         w1 = P_[pre + 'conv1.0.weight']
         small = torch.matmul(torch.relu(x4), w1[:, :4, 0, 0].t())
         x = ops.conv_nhwc(torch.relu(map_skip[-1]), w1[:, 4:], P_[pre + 'conv1.0.bias'], True, small, self.terms)
+        x = x + map_skip[len(map_skip) - 1]
+        if x.is_cuda:
+            x = ops.attach_split(x, *ops.split_bf16(x))            # conv1 and the first gate conv both read it
         for i in range(4):
-            x = x + map_skip[len(map_skip) - i - 1]
             rp = pre + 'res.%d.' % i                                   # GatedResBlock, module_utils.py:224-231
             r = self.conv_nhwc(rp + 'conv2', self.conv_nhwc(rp + 'conv1', x, relu=True, split='only'))
             g = x
             for j in range(4):
                 g = self.conv_nhwc(rp + 'GateWeightG.%d' % j, g, relu=(j < 3), split=('only' if j < 3 else False))
-            x = torch.relu(torch.tanh(r * torch.sigmoid(g)) * P_[rp + 'UpdateSP'] + x)
+            # gate + residual + ReLU, and the `x + map_skip` that opens the next block, in one pass
+            x = ops.gate_update(r, g, x, P_[rp + 'UpdateSP'], map_skip[len(map_skip) - i - 2] if i < 3 else None)
         # up-sampling stages: the 3x3 taps are applied as nine shifted up-samplings of a low-resolution projection
         x = ops.upsample_conv3x3(x, P_[pre + 'upsample.0.0.weight'], P_[pre + 'upsample.0.0.bias'], True,
                                  pair_only=True)                                                       # [N,32,32,64]

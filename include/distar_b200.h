@@ -139,6 +139,15 @@ int dsb_upconv_fwd(const float* z, int ldz, const float* bias, int relu, float* 
 int dsb_upconv_bwd(const float* g, int ldg, void* gz_hi, void* gz_lo, int ldz, int64_t N, int H, int W, int C,
                    dsb_stream_t stream);
 
+/* ---- GatedResBlock tail  (module_utils.py:228-229, location head K14) ----
+ * out = relu(tanh(r * sigmoid(g)) * sp[0] + x) (+ skip: the next block's `x + map_skip`), fp32 [n] each, optionally also as
+ * the bf16 (hi, lo) pair the next convolutions read.  Backward recomputes the gate from (r, g, x), writes grad_r / grad_g /
+ * grad_x (grad of skip == grad_out) and ADDS the scalar gradient of sp into grad_sp[0]. */
+int dsb_gate_update_fwd(const float* r, const float* g, const float* x, const float* skip, const float* sp, float* out,
+                        void* out_hi, void* out_lo, int64_t n, dsb_stream_t stream);
+int dsb_gate_update_bwd(const float* grad_out, const float* r, const float* g, const float* x, const float* sp, float* grad_r,
+                        float* grad_g, float* grad_x, float* grad_sp, int64_t n, dsb_stream_t stream);
+
 /* ---- fp32 -> (hi, lo) bf16 split used by the split-precision tensor-core GEMM ---- */
 int dsb_split_bf16(const float* x, void* hi, void* lo, int64_t n, dsb_stream_t stream);
 

@@ -339,3 +339,28 @@ def test_relu_bwd_split_layouts(rows, N, bf16_mask):
     assert (gb.double().cpu() - ref).abs().max().item() <= 1e-5 * max(1.0, want.abs().sum(0).max().item())
     _, _, gb2, g2 = ops.relu_bwd_split(gy.to(DEV), mask, True, need_g=True, need_split=False)
     assert torch.equal(g2.cpu(), want) and torch.allclose(gb2, gb)
+
+
+@pytest.mark.parametrize('with_skip', [True, False])
+def test_gate_update_fwd_bwd(with_skip):
+    """GatedResBlock tail (module_utils.py:228-229) fused with the next block's skip add, against torch autograd."""
+    g_ = torch.Generator().manual_seed(21)
+    shape = (3, 16, 16, 128)
+    r, g, x, sk, go = [torch.randn(shape, generator=g_) for _ in range(5)]
+    sp = torch.tensor([0.1])
+    ref_in = [t.double().requires_grad_(True) for t in (r, g, x, sp, sk)]
+    y = torch.tanh(ref_in[0] * torch.sigmoid(ref_in[1])) * ref_in[3] + ref_in[2]
+    go = go * (y.detach().abs() > 1e-4).float()                      # stay off the ReLU boundary
+    out = torch.relu(y) + (ref_in[4] if with_skip else 0)
+    out.backward(go.double())
+    dev_in = [t.to(DEV).requires_grad_(True) for t in (r, g, x, sp, sk)]
+    got = ops.gate_update(dev_in[0], dev_in[1], dev_in[2], dev_in[3], dev_in[4] if with_skip else None)
+    got.backward(go.to(DEV))
+    assert (got.detach().double().cpu() - out.detach()).abs().max().item() <= 1e-5
+    hi, lo = got._dsb_split
+    assert torch.equal(hi, ops.split_bf16(got.detach().clone())[0]) and torch.equal(lo, ops.split_bf16(got.detach().clone())[1])
+    for a, b, n in zip(dev_in, ref_in, ['dr', 'dg', 'dx', 'dsp', 'dskip']):
+        if n == 'dskip' and not with_skip:
+            continue
+        err = (a.grad.double().cpu() - b.grad).abs().max().item()
+        assert err <= 1e-4 * max(b.grad.abs().max().item(), 1e-6), (n, err)

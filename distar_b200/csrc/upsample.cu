@@ -482,3 +482,88 @@ extern "C" int dsb_upshift9_bwd(const float* grad_out, float* grad_z, int64_t N,
     upshift9_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(grad_out, grad_z, total, H, W);
     return dsb::check_launch("upshift9_bwd");
 }
+
+
+// ---- 2x2 / stride-2 max-pool on channels-last activations (spatial encoder, between the down-sampling convolutions) ------
+// out[n, y, x, c] = max over the 2x2 window (first maximum in scan order, as ATen); also writes the bf16 (hi, lo) pair the
+// next convolution reads and a 2-bit argmax per element (one byte) so the backward does not re-read the input.
+namespace {
+__global__ void __launch_bounds__(256)
+maxpool2_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ out, uint2* __restrict__ out_hi, uint2* __restrict__ out_lo,
+                    uchar4* __restrict__ idx, int64_t total, int H, int W, int C4) {
+    const int OH = H / 2, OW = W / 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        const int ox = (int)((i / C4) % OW), oy = (int)((i / ((int64_t)C4 * OW)) % OH);
+        const int64_t n = i / ((int64_t)C4 * OW * OH);
+        const float4* base = x + ((n * H + 2 * oy) * (int64_t)W + 2 * ox) * C4 + c;
+        const float4 v[4] = {__ldcs(base), __ldcs(base + C4), __ldcs(base + (int64_t)W * C4), __ldcs(base + (int64_t)W * C4 + C4)};
+        float4 m = v[0];
+        uchar4 k = make_uchar4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 1; j < 4; ++j) {
+            if (v[j].x > m.x) { m.x = v[j].x; k.x = j; }
+            if (v[j].y > m.y) { m.y = v[j].y; k.y = j; }
+            if (v[j].z > m.z) { m.z = v[j].z; k.z = j; }
+            if (v[j].w > m.w) { m.w = v[j].w; k.w = j; }
+        }
+        out[i] = m;
+        idx[i] = k;
+        if (out_hi) {
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(m.x, m.y), h1 = __floats2bfloat162_rn(m.z, m.w);
+            const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+            const __nv_bfloat162 l0 = __floats2bfloat162_rn(m.x - f0.x, m.y - f0.y);
+            const __nv_bfloat162 l1 = __floats2bfloat162_rn(m.z - f1.x, m.w - f1.y);
+            out_hi[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+            out_lo[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+maxpool2_bwd_kernel(const float4* __restrict__ gout, const uchar4* __restrict__ idx, float4* __restrict__ gx, int64_t total,
+                    int H, int W, int C4) {
+    const int OH = H / 2, OW = W / 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        const int ox = (int)((i / C4) % OW), oy = (int)((i / ((int64_t)C4 * OW)) % OH);
+        const int64_t n = i / ((int64_t)C4 * OW * OH);
+        const float4 g = __ldcs(gout + i);
+        const uchar4 k = idx[i];
+        float4* base = gx + ((n * H + 2 * oy) * (int64_t)W + 2 * ox) * C4 + c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4 o;
+            o.x = (k.x == j) ? g.x : 0.f; o.y = (k.y == j) ? g.y : 0.f;
+            o.z = (k.z == j) ? g.z : 0.f; o.w = (k.w == j) ? g.w : 0.f;
+            base[(j & 1) * C4 + (j >> 1) * (int64_t)W * C4] = o;
+        }
+    }
+}
+}  // namespace
+
+extern "C" int dsb_maxpool2_nhwc_fwd(const float* x, float* out, void* out_hi, void* out_lo, uint8_t* argmax, int64_t N, int H,
+                                     int W, int C, dsb_stream_t stream) {
+    DSB_REQUIRE(x && out && argmax && (!out_hi == !out_lo) && N >= 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0,
+                "maxpool2_nhwc_fwd: bad argument (even H, W; C %% 4 == 0)");
+    const int64_t total = N * (H / 2) * (W / 2) * (C / 4);
+    if (total == 0) return DSB_OK;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    maxpool2_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)out, (uint2*)out_hi,
+                                                                            (uint2*)out_lo, (uchar4*)argmax, total, H, W, C / 4);
+    return dsb::check_launch("maxpool2_nhwc_fwd");
+}
+
+extern "C" int dsb_maxpool2_nhwc_bwd(const float* grad_out, const uint8_t* argmax, float* grad_x, int64_t N, int H, int W, int C,
+                                     dsb_stream_t stream) {
+    DSB_REQUIRE(grad_out && argmax && grad_x && N >= 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0,
+                "maxpool2_nhwc_bwd: bad argument");
+    const int64_t total = N * (H / 2) * (W / 2) * (C / 4);
+    if (total == 0) return DSB_OK;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    maxpool2_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)grad_out, (const uchar4*)argmax,
+                                                                            (float4*)grad_x, total, H, W, C / 4);
+    return dsb::check_launch("maxpool2_nhwc_bwd");
+}

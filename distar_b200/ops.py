@@ -1144,6 +1144,43 @@ def upsample_conv3x3_single(x: torch.Tensor, weight: torch.Tensor, bias: Optiona
     return out + bias if bias is not None else out
 
 
+class _MaxPool2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, want_split):
+        N, H, W, C = x.shape
+        x = x.contiguous()
+        oshape = (N, H // 2, W // 2, C)
+        out = torch.empty(oshape, dtype=torch.float32, device=x.device)
+        hi = torch.empty(oshape, dtype=torch.bfloat16, device=x.device) if want_split else None
+        lo = torch.empty(oshape, dtype=torch.bfloat16, device=x.device) if want_split else None
+        idx = torch.empty(oshape, dtype=torch.uint8, device=x.device)
+        lib.call('dsb_maxpool2_nhwc_fwd', x, out, hi, lo, idx, N, H, W, C)
+        ctx.save_for_backward(idx)
+        ctx.xshape = x.shape
+        ctx.set_materialize_grads(False)
+        if want_split:
+            ctx.mark_non_differentiable(hi, lo)
+        return out, hi, lo
+
+    @staticmethod
+    def backward(ctx, gout, _ghi=None, _glo=None):
+        (idx,) = ctx.saved_tensors
+        if gout is None:
+            return None, None
+        N, H, W, C = ctx.xshape
+        gx = torch.empty(ctx.xshape, dtype=torch.float32, device=gout.device)
+        lib.call('dsb_maxpool2_nhwc_bwd', gout.contiguous(), idx, gx, N, H, W, C)
+        return gx, None
+
+
+def max_pool2_nhwc(x: torch.Tensor, want_split: bool = True) -> torch.Tensor:
+    """F.max_pool2d(x, 2, 2) on a channels-last [N,H,W,C] activation; the bf16 pair of the result is attached."""
+    if _use_kernel(x) and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0 and x.shape[3] % 4 == 0:
+        out, hi, lo = _MaxPool2.apply(x, want_split)
+        return attach_split(out, hi, lo) if want_split else out
+    return F.max_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).contiguous()
+
+
 class _GateUpdate(torch.autograd.Function):
     """relu(tanh(r * sigmoid(g)) * sp + x) [+ skip] in one kernel each way (csrc/optim.cu: dsb_gate_update_*)."""
 

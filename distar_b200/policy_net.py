@@ -236,7 +236,7 @@ class Net:
 
     @staticmethod
     def pool_nhwc(x: Tensor) -> Tensor:
-        return F.max_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).contiguous()
+        return ops.max_pool2_nhwc(x)
 
     def encoder(self, spatial_info, entity_info, scalar_info, entity_num, entity_fn=None):
         """model/encoder.py:28-45.  entity_fn lets the caller wrap the entity transformer (the activation-memory hog)

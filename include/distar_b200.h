@@ -139,6 +139,14 @@ int dsb_upconv_fwd(const float* z, int ldz, const float* bias, int relu, float* 
 int dsb_upconv_bwd(const float* g, int ldg, void* gz_hi, void* gz_lo, int ldz, int64_t N, int H, int W, int C,
                    dsb_stream_t stream);
 
+/* ---- 2x2 stride-2 max-pool, channels-last  (spatial_encoder.py:74-79 `F.max_pool2d` between the down-sampling convs) ----
+ * x [N,H,W,C] fp32 -> out [N,H/2,W/2,C] (+ optional bf16 pair for the next convolution) and a one-byte argmax (0..3, window
+ * scan order, first maximum) per output element; the backward scatters grad_out through it (grad_x fully written). */
+int dsb_maxpool2_nhwc_fwd(const float* x, float* out, void* out_hi, void* out_lo, uint8_t* argmax, int64_t N, int H, int W, int C,
+                          dsb_stream_t stream);
+int dsb_maxpool2_nhwc_bwd(const float* grad_out, const uint8_t* argmax, float* grad_x, int64_t N, int H, int W, int C,
+                          dsb_stream_t stream);
+
 /* ---- GatedResBlock tail  (module_utils.py:228-229, location head K14) ----
  * out = relu(tanh(r * sigmoid(g)) * sp[0] + x) (+ skip: the next block's `x + map_skip`), fp32 [n] each, optionally also as
  * the bf16 (hi, lo) pair the next convolutions read.  Backward recomputes the gate from (r, g, x), writes grad_r / grad_g /

@@ -3,6 +3,7 @@ import math
 
 import pytest
 import torch
+import torch.nn.functional as F
 
 import alphastar_ref as O
 from distar_b200 import ops
@@ -364,3 +365,26 @@ def test_gate_update_fwd_bwd(with_skip):
             continue
         err = (a.grad.double().cpu() - b.grad).abs().max().item()
         assert err <= 1e-4 * max(b.grad.abs().max().item(), 1e-6), (n, err)
+
+
+@pytest.mark.parametrize('N,H,W,C', [(3, 64, 64, 64), (2, 32, 32, 128), (1, 2, 4, 8)])
+def test_max_pool2_nhwc_fwd_bwd(N, H, W, C):
+    g = torch.Generator().manual_seed(H + C)
+    x = torch.relu(torch.randn(N, H, W, C, generator=g))                  # post-ReLU input, like the spatial encoder's
+    go = torch.randn(N, H // 2, W // 2, C, generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref = F.max_pool2d(xr.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    ref.backward(go)
+    xd = x.to(DEV).requires_grad_(True)
+    out = ops.max_pool2_nhwc(xd)
+    out.backward(go.to(DEV))
+    assert torch.equal(out.detach().cpu(), ref.detach())
+    hi, lo = out._dsb_split
+    eh, el = ops.split_bf16(out.detach().clone())
+    assert torch.equal(hi, eh) and torch.equal(lo, el)
+    # ties only happen at 0 (both pick some zero of the window); compare the gradient where the input is positive, and
+    # check that every window passes its whole gradient to exactly one position
+    pos = x > 0
+    assert torch.equal(xd.grad.cpu()[pos], xr.grad[pos])
+    win = xd.grad.cpu().view(N, H // 2, 2, W // 2, 2, C).sum(dim=(2, 4))
+    assert torch.allclose(win, go)

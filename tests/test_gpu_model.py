@@ -258,6 +258,6 @@ def test_encoder_chunking_is_invisible(sd):
                      float(info['total_loss'])))
     (la, ga, ta), (lb, gb, tb) = outs
     for k in O.HEADS:
-        close(lb[k], la[k], 'chunked/' + k, rtol=1e-5)
+        close(lb[k], la[k], 'chunked/' + k, rtol=1e-4)          # tile shapes (hence summation order) depend on the row count
     assert abs(ta - tb) <= 1e-5 * max(1.0, abs(ta))
     assert (ga - gb).norm().item() <= 1e-3 * ga.norm().item()      # split-K / accumulation order differ between chunkings

@@ -310,6 +310,7 @@ def run_b200(args, rank, world, local_rank):
         learner._train(resident)
 
     last_loss = [None]
+    last_info = [None]
     copy_stream = torch.cuda.Stream(device=dev)
     staged = {}
 
@@ -329,7 +330,11 @@ def run_b200(args, rank, world, local_rank):
         tree_map(lambda t: t.record_stream(torch.cuda.current_stream()) or t, data)
         prefetch()                                          # overlaps with this step's compute
         info = learner._train(data)
-        last_loss[0] = info['total_loss'].item()           # device -> host read of the step result
+        # device -> host read of the step result: the loss and the ~45 logged scalars arrive in ONE asynchronous copy queued
+        # right after the loss (rl_loss.LazyScalars); reading them waits for forward + loss only, so the host queues the next
+        # step while this step's backward is still running
+        last_loss[0] = info['total_loss_value']
+        last_info[0] = info
 
     if os.environ.get('DSB_ANOMALY') == '1':
         torch.autograd.set_detect_anomaly(True)
@@ -347,7 +352,7 @@ def run_b200(args, rank, world, local_rank):
         step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
         e2e = {'value': world * B * T / (ms_e2e / 1e3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d,
-               'd2h_bytes_per_step': 4 + 4 * 45, 'ms_per_step': ms_e2e}
+               'd2h_bytes_per_step': 4 * len(last_info[0]) if last_info[0] is not None else 0, 'ms_per_step': ms_e2e}
     if world > 1:
         dist.barrier()
     if rank != 0:

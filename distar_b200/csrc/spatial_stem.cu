@@ -19,7 +19,7 @@ namespace {
 constexpr int kOC = 32;            // output channels of the project conv
 constexpr int kIC = 56;            // input planes
 constexpr int kRows = 4;           // input rows per tile
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;          // 2 CTAs (2 x 93 KB of shared memory) x 16 warps per SM: the tile phases are latency bound
 constexpr int kWarps = kThreads / 32;
 constexpr int kPlanes = 7;         // height, visibility, creep, player_relative, alerts, pathable, buildable
 constexpr int kEffects = 6;
@@ -151,7 +151,7 @@ __device__ __forceinline__ void load_weight_t(const StemArgs& a, const Smem& s) 
     }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 stem_fwd_kernel(const StemArgs a, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
                 __nv_bfloat16* __restrict__ out_lo, int out_c) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -185,7 +185,7 @@ stem_fwd_kernel(const StemArgs a, float* __restrict__ out, __nv_bfloat16* __rest
 }
 
 // Backward: dW/db accumulate in shared memory across the tiles of a persistent CTA and are flushed once.
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 stem_bwd_kernel(const StemArgs a, const float* __restrict__ gout, int out_c, float* __restrict__ gweight,
                 float* __restrict__ gbias, float* __restrict__ gproject) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

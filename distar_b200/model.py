@@ -176,6 +176,8 @@ class Model(nn.Module):
         if self.flat_param.is_cuda:
             if getattr(self, '_bad_input_flag', None) is None or self._bad_input_flag.device != self.flat_param.device:
                 self._bad_input_flag = torch.zeros(1, dtype=torch.int32, device=self.flat_param.device)
+            self._bad_input_flag.zero_()          # one flag per forward pass (a raise may leave queued recomputations behind)
+            self._flag_handle = None
             net.bad_input_flag = self._bad_input_flag
         self._last_net = net
         return net
@@ -185,6 +187,15 @@ class Model(nn.Module):
         (entity_encoder.py:69-72).  compute_logp_action / compute_teacher_logit / sl_train call this before returning;
         rl_learner_forward leaves it to the caller (RLLearner._train checks after backward, before the optimiser step)
         because reading the flag is a host<->device synchronisation."""
+        handle = getattr(self, '_flag_handle', None)
+        if handle is not None:
+            # rl_learner_forward queued an asynchronous copy of the flag right behind the forward pass: waiting for it does
+            # not wait for the backward pass the caller has queued since, so the host keeps its lead over the GPU
+            self._flag_handle = None
+            if int(handle()) != 0:
+                self._bad_input_flag.zero_()
+                raise RuntimeError('negative categorical id in an entity field')
+            return
         net = getattr(self, '_last_net', None)
         if net is not None:
             net.raise_on_bad_input()
@@ -272,6 +283,7 @@ class Model(nn.Module):
         logits = {k: v.view(T, B, *v.shape[1:]) for k, v in logits.items()}
         su = logits['selected_units']
         logits['selected_units'] = F.pad(su, (0, 0, 0, MAX_SELECTED_UNITS_NUM - su.shape[2]), 'constant', -1e9)
+        self._flag_handle = _async_scalar(self._bad_input_flag) if lstm_out.is_cuda else None
         return {'unroll_len': T, 'batch_size': B, 'selected_units_num': selected_units_num,
                 'target_logit': logits, 'value': values, 'action_log_prob': behaviour_logp,
                 'teacher_logit': teacher_logit, 'mask': mask, 'action': action_info, 'reward': reward,

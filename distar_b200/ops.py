@@ -924,6 +924,86 @@ class _LstmCell(torch.autograd.Function):
         return d_ig, d_hg, d_cin, dgh, dbh, dgc, dbc
 
 
+class _LstmLayer(torch.autograd.Function):
+    """One LayerNorm-LSTM layer over all timesteps (model/lstm.py:120-167) as ONE autograd node.
+
+    Per step the forward is a recurrent product h W_hh^T (library fp32 GEMM, M = batch) + the fused cell kernel; the backward
+    walks the steps in reverse with the cell-backward kernel and dh = d_hg W_hh.  What the per-cell formulation paid per
+    (layer, step) and this does once per layer: the W_hh gradient (one tensor-core GEMM over all L*B rows instead of L small
+    fp32 GEMMs + L accumulate adds), the LayerNorm parameter gradients (accumulated in place by the kernel's atomics instead of
+    4 zero-fills + 4 adds per step) and ~10 autograd nodes of Python bookkeeping."""
+
+    @staticmethod
+    def forward(ctx, ig_all, h0, c0, w_hh, gam_h, bet_h, gam_c, bet_c):
+        L, B, G = ig_all.shape
+        H = G // 4
+        dev = ig_all.device
+        ig_all, h0, c0 = ig_all.contiguous(), h0.contiguous(), c0.contiguous()
+        f32 = dict(dtype=torch.float32, device=dev)
+        hs, cs = torch.empty((L, B, H), **f32), torch.empty((L, B, H), **f32)
+        gates, hg_all = torch.empty((L, B, G), **f32), torch.empty((L, B, G), **f32)
+        pre_c, st_h, st_c = torch.empty((L, B, H), **f32), torch.empty((L, B, 2), **f32), torch.empty((L, B, 2), **f32)
+        w_t = w_hh.detach().t()
+        h, c = h0, c0
+        for t in range(L):
+            torch.mm(h, w_t, out=hg_all[t])
+            lib.call('dsb_lstm_cell_fwd', ig_all[t], hg_all[t], c, gam_h, bet_h, gam_c, bet_c, hs[t], cs[t], gates[t], st_h[t],
+                     pre_c[t], st_c[t], B, H, 1e-5)
+            h, c = hs[t], cs[t]
+        ctx.save_for_backward(gates, hg_all, st_h, pre_c, st_c, hs, cs, h0, c0, w_hh, gam_h, gam_c, bet_c)
+        ctx.refs = (w_hh, gam_h, bet_h, gam_c, bet_c)
+        ctx.set_materialize_grads(False)
+        return hs, cs[L - 1].clone()
+
+    @staticmethod
+    def backward(ctx, g_hs, g_clast):
+        gates, hg_all, st_h, pre_c, st_c, hs, cs, h0, c0, w_hh, gam_h, gam_c, bet_c = ctx.saved_tensors
+        L, B, G = gates.shape
+        H = G // 4
+        dev = gates.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        d_ig, d_hg = torch.empty((L, B, G), **f32), torch.empty((L, B, G), **f32)
+        refs = ctx.refs
+        slots = [_grad_slot(p) for p in refs[1:]]
+        direct = all(s_ is not None for s_ in slots)
+        if direct:
+            dgh, dbh, dgc, dbc = slots
+        else:
+            dgh, dbh = torch.zeros(G, **f32), torch.zeros(G, **f32)
+            dgc, dbc = torch.zeros(H, **f32), torch.zeros(H, **f32)
+        dh_next = None
+        dc_next = g_clast.contiguous() if g_clast is not None else None
+        w = w_hh.detach()
+        for t in range(L - 1, -1, -1):
+            if g_hs is not None:
+                gh = g_hs[t] if dh_next is None else g_hs[t] + dh_next
+            else:
+                gh = dh_next if dh_next is not None else torch.zeros((B, H), **f32)
+            gh = gh.contiguous()
+            c_in = cs[t - 1] if t > 0 else c0
+            d_cin = torch.empty((B, H), **f32)
+            lib.call('dsb_lstm_cell_bwd', gh, dc_next, gates[t], hg_all[t], st_h[t], c_in, pre_c[t], st_c[t], gam_h, gam_c, bet_c,
+                     d_ig[t], d_hg[t], d_cin, dgh, dbh, dgc, dbc, B, H)
+            dh_next = torch.mm(d_hg[t], w)
+            dc_next = d_cin
+        gw = None
+        if ctx.needs_input_grad[3]:
+            h_prev = torch.cat([h0.unsqueeze(0), hs[:L - 1]], dim=0).reshape(L * B, H)
+            dg2 = d_hg.reshape(L * B, G)
+            if (L * B) % 64 == 0 and L * B >= 128 and G % 128 == 0 and H % 128 == 0:
+                g_hi, g_lo = split_bf16(dg2)
+                x_hi, x_lo = split_bf16(h_prev)
+                gw = weight_grad(g_hi, g_lo, x_hi, x_lo, 3, accumulate_into=_grad_slot(refs[0]))
+            else:
+                gw = dg2.t() @ h_prev
+        return (d_ig, dh_next, dc_next, gw) + ((None,) * 4 if direct else (dgh, dbh, dgc, dbc))
+
+
+def lstm_layer(ig_all, h0, c0, w_hh, gam_h, bet_h, gam_c, bet_c):
+    """LayerNorm-LSTM layer over [L,B,4H] pre-computed input gates -> (h for every step [L,B,H], c after the last step)."""
+    return _LstmLayer.apply(ig_all, h0, c0, w_hh, gam_h, bet_h, gam_c, bet_c)
+
+
 def lstm_cell(ig, hg, c_in, gam_h, bet_h, gam_c, bet_c):
     """LayerNormLSTMCell (model/lstm.py:138-153) after the two matmuls, fused: returns (h', c')."""
     H = c_in.shape[-1]

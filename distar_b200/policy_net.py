@@ -269,11 +269,17 @@ class Net:
             ig = self.ln(cp + '.layernorm_i', ops.linear(x.reshape(L * B, D), self.P[cp + '.weight_ih'], None, False,
                                                          self.terms)).view(L, B, -1)
             h, c = state[l]
-            ys = []
-            for t in range(L):
-                h, c = self.lstm_cell(cp, ig[t], h, c)
-                ys.append(h)
-            x = torch.stack(ys)
+            if ig.is_cuda and h.shape[-1] in (128, 384):
+                P = self.P
+                x, c = ops.lstm_layer(ig, h, c, P[cp + '.weight_hh'], P[cp + '.layernorm_h.weight'], P[cp + '.layernorm_h.bias'],
+                                      P[cp + '.layernorm_c.weight'], P[cp + '.layernorm_c.bias'])
+                h = x[L - 1]
+            else:
+                ys = []
+                for t in range(L):
+                    h, c = self.lstm_cell(cp, ig[t], h, c)
+                    ys.append(h)
+                x = torch.stack(ys)
             out_state.append((h, c))
         return x, out_state
 

@@ -253,6 +253,7 @@ class ReinforcementLoss:
             total = total_pg + total_upgo + total_critic + total_ent + total_kl + at_kl
         # one device->host copy for every logged scalar, and it is not waited for here: the values materialise on first
         # access, so backward can be queued behind the forward pass without draining the launch queue in between
+        log['total_loss_value'] = total          # the float of total_loss rides in the same copy (total_loss itself stays a tensor)
         keys = list(log.keys())
         out = LazyScalars(keys, torch.stack([log[k].detach().float() for k in keys]))
         out['total_loss'] = total

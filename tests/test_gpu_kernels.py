@@ -388,3 +388,35 @@ def test_max_pool2_nhwc_fwd_bwd(N, H, W, C):
     assert torch.equal(xd.grad.cpu()[pos], xr.grad[pos])
     win = xd.grad.cpu().view(N, H // 2, 2, W // 2, 2, C).sum(dim=(2, 4))
     assert torch.allclose(win, go)
+
+
+@pytest.mark.parametrize('L,B,H', [(5, 64, 384), (1, 3, 384), (4, 128, 128)])
+def test_lstm_layer_matches_cell_loop(L, B, H):
+    """the layer-level autograd node (one dW_hh GEMM, in-place LayerNorm gradients) against the per-cell formulation"""
+    g = torch.Generator().manual_seed(L + B + H)
+    G4 = 4 * H
+    ig = torch.randn(L, B, G4, generator=g)
+    h0, c0 = torch.randn(B, H, generator=g), torch.randn(B, H, generator=g)
+    w = torch.randn(G4, H, generator=g) / H ** 0.5
+    gh, bh = 1 + 0.1 * torch.randn(G4, generator=g), 0.1 * torch.randn(G4, generator=g)
+    gc, bc = 1 + 0.1 * torch.randn(H, generator=g), 0.1 * torch.randn(H, generator=g)
+    go, gcl = torch.randn(L, B, H, generator=g), torch.randn(B, H, generator=g)
+
+    def run(layer):
+        leaves = [t.to(DEV).requires_grad_(True) for t in (ig, h0, c0, w, gh, bh, gc, bc)]
+        a_ig, a_h, a_c, a_w, a_gh, a_bh, a_gc, a_bc = leaves
+        if layer:
+            hs, cl = ops.lstm_layer(a_ig, a_h, a_c, a_w, a_gh, a_bh, a_gc, a_bc)
+        else:
+            h, c, ys = a_h, a_c, []
+            for t in range(L):
+                h, c = ops.lstm_cell(a_ig[t], h @ a_w.t(), c, a_gh, a_bh, a_gc, a_bc)
+                ys.append(h)
+            hs, cl = torch.stack(ys), c
+        ((hs * go.to(DEV)).sum() + (cl * gcl.to(DEV)).sum()).backward()
+        return hs.detach(), cl.detach(), [t.grad for t in leaves]
+    hs_a, cl_a, ga = run(True)
+    hs_b, cl_b, gb = run(False)
+    assert torch.allclose(hs_a, hs_b, rtol=1e-5, atol=1e-6) and torch.allclose(cl_a, cl_b, rtol=1e-5, atol=1e-6)
+    for a, b, n in zip(ga, gb, ['ig', 'h0', 'c0', 'w_hh', 'gam_h', 'bet_h', 'gam_c', 'bet_c']):
+        assert (a - b).abs().max().item() <= 2e-4 * max(b.abs().max().item(), 1e-6), n

@@ -567,3 +567,84 @@ extern "C" int dsb_maxpool2_nhwc_bwd(const float* grad_out, const uint8_t* argma
                                                                             (float4*)grad_x, total, H, W, C / 4);
     return dsb::check_launch("maxpool2_nhwc_bwd");
 }
+
+
+// ---- location-head tail projection z[p, t] = sum_c x[p, c] w[c, t]  (32 channels -> the 9 taps of the last 3x3 conv) -------
+// A [16.7 M x 32] x [32 x 9] product: far too skinny for the library GEMMs (the weight gradient ran as a 4.5 ms "large-k"
+// kernel).  Forward: one thread per pixel.  Backward: one warp walks pixels with lane = channel; every lane keeps its 9
+// weight-gradient accumulators in registers and writes its channel of dL/dx; partials are reduced per block and added
+// atomically into gw [32, 9].
+namespace {
+constexpr int kP9C = 32, kP9T = 9;
+
+__global__ void __launch_bounds__(256)
+proj9_fwd_kernel(const float4* __restrict__ x, const float* __restrict__ w, float* __restrict__ z, int64_t pixels) {
+    __shared__ float ws[kP9C * kP9T];
+    for (int i = threadIdx.x; i < kP9C * kP9T; i += blockDim.x) ws[i] = w[i];
+    __syncthreads();
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < pixels; p += (int64_t)gridDim.x * blockDim.x) {
+        float acc[kP9T];
+#pragma unroll
+        for (int t = 0; t < kP9T; ++t) acc[t] = 0.f;
+#pragma unroll
+        for (int j = 0; j < kP9C / 4; ++j) {
+            const float4 v = __ldcs(x + p * (kP9C / 4) + j);
+#pragma unroll
+            for (int t = 0; t < kP9T; ++t)
+                acc[t] += v.x * ws[(4 * j) * kP9T + t] + v.y * ws[(4 * j + 1) * kP9T + t] + v.z * ws[(4 * j + 2) * kP9T + t] +
+                          v.w * ws[(4 * j + 3) * kP9T + t];
+        }
+#pragma unroll
+        for (int t = 0; t < kP9T; ++t) z[p * kP9T + t] = acc[t];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+proj9_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gz, const float* __restrict__ w, float* __restrict__ gx,
+                 float* __restrict__ gw, int64_t pixels) {
+    __shared__ float red[8][kP9C * kP9T];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float wl[kP9T], acc[kP9T];
+#pragma unroll
+    for (int t = 0; t < kP9T; ++t) { wl[t] = __ldg(w + lane * kP9T + t); acc[t] = 0.f; }
+    const int64_t warps = (int64_t)gridDim.x * 8;
+    for (int64_t p = (int64_t)blockIdx.x * 8 + warp; p < pixels; p += warps) {
+        const float xv = __ldcs(x + p * kP9C + lane);
+        float g[kP9T];
+#pragma unroll
+        for (int t = 0; t < kP9T; ++t) g[t] = __ldg(gz + p * kP9T + t);       // same address in every lane: one broadcast load
+        float d = 0.f;
+#pragma unroll
+        for (int t = 0; t < kP9T; ++t) { d += g[t] * wl[t]; acc[t] += xv * g[t]; }
+        gx[p * kP9C + lane] = d;
+    }
+#pragma unroll
+    for (int t = 0; t < kP9T; ++t) red[warp][lane * kP9T + t] = acc[t];
+    __syncthreads();
+    for (int i = threadIdx.x; i < kP9C * kP9T; i += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][i];
+        atomicAdd(gw + i, s);
+    }
+}
+}  // namespace
+
+extern "C" int dsb_proj9_fwd(const float* x, const float* w, float* z, int64_t pixels, int C, dsb_stream_t stream) {
+    DSB_REQUIRE(x && w && z && pixels >= 0 && C == kP9C, "proj9_fwd: bad argument (C must be 32)");
+    if (pixels == 0) return DSB_OK;
+    int64_t blocks = (pixels + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    proj9_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)x, w, z, pixels);
+    return dsb::check_launch("proj9_fwd");
+}
+
+extern "C" int dsb_proj9_bwd(const float* x, const float* grad_z, const float* w, float* grad_x, float* grad_w, int64_t pixels,
+                             int C, dsb_stream_t stream) {
+    DSB_REQUIRE(x && grad_z && w && grad_x && grad_w && pixels >= 0 && C == kP9C, "proj9_bwd: bad argument (C must be 32)");
+    if (pixels == 0) return DSB_OK;
+    int64_t blocks = (pixels + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    proj9_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, grad_z, w, grad_x, grad_w, pixels);
+    return dsb::check_launch("proj9_bwd");
+}

@@ -46,6 +46,8 @@ _SIGNATURES = {
     'dsb_lstm_cell_bwd': (_i, [_vp] * 18 + [_i, _i, _vp]),
     'dsb_upconv_fwd': (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp]),
     'dsb_upconv_bwd': (_i, [_vp, _i, _vp, _vp, _i, _i64, _i, _i, _i, _vp]),
+    'dsb_proj9_fwd': (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
+    'dsb_proj9_bwd': (_i, [_vp] * 5 + [_i64, _i, _vp]),
     'dsb_maxpool2_nhwc_fwd': (_i, [_vp] * 5 + [_i64, _i, _i, _i, _vp]),
     'dsb_maxpool2_nhwc_bwd': (_i, [_vp] * 3 + [_i64, _i, _i, _i, _vp]),
     'dsb_gate_update_fwd': (_i, [_vp] * 8 + [_i64, _vp]),

@@ -1206,6 +1206,28 @@ class _UpShift9(torch.autograd.Function):
         return gz, (g.sum().reshape(1) if ctx.has_bias else None)
 
 
+class _Proj9(torch.autograd.Function):
+    """z = x @ wm for x [..., 32], wm [32, 9] (csrc/upsample.cu: dsb_proj9_*): the library GEMMs are very slow at this shape."""
+
+    @staticmethod
+    def forward(ctx, x, wm):
+        x = x.contiguous()
+        wm = wm.contiguous()
+        pixels = x.numel() // 32
+        z = torch.empty((*x.shape[:-1], 9), dtype=torch.float32, device=x.device)
+        lib.call('dsb_proj9_fwd', x, wm, z, pixels, 32)
+        ctx.save_for_backward(x, wm)
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        x, wm = ctx.saved_tensors
+        gx = torch.empty_like(x)
+        gw = torch.zeros((32, 9), dtype=torch.float32, device=x.device)
+        lib.call('dsb_proj9_bwd', x, gz.contiguous(), wm, gx, gw, x.numel() // 32, 32)
+        return gx, gw
+
+
 def upsample_conv3x3_single(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
     """conv2d(F.interpolate(x, 2, 'bilinear'), weight[1,C,3,3], bias, padding=1) for a channels-last x [N,H,W,Cpad>=C]
     -> [N, 2H, 2W].  Up-sampling commutes with the channel contraction, so the 3x3 taps are applied as nine shifted
@@ -1214,7 +1236,10 @@ def upsample_conv3x3_single(x: torch.Tensor, weight: torch.Tensor, bias: Optiona
     wm = weight[0].reshape(C, 9)
     if x.shape[-1] > C:
         wm = F.pad(wm, (0, 0, 0, x.shape[-1] - C))
-    z = torch.matmul(x, wm)                                   # [N,H,W,9]  (small library GEMM, N = 9)
+    if x.is_cuda and x.shape[-1] == 32 and not _HOST_LOGIC_TESTING:
+        z = _Proj9.apply(x, wm)                               # [N,H,W,9]
+    else:
+        z = torch.matmul(x, wm)                               # [N,H,W,9]  (small library GEMM, N = 9)
     if _use_kernel(x):
         return _UpShift9.apply(z, bias)
     up = F.interpolate(z.permute(0, 3, 1, 2), scale_factor=2., mode='bilinear')          # [N,9,2H,2W]

@@ -205,7 +205,8 @@ class Net:
             x = self.ln(lp + '.layernorm2', x, residual=m, split=(i < 2))
         x = torch.relu(x)
         entity_embeddings = self.fc(pre + 'entity_fc', x, relu=True)
-        pooled = (x * mask.unsqueeze(2)).sum(dim=1) / entity_num.unsqueeze(-1)
+        # masked mean over entities as a batched [1,E] x [E,256] product: reads x once instead of materialising x * mask
+        pooled = torch.bmm(mask.to(x.dtype).unsqueeze(1), x).squeeze(1) / entity_num.unsqueeze(-1)
         return entity_embeddings, self.fc(pre + 'embed_fc', pooled, relu=True), mask
 
     def spatial_encoder(self, sp: Dict[str, Tensor], project: Tensor, ex: Tensor, ey: Tensor, entity_num: Tensor):

@@ -139,6 +139,13 @@ int dsb_upconv_fwd(const float* z, int ldz, const float* bias, int relu, float* 
 int dsb_upconv_bwd(const float* g, int ldg, void* gz_hi, void* gz_lo, int ldz, int64_t N, int H, int W, int C,
                    dsb_stream_t stream);
 
+/* ---- location-head tail projection: z[p, t] = sum_c x[p, c] w[c, t], C = 32 channels -> the 9 taps of the last conv ----
+ * (the channel contraction of `upsample.2`, commuted in front of the up-sampling; see dsb_upshift9_*).  x [pixels, 32],
+ * w [32, 9], z [pixels, 9] fp32.  Backward writes grad_x [pixels, 32] and ADDS the weight gradient into grad_w [32, 9]. */
+int dsb_proj9_fwd(const float* x, const float* w, float* z, int64_t pixels, int C, dsb_stream_t stream);
+int dsb_proj9_bwd(const float* x, const float* grad_z, const float* w, float* grad_x, float* grad_w, int64_t pixels, int C,
+                  dsb_stream_t stream);
+
 /* ---- 2x2 stride-2 max-pool, channels-last  (spatial_encoder.py:74-79 `F.max_pool2d` between the down-sampling convs) ----
  * x [N,H,W,C] fp32 -> out [N,H/2,W/2,C] (+ optional bf16 pair for the next convolution) and a one-byte argmax (0..3, window
  * scan order, first maximum) per output element; the backward scatters grad_out through it (grad_x fully written). */

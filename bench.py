@@ -312,24 +312,55 @@ def run_b200(args, rank, world, local_rank):
     last_loss = [None]
     last_info = [None]
     copy_stream = torch.cuda.Stream(device=dev)
-    staged = {}
+    # two persistent device staging batches (double buffering): allocating 1.5 GB of fresh device tensors per step on a side
+    # stream made the caching allocator fall back to cudaMalloc / cudaFree under a 150 GiB working set (+46 ms per step)
+    stage = [tree_map(lambda t: torch.empty(t.shape, dtype=t.dtype, device=dev), host) for _ in range(2)]
+    ready = [None, None]      # copy-stream event: staging batch i holds the next batch
+    consumed = [None, None]   # main-stream event: the step that read staging batch i is completely queued behind it
+    counter = [0]
+    copy_times = []
 
-    def prefetch():
+    def _copy_tree(dst, src):
+        if isinstance(src, dict):
+            for k in src:
+                _copy_tree(dst[k], src[k])
+        elif isinstance(src, (list, tuple)):
+            for d, s_ in zip(dst, src):
+                _copy_tree(d, s_)
+        elif torch.is_tensor(src):
+            dst.copy_(src, non_blocking=True)
+
+    def prefetch(i):
         """host -> device copy of the NEXT step's batch from pinned memory on a side stream (what the reference's
         `use_async_cuda` dataloader does, rl_dataloader.py:113-127); every step pays for exactly one such copy."""
         with torch.cuda.stream(copy_stream):
-            staged['data'] = tree_map(lambda t: t.to(dev, non_blocking=True), host)
-            staged['event'] = torch.cuda.Event()
-            staged['event'].record(copy_stream)
+            if consumed[i] is not None:
+                copy_stream.wait_event(consumed[i])        # the step that used this staging batch must be done with it
+            t0 = torch.cuda.Event(enable_timing=True) if os.environ.get('DSB_E2E_TIMECOPY') == '1' else None
+            if t0 is not None:
+                t0.record(copy_stream)
+            _copy_tree(stage[i], host)
+            ready[i] = torch.cuda.Event(enable_timing=t0 is not None)
+            ready[i].record(copy_stream)
+            if t0 is not None:
+                copy_times.append((t0, ready[i]))
 
     def step_e2e():
-        if 'data' not in staged:
-            prefetch()
-        torch.cuda.current_stream().wait_event(staged['event'])
-        data = staged.pop('data')
-        tree_map(lambda t: t.record_stream(torch.cuda.current_stream()) or t, data)
-        prefetch()                                          # overlaps with this step's compute
-        info = learner._train(data)
+        if os.environ.get('DSB_E2E_NOCOPY') == '1':        # DEV ONLY: isolates the cost of the per-step result read
+            info = learner._train(resident)
+            last_loss[0] = info['total_loss_value']
+            last_info[0] = info
+            return
+        i = counter[0] & 1
+        counter[0] += 1
+        if ready[i] is None:
+            prefetch(i)
+        torch.cuda.current_stream().wait_event(ready[i])
+        ready[i] = None
+        prefetch(1 - i)                                     # next step's batch; overlaps with this step's compute
+        info = learner._train(stage[i])
+        consumed[i] = torch.cuda.Event()
+        consumed[i].record(torch.cuda.current_stream())
         # device -> host read of the step result: the loss and the ~45 logged scalars arrive in ONE asynchronous copy queued
         # right after the loss (rl_loss.LazyScalars); reading them waits for forward + loss only, so the host queues the next
         # step while this step's backward is still running
@@ -351,6 +382,9 @@ def run_b200(args, rank, world, local_rank):
     if not args.no_e2e:
         step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
+        if copy_times:
+            torch.cuda.synchronize()
+            print('H2D batch copy durations (ms):', ['%.1f' % a.elapsed_time(b) for a, b in copy_times], file=sys.stderr)
         e2e = {'value': world * B * T / (ms_e2e / 1e3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d,
                'd2h_bytes_per_step': 4 * len(last_info[0]) if last_info[0] is not None else 0, 'ms_per_step': ms_e2e}
     if world > 1:

@@ -472,7 +472,7 @@ def gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu: bool, terms: int = 3, want_sp
     a_lo None: A is exact in bf16 (two products instead of three)."""
     M, K = a_hi.shape
     N = w_hi.shape[0]
-    assert w_hi.shape[1] == K and gemm_eligible(N, K), (M, N, K)
+    assert w_hi.shape[1] == K and N % 64 == 0 and K % 64 == 0, (M, N, K)
     if a_lo is None and a_hi.is_cuda:
         c = torch.empty((M, N), dtype=torch.float32, device=a_hi.device) if want_split != 'only' else None
         c_hi = torch.empty((M, N), dtype=torch.bfloat16, device=a_hi.device) if want_split else None
@@ -578,7 +578,7 @@ def weight_grad(g_hi, g_lo, x_hi, x_lo, terms: int = 3, accumulate_into: Optiona
     result is added to that [N,K] tensor (the parameter's .grad) and None is returned."""
     M, N = g_hi.shape
     K = x_hi.shape[1]
-    splits = _pick_splits((N // 128) * (K // 128), M)
+    splits = _pick_splits(((N + 127) // 128) * (K // 128), M)
     bx = 1 if x_lo is None else 0                       # the activation is exact in bf16: no dY_hi x X_lo product
     if accumulate_into is not None:
         _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=x_hi, b_lo=x_lo, a_mn=1, b_mn=1, alpha=1.0, terms=terms, c=accumulate_into, m=N,
@@ -650,7 +650,7 @@ class _SplitLinear(torch.autograd.Function):
                 gx = gfull @ (w_hi.float() + w_lo.float())
             gx = gx.view(ctx.xshape)
         if ctx.needs_input_grad[1]:
-            if on_gpu and N % 128 == 0 and K % 128 == 0 and M % 64 == 0 and M >= 128:
+            if on_gpu and N % 64 == 0 and K % 128 == 0 and M % 64 == 0 and M >= 128:
                 gw = weight_grad(g_hi, g_lo, a_hi, a_lo, ctx.terms, accumulate_into=_grad_slot(ctx.weight_ref))
             else:
                 gfull = g if g is not None else (g_hi.float() + g_lo.float())
@@ -809,11 +809,12 @@ def entity_attention(qkv: torch.Tensor, entity_num: torch.Tensor, heads: int, hd
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = False,
-           terms: int = 3, emit_split: bool = False) -> torch.Tensor:
+           terms: int = 3, emit_split: bool = False, allow_n64: bool = False) -> torch.Tensor:
     """fc_block forward (ctools/torch_utils/network/nn_module.py:231-270): tcgen05 split GEMM when the shape
     tiles (N % 128 == 0, K % 64 == 0), plain library matmul for the odd small layers."""
     N, K = weight.shape
-    if gemm_eligible(N, K) and (x.is_cuda or _HOST_LOGIC_TESTING) and x.numel() // K >= 1:
+    elig = gemm_eligible(N, K) or (allow_n64 and not _TCGEN05_OFF and N % 64 == 0 and K % 128 == 0)   # 64-wide tiles
+    if elig and (x.is_cuda or _HOST_LOGIC_TESTING) and x.numel() // K >= 1:
         sp = getattr(x, '_dsb_split', None)
         if sp is None or sp[0].shape != x.shape:
             sp = (None, None)

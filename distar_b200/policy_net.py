@@ -316,11 +316,31 @@ class Net:
         e = torch.relu(w1.t()[action.long()] + self.P[pre + 'embed_fc1.0.bias'])
         return x, action, emb + self.fc(pre + 'embed_fc2', e)
 
+    def head_keys(self, entity_embeddings):
+        """key_fc of the selected-units head and of the target-unit head (action_arg_head.py:118-129, 343-349): two 256 -> 32
+        projections of the same [P, 512, 256] entity embeddings.  32 outputs are too narrow for a tensor-core tile and ran as
+        skinny fp32 library GEMMs (6.6 ms / step with their gradients); stacked they are one 64-wide tcgen05 GEMM."""
+        cached = getattr(self, '_head_keys', None)
+        if cached is not None and cached[0] is entity_embeddings:
+            return cached[1], cached[2]
+        P = self.P
+        a, b = 'policy.selected_units_head.key_fc.0.', 'policy.target_unit_head.key_fc.0.'
+        if entity_embeddings.is_cuda:
+            w = torch.cat([P[a + 'weight'], P[b + 'weight']], dim=0)
+            bias = torch.cat([P[a + 'bias'], P[b + 'bias']], dim=0)
+            k = ops.linear(entity_embeddings, w, bias, False, self.terms, allow_n64=True)
+            ksu, ktu = k[..., :32], k[..., 32:]
+        else:
+            ksu = self.fc('policy.selected_units_head.key_fc', entity_embeddings)
+            ktu = self.fc('policy.target_unit_head.key_fc', entity_embeddings)
+        self._head_keys = (entity_embeddings, ksu, ktu)
+        return ksu, ktu
+
     def su_keys(self, entity_embeddings, entity_num):
         """_get_key_mask, action_arg_head.py:118-143."""
         pre = 'policy.selected_units_head.'
         N, E, _ = entity_embeddings.shape
-        key = self.fc(pre + 'key_fc', entity_embeddings)
+        key = self.head_keys(entity_embeddings)[0]
         slot = torch.arange(E + 1, device=key.device).unsqueeze(0)
         is_end = (slot == entity_num.unsqueeze(1)).unsqueeze(-1)
         key = torch.where(is_end, self.P[pre + 'end_embedding'].view(1, 1, -1),
@@ -425,7 +445,7 @@ class Net:
     def target_unit_head(self, emb, entity_embeddings, entity_num, target_unit=None):
         """action_arg_head.py:343-363 (K13)."""
         pre = 'policy.target_unit_head.'
-        key = self.fc(pre + 'key_fc', entity_embeddings)
+        key = self.head_keys(entity_embeddings)[1]
         q = self.fc(pre + 'query_fc2', self.fc(pre + 'query_fc1', emb, relu=True))
         logits = torch.matmul(key, q.unsqueeze(-1)).squeeze(-1)
         E = entity_embeddings.shape[1]

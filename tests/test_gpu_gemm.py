@@ -310,3 +310,22 @@ def test_gemm_ex_exact_operands(mc):
     _lib.gemm_ex(a_hi=d_hi, a_lo=d_lo, b_hi=a_hi, b_lo=None, a_mn=1, b_mn=1, alpha=1.0, terms=3, c=gw, m=N, n=K, k=M, batch=1,
                  inner=1, splits=4, c_accumulate=1, b_exact=1, bn=128, mc=mc)
     _check(gw, dy.double().t() @ a.double(), tol=5e-5)
+
+
+def test_linear_64_wide_output():
+    """N = 64 (the stacked key projections of the two pointer heads): 64-wide tiles forward, dX and dW on the tensor cores"""
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(5, 512, 256, generator=g)
+    w = torch.randn(64, 256, generator=g) / 16
+    b = torch.randn(64, generator=g)
+    go = torch.randn(5, 512, 64, generator=g)
+    xr, wr, br = [t.double().requires_grad_(True) for t in (x, w, b)]
+    torch.nn.functional.linear(xr, wr, br).backward(go.double())
+    xd, wd, bd = [t.to(DEV).requires_grad_(True) for t in (x, w, b)]
+    y = ops.linear(xd, wd, bd, relu=False, allow_n64=True)
+    assert type(y.grad_fn).__name__.startswith('_SplitLinear')
+    y.backward(go.to(DEV))
+    _check(y.detach(), torch.nn.functional.linear(xr, wr, br).detach(), tol=3e-5)
+    for got, want, n in [(xd.grad, xr.grad, 'dx'), (wd.grad, wr.grad, 'dw'), (bd.grad, br.grad, 'db')]:
+        err = (got.double().cpu() - want).abs().max().item()
+        assert err <= 1e-4 * want.abs().max().item(), (n, err)

@@ -261,3 +261,21 @@ def test_encoder_chunking_is_invisible(sd):
         close(lb[k], la[k], 'chunked/' + k, rtol=1e-4)          # tile shapes (hence summation order) depend on the row count
     assert abs(ta - tb) <= 1e-5 * max(1.0, abs(ta))
     assert (ga - gb).norm().item() <= 1e-3 * ga.norm().item()      # split-K / accumulation order differ between chunkings
+
+
+def test_single_observation_inference_matches_oracle(model, sd):
+    """BASELINE configs[0]: one observation through compute_logp_action (the actor's call), sampled actions identical."""
+    from distar_b200.synth import synth_obs
+    obs = synth_obs(1, seed=41, entity_num=torch.tensor([97]))
+    from distar_b200.constants import SELECTED_UNITS_ACTION_MASK
+    su_action_mask = torch.tensor(SELECTED_UNITS_ACTION_MASK, dtype=torch.bool)
+    torch.manual_seed(1234)
+    with torch.no_grad():
+        want = O.compute_logp_action(sd, **tree_clone(obs), su_action_mask=su_action_mask)
+    torch.manual_seed(1234)
+    with torch.no_grad():
+        got = model.compute_logp_action(**to_dev(obs))
+    for k in O.HEADS:
+        close(got['logit'][k], want['logit'][k], 'single/' + k)
+        assert torch.equal(got['action_info'][k].cpu(), want['action_info'][k]), k
+    assert torch.equal(got['selected_units_num'].cpu(), want['selected_units_num'])

@@ -134,7 +134,7 @@ def linear_presplit(x_hi: torch.Tensor, x_lo: Optional[torch.Tensor], weight: to
                     emit_split: bool = False) -> torch.Tensor:
     """fc_block on an input that only exists as a bf16 (hi, lo) pair (no gradient flows to it).  x_lo None: the input is
     exactly representable in bf16 (one product less)."""
-    y, y_hi, y_lo = _SplitLinear.apply(x_hi, weight, bias, relu, terms, x_hi, x_lo, emit_split)
+    y, y_hi, y_lo, _ = _SplitLinear.apply(x_hi, weight, bias, relu, terms, x_hi, x_lo, emit_split)
     return attach_split(y, y_hi, y_lo) if emit_split else y
 
 
@@ -596,7 +596,7 @@ class _SplitLinear(torch.autograd.Function):
     (dY^T . X, split-K over tokens) all on the tcgen05 kernel with 3-term split products."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, relu, terms, x_hi=None, x_lo=None, emit_split=False):
+    def forward(ctx, x, weight, bias, relu, terms, x_hi=None, x_lo=None, emit_split=False, fork=False):
         x2 = x.reshape(-1, x.shape[-1])
         if x_hi is not None:
             a_hi, a_lo = x_hi.reshape(x2.shape), (x_lo.reshape(x2.shape) if x_lo is not None else None)
@@ -616,17 +616,21 @@ class _SplitLinear(torch.autograd.Function):
         ctx.save_for_backward(a_hi, a_lo, w_hi, w_lo, (y_hi if emit_split else y) if relu else None)
         ctx.relu, ctx.terms, ctx.has_bias, ctx.xshape = relu, terms, bias is not None, x.shape
         ctx.weight_ref, ctx.bias_ref = weight, bias
+        # fork: also hand the input back as a second differentiable output (the residual branch of a transformer sub-layer
+        # takes it from here), so both gradients of x meet INSIDE this node and the dX GEMM adds the branch's gradient in its
+        # epilogue instead of autograd launching a separate add over [tokens, d]
+        x_pass = x.view_as(x) if fork else None
         if emit_split:
             y_hi, y_lo = y_hi.view(oshape), y_lo.view(oshape)
             ctx.mark_non_differentiable(y_hi, y_lo)
-            return y.view(oshape), y_hi, y_lo
-        return y.view(oshape), None, None
+            return y.view(oshape), y_hi, y_lo, x_pass
+        return y.view(oshape), None, None, x_pass
 
     @staticmethod
-    def backward(ctx, gy, _ghi=None, _glo=None):
+    def backward(ctx, gy, _ghi=None, _glo=None, g_pass=None):
         a_hi, a_lo, w_hi, w_lo, y = ctx.saved_tensors
         if gy is None:
-            return (None,) * 8
+            return (g_pass,) + (None,) * 8
         gy2 = gy.reshape(-1, gy.shape[-1]).contiguous()
         M, N = gy2.shape
         K = a_hi.shape[1]
@@ -643,19 +647,24 @@ class _SplitLinear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             if on_gpu and K % 128 == 0 and N % 64 == 0:
                 gx = torch.empty((M, K), dtype=torch.float32, device=gy2.device)
+                res = g_pass.reshape(M, K).contiguous() if g_pass is not None else None
                 _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=w_hi, b_lo=w_lo, b_mn=1, alpha=1.0, terms=ctx.terms, c=gx, m=M, n=K,
-                         k=N, batch=1, inner=1, splits=1)
+                         k=N, batch=1, inner=1, splits=1, residual=res)
             else:
                 gfull = g if g is not None else (g_hi.float() + g_lo.float())
                 gx = gfull @ (w_hi.float() + w_lo.float())
+                if g_pass is not None:
+                    gx = gx + g_pass.reshape(gx.shape)
             gx = gx.view(ctx.xshape)
+        elif g_pass is not None:
+            gx = g_pass
         if ctx.needs_input_grad[1]:
             if on_gpu and N % 64 == 0 and K % 128 == 0 and M % 64 == 0 and M >= 128:
                 gw = weight_grad(g_hi, g_lo, a_hi, a_lo, ctx.terms, accumulate_into=_grad_slot(ctx.weight_ref))
             else:
                 gfull = g if g is not None else (g_hi.float() + g_lo.float())
                 gw = gfull.t() @ (a_hi.float() + (a_lo.float() if a_lo is not None else 0))
-        return gx, gw, gb, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None
 
 
 class _FFN(torch.autograd.Function):
@@ -665,7 +674,7 @@ class _FFN(torch.autograd.Function):
     chunk, which is what running out of HBM otherwise forces (model.py: keep_chunks)."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, terms, x_hi, x_lo):
+    def forward(ctx, x, w1, b1, w2, b2, terms, x_hi, x_lo, fork=False):
         K = x.shape[-1]
         a_hi, a_lo = x_hi.reshape(-1, K), x_lo.reshape(-1, K)
         w1_hi, w1_lo = weight_split(w1)
@@ -675,13 +684,16 @@ class _FFN(torch.autograd.Function):
         ctx.save_for_backward(a_hi, a_lo, w1_hi, w1_lo, w2_hi, w2_lo, m)
         ctx.refs = (w1, b1, w2, b2)
         ctx.terms, ctx.xshape = terms, x.shape
-        return m.view(*x.shape[:-1], w2.shape[0])
+        ctx.set_materialize_grads(False)
+        return m.view(*x.shape[:-1], w2.shape[0]), (x.view_as(x) if fork else None)
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, g_pass=None):
         a_hi, a_lo, w1_hi, w1_lo, w2_hi, w2_lo, m = ctx.saved_tensors
         w1, b1, w2, b2 = ctx.refs
         terms = ctx.terms
+        if gy is None:
+            return (g_pass,) + (None,) * 8
         gy2 = gy.reshape(m.shape).contiguous()
         M = gy2.shape[0]
         H, K = w1_hi.shape
@@ -701,20 +713,26 @@ class _FFN(torch.autograd.Function):
         gx = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty((M, K), dtype=torch.float32, device=dev)
+            res = g_pass.reshape(M, K).contiguous() if g_pass is not None else None      # the residual branch's gradient
             _gemm_ex(a_hi=g1_hi, a_lo=g1_lo, b_hi=w1_hi, b_lo=w1_lo, b_mn=1, alpha=1.0, terms=terms, c=gx, m=M, n=K, k=H, batch=1,
-                     inner=1, splits=1)
+                     inner=1, splits=1, residual=res)
             gx = gx.view(ctx.xshape)
-        return gx, gw1, gb1, gw2, gb2, None, None, None
+        elif g_pass is not None:
+            gx = g_pass
+        return gx, gw1, gb1, gw2, gb2, None, None, None, None
 
 
-def ffn(x: torch.Tensor, w1, b1, w2, b2, terms: int = 3) -> torch.Tensor:
-    """relu(fc2(relu(fc1(x)))) of a transformer layer; on the GPU (x carrying its bf16 pair) through _FFN."""
+def ffn(x: torch.Tensor, w1, b1, w2, b2, terms: int = 3, fork: bool = False):
+    """relu(fc2(relu(fc1(x)))) of a transformer layer; on the GPU (x carrying its bf16 pair) through _FFN.  fork=True returns
+    (m, x') with x' the input handed back for the residual branch (see _SplitLinear.forward)."""
     sp = getattr(x, '_dsb_split', None)
     H, K = w1.shape
     if (x.is_cuda and sp is not None and sp[0].shape == x.shape and gemm_eligible(H, K) and gemm_eligible(w2.shape[0], H)
             and K % 128 == 0 and w2.shape[0] % 128 == 0 and (x.numel() // K) % 64 == 0 and x.numel() // K >= 128):
-        return _FFN.apply(x, w1, b1, w2, b2, terms, sp[0], sp[1])
-    return linear(linear(x, w1, b1, True, terms, emit_split='only' if x.is_cuda else False), w2, b2, True, terms)
+        m, x_pass = _FFN.apply(x, w1, b1, w2, b2, terms, sp[0], sp[1], fork)
+        return (m, x_pass) if fork else m
+    m = linear(linear(x, w1, b1, True, terms, emit_split='only' if x.is_cuda else False), w2, b2, True, terms)
+    return (m, x) if fork else m
 
 
 class _EntityAttention(torch.autograd.Function):
@@ -809,7 +827,7 @@ def entity_attention(qkv: torch.Tensor, entity_num: torch.Tensor, heads: int, hd
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = False,
-           terms: int = 3, emit_split: bool = False, allow_n64: bool = False) -> torch.Tensor:
+           terms: int = 3, emit_split: bool = False, allow_n64: bool = False, fork: bool = False):
     """fc_block forward (ctools/torch_utils/network/nn_module.py:231-270): tcgen05 split GEMM when the shape
     tiles (N % 128 == 0, K % 64 == 0), plain library matmul for the odd small layers."""
     N, K = weight.shape
@@ -819,11 +837,13 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
         if sp is None or sp[0].shape != x.shape:
             sp = (None, None)
         emit = emit_split and x.is_cuda
-        y, y_hi, y_lo = _SplitLinear.apply(x, weight, bias, relu, terms, sp[0], sp[1], emit)
-        return attach_split(y, y_hi, y_lo) if emit else y
+        y, y_hi, y_lo, x_pass = _SplitLinear.apply(x, weight, bias, relu, terms, sp[0], sp[1], emit, fork and x.is_cuda)
+        y = attach_split(y, y_hi, y_lo) if emit else y
+        return (y, x_pass if x_pass is not None else x) if fork else y
     _use_kernel(x)
     y = F.linear(x, weight, bias)
-    return torch.relu(y) if relu else y
+    y = torch.relu(y) if relu else y
+    return (y, x) if fork else y
 
 
 # ------------------------------------------------------------------------------------------------

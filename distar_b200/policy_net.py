@@ -197,12 +197,15 @@ class Net:
                            True, self.terms)
         for i in range(3):
             lp = '%stransformer.layers.%d' % (pre, i)
-            qkv = self.fc(lp + '.attention.attention_pre', x, split='only')
+            # the two consumers of x in each sub-layer (the GEMM and the residual input of the LayerNorm) are routed through
+            # the GEMM's autograd node (fork=True): its dX epilogue adds the residual branch's gradient
+            qkv, xr = ops.linear(x, P[lp + '.attention.attention_pre.0.weight'], P[lp + '.attention.attention_pre.0.bias'], False,
+                                 self.terms, 'only' if x.is_cuda else False, fork=True)
             a = self.fc(lp + '.attention.project', ops.entity_attention(qkv, entity_num, 2, 128))
-            x = self.ln(lp + '.layernorm1', x, residual=a, split=True)
-            m = ops.ffn(x, P[lp + '.mlp.0.0.weight'], P[lp + '.mlp.0.0.bias'], P[lp + '.mlp.1.0.weight'],
-                        P[lp + '.mlp.1.0.bias'], self.terms)
-            x = self.ln(lp + '.layernorm2', x, residual=m, split=(i < 2))
+            x = self.ln(lp + '.layernorm1', xr, residual=a, split=True)
+            m, xr = ops.ffn(x, P[lp + '.mlp.0.0.weight'], P[lp + '.mlp.0.0.bias'], P[lp + '.mlp.1.0.weight'],
+                            P[lp + '.mlp.1.0.bias'], self.terms, fork=True)
+            x = self.ln(lp + '.layernorm2', xr, residual=m, split=(i < 2))
         x = torch.relu(x)
         entity_embeddings = self.fc(pre + 'entity_fc', x, relu=True)
         # masked mean over entities as a batched [1,E] x [E,256] product: reads x once instead of materialising x * mask

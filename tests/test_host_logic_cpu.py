@@ -129,3 +129,26 @@ def test_sl_loss_matches_oracle(sd):
     got = SupervisedLoss({'learner': {'su_mask': False}}).compute_loss(ml, act, amask, num, en, ma)
     for k, v in want.items():
         assert abs(got[k].item() - v.item()) <= 1e-3 * max(1.0, abs(v.item())), k
+
+
+def test_lazy_scalars_behave_like_the_reference_dict():
+    """ReinforcementLoss.compute_loss returns floats + the total_loss tensor (rl_loss.py:40-47); ours defers the floats
+    until first access - on the CPU path they must still read like a plain dict."""
+    import torch
+    from distar_b200.rl_loss import LazyScalars
+    d = LazyScalars(['a', 'b/c'], torch.tensor([1.5, -2.0]))
+    d['total_loss'] = torch.tensor(3.0, requires_grad=True)
+    assert 'a' in d and 'b/c' in d and 'zzz' not in d
+    assert torch.is_tensor(d['total_loss'])                 # tensor entries never wait
+    assert d['a'] == 1.5 and d.get('b/c') == -2.0 and d.get('zzz', 7) == 7
+    assert set(d.keys()) == {'a', 'b/c', 'total_loss'} and len(d) == 3
+    assert dict(d.items())['a'] == 1.5
+
+
+def test_weight_cache_is_bypassed_off_gpu():
+    import torch
+    from distar_b200 import ops
+    w = torch.nn.Parameter(torch.randn(4, 4))
+    calls = []
+    assert ops.weight_cached(w, 'k', lambda: calls.append(1) or 5) == 5
+    assert ops.weight_cached(w, 'k', lambda: calls.append(1) or 6) == 6 and len(calls) == 2   # CPU tensors are never cached

@@ -1,6 +1,6 @@
 """Dev helper: device time of every non-GEMM C-ABI call of one learner step, grouped by (entry point, integer arguments)."""
 import os, sys, collections
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
 from distar_b200 import lib
 from distar_b200.learner import RLLearner

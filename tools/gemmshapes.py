@@ -1,6 +1,6 @@
 """Dev helper: per-shape device time of every dsb_gemm_ex launch in one learner step (CUDA events around each call)."""
 import os, sys, collections
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
 from distar_b200 import lib
 from distar_b200.learner import RLLearner

@@ -1,6 +1,6 @@
 """Dev helper: host-side time of one learner step (how long until every kernel is queued) + cProfile of it."""
 import os, sys, time, cProfile, pstats
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
 from distar_b200.learner import RLLearner
 from distar_b200.model import Model

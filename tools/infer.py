@@ -1,6 +1,6 @@
 """Dev helper: where does a batch-32 compute_logp_action call spend its time?"""
 import os, sys, time
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
 from distar_b200.model import Model
 from distar_b200.synth import synth_obs, tree_map

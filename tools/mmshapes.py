@@ -1,6 +1,6 @@
 """Dev helper: which library matmuls (aten::mm / addmm / bmm / matmul) are left in a learner step, by input shape."""
 import os, sys, collections
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
 from torch.profiler import profile, ProfilerActivity
 from distar_b200.learner import RLLearner

@@ -1,6 +1,6 @@
 """Dev helper for ncu: the FFN-shaped GEMM once per mode (single-CTA 128x256, CTA-pair 256x256)."""
 import os, sys
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
 from distar_b200 import lib, ops
 dev = torch.device('cuda', 0)

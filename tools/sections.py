@@ -1,6 +1,6 @@
 """Dev helper: forward time per section of the learner step at full size (CUDA events, no_grad)."""
 import os, sys
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
 from distar_b200.model import Model
 from distar_b200.synth import synth_rl_batch, tree_map

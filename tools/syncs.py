@@ -1,6 +1,6 @@
 """Dev helper: list every host<->device synchronisation of one learner step (torch sync debug mode)."""
 import os, sys, warnings, traceback, collections
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
 from distar_b200.learner import RLLearner
 from distar_b200.model import Model

@@ -1,6 +1,6 @@
 """Dev helper: aggregated per-kernel device time of one learner step (torch.profiler, not a number of record)."""
 import os, sys, json, collections
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
 from torch.profiler import profile, ProfilerActivity
 from distar_b200.learner import RLLearner

@@ -248,7 +248,15 @@ class Net:
         embedded_scalar, scalar_context, baseline_feature = self.scalar_encoder(scalar_info)
         run_entity = entity_fn or self.entity_encoder
         entity_embeddings, embedded_entity, _mask = run_entity(entity_info, entity_num)
-        project = self.fc('encoder.scatter_project', entity_embeddings, relu=True)
+        if entity_embeddings.is_cuda:
+            # 256 -> 32: too narrow for a tensor-core tile, so the weight is zero-padded to 64 rows (one 64-wide tcgen05 GEMM each
+            # for forward, dX and dW instead of three skinny fp32 library GEMMs) and the real 32 columns are sliced back out
+            P = self.P
+            w = F.pad(P['encoder.scatter_project.0.weight'], (0, 0, 0, 32))
+            b = F.pad(P['encoder.scatter_project.0.bias'], (0, 32))
+            project = ops.linear(entity_embeddings, w, b, True, self.terms, allow_n64=True)[..., :32].contiguous()
+        else:
+            project = self.fc('encoder.scatter_project', entity_embeddings, relu=True)
         # scatter_connection (ops.scatter_connection, K6) is fused into the spatial stem; the stand-alone operator is
         # kept for API parity / measurement
         embedded_spatial, map_skip = self.spatial_encoder(spatial_info, project, entity_info['x'], entity_info['y'],

@@ -18,13 +18,20 @@
 // consumed through MN-major UMMA descriptors (LBO = 8 KiB between the 64-wide halves, SBO = 1 KiB between 8-row
 // k groups).  No transposed copy of any activation is ever materialised.
 //
-// Structure (one CTA per SM, persistent over 128x128 output tiles, n-fastest tile order so CTAs that share an A
-// tile run together and A streams from HBM once):
-//   warp 0      TMA producer : cp.async.bulk.tensor boxes for A_hi/A_lo/B_hi/B_lo into a 3-deep smem ring
-//   warp 1      MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 N128 K16);
+// Structure (one CTA per SM, persistent over 128 x BN output tiles with BN in {64, 128, 256}, n-fastest tile order so CTAs
+// that share an A tile run together and A streams from HBM once):
+//   warp 0      TMA producer : cp.async.bulk.tensor boxes for A_hi/A_lo/B_hi/B_lo into a 2-3 deep smem ring (implicit-GEMM
+//               convolutions read NHWC activations through 4-D boxes, halos are TMA zero fill)
+//   warp 1      MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 N=BN K16), up to three per
+//               k step (lo x hi, hi x lo, hi x hi; operands flagged exact skip their lo product and loads);
 //               tcgen05.commit frees smem stages and publishes the TMEM accumulator (2-deep ring)
-//   warps 2..5  epilogue     : tcgen05.ld 32x32b -> alpha, +bias, ReLU -> swizzled smem box -> TMA store of fp32 C
-//               (optional bf16 hi/lo split of C for a following GEMM)
+//   warps 2..9  epilogue     : tcgen05.ld 32x32b -> alpha, +bias, (+residual), ReLU -> swizzled smem box -> TMA store of fp32 C
+//               and / or of the bf16 (hi, lo) pair of C (SWIZZLE_64B boxes), or TMA reduce-add (split-K, accumulation
+//               into a gradient buffer)
+// Cluster variants (template MC): 2 = two CTAs share every B tile by TMA multicast; 4 = CTA pair issuing
+// tcgen05.mma.cta_group::2 (M = 256 across two SMs, each CTA stages half of B, barriers in the leader CTA).  Both are
+// correct and tested; neither beats the single-CTA kernel for 3-term products yet, so the automatic choice
+// uses them only for 1-term products (multicast).
 #include <cuda.h>
 #include <cstdlib>
 #include "common.cuh"

@@ -201,7 +201,7 @@ int dsb_gemm_bf16_split(const void* a_hi, const void* a_lo, const void* w_hi, co
  * residual (optional fp32, same layout as c) is added before the ReLU.  bn: output tile width 64 or 128 (0 = auto).
  * Requirements: n % bn == 0, k % (64*splits) == 0, m % 128 == 0 when batch > 1, c_row_split % 128 == 0 when splits > 1. */
 typedef struct dsb_gemm_args {
-    const void *a_hi, *a_lo, *b_hi, *b_lo;   /* bf16 tensors (lo may be NULL when terms == 1) */
+    const void *a_hi, *a_lo, *b_hi, *b_lo;   /* bf16 tensors (lo may be NULL when terms == 1 or the operand is flagged exact) */
     int64_t a_rows, a_cols, b_rows, b_cols;  /* their full 2-D shapes (cols contiguous) */
     int32_t a_mn, b_mn;
     int32_t a_col_base, a_col_inner, a_row_outer, a_row_inner;
@@ -209,14 +209,14 @@ typedef struct dsb_gemm_args {
     const float* bias;
     float alpha;
     int32_t relu, terms;
-    float* c;
+    float* c;                                /* fp32 result; may be NULL when only the bf16 pair is wanted (no split-K then) */
     int64_t c_rows, c_cols;
-    void *c_hi, *c_lo;                       /* optional bf16 split of C, same [c_rows, c_cols] layout */
+    void *c_hi, *c_lo;                       /* optional bf16 (hi, lo) split of C, same [c_rows, c_cols] layout */
     int64_t m;
     int32_t n, k;
     int32_t batch, inner, splits;
     int32_t c_row_outer, c_row_inner, c_row_split, c_col_base, c_col_inner;
-    const float* residual;
+    const float* residual;                   /* optional fp32 [c_rows, c_cols] added before the ReLU */
     int32_t bn;
     int32_t a_conv, b_conv, conv_h, conv_w, conv_c, conv_taps;
     int64_t conv_imgs;

@@ -348,7 +348,7 @@ def run_b200(args, rank, world, local_rank):
     def step_e2e():
         if os.environ.get('DSB_E2E_NOCOPY') == '1':        # DEV ONLY: isolates the cost of the per-step result read
             info = learner._train(resident)
-            last_loss[0] = info['total_loss_value']
+            last_loss[0] = info['_total_loss_value']
             last_info[0] = info
             return
         i = counter[0] & 1
@@ -364,7 +364,7 @@ def run_b200(args, rank, world, local_rank):
         # device -> host read of the step result: the loss and the ~45 logged scalars arrive in ONE asynchronous copy queued
         # right after the loss (rl_loss.LazyScalars); reading them waits for forward + loss only, so the host queues the next
         # step while this step's backward is still running
-        last_loss[0] = info['total_loss_value']
+        last_loss[0] = info['_total_loss_value']
         last_info[0] = info
 
     if os.environ.get('DSB_ANOMALY') == '1':

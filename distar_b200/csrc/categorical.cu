@@ -13,8 +13,8 @@ namespace {
 struct RowStats { float m, s; };  // running max and sum(exp(x - m))
 
 __device__ __forceinline__ void online_update(RowStats& a, float x) {
-    if (x > a.m) { a.s = a.s * __expf(a.m - x) + 1.f; a.m = x; }
-    else a.s += __expf(x - a.m);
+    if (x > a.m) { a.s = a.s * __expf(a.m - x) + 1.f; a.m = x; }      // a.m = -inf, a.s = 0 on the first element: 0 * 0 + 1
+    else if (x > -CUDART_INF_F) a.s += __expf(x - a.m);               // a logit of -inf contributes nothing (never -inf - -inf)
 }
 __device__ __forceinline__ RowStats merge(RowStats a, RowStats b) {
     if (b.m > a.m) { RowStats t = a; a = b; b = t; }
@@ -61,7 +61,8 @@ template <int WARPS>
 __global__ void stats_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ teacher,
                                  const int64_t* __restrict__ action, float* __restrict__ lse_out,
                                  float* __restrict__ logp_out, float* __restrict__ ent_out,
-                                 float* __restrict__ kl_out, float* __restrict__ lse_t_out, int64_t rows, int C) {
+                                 float* __restrict__ kl_out, float* __restrict__ lse_t_out,
+                                 float* __restrict__ mean_lp_out, int* __restrict__ error_flag, int64_t rows, int C) {
     __shared__ float red[WARPS * 2 + 2];
     Coop<WARPS> coop{red};
     const int64_t r = (WARPS == 1) ? (int64_t)blockIdx.x * blockDim.y + threadIdx.y : blockIdx.x;
@@ -82,11 +83,12 @@ __global__ void stats_fwd_kernel(const float* __restrict__ logits, const float* 
     float tm = 0.f, tl = 0.f;
     if (tz) { b = coop.stats(b); tm = b.m; tl = logf(b.s); }
     // second pass (row is L1/L2 resident): entropy and KL
-    float ent = 0.f, kl = 0.f;
+    float ent = 0.f, kl = 0.f, slp = 0.f;
     for (int j = t; j < C; j += nth) {
         const float l = (z[j] - zm) - zl;
         const float p = __expf(l);
         ent -= p * l;
+        slp += l;
         if (tz) {
             const float lt = (tz[j] - tm) - tl;
             kl += __expf(lt) * (lt - l);
@@ -94,10 +96,18 @@ __global__ void stats_fwd_kernel(const float* __restrict__ logits, const float* 
     }
     ent = coop.sum(ent);
     if (tz) kl = coop.sum(kl);
+    if (mean_lp_out) slp = coop.sum(slp);
     if (t == 0) {
         lse_out[2 * r] = zm;
         lse_out[2 * r + 1] = zl;
-        if (logp_out) logp_out[r] = (z[action[r]] - zm) - zl;
+        if (logp_out) {
+            // torch's Categorical.log_prob / cross_entropy fail on a label outside [0, C); here the label is clamped (no
+            // out-of-bounds read) and the error recorded for the host to raise
+            int64_t a = action[r];
+            if (a < 0 || a >= C) { if (error_flag) atomicOr(error_flag, 2); a = a < 0 ? 0 : C - 1; }
+            logp_out[r] = (z[a] - zm) - zl;
+        }
+        if (mean_lp_out) mean_lp_out[r] = slp / (float)C;
         if (ent_out) ent_out[r] = ent;
         if (tz) { kl_out[r] = kl; lse_t_out[2 * r] = tm; lse_t_out[2 * r + 1] = tl; }
     }
@@ -108,24 +118,28 @@ __global__ void stats_bwd_kernel(const float* __restrict__ logits, const float* 
                                  const int64_t* __restrict__ action, const float* __restrict__ lse_in,
                                  const float* __restrict__ ent_in, const float* __restrict__ lse_t_in,
                                  const float* __restrict__ g_logp, const float* __restrict__ g_ent,
-                                 const float* __restrict__ g_kl, float* __restrict__ grad, int64_t rows, int C) {
+                                 const float* __restrict__ g_kl, const float* __restrict__ g_mean,
+                                 float* __restrict__ grad, int64_t rows, int C) {
     const int64_t r = (WARPS == 1) ? (int64_t)blockIdx.x * blockDim.y + threadIdx.y : blockIdx.x;
     if (r >= rows) return;
     const int nth = 32 * WARPS;
     const float* z = logits + r * C;
     const float* tz = teacher ? teacher + r * C : nullptr;
     float* g = grad + r * C;
+    const float gm = g_mean ? g_mean[r] : 0.f;           // d mean_j(log p_j) / dz_j = 1/C - p_j
+    const float gm_c = gm / (float)C;
     const float zm = lse_in[2 * r], zl = lse_in[2 * r + 1];
     const float gl = g_logp ? g_logp[r] : 0.f;
     const float ge = g_ent ? g_ent[r] : 0.f;
     const float gk = (g_kl && tz) ? g_kl[r] : 0.f;
     const float H = ge != 0.f ? ent_in[r] : 0.f;
     const float tm = tz ? lse_t_in[2 * r] : 0.f, tl = tz ? lse_t_in[2 * r + 1] : 0.f;
-    const int a = (int)action[r];
+    int64_t a64 = action[r];
+    const int a = a64 < 0 ? 0 : (a64 >= C ? C - 1 : (int)a64);      // clamped as in the forward (which flagged it)
     for (int j = threadIdx.x; j < C; j += nth) {
         const float l = (z[j] - zm) - zl;
         const float p = __expf(l);
-        float v = gl * ((j == a ? 1.f : 0.f) - p);
+        float v = gl * ((j == a ? 1.f : 0.f) - p) + (gm_c - gm * p);
         if (ge != 0.f) v -= ge * p * (l + H);
         if (gk != 0.f) v += gk * (p - __expf((tz[j] - tm) - tl));
         g[j] = v;
@@ -186,7 +200,7 @@ constexpr int kRowsPerBlock = 8;
 
 extern "C" int dsb_categorical_stats_fwd(const float* logits, const float* teacher, const int64_t* action,
                                          float* lse, float* logp, float* entropy, float* kl, float* lse_t,
-                                         int64_t rows, int C, dsb_stream_t stream) {
+                                         float* mean_logp, int* error_flag, int64_t rows, int C, dsb_stream_t stream) {
     DSB_REQUIRE(logits && lse && C > 0 && rows >= 0, "categorical_stats_fwd: bad argument");
     DSB_REQUIRE(!logp || action, "categorical_stats_fwd: logp needs action");
     DSB_REQUIRE(!teacher || (kl && lse_t), "categorical_stats_fwd: teacher needs kl and lse_t outputs");
@@ -195,10 +209,10 @@ extern "C" int dsb_categorical_stats_fwd(const float* logits, const float* teach
     if (C <= 1024) {
         dim3 block(32, kRowsPerBlock);
         stats_fwd_kernel<1><<<(unsigned)((rows + kRowsPerBlock - 1) / kRowsPerBlock), block, 0, s>>>(
-            logits, teacher, action, lse, logp, entropy, kl, lse_t, rows, C);
+            logits, teacher, action, lse, logp, entropy, kl, lse_t, mean_logp, error_flag, rows, C);
     } else {
-        stats_fwd_kernel<kBigWarps><<<(unsigned)rows, 32 * kBigWarps, 0, s>>>(logits, teacher, action, lse, logp,
-                                                                              entropy, kl, lse_t, rows, C);
+        stats_fwd_kernel<kBigWarps><<<(unsigned)rows, 32 * kBigWarps, 0, s>>>(logits, teacher, action, lse, logp, entropy,
+                                                                              kl, lse_t, mean_logp, error_flag, rows, C);
     }
     return dsb::check_launch("categorical_stats_fwd");
 }
@@ -206,7 +220,8 @@ extern "C" int dsb_categorical_stats_fwd(const float* logits, const float* teach
 extern "C" int dsb_categorical_stats_bwd(const float* logits, const float* teacher, const int64_t* action,
                                          const float* lse, const float* entropy, const float* lse_t,
                                          const float* g_logp, const float* g_ent, const float* g_kl,
-                                         float* grad_logits, int64_t rows, int C, dsb_stream_t stream) {
+                                         const float* g_mean, float* grad_logits, int64_t rows, int C,
+                                         dsb_stream_t stream) {
     DSB_REQUIRE(logits && action && lse && grad_logits && C > 0, "categorical_stats_bwd: bad argument");
     DSB_REQUIRE(!g_ent || entropy, "categorical_stats_bwd: g_ent needs the forward entropy");
     DSB_REQUIRE(!(g_kl && teacher) || lse_t, "categorical_stats_bwd: g_kl needs lse_t");
@@ -215,10 +230,10 @@ extern "C" int dsb_categorical_stats_bwd(const float* logits, const float* teach
     if (C <= 1024) {
         dim3 block(32, kRowsPerBlock);
         stats_bwd_kernel<1><<<(unsigned)((rows + kRowsPerBlock - 1) / kRowsPerBlock), block, 0, s>>>(
-            logits, teacher, action, lse, entropy, lse_t, g_logp, g_ent, g_kl, grad_logits, rows, C);
+            logits, teacher, action, lse, entropy, lse_t, g_logp, g_ent, g_kl, g_mean, grad_logits, rows, C);
     } else {
         stats_bwd_kernel<kBigWarps><<<(unsigned)rows, 32 * kBigWarps, 0, s>>>(
-            logits, teacher, action, lse, entropy, lse_t, g_logp, g_ent, g_kl, grad_logits, rows, C);
+            logits, teacher, action, lse, entropy, lse_t, g_logp, g_ent, g_kl, g_mean, grad_logits, rows, C);
     }
     return dsb::check_launch("categorical_stats_bwd");
 }

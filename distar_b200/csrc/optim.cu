@@ -31,7 +31,7 @@ __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float* __re
     }
 }
 
-__global__ void norm_finish_kernel(const float* __restrict__ partial, int np, float* __restrict__ norm_out) {
+__global__ void norm_finish_kernel(const float* __restrict__ partial, int np, float scale, float* __restrict__ norm_out) {
     double acc = 0.0;
     for (int i = threadIdx.x; i < np; i += blockDim.x) acc += (double)partial[i];
     __shared__ double red[32];
@@ -41,7 +41,7 @@ __global__ void norm_finish_kernel(const float* __restrict__ partial, int np, fl
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
-        norm_out[0] = (float)sqrt(t);
+        norm_out[0] = (float)sqrt(t) * scale;      // scale = 1/world: the norm of the AVERAGED gradient (dist_helper.py:421-431)
     }
 }
 
@@ -53,18 +53,21 @@ __device__ __forceinline__ void split_store(float x, __nv_bfloat16* hi, __nv_bfl
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, const float* __restrict__ norm, float max_norm,
-                            float grad_scale, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
-                            __nv_bfloat16* __restrict__ sh, __nv_bfloat16* __restrict__ sl) {
+                            float grad_scale, float lr, float b1, float b2, float eps, float weight_decay, float bc1,
+                            float bc2_sqrt, __nv_bfloat16* __restrict__ sh, __nv_bfloat16* __restrict__ sl,
+                            const float* __restrict__ skip) {
+    if (skip && skip[0] != 0.f) return;      // some rank flagged its batch as invalid: no weight moves anywhere
     float scale = grad_scale;
-    if (norm) {
-        // clip_grad_norm_: clip_coef = max_norm / (total_norm + 1e-6), clamped to 1
-        const float total = norm[0] * grad_scale;
+    if (norm && max_norm > 0.f) {
+        // clip_grad_norm_: clip_coef = max_norm / (total_norm + 1e-6), clamped to 1 (norm[0] is already the averaged norm)
+        const float total = norm[0];
         scale *= fminf(1.0f, max_norm / (total + 1e-6f));
     }
     const float step_size = lr / bc1;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float gi = g[i] * scale;
+        // torch.optim.Adam (not AdamW): the L2 term joins the (already clipped) gradient, adam.py `grad.add(param, alpha=wd)`
+        const float gi = fmaf(weight_decay, p[i], g[i] * scale);
         const float mi = b1 * m[i] + (1.f - b1) * gi;
         const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
         m[i] = mi;
@@ -108,27 +111,29 @@ inline unsigned grid_for(int64_t n, int per_thread) {
 
 extern "C" int dsb_sumsq_partials(void) { return kPartials; }
 
-extern "C" int dsb_grad_norm(const float* grad, int64_t n, float* partial, float* norm_out, dsb_stream_t stream) {
+extern "C" int dsb_grad_norm(const float* grad, int64_t n, float* partial, float* norm_out, float scale,
+                             dsb_stream_t stream) {
     DSB_REQUIRE(grad && partial && norm_out && n > 0, "grad_norm: bad argument");
     DSB_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0, "grad_norm: grad must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     sumsq_kernel<<<kPartials, kThreads, 0, s>>>(grad, n, partial);
     int rc = dsb::check_launch("grad_norm/sumsq");
     if (rc) return rc;
-    norm_finish_kernel<<<1, 256, 0, s>>>(partial, kPartials, norm_out);
+    norm_finish_kernel<<<1, 256, 0, s>>>(partial, kPartials, scale, norm_out);
     return dsb::check_launch("grad_norm/finish");
 }
 
 extern "C" int dsb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                              const float* norm, float max_norm, float grad_scale, float lr, float beta1, float beta2,
-                             float eps, int t, void* shadow_hi, void* shadow_lo, dsb_stream_t stream) {
+                             float eps, float weight_decay, int t, void* shadow_hi, void* shadow_lo, const float* skip_flag,
+                             dsb_stream_t stream) {
     DSB_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && t >= 1, "adam_step: bad argument");
     DSB_REQUIRE(!shadow_hi == !shadow_lo, "adam_step: shadow_hi and shadow_lo go together");
     const float bc1 = 1.0f - powf(beta1, (float)t);
     const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)t));
     adam_kernel<<<grid_for(n, 4), kThreads, 0, (cudaStream_t)stream>>>(
-        param, grad, exp_avg, exp_avg_sq, n, norm, max_norm, grad_scale, lr, beta1, beta2, eps, bc1, bc2_sqrt,
-        (__nv_bfloat16*)shadow_hi, (__nv_bfloat16*)shadow_lo);
+        param, grad, exp_avg, exp_avg_sq, n, norm, max_norm, grad_scale, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt,
+        (__nv_bfloat16*)shadow_hi, (__nv_bfloat16*)shadow_lo, skip_flag);
     return dsb::check_launch("adam_step");
 }
 

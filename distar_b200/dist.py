@@ -80,7 +80,8 @@ class DistModule(torch.nn.Module):
     def sync_gradients(self):
         """ONE all-reduce(SUM) of the flat gradient arena; the 1/world average is applied by the optimiser."""
         if self.sync and get_world_size() > 1:
-            dist.all_reduce(self.module.flat_grad)
+            # the tail slots behind the gradients ride along (learner.py: the "a rank saw an invalid batch" flag)
+            dist.all_reduce(getattr(self.module, 'flat_grad_full', self.module.flat_grad))
 
     def broadcast_params(self):
         from . import ops

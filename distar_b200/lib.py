@@ -24,8 +24,8 @@ _SIGNATURES = {
     'dsb_spatial_stem_fwd': (_i, [_vp] * 11 + [_i] * 5 + [_vp]),
     'dsb_spatial_stem_bwd': (_i, [_vp] * 9 + [_i] + [_vp] * 3 + [_i] * 4 + [_vp]),
     'dsb_return_scan': (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    'dsb_categorical_stats_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
-    'dsb_categorical_stats_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    'dsb_categorical_stats_fwd': (_i, [_vp] * 10 + [_i64, _i, _vp]),
+    'dsb_categorical_stats_bwd': (_i, [_vp] * 11 + [_i64, _i, _vp]),
     'dsb_su_sample_step': (_i, [_vp] * 17 + [_i, _i, _i, _f, _vp]),
     'dsb_sample_categorical': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     'dsb_split_bf16': (_i, [_vp, _vp, _vp, _i64, _vp]),
@@ -55,8 +55,8 @@ _SIGNATURES = {
     'dsb_relu_bwd_split_blocks': (_i, [_i64, _i]),
     'dsb_relu_bwd_split': (_i, [_vp, _vp, _i] + [_vp] * 4 + [_i, _i64, _i, _vp]),
     'dsb_sumsq_partials': (_i, []),
-    'dsb_grad_norm': (_i, [_vp, _i64, _vp, _vp, _vp]),
-    'dsb_adam_step': (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp]),
+    'dsb_grad_norm': (_i, [_vp, _i64, _vp, _vp, _f, _vp]),
+    'dsb_adam_step': (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp, _vp]),
 }
 
 

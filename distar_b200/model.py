@@ -50,6 +50,9 @@ def _to_cfg(d):
 
 
 def _async_scalar(t: torch.Tensor):
+    if not t.is_cuda:
+        v = t.detach().reshape(-1)[0].item()
+        return lambda: v
     """Start a device->host copy of a 0-d tensor now; the returned thunk waits for that copy only (an event recorded
     right behind it), not for whatever was queued on the stream afterwards."""
     host = torch.empty(1, dtype=t.dtype, pin_memory=True)
@@ -104,7 +107,7 @@ class Model(nn.Module):
         flat = torch.zeros(off, dtype=torch.float32)
         self._arena_numel = off
         object.__setattr__(self, '_flat_param', flat)
-        object.__setattr__(self, '_flat_grad', torch.zeros_like(flat))
+        self._new_grad_arena(flat)
         self._params: Dict[str, nn.Parameter] = {}
         for name, shape, kind in self._specs:
             node = self
@@ -134,6 +137,30 @@ class Model(nn.Module):
     def flat_grad(self) -> torch.Tensor:
         return self._flat_grad
 
+    _TAIL = 4       # floats behind the gradients that travel in the same all-reduce (slot 0: "this rank's batch was invalid")
+
+    def _new_grad_arena(self, like: torch.Tensor) -> None:
+        full = torch.zeros(like.numel() + self._TAIL, dtype=torch.float32, device=like.device)
+        object.__setattr__(self, '_flat_grad_full', full)
+        object.__setattr__(self, '_flat_grad', full[:like.numel()])
+
+    @property
+    def flat_grad_full(self) -> torch.Tensor:
+        """flat_grad plus the tail slots: the tensor DistModule.sync_gradients all-reduces."""
+        return self._flat_grad_full
+
+    @property
+    def grad_tail(self) -> torch.Tensor:
+        return self._flat_grad_full[self._arena_numel:]
+
+    def optimizer_layout(self) -> Dict:
+        """Where each trainable parameter lives in the arena, by its position in ``parameters()`` - what ops.FlatAdam needs
+        to read / write optimizer states in the reference's per-parameter format (torch.optim.Adam over
+        ``model.parameters()``, rl_learner.py:73-79; checkpoint_helper.py:124-131,254)."""
+        index = {id(p): i for i, p in enumerate(self.parameters())}
+        slots = [(index[id(self._params[name])], o, n, shp) for name, (o, n, shp) in self._offsets.items()]
+        return {'num_params': len(index), 'slots': sorted(slots)}
+
     def _bind_grads(self):
         for name, (o, n, shp) in self._offsets.items():
             p = self._params[name]
@@ -144,7 +171,7 @@ class Model(nn.Module):
         """Move the arena as a whole (``.cuda()``, ``.to()``, ``.share_memory()``) and re-bind the views."""
         new_flat = fn(self._flat_param)
         object.__setattr__(self, '_flat_param', new_flat)
-        object.__setattr__(self, '_flat_grad', torch.zeros_like(new_flat))
+        self._new_grad_arena(new_flat)
         for name, p in self._params.items():
             if name not in self._offsets:
                 p.data = fn(p.data)
@@ -154,7 +181,7 @@ class Model(nn.Module):
         return self
 
     def zero_grad(self, set_to_none: bool = False):
-        self._flat_grad.zero_()
+        self._flat_grad_full.zero_()
         self._bind_grads()
 
     def load_state_dict(self, state_dict, strict: bool = True):
@@ -290,8 +317,9 @@ class Model(nn.Module):
                 'step': step}
 
     def sl_train(self, spatial_info, entity_info, scalar_info, entity_num, selected_units_num, traj_lens,
-                 hidden_state, action_info, **kwargs):
-        """model.py:170-189 (observation rows batch-major [B*T])."""
+                 hidden_state, action_info, defer_input_check: bool = False, **kwargs):
+        """model.py:170-189 (observation rows batch-major [B*T]).  defer_input_check: record an invalid input instead of
+        raising here; the caller must call raise_on_bad_input() before the optimiser step (learner.SLLearner does)."""
         net = self._net()
         B = len(traj_lens)
         lstm_input, scalar_context, _bf, entity_embeddings, map_skip = self._encode(
@@ -301,5 +329,8 @@ class Model(nn.Module):
         lstm_out = lstm_out.permute(1, 0, 2).reshape(-1, lstm_out.shape[-1])
         action, su_num, logits = net.policy_train(lstm_out, entity_embeddings, map_skip, scalar_context, entity_num,
                                                   action_info, selected_units_num)
-        net.raise_on_bad_input()
+        if defer_input_check and lstm_out.is_cuda:
+            self._flag_handle = _async_scalar(self._bad_input_flag)
+        else:
+            net.raise_on_bad_input()
         return logits, action, out_state

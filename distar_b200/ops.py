@@ -260,7 +260,7 @@ def return_scan(reward: torch.Tensor, value: torch.Tensor, rho: torch.Tensor, ga
 # ------------------------------------------------------------------------------------------------
 class _CategoricalStats(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, teacher, action):
+    def forward(ctx, logits, teacher, action, want_mean, flag):
         rows, C = logits.shape
         dev = logits.device
         lse = torch.empty((rows, 2), dtype=torch.float32, device=dev)
@@ -268,26 +268,33 @@ class _CategoricalStats(torch.autograd.Function):
         ent = torch.empty_like(logp)
         kl = torch.empty_like(logp) if teacher is not None else None
         lse_t = torch.empty_like(lse) if teacher is not None else None
-        lib.call('dsb_categorical_stats_fwd', logits, teacher, action, lse, logp, ent, kl, lse_t, rows, C)
+        mean_lp = torch.empty_like(logp) if want_mean else None
+        lib.call('dsb_categorical_stats_fwd', logits, teacher, action, lse, logp, ent, kl, lse_t, mean_lp, flag, rows, C)
         ctx.save_for_backward(logits, teacher, action, lse, ent, lse_t)
         ctx.mark_non_differentiable(lse)
+        ctx.set_materialize_grads(False)
         if teacher is None:
             kl = torch.zeros_like(logp)
-        return logp, ent, kl, lse
+        if mean_lp is None:
+            mean_lp = torch.zeros_like(logp)
+        return logp, ent, kl, mean_lp, lse
 
     @staticmethod
-    def backward(ctx, g_logp, g_ent, g_kl, _g_lse):
+    def backward(ctx, g_logp, g_ent, g_kl, g_mean, _g_lse):
         logits, teacher, action, lse, ent, lse_t = ctx.saved_tensors
         rows, C = logits.shape
         grad = torch.empty_like(logits)
         cont = lambda g: None if g is None else g.contiguous().float()
         lib.call('dsb_categorical_stats_bwd', logits, teacher, action, lse, ent, lse_t, cont(g_logp), cont(g_ent),
-                 cont(g_kl) if teacher is not None else None, grad, rows, C)
-        return grad, None, None
+                 cont(g_kl) if teacher is not None else None, cont(g_mean), grad, rows, C)
+        return grad, None, None, None, None
 
 
-def categorical_stats(logits: torch.Tensor, action: torch.Tensor, teacher: Optional[torch.Tensor] = None):
+def categorical_stats(logits: torch.Tensor, action: torch.Tensor, teacher: Optional[torch.Tensor] = None,
+                      want_mean: bool = False, flag: Optional[torch.Tensor] = None):
     """Per row of ``logits[..., C]``: (log p(action), entropy, KL(teacher || target)); all differentiable wrt logits.
+    With want_mean a fourth result, mean_j log p_j (the label-smoothing term of sl_loss.py:16-34), is returned.
+    ``flag`` (device int32[1]): bit 2 is set when a label lies outside [0, C) (torch raises there; the kernel clamps).
 
     One fused pass instead of Categorical(...).probs/.logits/.log_prob + the entropy and KL passes of
     rl_training/rl_loss.py:63-90 and as_rl_utils.py:52-103.
@@ -299,16 +306,23 @@ def categorical_stats(logits: torch.Tensor, action: torch.Tensor, teacher: Optio
     a = action.reshape(-1).to(torch.int64)
     if _use_kernel(z):
         z = z.contiguous().float()
-        logp, ent, kl, _ = _CategoricalStats.apply(z, t.contiguous() if t is not None else None, a.contiguous())
+        logp, ent, kl, mean_lp, _ = _CategoricalStats.apply(z, t.contiguous() if t is not None else None, a.contiguous(),
+                                                            want_mean, flag)
     else:
+        if flag is not None:
+            flag |= 2 * int(((a < 0) | (a >= C)).any())
+        a = a.clamp(0, C - 1)
         lp = torch.log_softmax(z, -1)
         logp = lp.gather(-1, a.unsqueeze(-1)).squeeze(-1)
         ent = -(lp.exp() * lp).sum(-1)
+        mean_lp = lp.mean(-1)
         if t is not None:
             tl = torch.log_softmax(t, -1)
             kl = (tl.exp() * (tl - lp)).sum(-1)
         else:
             kl = torch.zeros_like(logp)
+    if want_mean:
+        return logp.view(shape), ent.view(shape), kl.view(shape), mean_lp.view(shape)
     return logp.view(shape), ent.view(shape), kl.view(shape)
 
 
@@ -1448,48 +1462,146 @@ def upsample_bilinear2x(x: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # flat-arena optimiser (K20)
 # ------------------------------------------------------------------------------------------------
-class FlatAdam:
-    """clip_grad_norm_(max_norm) + Adam(betas, eps) over one contiguous fp32 arena, two kernels per step.
+class FlatAdam(torch.optim.Optimizer):
+    """Gradient clip + Adam over one contiguous fp32 arena: two kernels per step (norm, clip+Adam).
 
-    Reference: RLLearner._setup_optimizer rl_learner.py:73-80 (Adam(betas=(0, 0.99), eps=1e-5)),
-    GradClip 'pytorch_norm' ctools/torch_utils/grad_clip.py:141-144, applied in rl_learner.py:125,132.
+    Reference: RLLearner._setup_optimizer rl_learner.py:73-80 (Adam(betas=(0, 0.99), eps=1e-5)), BaseLearner._setup_optimizer
+    base_learner.py:157-181 (SL: Adam(lr, weight_decay) + warm-up / MultiStepLR schedulers), GradClip
+    ctools/torch_utils/grad_clip.py:20-144 applied in rl_learner.py:125 / sl_learner.py:70.
     ``grad_scale`` folds DistModule.sync_gradients' division by world size (dist_helper.py:421-431).
+
+    It IS a ``torch.optim.Optimizer`` (one param group holding the arena) so the reference's own plumbing works on it:
+    ``MultiStepLR(optimizer)`` / ``GradualWarmupScheduler`` change ``param_groups[0]['lr']`` which ``step`` reads,
+    ``update_config`` sets ``g['lr']`` (rl_learner.py:205-206), and the checkpoint hooks call ``state_dict()`` /
+    ``load_state_dict()`` (checkpoint_helper.py:124-131,254).  With ``layout`` (Model.optimizer_layout()) the state dict is in
+    the reference's per-parameter format ({'state': {param index: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [...]},
+    indices = position in model.parameters()), so optimizer states interchange with reference checkpoints in both directions.
+
+    clip_type (GradClip): 'pytorch_norm' / 'clip_norm' = clip_grad_norm_(max_norm); 'none' = norm only; 'momentum_norm' = what
+    the reference's implementation DOES: its per-tensor norm momenta are appended to the end of the list instead of stored at
+    their index (grad_clip.py:100-103), so ``norm_mom[idx]`` stays None, no gradient is ever scaled and apply() returns the
+    global 2-norm - i.e. 'none'.  ``owner``: the Model whose arenas these are; if it is moved (.cuda() / .to()) after the
+    optimiser was built the new arenas are picked up (and the moments moved) at the next step.
     """
 
     def __init__(self, param: torch.Tensor, grad: torch.Tensor, lr: float, betas=(0.0, 0.99), eps: float = 1e-5,
-                 max_norm: Optional[float] = 1.0):
+                 max_norm: Optional[float] = 1.0, weight_decay: float = 0.0, clip_type: str = 'pytorch_norm',
+                 layout=None, owner=None):
         assert param.is_contiguous() and grad.is_contiguous() and param.numel() == grad.numel()
+        assert clip_type in ('pytorch_norm', 'clip_norm', 'none', 'momentum_norm'), clip_type
         self.param, self.grad = param, grad
-        self.lr, self.betas, self.eps, self.max_norm = lr, betas, eps, max_norm
+        self.clip_type = clip_type
+        self.max_norm = max_norm if clip_type in ('pytorch_norm', 'clip_norm') else None
+        self.layout, self.owner = layout, owner
+        super().__init__([param], dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, amsgrad=False))
         self.exp_avg = torch.zeros_like(param)
         self.exp_avg_sq = torch.zeros_like(param)
         self.t = 0
         self.norm = torch.zeros(1, dtype=torch.float32, device=param.device)
         self._partial = None
 
-    def step(self, grad_scale: float = 1.0):
+    # ---- attribute view of the single param group (bench / tests read and set these)
+    @property
+    def lr(self):
+        return self.param_groups[0]['lr']
+
+    @lr.setter
+    def lr(self, v):
+        self.param_groups[0]['lr'] = v
+
+    @property
+    def betas(self):
+        return self.param_groups[0]['betas']
+
+    @property
+    def eps(self):
+        return self.param_groups[0]['eps']
+
+    def _rebind(self):
+        """The owner's arenas were replaced (Model._apply): follow them and carry the moments along."""
+        new_p, new_g = self.owner.flat_param, self.owner.flat_grad
+        if new_p is self.param and new_g is self.grad:
+            return
+        assert new_p.numel() == self.param.numel()
+        self.param, self.grad = new_p, new_g
+        self.param_groups[0]['params'] = [new_p]
+        self.exp_avg, self.exp_avg_sq = self.exp_avg.to(new_p.device), self.exp_avg_sq.to(new_p.device)
+        self.norm = self.norm.to(new_p.device)
+        self._partial = None
+
+    def zero_grad(self, set_to_none: bool = False):
+        if self.owner is not None:
+            self._rebind()
+        self.grad.zero_()
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0, skip_flag: Optional[torch.Tensor] = None):
+        """skip_flag: device float[>=1]; non-zero = leave the weights and moments untouched (see dsb_adam_step)."""
+        if self.owner is not None:
+            self._rebind()
         self.t += 1
         WEIGHT_EPOCH[0] += 1            # the arena is about to change under every cached weight form
         n = self.param.numel()
+        g0 = self.param_groups[0]
+        lr, (b1, b2), eps, wd = float(g0['lr']), g0['betas'], float(g0['eps']), float(g0.get('weight_decay', 0.0))
         if _use_kernel(self.param):
             if self._partial is None:
                 self._partial = torch.empty(lib.load().dsb_sumsq_partials(), dtype=torch.float32, device=self.param.device)
-            norm = None
-            if self.max_norm is not None:
-                lib.call('dsb_grad_norm', self.grad, n, self._partial, self.norm)
-                norm = self.norm
-            lib.call('dsb_adam_step', self.param, self.grad, self.exp_avg, self.exp_avg_sq, n, norm,
-                     float(self.max_norm or 0.0), float(grad_scale), float(self.lr), float(self.betas[0]),
-                     float(self.betas[1]), float(self.eps), int(self.t), None, None)
+            lib.call('dsb_grad_norm', self.grad, n, self._partial, self.norm, float(grad_scale))
+            lib.call('dsb_adam_step', self.param, self.grad, self.exp_avg, self.exp_avg_sq, n, self.norm,
+                     float(self.max_norm or 0.0), float(grad_scale), lr, float(b1), float(b2), eps, wd, int(self.t), None, None,
+                     skip_flag)
+            return self.norm
+        if skip_flag is not None and float(skip_flag.reshape(-1)[0]) != 0.0:
             return self.norm
         g = self.grad * grad_scale
         self.norm = g.norm().reshape(1)
         if self.max_norm is not None:
             g = g * torch.clamp(self.max_norm / (self.norm + 1e-6), max=1.0)
-        b1, b2 = self.betas
+        if wd != 0.0:
+            g = g + wd * self.param
         self.exp_avg.mul_(b1).add_(g, alpha=1 - b1)
         self.exp_avg_sq.mul_(b2).addcmul_(g, g, value=1 - b2)
         bc1, bc2 = 1 - b1 ** self.t, 1 - b2 ** self.t
-        denom = self.exp_avg_sq.sqrt() / math.sqrt(bc2) + self.eps
-        self.param.addcdiv_(self.exp_avg, denom, value=-self.lr / bc1)
+        denom = self.exp_avg_sq.sqrt() / math.sqrt(bc2) + eps
+        self.param.addcdiv_(self.exp_avg, denom, value=-lr / bc1)
         return self.norm
+
+    # ---- checkpoint interchange (checkpoint_helper.py:85-140,254: {'model', 'optimizer', 'last_iter'})
+    def state_dict(self):
+        group = {k: v for k, v in self.param_groups[0].items() if k != 'params'}
+        if self.layout is None:
+            return {'flat': True, 'step': self.t, 'exp_avg': self.exp_avg.clone(), 'exp_avg_sq': self.exp_avg_sq.clone(),
+                    'param_groups': [dict(group, params=[0])]}
+        state = {}
+        if self.t > 0:
+            for idx, off, n, shape in self.layout['slots']:
+                state[idx] = {'step': torch.tensor(float(self.t)), 'exp_avg': self.exp_avg[off:off + n].view(shape).clone(),
+                              'exp_avg_sq': self.exp_avg_sq[off:off + n].view(shape).clone()}
+        return {'state': state, 'param_groups': [dict(group, params=list(range(self.layout['num_params'])))]}
+
+    def load_state_dict(self, sd):
+        group = sd['param_groups'][0]
+        for k in ('lr', 'betas', 'eps', 'weight_decay'):
+            if k in group:
+                self.param_groups[0][k] = tuple(group[k]) if k == 'betas' else group[k]
+        if sd.get('flat'):
+            self.t = int(sd['step'])
+            self.exp_avg.copy_(sd['exp_avg'])
+            self.exp_avg_sq.copy_(sd['exp_avg_sq'])
+            return
+        assert self.layout is not None, 'a per-parameter optimizer state needs the model layout (Model.optimizer_layout())'
+        state = sd['state']
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        steps = set()
+        for idx, off, n, shape in self.layout['slots']:
+            st = state.get(idx, state.get(str(idx)))
+            if st is None:
+                continue
+            steps.add(int(float(st['step'])))
+            self.exp_avg[off:off + n].copy_(st['exp_avg'].reshape(-1))
+            self.exp_avg_sq[off:off + n].copy_(st['exp_avg_sq'].reshape(-1))
+        # one bias-correction step for the whole arena: the reference steps every parameter together, so they agree
+        assert len(steps) <= 1, 'per-parameter Adam steps differ: %s' % sorted(steps)
+        self.t = steps.pop() if steps else 0

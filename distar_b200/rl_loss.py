@@ -1,5 +1,6 @@
 """``ReinforcementLoss`` — drop-in for DI-star ``rl_training/rl_loss.py:9-199`` (V-trace PG + UPGO + TD(lambda)
-critic + entropy + teacher KL; DAPO as in the reference is honoured only for 'MP' players and off by default).
+critic + entropy + teacher KL + DAPO (KL towards the 'successive' model's logits, honoured only for 'MP' players and off
+by default: rl_loss.py:22-24,164-172, as_rl_utils.py:105-127).
 
 Same constructor ``ReinforcementLoss(learner_cfg, player_id)``, same ``compute_loss(model_output) -> dict`` with
 'total_loss' (autograd scalar) plus the '{field}/{head}', '{field}/td', 'upgo/*', 'entropy/*', 'kl/*' floats the
@@ -64,11 +65,17 @@ class LazyScalars(dict):
 
     The reference returns ``.item()`` floats (rl_loss.py:40-47 / as_rl_utils); fetching them synchronises host and
     device.  Here all of them travel in one asynchronous copy into pinned memory and turn into floats the first time any
-    of them is read (tensor entries such as ``total_loss`` are stored directly and never wait)."""
+    of them is read (tensor entries such as ``total_loss`` are stored directly and never wait).
+
+    Keys starting with '_' are side-band values (``_total_loss_value``: the float of total_loss; ``_bad_action``: the
+    out-of-range-label flag): ``d['_key']`` reads them but they never show up in keys() / items() / iteration, because the
+    reference's learner feeds the whole dict to its variable record, which raises on names it has not registered
+    (log_helper.py:356-364)."""
 
     def __init__(self, keys, stacked: torch.Tensor):
         super().__init__()
         self._pending_keys = list(keys)
+        self._hidden = {}
         if stacked.is_cuda:
             self._host = torch.empty(stacked.shape, dtype=stacked.dtype, pin_memory=True)
             self._host.copy_(stacked, non_blocking=True)
@@ -83,14 +90,22 @@ class LazyScalars(dict):
                 self._event.synchronize()
             keys, self._pending_keys = self._pending_keys, None
             for k, v in zip(keys, self._host.tolist()):
-                dict.setdefault(self, k, v)
+                if k.startswith('_'):
+                    self._hidden.setdefault(k, v)
+                else:
+                    dict.setdefault(self, k, v)
 
     def __getitem__(self, k):
+        if isinstance(k, str) and k.startswith('_'):
+            self._settle()
+            return self._hidden[k]
         if not dict.__contains__(self, k):
             self._settle()
         return dict.__getitem__(self, k)
 
     def __contains__(self, k):
+        if isinstance(k, str) and k.startswith('_'):
+            return False
         return dict.__contains__(self, k) or (self._pending_keys is not None and k in self._pending_keys)
 
     def get(self, k, default=None):
@@ -161,9 +176,13 @@ class ReinforcementLoss:
         su_mask_f = su_mask.float()
         act_mask = {h: (mask['actions_mask'][h].float() if h not in ('action_type', 'delay') else None) for h in HEADS}
 
+        dev = reward['winloss'].device
+        if getattr(self, '_flag', None) is None or self._flag.device != dev:
+            self._flag = torch.zeros(1, dtype=torch.int32, device=dev)     # bit 2: an action label outside its head
+        self._flag.zero_()
         lam, ent_rows, kl_rows, rho = {}, {}, {}, {}
         for h in HEADS:                                      # rl_loss.py:63-90 — one fused pass per head
-            lp, ent, kl = ops.categorical_stats(logits[h], action[h], teacher[h])
+            lp, ent, kl = ops.categorical_stats(logits[h], action[h], teacher[h], flag=self._flag)
             with torch.no_grad():
                 lr = lp.detach() - mu[h]
                 if h == 'selected_units':
@@ -245,16 +264,35 @@ class ReinforcementLoss:
         log['kl/total'] = total_kl
         total_kl = total_kl * self.loss_weights['kl']
         at_kl = at_kl * self.loss_weights['action_type_kl']
-        if self.use_dapo:
-            raise NotImplementedError('DAPO (use_dapo=True) needs successive_logit batches; off in the reference default')
+        total_dapo = 0.
+        if self.use_dapo:                                    # as_rl_utils.py:105-127: KL(successive || target) per head
+            successive = inputs['successive_logit']
+            early = (step < self.dapo_steps)
+            for h in HEADS:
+                kl_d = ops.categorical_stats(logits[h], action[h], successive[h])[2]
+                if h == 'selected_units':
+                    kl_d = (kl_d * su_mask_f).sum(-1)
+                kl_d = (masked(kl_d, h) * early).mean()
+                log['battle/' + h] = kl_d                    # the reference logs DAPO under 'battle/*' (as_rl_utils.py:125-126)
+                total_dapo = total_dapo + kl_d * self.dapo_head_weights[h]
+            log['battle/total'] = total_dapo
+            total_dapo = total_dapo * self.loss_weights['dapo']
         if self.only_update_value:
             total = total_critic
         else:
-            total = total_pg + total_upgo + total_critic + total_ent + total_kl + at_kl
+            total = total_pg + total_upgo + total_critic + total_ent + total_kl + at_kl + total_dapo
         # one device->host copy for every logged scalar, and it is not waited for here: the values materialise on first
         # access, so backward can be queued behind the forward pass without draining the launch queue in between
-        log['total_loss_value'] = total          # the float of total_loss rides in the same copy (total_loss itself stays a tensor)
+        log['_total_loss_value'] = total         # the float of total_loss rides in the same copy (total_loss itself stays a tensor)
         keys = list(log.keys())
-        out = LazyScalars(keys, torch.stack([log[k].detach().float() for k in keys]))
+        out = LazyScalars(keys + ['_bad_action'], torch.stack([log[k].detach().float() for k in keys] + [self._flag[0].float()]))
         out['total_loss'] = total
+        self._last = out
         return out
+
+    def raise_on_bad_action(self) -> None:
+        """torch's Categorical.log_prob raises on an action id outside its head (rl_loss.py:73); the kernels clamp and record
+        it, and the record travels with the logged scalars (waiting for it waits only for the loss forward, not backward)."""
+        last = getattr(self, '_last', None)
+        if last is not None and last['_bad_action'] != 0:
+            raise RuntimeError('action id outside its head in the learner batch')

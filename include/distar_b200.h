@@ -84,15 +84,18 @@ int dsb_return_scan(const float* reward, const float* value, const float* rho, c
  * For each of `rows` rows of `logits` [rows,C] (and optional `teacher` [rows,C]) with label action[rows] (i64):
  *   lse[r] = (row max, log sum exp(z - max)) as two floats, logp[r] = (logits[r,a]-max)-logsum,
  *   entropy[r] = -sum p log p, kl[r] = sum pt (log pt - log p), lse_t[r] likewise two floats for the teacher.
- * Masked classes carry -1e9 as in the reference.  teacher/kl/lse_t may be NULL. */
+ * Masked classes carry -1e9 as in the reference.  teacher/kl/lse_t may be NULL.  mean_logp (optional) receives
+ * mean_j log p_j, the smoothing term of LabelSmoothingCrossEntropy (sl_training/sl_loss.py:16-34).  A label outside [0, C)
+ * (torch raises there) is clamped and bit 2 is OR-ed into error_flag (optional device int, zeroed by the caller). */
 int dsb_categorical_stats_fwd(const float* logits, const float* teacher, const int64_t* action, float* lse,
-                              float* logp, float* entropy, float* kl, float* lse_t, int64_t rows, int C,
-                              dsb_stream_t stream);
-/* grad_logits[r,j] = g_logp[r]*(1[j==a]-p_j) - g_ent[r]*p_j*(log p_j + H_r) + g_kl[r]*(p_j - pt_j)
- * (g_* are per-row upstream gradients; entropy = H_r from the forward). */
+                              float* logp, float* entropy, float* kl, float* lse_t, float* mean_logp, int* error_flag,
+                              int64_t rows, int C, dsb_stream_t stream);
+/* grad_logits[r,j] = g_logp[r]*(1[j==a]-p_j) - g_ent[r]*p_j*(log p_j + H_r) + g_kl[r]*(p_j - pt_j) + g_mean[r]*(1/C - p_j)
+ * (g_* are per-row upstream gradients, each may be NULL; entropy = H_r from the forward). */
 int dsb_categorical_stats_bwd(const float* logits, const float* teacher, const int64_t* action, const float* lse,
                               const float* entropy, const float* lse_t, const float* g_logp, const float* g_ent,
-                              const float* g_kl, float* grad_logits, int64_t rows, int C, dsb_stream_t stream);
+                              const float* g_kl, const float* g_mean, float* grad_logits, int64_t rows, int C,
+                              dsb_stream_t stream);
 
 /* ---- selected-units pointer network: one sampling step  (SelectedUnitsHead._query loop body, action_arg_head.py:267-306) ----
  * weights16: host array of 16 device pointers in this order: query_fc1 W,b; query_fc2 W,b; lstm W_ih, W_hh;
@@ -266,15 +269,20 @@ int dsb_lstm_cell_bwd(const float* gh, const float* gcy, const float* gates, con
 
 /* ---- fused grad-norm -> clip -> Adam over the flat arena  (rl_learner.py:73-80,125,132; grad_clip.py:141-144) ----
  * step 1: dsb_sumsq partial sums of grad^2 into `partial` [>= dsb_sumsq_partials()] then a finishing reduction
- *         into norm_out[0] = sqrt(sum) (all on device, no host sync).
- * step 2: dsb_adam_step reads norm_out on device: scale = min(1, max_norm/(norm*grad_scale + 1e-6)) * grad_scale
- *         (grad_scale = 1/world folds the DP average, dist_helper.py:421-431), then Adam(beta1,beta2,eps, no decay)
- *         with bias correction for step `t` (1-based); optionally refreshes the bf16 hi/lo shadow of the weights. */
+ *         into norm_out[0] = sqrt(sum) * scale (all on device, no host sync); scale = 1/world makes it the norm of the
+ *         AVERAGED gradient, which is what the reference clips and logs (dist_helper.py:421-431, rl_learner.py:125).
+ * step 2: dsb_adam_step reads norm_out on device: g = grad * grad_scale * min(1, max_norm/(norm + 1e-6)) (no clipping when
+ *         norm is NULL or max_norm <= 0; grad_scale = 1/world folds the DP average), then torch.optim.Adam(beta1, beta2,
+ *         eps, weight_decay: g += weight_decay * param, base_learner.py:164-168) with bias correction for step `t`
+ *         (1-based); optionally refreshes the bf16 hi/lo shadow of the weights.  skip_flag (optional device float): when
+ *         skip_flag[0] != 0 the launch leaves every buffer untouched - the data-parallel learner all-reduces one extra
+ *         "my batch was invalid" slot together with the gradients, so a bad batch on ANY rank freezes the step on ALL ranks
+ *         without a host round trip (the reference raises inside forward, entity_encoder.py:69-72). */
 int dsb_sumsq_partials(void);
-int dsb_grad_norm(const float* grad, int64_t n, float* partial, float* norm_out, dsb_stream_t stream);
+int dsb_grad_norm(const float* grad, int64_t n, float* partial, float* norm_out, float scale, dsb_stream_t stream);
 int dsb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* norm,
-                  float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps, int t,
-                  void* shadow_hi, void* shadow_lo, dsb_stream_t stream);
+                  float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  int t, void* shadow_hi, void* shadow_lo, const float* skip_flag, dsb_stream_t stream);
 
 #ifdef __cplusplus
 }

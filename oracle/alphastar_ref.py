@@ -686,8 +686,10 @@ DEFAULT_RL_LOSS_CFG = {  # bin/rl_user_config.yaml:58-117 merged over rl_trainin
 }
 
 
-def rl_loss(out: dict, cfg: dict = None, only_update_value: bool = False) -> Dict[str, Tensor]:
-    """ReinforcementLoss.compute_loss, rl_loss.py:33-185 (DAPO off).  Returns tensors (no .item())."""
+def rl_loss(out: dict, cfg: dict = None, only_update_value: bool = False, use_dapo: bool = False,
+            dapo_w: float = 0.1, dapo_steps: int = 2400) -> Dict[str, Tensor]:
+    """ReinforcementLoss.compute_loss, rl_loss.py:33-185.  Returns tensors (no .item()).  use_dapo: the 'MP' players' extra
+    KL(successive || target) term (rl_loss.py:164-172, as_rl_utils.py:105-127) over out['successive_logit']."""
     cfg = cfg or DEFAULT_RL_LOSS_CFG
     logits, values = out['target_logit'], out['value']          # zeroing below is visible to the caller, as in the reference
     mu, teacher, mask, action, reward, step = (out['action_log_prob'], out['teacher_logit'], out['mask'],
@@ -786,10 +788,23 @@ def rl_loss(out: dict, cfg: dict = None, only_update_value: bool = False) -> Dic
     info['kl/total'] = total_kl.detach()
     total_kl = total_kl * cfg['kl_w']
     at_kl = at_kl * cfg['action_type_kl_w']
+    total_dapo = 0.
+    if use_dapo:                                                         # as_rl_utils.py:105-127
+        early = step < dapo_steps
+        for h in HEADS:
+            slp = torch.log_softmax(out['successive_logit'][h], dim=-1)
+            kl = (slp.exp() * (slp - logp_all[h])).sum(-1)
+            if h == 'selected_units':
+                kl = (kl * su_mask).sum(-1)
+            kl = (kl * am(h) * early).mean()
+            info['battle/' + h] = kl.detach()                            # logged under 'battle/*' (overrides the pg entries)
+            total_dapo = total_dapo + kl * cfg['head_w'][h]
+        info['battle/total'] = total_dapo.detach()
+        total_dapo = total_dapo * dapo_w
     if only_update_value:
         info['total_loss'] = total_critic
     else:
-        info['total_loss'] = total_pg + total_upgo + total_critic + total_ent + total_kl + at_kl
+        info['total_loss'] = total_pg + total_upgo + total_critic + total_ent + total_kl + at_kl + total_dapo
     return info
 
 
@@ -800,19 +815,70 @@ SL_LOSS_WEIGHTS = {'action_type': 30.0, 'delay': 9.0, 'queued': 1.0, 'selected_u
                    'target_location': 8.0}
 
 
-def sl_loss(logits: dict, actions: dict, actions_mask: dict, selected_units_num: Tensor) -> Dict[str, Tensor]:
-    """SupervisedLoss.compute_loss (losses only; acc/IoU metrics are no-grad extras not restated)."""
+def sl_loss(logits: dict, actions: dict, actions_mask: dict, selected_units_num: Tensor, entity_num: Tensor = None,
+            infer_selected_units: Tensor = None, su_mask: bool = False, label_smooth: bool = False) -> Dict[str, Tensor]:
+    """SupervisedLoss.compute_loss, sl_loss.py:100-286: the six losses plus the no-grad metrics."""
     out = {}
+
+    def criterion(x, y):                                                 # sl_loss.py:16-34,54-57
+        if not label_smooth:
+            return F.cross_entropy(x, y, reduction='none')
+        lp = torch.log_softmax(x, dim=-1)
+        return 0.9 * (-lp.gather(-1, y.unsqueeze(1)).squeeze(1)) + 0.1 * (-lp.mean(dim=-1))
+
     for h in HEADS:
-        if h == 'selected_units':
-            lg = logits[h]
+        mask = actions_mask[h]
+        if h == 'selected_units':                                        # sl_loss.py:174-238
+            lg, labels = logits[h], actions[h]
             b, s, n = lg.shape
-            ce = F.cross_entropy(lg.reshape(-1, n), actions[h][:, :s].reshape(-1), reduction='none').view(b, s)
-            ce = ce.masked_fill(~sequence_mask(selected_units_num, s), 0) * actions_mask[h].unsqueeze(1)
+            if su_mask:                                                  # :177-192: other selected units masked at every step
+                keep = sequence_mask((selected_units_num - 1).clamp(min=0), labels.shape[1])
+                nl = labels.clone()
+                nl[~keep] = n
+                nl = nl[:, :s]
+                lg = torch.cat([lg, torch.zeros(b, s, 1)], dim=-1)
+                lm = torch.ones_like(lg)
+                lm = torch.scatter(lm, 2, nl.unsqueeze(1).repeat(1, s, 1), 0.)
+                lm = torch.scatter(lm, 2, nl.unsqueeze(2), 1.)
+                lg = lg.masked_fill(~lm.bool(), -1e9)[:, :, :-1]
+            select = sequence_mask(selected_units_num, s)
+            ce = F.cross_entropy(lg.reshape(-1, n), labels[:, :s].reshape(-1), reduction='none').view(b, s)
+            ce = ce.masked_fill(~select, 0) * mask.unsqueeze(1)
             out[h + '_loss'] = ce.sum() / b
-        else:
-            ce = F.cross_entropy(logits[h], actions[h], reduction='none') * actions_mask[h]
-            valid = actions_mask[h].sum()
-            out[h + '_loss'] = ce.sum() / valid if valid > 0 else ce.sum() * 0
+            out['selected_units_loss_norm'] = (ce.sum() / (selected_units_num.sum() + 1e-6)).detach()
+            out['selected_units_end_flag_loss'] = ce[torch.arange(b), selected_units_num - 1].mean().detach()
+            if infer_selected_units is not None:                         # :206-232
+                preds = infer_selected_units
+                end = (preds == entity_num.unsqueeze(1)).long().argmax(dim=-1)
+                invalid = end == 0
+                end = end + 1
+                end[invalid] += s
+                pm = sequence_mask(end, s)
+                lab = (labels[:, :s] + 1) * select
+                prd = (preds + 1) * pm
+                ps = torch.zeros(b, n + 1, dtype=torch.bool).scatter(1, prd.long(), True)
+                ls = torch.zeros(b, n + 1, dtype=torch.bool).scatter(1, lab.long(), True)
+                inter, union = (ps & ls)[:, 1:].sum(1), (ps | ls)[:, 1:].sum(1)
+                out['selected_units_iou'] = (inter / (union + 1e-6) * mask).sum() / (mask.sum() + 1e-6)
+            else:
+                out['selected_units_iou'] = torch.tensor(0.)
+            continue
+        ce = criterion(logits[h], actions[h]) * mask
+        valid = mask.sum()
+        out[h + '_loss'] = ce.sum() / valid if valid > 0 else ce.sum() * 0
+        with torch.no_grad():
+            pred = logits[h].argmax(dim=-1)
+            if h == 'action_type':
+                out['action_type_acc'] = (pred == actions[h]).float().sum() / len(actions[h])
+            elif h == 'delay':
+                out['delay_distance_L1'] = ((pred - actions[h]).abs() * mask).sum() / (mask.sum() + 1e-6)
+            elif h == 'queued':
+                out['queued_acc'] = ((pred - actions[h]).abs() * mask).sum() / (mask.sum() + 1e-6)
+            elif h == 'target_unit':
+                out['target_unit_acc'] = ((pred == actions[h]) * mask).sum() / (mask.sum() + 1e-6)
+            else:
+                W = 160                                                  # hard-coded in the reference (sl_loss.py:257)
+                d = ((pred % W - actions[h] % W) ** 2 + (pred // W - actions[h] // W) ** 2).float().sqrt()
+                out['target_location_distance_L2'] = (d * mask).sum() / (mask.sum() + 1e-6)
     out['total_loss'] = sum(out[h + '_loss'] * SL_LOSS_WEIGHTS[h] for h in HEADS)
     return out

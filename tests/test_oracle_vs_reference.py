@@ -122,3 +122,123 @@ def test_sl_forward_matches_reference(ref):
     o_loss = O.sl_loss(ol, act, amask, num)
     for k, v in o_loss.items():
         assert abs(v.item() - float(r_loss[k])) <= 1e-4 * max(1.0, abs(float(r_loss[k]))), k
+
+
+def test_dapo_loss_matches_reference(ref):
+    """rl_loss.py:164-172 / as_rl_utils.py:105-127: the 'MP' players' KL towards the successive model's logits."""
+    model, cfg, mods, sd = ref
+    batch = synth_rl_batch(2, 3, seed=23, entity_num='random', max_su=5)
+    g = torch.Generator().manual_seed(9)
+    succ = {k: (v + 0.5 * torch.randn(v.shape, generator=g)).masked_fill(v < -1e8, -1e9) for k, v in batch['teacher_logit'].items()}
+    batch['step'][0, 0] = 100.0                                         # at least one frame inside dapo_steps
+    import copy
+    lcfg = copy.deepcopy(cfg.learner)
+    lcfg.use_dapo = True
+    loss_fn = mods['ReinforcementLoss'](lcfg, 'MP0')
+    with torch.no_grad():
+        r_out = model.rl_learner_forward(**tree_clone(batch))
+        r_out['successive_logit'] = tree_clone(succ)
+        r_info = loss_fn.compute_loss(r_out)
+        o_out = O.rl_learner_forward(sd, **tree_clone(batch))
+        o_out['successive_logit'] = tree_clone(succ)
+        o_info = O.rl_loss(o_out, use_dapo=True, dapo_w=float(lcfg.loss_weights.dapo), dapo_steps=int(lcfg.dapo.dapo_steps))
+    for k, v in r_info.items():
+        rv = v.item() if torch.is_tensor(v) else v
+        assert abs(o_info[k].item() - rv) <= 1e-4 * max(1.0, abs(rv)), (k, o_info[k].item(), rv)
+    assert abs(r_info['battle/total']) > 0
+    # non-'MP' players never use it (rl_loss.py:22-24)
+    assert mods['ReinforcementLoss'](lcfg, 'EP0').use_dapo is False
+
+
+@pytest.mark.parametrize('su_mask,label_smooth', [(True, False), (False, True), (True, True)])
+def test_sl_loss_options_match_reference(ref, su_mask, label_smooth):
+    """sl_loss.py:54-57 (label smoothing), :177-192 (su_mask), :206-232 (IoU) on seeded logits."""
+    model, cfg, mods, sd = ref
+    g = torch.Generator().manual_seed(17)
+    b, s, E = 6, 5, 512
+    en = torch.tensor([512, 40, 333, 200, 64, 7])
+    act, num = synth_actions(b, en, g, max_su=5)
+    valid = torch.arange(E + 1).unsqueeze(0) < (en + 1).unsqueeze(1)
+    logits = {'action_type': torch.randn(b, 327, generator=g), 'delay': torch.randn(b, 128, generator=g),
+              'queued': torch.randn(b, 2, generator=g),
+              'selected_units': torch.randn(b, s, E + 1, generator=g).masked_fill(~valid.unsqueeze(1), -1e9),
+              'target_unit': torch.randn(b, E, generator=g).masked_fill(~valid[:, :E], -1e9),
+              'target_location': torch.randn(b, 128 * 128, generator=g)}
+    amask = {k: (torch.rand(b, generator=g) < 0.7).float() for k in O.HEADS}
+    # a plausible sampled selection: the labels with one unit swapped, end token kept
+    preds = act['selected_units'][:, :s].clone()
+    preds[:, 0] = (preds[:, 0] + 1) % en.clamp(min=2)
+    sl = mods['SupervisedLoss']({'learner': {'su_mask': su_mask, 'label_smooth': label_smooth}})
+    r = sl.compute_loss(tree_clone(logits), tree_clone(act), tree_clone(amask), num.clone(), en.clone(),
+                        {'selected_units': preds.clone()})
+    o = O.sl_loss(tree_clone(logits), tree_clone(act), tree_clone(amask), num.clone(), en.clone(), preds.clone(),
+                  su_mask=su_mask, label_smooth=label_smooth)
+    assert set(o.keys()) == set(r.keys())
+    for k, v in r.items():
+        assert abs(float(o[k]) - float(v)) <= 1e-5 * max(1.0, abs(float(v))), (k, float(o[k]), float(v))
+    assert mods['SupervisedLoss']({'learner': {}}).su_mask is True          # default_supervised_loss.yaml:10
+
+
+def test_momentum_norm_clip_never_scales(ref):
+    """grad_clip.py:74-107 as written: the norm momenta are appended instead of stored at their index, so no gradient is
+    ever scaled and apply() returns the global 2-norm.  ops.FlatAdam(clip_type='momentum_norm') relies on exactly this."""
+    ref_import.install_shims()
+    from distar.ctools.torch_utils.grad_clip import build_grad_clip
+    clip = build_grad_clip({'type': 'momentum_norm', 'threshold': 1.4})
+    g = torch.Generator().manual_seed(3)
+    params = [torch.nn.Parameter(torch.randn(7, 5, generator=g)), torch.nn.Parameter(torch.randn(11, generator=g))]
+    for it in range(4):
+        for p in params:
+            p.grad = torch.randn(p.shape, generator=g) * (10.0 ** it)      # growing norms would trigger a working clip
+        before = [p.grad.clone() for p in params]
+        total = clip.apply(params)
+        want = torch.sqrt(sum((b ** 2).sum() for b in before)).item()
+        assert abs(total - want) <= 1e-5 * want
+        for p, b in zip(params, before):
+            assert torch.equal(p.grad, b)
+
+
+def test_adam_state_interchanges_with_reference_optimizer(ref):
+    """rl_learner.py:73-79 builds torch.optim.Adam over model.parameters(); checkpoints carry its state_dict()
+    (checkpoint_helper.py:124-131).  FlatAdam must read it, continue identically, and write it back in the same layout."""
+    from distar_b200 import ops
+    from distar_b200.model import Model
+    model, cfg, mods, sd = ref
+    ops.enable_host_logic_testing(True)
+    try:
+        mine = Model({'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': ['winloss', 'build_order']}},
+                     use_value_network=True, seed=0)
+        mine.load_state_dict(sd)
+        ref_model = mods['Model'](cfg, use_value_network=True)
+        ref_model.load_state_dict(sd, strict=True)
+        opt_ref = torch.optim.Adam(ref_model.parameters(), lr=1e-3, betas=(0.0, 0.99), eps=1e-5)
+        gen = torch.Generator().manual_seed(0)
+        grads = {n: torch.randn(p.shape, generator=gen) for n, p in ref_model.named_parameters() if p.requires_grad}
+
+        def set_grads(m):
+            for n, p in m.named_parameters():
+                if p.requires_grad:
+                    p.grad.copy_(grads[n]) if p.grad is not None else setattr(p, 'grad', grads[n].clone())
+        set_grads(ref_model)
+        opt_ref.step()
+        # hand the reference's optimizer state + weights to FlatAdam and take the SECOND step on both sides
+        opt = ops.FlatAdam(mine.flat_param, mine.flat_grad, lr=1e-3, betas=(0.0, 0.99), eps=1e-5, max_norm=None, clip_type="none",
+                           layout=mine.optimizer_layout(), owner=mine)
+        mine.load_state_dict(ref_model.state_dict())
+        opt.load_state_dict(opt_ref.state_dict())
+        assert opt.t == 1
+        set_grads(ref_model)
+        set_grads(mine)
+        opt_ref.step()
+        opt.step()
+        for (n, a), (_, b) in zip(mine.named_parameters(), ref_model.named_parameters()):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), n
+        back, want = opt.state_dict(), opt_ref.state_dict()
+        assert back['param_groups'][0]['params'] == want['param_groups'][0]['params']
+        assert set(back['state'].keys()) == set(want['state'].keys())
+        for i, st in want['state'].items():
+            assert float(back['state'][i]['step']) == float(st['step']) == 2
+            assert torch.allclose(back['state'][i]['exp_avg_sq'], st['exp_avg_sq'], rtol=1e-5, atol=1e-9), i
+            assert torch.allclose(back['state'][i]['exp_avg'], st['exp_avg'], rtol=1e-5, atol=1e-9), i
+    finally:
+        ops.enable_host_logic_testing(False)

@@ -19,6 +19,7 @@ sys.path[:0] = [os.path.dirname(HERE), HERE]
 import ref_import  # noqa: E402
 from distar_b200.params import init_state_dict  # noqa: E402
 from distar_b200.synth import synth_obs, synth_rl_batch, synth_actions, tree_clone, tree_map  # noqa: E402
+from golden_util import compact_logits  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
 BASELINES = ('winloss', 'build_order')
@@ -54,6 +55,43 @@ def rl_case():
     return batch
 
 
+def infer32_case():
+    """BASELINE configs[1]: batch-32 inference (compute_logp_action), ragged entity counts."""
+    return synth_obs(32, seed=51, entity_num='random')
+
+
+def rl_chunk_case():
+    """An RL batch whose (T+1)*B = 36 observation rows span three encoder chunks at encoder_chunk=16."""
+    batch = synth_rl_batch(4, 8, seed=61, entity_num='random', max_su=6)
+    batch['reward']['winloss'][-1, 1] = -1.0
+    return batch
+
+
+FULL_GRADS = ['policy.action_type_head.action_fc.layer2.0.bias', 'core_lstm.layers.2.cell.layernorm_c.weight',
+              'encoder.scatter_project.0.weight', 'value_networks.winloss.value_fc.0.weight',
+              'policy.selected_units_head.end_embedding', 'encoder.spatial_encoder.project.0.weight']
+
+
+def dump_rl(model, loss_fn, batch, meta, path, compact):
+    model.zero_grad()
+    out = model.rl_learner_forward(**tree_clone(batch))
+    info = loss_fn.compute_loss(out)
+    info['total_loss'].backward()
+    scalars = {k: (v.item() if torch.is_tensor(v) else float(v)) for k, v in info.items()}
+    grad_norm = {n: p.grad.norm().item() for n, p in model.named_parameters() if p.requires_grad}
+    # a second scalar per tensor: its projection on a seeded random direction (pins the direction, not only the length)
+    proj = {}
+    for n, p in model.named_parameters():
+        if p.requires_grad:
+            g = torch.Generator().manual_seed(len(n) * 7919 + p.numel())
+            proj[n] = float((p.grad.reshape(-1) * torch.randn(p.numel(), generator=g)).sum())
+    grads = {n: p.grad.clone() for n, p in model.named_parameters() if n in FULL_GRADS}
+    logits = {k: (compact_logits(v) if compact else v.detach()) for k, v in out['target_logit'].items()}
+    torch.save({'meta': meta, 'input_checksum': checksum(batch), 'target_logit': logits, 'compact': compact,
+                'value': {k: v.detach() for k, v in out['value'].items()}, 'loss': scalars,
+                'grad_norm': grad_norm, 'grad_proj': proj, 'grads': grads}, path)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     model, cfg, mods = ref_import.load_reference(spatial=128, enable_baselines=BASELINES)
@@ -77,23 +115,20 @@ def main():
         r = model.compute_teacher_logit(**tree_clone(obs), selected_units_num=num.clone(), action_info=tree_clone(act))
     torch.save({'meta': meta, 'input_checksum': checksum((obs, act, num)), 'logit': r['logit'],
                 'hidden_state': r['hidden_state']}, os.path.join(OUT, 'teacher.pt'))
-    # ---- config 4: RL step
-    batch = rl_case()
+    # ---- config 4: RL step (6 frames), and a 36-row batch that spans several encoder chunks
     loss_fn = mods['ReinforcementLoss'](cfg.learner, 'MP0')
-    model.zero_grad()
-    out = model.rl_learner_forward(**tree_clone(batch))
-    info = loss_fn.compute_loss(out)
-    info['total_loss'].backward()
-    scalars = {k: (v.item() if torch.is_tensor(v) else float(v)) for k, v in info.items()}
-    grad_norm = {n: p.grad.norm().item() for n, p in model.named_parameters() if p.requires_grad}
-    keep = ['policy.action_type_head.action_fc.layer2.0.bias', 'core_lstm.layers.2.cell.layernorm_c.weight',
-            'encoder.scatter_project.0.weight', 'value_networks.winloss.value_fc.0.weight',
-            'policy.selected_units_head.end_embedding', 'encoder.spatial_encoder.project.0.weight']
-    grads = {n: p.grad.clone() for n, p in model.named_parameters() if n in keep}
-    torch.save({'meta': meta, 'input_checksum': checksum(batch),
-                'target_logit': {k: v.detach() for k, v in out['target_logit'].items()},
-                'value': {k: v.detach() for k, v in out['value'].items()}, 'loss': scalars,
-                'grad_norm': grad_norm, 'grads': grads}, os.path.join(OUT, 'rl_step.pt'))
+    dump_rl(model, loss_fn, rl_case(), meta, os.path.join(OUT, 'rl_step.pt'), compact=False)
+    dump_rl(model, loss_fn, rl_chunk_case(), meta, os.path.join(OUT, 'rl_chunks.pt'), compact=True)
+    # ---- config 2: batch-32 sampling forward (compact logits)
+    obs = infer32_case()
+    torch.manual_seed(7)
+    with torch.no_grad():
+        r = model.compute_logp_action(**tree_clone(obs))
+    torch.save({'meta': meta, 'input_checksum': checksum(obs), 'rng_seed': 7,
+                'action_info': r['action_info'], 'action_logp': r['action_logp'],
+                'selected_units_num': r['selected_units_num'],
+                'logit': {k: compact_logits(v) for k, v in r['logit'].items()},
+                'hidden_state': r['hidden_state']}, os.path.join(OUT, 'infer32.pt'))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -420,3 +420,68 @@ def test_lstm_layer_matches_cell_loop(L, B, H):
     assert torch.allclose(hs_a, hs_b, rtol=1e-5, atol=1e-6) and torch.allclose(cl_a, cl_b, rtol=1e-5, atol=1e-6)
     for a, b, n in zip(ga, gb, ['ig', 'h0', 'c0', 'w_hh', 'gam_h', 'bet_h', 'gam_c', 'bet_c']):
         assert (a - b).abs().max().item() <= 2e-4 * max(b.abs().max().item(), 1e-6), n
+
+
+@pytest.mark.parametrize('rows,C', [(300, 327), (40, 16384), (64, 2)])
+def test_categorical_label_smoothing_term_and_label_flag(rows, C):
+    """mean_j log p_j (LabelSmoothingCrossEntropy, sl_loss.py:16-34) from the same pass, its gradient, and the out-of-range
+    label flag (torch raises on such a label; the kernel clamps and records)."""
+    g = torch.Generator().manual_seed(rows * 3 + C)
+    z = torch.randn(rows, C, generator=g) * 2
+    a = torch.randint(0, C, (rows,), generator=g)
+    zr = z.clone().requires_grad_(True)
+    lp = torch.log_softmax(zr, -1)
+    want = 0.9 * (-lp.gather(-1, a.unsqueeze(-1)).squeeze(-1)) + 0.1 * (-lp.mean(-1))
+    w = torch.randn(rows, generator=g)
+    (want * w).sum().backward()
+    zd = z.to(DEV).requires_grad_(True)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    logp, _, _, mean_lp = ops.categorical_stats(zd, a.to(DEV), want_mean=True, flag=flag)
+    got = 0.9 * (-logp) + 0.1 * (-mean_lp)
+    (got * w.to(DEV)).sum().backward()
+    assert torch.allclose(got.cpu(), want.detach(), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(zd.grad.cpu(), zr.grad, rtol=1e-4, atol=5e-5)
+    assert int(flag.item()) == 0
+    bad = a.clone()
+    bad[rows // 2] = C
+    bad[0] = -1
+    lp2 = ops.categorical_stats(z.to(DEV), bad.to(DEV), flag=flag)[0]
+    assert int(flag.item()) == 2 and bool(torch.isfinite(lp2).all())
+    # a logit of -inf is a legal mask value for the kernel (the reference itself uses -1e9)
+    zi = z.clone()
+    zi[:, 0] = float('-inf')
+    a1 = a.clamp(min=1)
+    li = ops.categorical_stats(zi.to(DEV), a1.to(DEV))[0]
+    assert torch.allclose(li.cpu(), torch.log_softmax(zi, -1).gather(-1, a1.unsqueeze(-1)).squeeze(-1), rtol=1e-5, atol=1e-5)
+
+
+def test_flat_adam_weight_decay_schedule_and_skip_flag():
+    g = torch.Generator().manual_seed(5)
+    n = 300_001
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    p = p0.clone().to(DEV)
+    grad = torch.zeros(n, device=DEV)
+    mine = ops.FlatAdam(p, grad, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_norm=1.4, clip_type='momentum_norm')
+    sched, sched_ref = (torch.optim.lr_scheduler.MultiStepLR(o, milestones=[2], gamma=0.1) for o in (mine, opt))
+    for it in range(4):
+        gr = torch.randn(n, generator=g) * 3
+        ref.grad = gr.clone()
+        opt.step()
+        sched_ref.step()
+        grad.copy_(gr.to(DEV))
+        norm = mine.step(grad_scale=0.5) if it == 1 else mine.step()
+        sched.step()
+        if it == 1:                                   # grad_scale = 1/world: the norm reported is the averaged gradient's
+            assert abs(norm.item() - 0.5 * gr.norm().item()) <= 1e-4 * gr.norm().item()
+            ref.data.copy_(p.cpu())                   # (the reference side did not scale: re-synchronise the two)
+            opt.state[ref]['exp_avg'].copy_(mine.exp_avg.cpu())
+            opt.state[ref]['exp_avg_sq'].copy_(mine.exp_avg_sq.cpu())
+        else:
+            assert abs(norm.item() - gr.norm().item()) <= 1e-4 * gr.norm().item()      # 'momentum_norm' never clips
+            assert torch.allclose(p.cpu(), ref.detach(), rtol=1e-5, atol=1e-6), it
+    before, m_before = p.clone(), mine.exp_avg.clone()
+    grad.normal_()
+    mine.step(skip_flag=torch.ones(4, device=DEV))
+    assert torch.equal(p, before) and torch.equal(mine.exp_avg, m_before)

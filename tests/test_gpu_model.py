@@ -49,6 +49,15 @@ def model(sd):
     return m.cuda()
 
 
+@pytest.fixture
+def fresh_model(sd):
+    """a private model for the tests that train (the module-scoped `model` stays untouched, no order dependence)"""
+    cfg = {'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': list(G.BASELINES)}}
+    m = Model(cfg, use_value_network=True, seed=0, sample_rng='cpu')
+    m.load_state_dict(sd)
+    return m.cuda()
+
+
 def test_model_lives_in_one_arena(model, sd):
     assert model.flat_param.is_cuda and model.flat_grad.is_cuda
     for n, p in model.named_parameters():
@@ -84,7 +93,59 @@ def test_teacher_forward_vs_golden(model):
         close(o['logit'][k], g['logit'][k], 'logit/' + k)
 
 
-def test_rl_step_vs_golden(model):
+def _elementwise_report(name, a, b):
+    """north_star states the contract as 1e-3 rtol; the asserted form is max-normalised (per tensor).  Print the
+    element-wise relative error percentiles next to it so both readings are on record in the test log."""
+    a, b = a.detach().float().cpu().reshape(-1), b.detach().float().cpu().reshape(-1)
+    fin = b.abs() < 1e8
+    a, b = a[fin], b[fin]
+    if b.numel() == 0:
+        return
+    rel = (a - b).abs() / b.abs().clamp(min=1e-3 * float(b.abs().max()))
+    q = torch.quantile(rel[:2_000_000].double(), torch.tensor([0.5, 0.99, 1.0], dtype=torch.float64))
+    print('[parity] %-28s max-normalised %.2e | element-wise rel (floor 1e-3*max) p50 %.2e p99 %.2e max %.2e'
+          % (name, float((a - b).abs().max() / b.abs().max().clamp(min=1e-12)), q[0], q[1], q[2]))
+
+
+def _oracle_gradients(sd, batch):
+    P = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    info = O.rl_loss(O.rl_learner_forward(P, **tree_clone(batch)))
+    info['total_loss'].backward()
+    return {k: v.grad for k, v in P.items() if v.grad is not None}
+
+
+def _check_gradients(m, g, og, cos_floor, frac_4nines):
+    """(1) norms of all tensors against the reference's, (2) the reference's stored full gradients element-wise, (3) cosine of
+    EVERY tensor against the oracle's gradient (the oracle is pinned to the reference at 1e-4 in test_oracle_vs_reference)."""
+    gmax = max(g['grad_norm'].values())
+    bad = []
+    for n, p in m.named_parameters():
+        if p.requires_grad:
+            v = g['grad_norm'][n]
+            if abs(p.grad.norm().item() - v) > 2e-2 * max(v, 1e-2 * gmax):
+                bad.append((n, p.grad.norm().item(), v))
+    assert not bad, bad[:5]
+    for n, v in g['grads'].items():
+        got = dict(m.named_parameters())[n].grad
+        _elementwise_report('grad/' + n[-24:], got, v)
+        close(got, v, 'grad/' + n, rtol=2e-2)
+    cos = {}
+    for n, p in m.named_parameters():
+        if p.requires_grad:
+            a, b = p.grad.detach().float().cpu().reshape(-1).double(), og[n].reshape(-1).double()
+            if float(b.norm()) < 1e-6 * gmax:
+                continue                                     # a tensor the loss does not reach (norm ~ 0 on both sides)
+            cos[n] = float((a * b).sum() / (a.norm() * b.norm()).clamp(min=1e-300))
+    vals = sorted(cos.values())
+    worst = sorted(cos.items(), key=lambda kv: kv[1])[:3]
+    share = sum(v >= 0.9999 for v in vals) / len(vals)
+    print('[parity] gradient cosine over %d tensors: min %.6f p05 %.6f median %.6f; >= 0.9999: %.1f %%; worst %s'
+          % (len(vals), vals[0], vals[len(vals) // 20], vals[len(vals) // 2], 100 * share, worst))
+    assert vals[0] >= cos_floor, worst
+    assert share >= frac_4nines, (share, worst)
+
+
+def test_rl_step_vs_golden(model, sd):
     g = torch.load(os.path.join(GOLD, 'rl_step.pt'))
     model.zero_grad()
     out = model.rl_learner_forward(**to_dev(G.rl_case()))
@@ -92,20 +153,58 @@ def test_rl_step_vs_golden(model):
     info['total_loss'].backward()
     for k in O.HEADS:
         close(out['target_logit'][k], g['target_logit'][k], 'target_logit/' + k)
+        _elementwise_report('target_logit/' + k, out['target_logit'][k], g['target_logit'][k])
     for k, v in g['value'].items():
         close(out['value'][k], v, 'value/' + k)
     for k, v in g['loss'].items():
         got = info[k].item() if torch.is_tensor(info[k]) else info[k]
         assert abs(got - v) <= 2e-3 * max(1.0, abs(v)), (k, got, v)
-    # gradient norms: the 6-frame batch is ReLU/max-pool-decision sensitive, so this is a 2 % check per tensor
-    gmax = max(g['grad_norm'].values())
-    bad = []
-    for n, p in model.named_parameters():
-        if p.requires_grad:
-            v = g['grad_norm'][n]
-            if abs(p.grad.norm().item() - v) > 2e-2 * max(v, 1e-2 * gmax):
-                bad.append((n, p.grad.norm().item(), v))
-    assert not bad, bad[:5]
+    # the 6-frame batch is ReLU / max-pool-decision sensitive (a 1e-5 perturbation flips a few decisions), hence the
+    # looser floor here than on the 32-frame batch below
+    _check_gradients(model, g, _oracle_gradients(sd, G.rl_case()), cos_floor=0.995, frac_4nines=0.80)
+
+
+def test_multi_chunk_rl_vs_golden(sd):
+    """(T+1)*B = 36 observation rows through the product's chunked encoder path (encoder_chunk=16 -> 3 chunks, the last one
+    ragged) against what the reference produced on the same batch: logits, values, loss scalars, gradients."""
+    from golden_util import assert_compact_close
+    g = torch.load(os.path.join(GOLD, 'rl_chunks.pt'))
+    cfg = {'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': list(G.BASELINES)}}
+    m = Model(cfg, use_value_network=True, seed=0, encoder_chunk=16)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    m.zero_grad()
+    batch = G.rl_chunk_case()
+    out = m.rl_learner_forward(**to_dev(batch))
+    info = ReinforcementLoss(None, 'MP0').compute_loss(out)
+    info['total_loss'].backward()
+    m.raise_on_bad_input()
+    for k in O.HEADS:
+        assert_compact_close(out['target_logit'][k], g['target_logit'][k], 'target_logit/' + k)
+    for k, v in g['value'].items():
+        close(out['value'][k], v, 'value/' + k)
+    for k, v in g['loss'].items():
+        got = info[k].item() if torch.is_tensor(info[k]) else info[k]
+        assert abs(got - v) <= 2e-3 * max(1.0, abs(v)), (k, got, v)
+    _check_gradients(m, g, _oracle_gradients(sd, batch), cos_floor=0.999, frac_4nines=0.90)
+
+
+def test_batch32_sampling_vs_golden(model):
+    """BASELINE configs[1]: batch-32 compute_logp_action, all six sampled heads identical to the reference's under its RNG
+    stream, logits / log-probs / LSTM state within tolerance."""
+    from golden_util import assert_compact_close
+    g = torch.load(os.path.join(GOLD, 'infer32.pt'))
+    torch.manual_seed(g['rng_seed'])
+    with torch.no_grad():
+        o = model.compute_logp_action(**to_dev(G.infer32_case()))
+    for k in O.HEADS:
+        assert torch.equal(o['action_info'][k].cpu(), g['action_info'][k]), 'sampled %s differs' % k
+        assert_compact_close(o['logit'][k], g['logit'][k], 'logit/' + k)
+        close(o['action_logp'][k], g['action_logp'][k], 'logp/' + k)
+    assert torch.equal(o['selected_units_num'].cpu(), g['selected_units_num'])
+    for (h, c), (gh, gc) in zip(o['hidden_state'], g['hidden_state']):
+        close(h, gh, 'h')
+        close(c, gc, 'c')
 
 
 def test_sl_forward_matches_oracle(model, sd):
@@ -174,7 +273,8 @@ def test_pointer_sampling_device_rng_is_consistent(sd):
             assert len(set(picked)) == len(picked) and all(p < int(en[n].item()) for p in picked)
 
 
-def test_negative_entity_id_raises(model):
+def test_negative_entity_id_raises(fresh_model):
+    model = fresh_model
     """entity_encoder.py:69-72: a negative categorical id is an error.  The sampling / teacher entry points raise before
     returning; the learner forward records it and RLLearner._train raises before the optimiser step."""
     from distar_b200.learner import RLLearner
@@ -199,10 +299,10 @@ def test_negative_entity_id_raises(model):
     # and a clean batch still trains afterwards
     log = learner._train(to_dev(G.rl_case()))
     assert abs(float(log['total_loss'])) < 1e6 and log['kl/total'] == log['kl/total']
-    model.load_state_dict(init_state_dict(seed=G.WEIGHT_SEED, baselines=G.BASELINES))
 
 
-def test_weight_cache_follows_updates(model):
+def test_weight_cache_follows_updates(fresh_model):
+    model = fresh_model
     """the per-step cache of derived weight forms (bf16 pairs, conv matrices) must refresh after the optimiser kernel
     (which updates the arena behind torch's version counters), after in-place torch edits and after load_state_dict."""
     from distar_b200 import ops
@@ -279,3 +379,59 @@ def test_single_observation_inference_matches_oracle(model, sd):
         close(got['logit'][k], want['logit'][k], 'single/' + k)
         assert torch.equal(got['action_info'][k].cpu(), want['action_info'][k]), k
     assert torch.equal(got['selected_units_num'].cpu(), want['selected_units_num'])
+
+
+def test_dapo_on_gpu_matches_oracle(model, sd):
+    """rl_loss.py:164-172: DAPO term (KL towards the successive model) for an 'MP' player, scalars and gradient."""
+    from distar_b200.rl_loss import USER_LEARNER_CFG
+    from distar_b200.synth import synth_rl_batch
+    batch = synth_rl_batch(2, 3, seed=23, entity_num='random', max_su=5)
+    g = torch.Generator().manual_seed(9)
+    succ = {k: (v + 0.5 * torch.randn(v.shape, generator=g)).masked_fill(v < -1e8, -1e9) for k, v in batch['teacher_logit'].items()}
+    batch['step'][0, 0] = 100.0
+    with torch.no_grad():
+        o_out = O.rl_learner_forward(sd, **tree_clone(batch))
+        o_out['successive_logit'] = tree_clone(succ)
+        want = O.rl_loss(o_out, use_dapo=True, dapo_w=0.1, dapo_steps=2400)
+    model.zero_grad()
+    out = model.rl_learner_forward(**to_dev(batch))
+    out['successive_logit'] = to_dev(succ)
+    got = ReinforcementLoss(dict(USER_LEARNER_CFG, use_dapo=True), 'MP0').compute_loss(out)
+    got['total_loss'].backward()
+    for k, v in want.items():
+        gk = got[k].item() if torch.is_tensor(got[k]) else got[k]
+        assert abs(gk - v.item()) <= 2e-3 * max(1.0, abs(v.item())), (k, gk, v.item())
+    assert abs(got['battle/total']) > 0 and float(model.flat_grad.abs().sum()) > 0
+    model.zero_grad()
+
+
+@pytest.mark.parametrize('su_mask,label_smooth', [(True, False), (True, True)])
+def test_sl_loss_options_on_gpu(su_mask, label_smooth):
+    from distar_b200.sl_loss import SupervisedLoss
+    from distar_b200.synth import synth_actions
+    g = torch.Generator().manual_seed(17)
+    b, s, E = 6, 5, 512
+    en = torch.tensor([512, 40, 333, 200, 64, 7])
+    act, num = synth_actions(b, en, g, max_su=5)
+    valid = torch.arange(E + 1).unsqueeze(0) < (en + 1).unsqueeze(1)
+    logits = {'action_type': torch.randn(b, 327, generator=g), 'delay': torch.randn(b, 128, generator=g),
+              'queued': torch.randn(b, 2, generator=g),
+              'selected_units': torch.randn(b, s, E + 1, generator=g).masked_fill(~valid.unsqueeze(1), -1e9),
+              'target_unit': torch.randn(b, E, generator=g).masked_fill(~valid[:, :E], -1e9),
+              'target_location': torch.randn(b, 128 * 128, generator=g)}
+    amask = {k: (torch.rand(b, generator=g) < 0.7).float() for k in O.HEADS}
+    preds = act['selected_units'][:, :s].clone()
+    preds[:, 0] = (preds[:, 0] + 1) % en.clamp(min=2)
+    lg = {k: v.clone().to(DEV).requires_grad_(True) for k, v in logits.items()}
+    og = {k: v.clone().requires_grad_(True) for k, v in logits.items()}
+    got = SupervisedLoss({'learner': {'su_mask': su_mask, 'label_smooth': label_smooth}}).compute_loss(
+        lg, to_dev(act), to_dev(amask), num.to(DEV), en.to(DEV), {'selected_units': preds.to(DEV)})
+    want = O.sl_loss(og, tree_clone(act), tree_clone(amask), num.clone(), en.clone(), preds.clone(), su_mask=su_mask,
+                     label_smooth=label_smooth)
+    assert set(got.keys()) == set(want.keys())
+    for k, v in want.items():
+        assert abs(float(got[k]) - float(v)) <= 1e-4 * max(1.0, abs(float(v))), (k, float(got[k]), float(v))
+    got['total_loss'].backward()
+    want['total_loss'].backward()
+    for k in lg:
+        assert torch.allclose(lg[k].grad.cpu(), og[k].grad, rtol=1e-3, atol=1e-6), k

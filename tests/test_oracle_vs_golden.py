@@ -72,3 +72,41 @@ def test_oracle_rl_step_vs_golden(sd):
         assert abs(P[n].grad.norm().item() - v) <= 1e-3 * max(v, 1e-3 * gmax), n
     for n, v in g['grads'].items():
         close(P[n].grad, v, 'grad/' + n, rtol=1e-3)
+
+
+def test_oracle_batch32_sampling_vs_golden(sd, su_action_mask):
+    """BASELINE configs[1] at its size: every sampled index of the reference reproduced, logits through their compact form."""
+    from golden_util import assert_compact_close
+    g = torch.load(os.path.join(GOLD, 'infer32.pt'))
+    assert g['input_checksum'] == G.checksum(G.infer32_case())
+    torch.manual_seed(g['rng_seed'])
+    with torch.no_grad():
+        o = O.compute_logp_action(sd, **tree_clone(G.infer32_case()), su_action_mask=su_action_mask)
+    for k in O.HEADS:
+        assert torch.equal(o['action_info'][k], g['action_info'][k]), k
+        assert_compact_close(o['logit'][k], g['logit'][k], 'logit/' + k, rtol=1e-4)
+        close(o['action_logp'][k], g['action_logp'][k], 'logp/' + k)
+    assert torch.equal(o['selected_units_num'], g['selected_units_num'])
+
+
+def test_oracle_multi_chunk_rl_vs_golden(sd):
+    from golden_util import assert_compact_close
+    g = torch.load(os.path.join(GOLD, 'rl_chunks.pt'))
+    P = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    out = O.rl_learner_forward(P, **tree_clone(G.rl_chunk_case()))
+    info = O.rl_loss(out)
+    info['total_loss'].backward()
+    for k in O.HEADS:
+        assert_compact_close(out['target_logit'][k], g['target_logit'][k], 'target_logit/' + k, rtol=1e-4)
+    for k, v in g['value'].items():
+        close(out['value'][k], v, 'value/' + k)
+    for k, v in g['loss'].items():
+        assert abs(info[k].item() - v) <= 1e-4 * max(1.0, abs(v)), (k, info[k].item(), v)
+    gmax = max(g['grad_norm'].values())
+    for n, v in g['grad_norm'].items():
+        assert abs(P[n].grad.norm().item() - v) <= 1e-3 * max(v, 1e-3 * gmax), n
+        gen = torch.Generator().manual_seed(len(n) * 7919 + P[n].numel())
+        pr = float((P[n].grad.reshape(-1) * torch.randn(P[n].numel(), generator=gen)).sum())
+        assert abs(pr - g['grad_proj'][n]) <= 2e-3 * max(v, 1e-3 * gmax) * max(1.0, P[n].numel() ** 0.5 / 30), n
+    for n, v in g['grads'].items():
+        close(P[n].grad, v, 'grad/' + n, rtol=1e-3)

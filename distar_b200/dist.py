@@ -30,8 +30,8 @@ def get_rank() -> int:
     return dist.get_rank() if dist.is_initialized() else 0
 
 
-def get_world_size() -> int:
-    return dist.get_world_size() if dist.is_initialized() else 1
+def get_world_size(group=None) -> int:
+    return dist.get_world_size(group) if dist.is_initialized() else 1
 
 
 def allreduce(x: torch.Tensor, reduce: bool = True):
@@ -53,9 +53,13 @@ class DistModule(torch.nn.Module):
     """dist_helper.py:369-439.  Exposes forward / state_dict / named_parameters / sl_train / rl_learner_forward of
     the wrapped model, ``.module``, ``sync_gradients()`` and ``broadcast_params()``."""
 
-    def __init__(self, module, sync: bool = True):
+    def __init__(self, module, sync: bool = True, group=None):
+        """group: the process group of THIS player's learners.  A league run trains several players at once, each on its own
+        set of GPUs (rl_train.py:26-51 starts one learner job per player id); their gradient exchanges are independent
+        communicators (BASELINE configs[4]); None = the default (world) group."""
         super().__init__()
         self.module = module
+        self.group = group
         for name in ('compute_logp_action', 'compute_teacher_logit', 'rl_learner_forward', 'sl_train'):
             if hasattr(module, name):
                 setattr(self, name, getattr(module, name))
@@ -79,15 +83,16 @@ class DistModule(torch.nn.Module):
 
     def sync_gradients(self):
         """ONE all-reduce(SUM) of the flat gradient arena; the 1/world average is applied by the optimiser."""
-        if self.sync and get_world_size() > 1:
+        if self.sync and get_world_size(self.group) > 1:
             # the tail slots behind the gradients ride along (learner.py: the "a rank saw an invalid batch" flag)
-            dist.all_reduce(getattr(self.module, 'flat_grad_full', self.module.flat_grad))
+            dist.all_reduce(getattr(self.module, 'flat_grad_full', self.module.flat_grad), group=self.group)
 
     def broadcast_params(self):
         from . import ops
-        if get_world_size() > 1:
-            dist.broadcast(self.module.flat_param, 0)
+        if get_world_size(self.group) > 1:
+            src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+            dist.broadcast(self.module.flat_param, src, group=self.group)
             for name, p in self.module.named_parameters():
                 if not p.requires_grad:
-                    dist.broadcast(p.data, 0)
+                    dist.broadcast(p.data, src, group=self.group)
         ops.invalidate_weight_cache()

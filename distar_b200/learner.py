@@ -34,10 +34,10 @@ class _LearnerBase:
     """What RL and SL learners share: the arena optimiser, the DP wrapper, checkpoint save / load."""
 
     def _setup(self, model: Model, lr: float, betas, eps: float, weight_decay: float, clip_type: str, max_norm: float,
-               distributed: Optional[bool]):
-        self.world = get_world_size()
+               distributed: Optional[bool], group=None):
+        self.world = get_world_size(group)          # the learners of THIS player (a league trains several players side by side)
         distributed = self.world > 1 if distributed is None else distributed
-        self._model = DistModule(model) if distributed else model
+        self._model = DistModule(model, group=group) if distributed else model
         self.model = model
         self._optimizer = ops.FlatAdam(model.flat_param, model.flat_grad, lr=lr, betas=betas, eps=eps, max_norm=max_norm,
                                        weight_decay=weight_decay, clip_type=clip_type, layout=model.optimizer_layout(),
@@ -113,8 +113,8 @@ class _LearnerBase:
 class RLLearner(_LearnerBase):
     def __init__(self, model: Model, player_id: str = 'MP0', learner_cfg: dict = None, lr: float = 1e-5,
                  max_norm: float = 1.0, distributed: bool = None, value_pretrain_iters: int = -1,
-                 clip_type: str = 'pytorch_norm'):
-        self._setup(model, lr, (0.0, 0.99), 1e-5, 0.0, clip_type, max_norm, distributed)
+                 clip_type: str = 'pytorch_norm', group=None):
+        self._setup(model, lr, (0.0, 0.99), 1e-5, 0.0, clip_type, max_norm, distributed, group)
         self._loss = ReinforcementLoss(learner_cfg, player_id)
         self._use_dapo = bool(_cfg_get(learner_cfg or {}, 'use_dapo', False))
         self._remain_value_pretrain_iters = int(_cfg_get(learner_cfg or {}, 'value_pretrain_iters', value_pretrain_iters))
@@ -155,14 +155,14 @@ class SLLearner(_LearnerBase):
 
     def __init__(self, model: Model, cfg: dict = None, batch_size: int = 2, lr: float = 1e-3, weight_decay: float = 1e-5,
                  clip_type: str = 'momentum_norm', max_norm: float = 1.4, distributed: bool = None,
-                 warm_up_steps: int = 0, ignore_steps: int = 5):
+                 warm_up_steps: int = 0, ignore_steps: int = 5, group=None):
         cfg = cfg or {}
         lr = float(_cfg_get(cfg, 'learner.learning_rate', lr))
         weight_decay = float(_cfg_get(cfg, 'learner.weight_decay', weight_decay))
         clip_type = _cfg_get(cfg, 'learner.grad_clip.type', clip_type)
         max_norm = float(_cfg_get(cfg, 'learner.grad_clip.threshold', max_norm))
         batch_size = int(_cfg_get(cfg, 'learner.data.batch_size', batch_size))
-        self._setup(model, lr, (0.9, 0.999), 1e-8, weight_decay, clip_type, max_norm, distributed)
+        self._setup(model, lr, (0.9, 0.999), 1e-8, weight_decay, clip_type, max_norm, distributed, group)
         self._loss = SupervisedLoss(cfg)
         dev = model.flat_param.device
         layers, hidden = model.cfg.encoder.core_lstm.num_layers, model.cfg.encoder.core_lstm.hidden_size

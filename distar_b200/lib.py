@@ -124,9 +124,27 @@ def _stream():
     return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
+# Measurement hook (bench.py): when GEMM_TRACE is a list, every tcgen05 GEMM launch is bracketed by CUDA events on the launching
+# stream and (event0, event1, algorithmic flop, MMA products per element) is appended to it.
+GEMM_TRACE = None
+
+
+def _trace_begin():
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _trace_end(e0, flops, products):
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    GEMM_TRACE.append((e0, e1, flops, products))
+
+
 def gemm_ex(**kw):
     """dsb_gemm_ex with tensors given by keyword (a_hi, a_lo, b_hi, b_lo, bias, c, c_hi, c_lo) plus the integer fields."""
     lib = _lib or load()
+    e0 = _trace_begin() if GEMM_TRACE is not None else None
     fields = {}
     for k, v in kw.items():
         if v is None:
@@ -143,6 +161,10 @@ def gemm_ex(**kw):
     rc = lib.dsb_gemm_ex(ctypes.byref(g), _stream())
     if rc != 0:
         raise DsbError('dsb_gemm_ex failed (%d): %s' % (rc, lib.dsb_last_error().decode()))
+    if e0 is not None:
+        terms = kw.get('terms', 3)
+        products = 1 if terms == 1 else 3 - (1 if kw.get('a_exact') else 0) - (1 if kw.get('b_exact') else 0)
+        _trace_end(e0, 2.0 * kw['m'] * kw['n'] * kw['k'] * max(1, kw.get('batch', 1)), products)
 
 
 def int_array(values):
@@ -158,6 +180,14 @@ def ptr_array(tensors):
 def call(name: str, *args):
     lib = _lib or load()
     conv = [(_ptr(a) if isinstance(a, torch.Tensor) else a) for a in args]
+    if GEMM_TRACE is not None and name == 'dsb_gemm_bf16_split':
+        e0 = _trace_begin()
+        rc = getattr(lib, name)(*conv, _stream())
+        M, N, K, terms = args[8], args[9], args[10], args[11]
+        _trace_end(e0, 2.0 * M * N * K, 3 if terms == 3 else 1)
+        if rc != 0:
+            raise DsbError('%s failed (%d): %s' % (name, rc, lib.dsb_last_error().decode()))
+        return
     rc = getattr(lib, name)(*conv, _stream())
     if rc != 0:
         raise DsbError('%s failed (%d): %s' % (name, rc, lib.dsb_last_error().decode()))

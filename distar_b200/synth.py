@@ -172,3 +172,21 @@ def tree_map(fn, x):
 
 def tree_clone(x):
     return tree_map(lambda t: t.clone(), x)
+
+
+def synth_sl_batch(batch_size: int, traj_len: int, seed: int = 0, entity_num=None, max_su: int = 12) -> Dict:
+    """One supervised-learning batch in the layout ``SLLearner._train`` feeds ``Model.sl_train`` (sl_learner.py:46-52,
+    sl_training/sl_dataloader.py collate): observation rows BATCH-major [B*T, ...], labels per row, ``action_mask`` per head
+    [B*T] float, ``traj_lens`` and the indices of trajectories that start a new episode (their LSTM state is reset)."""
+    B, T = batch_size, traj_len
+    obs = synth_obs(B * T, seed=seed, entity_num=entity_num, hidden=False)
+    g = torch.Generator(device='cpu')
+    g.manual_seed(seed + 104729)
+    act, num = synth_actions(B * T, obs['entity_num'], g, max_su)
+    mask = {k: (torch.ones(B * T) if k in ('action_type', 'delay') else (torch.rand(B * T, generator=g) < 0.7).float())
+            for k in HEADS}
+    new_episodes = [i for i in range(B) if float(torch.rand((), generator=g)) < 0.1]
+    batch = dict(obs)
+    batch.update({'action_info': act, 'selected_units_num': num, 'action_mask': mask, 'traj_lens': [T] * B,
+                  'new_episodes': new_episodes})
+    return batch

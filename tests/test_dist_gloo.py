@@ -58,3 +58,69 @@ def test_flat_gradient_allreduce_world2():
     for p in procs:
         p.join(timeout=60)
     assert all(same and ok for _, same, ok in res), res
+
+
+def _league_worker(rank, world, port, out):
+    """three ranks, two players: MP0 on ranks {0, 1}, ME0 on rank {2}; each player's learners exchange gradients inside their
+    own communicator only, and an invalid batch on ONE rank of a player freezes that step on all of that player's ranks
+    (the flag rides behind the gradients) without touching the other player."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from distar_b200 import ops
+    from distar_b200.dist import dist_init
+    from distar_b200.learner import RLLearner
+    from distar_b200.model import Model
+    from distar_b200.synth import synth_rl_batch
+    dist_init('gloo')
+    ops.enable_host_logic_testing(True)
+    groups = [dist.new_group([0, 1]), dist.new_group([2])]
+    mine = groups[0] if rank < 2 else groups[1]
+    torch.manual_seed(10 + rank)
+    m = Model({'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': ['winloss']}}, use_value_network=True)
+    learner = RLLearner(m, 'MP0' if rank < 2 else 'ME0', None, lr=1e-3, group=mine)
+    assert learner.world == (2 if rank < 2 else 1)
+    batch = synth_rl_batch(1, 2, seed=rank, max_su=4)
+    learner._train(batch)
+    after = [torch.zeros_like(m.flat_param) for _ in range(world)]
+    dist.all_gather(after, m.flat_param.clone())
+    ok = bool(torch.allclose(after[0], after[1])) and not bool(torch.allclose(after[0], after[2]))
+    # a bad batch on rank 1 only: rank 1 raises now, nobody's weights move, rank 0 learns about it at its next step
+    before = m.flat_param.clone()
+    bad = synth_rl_batch(1, 2, seed=50 + rank, max_su=4)
+    raised_now = False
+    if rank == 1:
+        # what the device flag of a negative entity id (entity_encoder.py:69-72) turns into when the learner reads it after
+        # backward has been queued; on the CPU stand-in path the id check raises eagerly, so the deferred read is simulated
+        def flagged():
+            raise RuntimeError('negative categorical id in an entity field')
+        m.raise_on_bad_input = flagged
+    try:
+        learner._train(bad)
+    except RuntimeError:
+        raised_now = True
+    if rank == 1:
+        del m.raise_on_bad_input
+    frozen = bool(torch.equal(before, m.flat_param))
+    raised_later = False
+    try:
+        learner._train(batch)
+    except RuntimeError:
+        raised_later = True
+    out.put((rank, ok, raised_now, frozen, raised_later))
+    dist.destroy_process_group()
+
+
+def test_league_groups_and_collective_bad_batch_world3():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_league_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    (_, ok0, now0, frozen0, later0), (_, ok1, now1, frozen1, later1), (_, ok2, now2, frozen2, later2) = res
+    assert ok0 and ok1 and ok2, res
+    assert now1 and not now0 and not now2, res                 # only the rank that saw the bad batch raises immediately
+    assert frozen0 and frozen1 and not frozen2, res            # the update was skipped on BOTH of the player's ranks, ME0 trained
+    assert later0 and not later2, res                          # the sibling rank raises at its next step

@@ -47,6 +47,9 @@ def parse():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--cpu-batch', type=int, default=4)
     ap.add_argument('--cpu-unroll', type=int, default=8)
+    ap.add_argument('--cpu-all-cores', action='store_true',
+                    help='also time the CPU arm on ALL host cores (BASELINE.md section 4 planned that; it is ~40x SLOWER than 16 '
+                         'threads on the GPU box, about a minute per pass, so it is opt-in; the recorded figure is in profiles/)')
     ap.add_argument('--cpu-threads', type=int, default=0,
                     help='threads for the CPU arm (0 = min(16, usable cores): the tiny-op-bound reference path gets '
                          'SLOWER beyond that: 128 threads measured 40x slower than 8 on the GPU box)')
@@ -142,12 +145,13 @@ def _oracle_step(batch, unroll, sl=False):
     return one
 
 
-def cpu_reference_rate(batch, unroll, repeats=2, threads=None, sl=False):
+def cpu_reference_rate(batch, unroll, repeats=2, threads=None, sl=False, warm=True):
     """Returns (frames/s, seconds per step, cores) of the oracle port on a bounded sample."""
     cores = threads or min(16, usable_cores())
     torch.set_num_threads(cores)
     one = _oracle_step(batch, unroll, sl)
-    one()
+    if warm:
+        one()
     best = float('inf')
     for _ in range(repeats):
         t = time.time()
@@ -594,9 +598,10 @@ def run_b200(args, rank, world, local_rank):
                                 'sample': 'oracle port, %s, B=%d x T=%d frames, best of 2 (%.1f s/step)' % (
                                     'rl_learner_forward+loss+backward' if rl else 'sl_train+loss+backward',
                                     args.cpu_batch, args.cpu_unroll, sec)}
-        if usable_cores() > cores and os.environ.get('DSB_NO_ALLCORES') != '1':
+        if usable_cores() > cores and args.cpu_all_cores:
             # BASELINE.md planned the CPU arm on all host cores; it is SLOWER there (tiny-op bound), so both are on record
-            v2, sec2, cores2 = cpu_reference_rate(args.cpu_batch, args.cpu_unroll, repeats=1, threads=usable_cores(), sl=not rl)
+            v2, sec2, cores2 = cpu_reference_rate(args.cpu_batch, args.cpu_unroll, repeats=1, threads=usable_cores(), sl=not rl,
+                                                   warm=False)     # one pass only: it is ~40x slower than the 16-thread run
             line['cpu_baseline']['all_cores'] = {'value': v2, 'cores': cores2, 's_per_step': sec2}
     print(json.dumps(line))
     if world > 1:

@@ -61,7 +61,7 @@ entity_features_kernel(const FieldTable t, __nv_bfloat16* __restrict__ hi, __nv_
             }
         }   // scalar fields are resolved per column below
     }
-    if (bad && lane == 0) atomicExch(error_flag, 1);
+    if (bad && lane == 0) atomicOr(error_flag, 1);
     // build the 32 columns; scalar fields may share a lane (e.g. columns 274..277), so resolve them per column
     uint32_t h[16], l[16];
 #pragma unroll

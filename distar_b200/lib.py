@@ -54,6 +54,15 @@ _SIGNATURES = {
     'dsb_gate_update_bwd': (_i, [_vp] * 9 + [_i64, _vp]),
     'dsb_relu_bwd_split_blocks': (_i, [_i64, _i]),
     'dsb_relu_bwd_split': (_i, [_vp, _vp, _i] + [_vp] * 4 + [_i, _i64, _i, _vp]),
+    'dsb_lstm_seq_fwd': (_i, [_vp] * 15 + [_i, _i, _i, _f, _vp]),
+    'dsb_lstm_seq_bwd': (_i, [_vp] * 21 + [_i, _i, _i, _vp]),
+    'dsb_pack_pair': (_i, [_vp, _i, _i64, _i, _i64, _vp, _vp, _i, _vp]),
+    'dsb_glu_gate_fwd': (_i, [_vp, _vp, _vp, _i64, _vp]),
+    'dsb_glu_gate_bwd': (_i, [_vp] * 5 + [_i64, _vp]),
+    'dsb_onehot_linear_fwd': (_i, [_vp] * 4 + [_i64, _i, _i, _i64, _i64, _i, _i, _vp, _vp]),
+    'dsb_onehot_linear_bwd': (_i, [_vp] * 5 + [_i64, _i, _i, _i64, _i64, _i, _vp]),
+    'dsb_target_unit_fwd': (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _f, _vp]),
+    'dsb_target_unit_bwd': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i64, _i, _f, _vp]),
     'dsb_sumsq_partials': (_i, []),
     'dsb_grad_norm': (_i, [_vp, _i64, _vp, _vp, _f, _vp]),
     'dsb_adam_step': (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp, _vp]),

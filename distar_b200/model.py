@@ -19,7 +19,7 @@ import torch.nn.functional as F
 from .constants import SELECTED_UNITS_ACTION_MASK
 from .params import init_state_dict
 from . import ops
-from .policy_net import BASELINE_ATAN, HEADS, MAX_SELECTED_UNITS_NUM, Net
+from .policy_net import BASELINE_ATAN, HEADS, MAX_SELECTED_UNITS_NUM, Net, bad_input_message
 from .spec import BASELINES, is_trainable, param_specs
 from .synth import tree_map
 from torch.utils.checkpoint import checkpoint as torch_checkpoint
@@ -219,9 +219,10 @@ class Model(nn.Module):
             # rl_learner_forward queued an asynchronous copy of the flag right behind the forward pass: waiting for it does
             # not wait for the backward pass the caller has queued since, so the host keeps its lead over the GPU
             self._flag_handle = None
-            if int(handle()) != 0:
+            code = int(handle())
+            if code != 0:
                 self._bad_input_flag.zero_()
-                raise RuntimeError('negative categorical id in an entity field')
+                raise RuntimeError(bad_input_message(code))
             return
         net = getattr(self, '_last_net', None)
         if net is not None:

@@ -841,11 +841,12 @@ def entity_attention(qkv: torch.Tensor, entity_num: torch.Tensor, heads: int, hd
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = False,
-           terms: int = 3, emit_split: bool = False, allow_n64: bool = False, fork: bool = False):
+           terms: int = 3, emit_split: bool = False, allow_n64: bool = False, fork: bool = False, exact_input: bool = False):
     """fc_block forward (ctools/torch_utils/network/nn_module.py:231-270): tcgen05 split GEMM when the shape
     tiles (N % 128 == 0, K % 64 == 0), plain library matmul for the odd small layers."""
     N, K = weight.shape
     elig = gemm_eligible(N, K) or (allow_n64 and not _TCGEN05_OFF and N % 64 == 0 and K % 128 == 0)   # 64-wide tiles
+    elig = elig and x.dtype == torch.float32
     if elig and (x.is_cuda or _HOST_LOGIC_TESTING) and x.numel() // K >= 1:
         sp = getattr(x, '_dsb_split', None)
         if sp is None or sp[0].shape != x.shape:
@@ -854,10 +855,231 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
         y, y_hi, y_lo, x_pass = _SplitLinear.apply(x, weight, bias, relu, terms, sp[0], sp[1], emit, fork and x.is_cuda)
         y = attach_split(y, y_hi, y_lo) if emit else y
         return (y, x_pass if x_pass is not None else x) if fork else y
-    _use_kernel(x)
-    y = F.linear(x, weight, bias)
+    if _use_kernel(x) and not _TCGEN05_OFF and x.numel() > 0:
+        y = linear_any(x, weight, bias, relu, terms, exact_input)
+        return (y, x) if fork else y
+    y = F.linear(x.float(), weight, bias)
     y = torch.relu(y) if relu else y
     return (y, x) if fork else y
+
+
+# ------------------------------------------------------------------------------------------------
+# fc_block for ANY (N, K): operands padded to tile multiples (scalar encoder inputs, head MLPs, value_fc)
+# ------------------------------------------------------------------------------------------------
+_PACK_DTYPE = {torch.uint8: 0, torch.int16: 1, torch.int8: 2, torch.float16: 3, torch.float32: 4, torch.int64: 5}
+
+
+def pack_pair(x2: torch.Tensor, Kp: int, want_lo: bool = True):
+    """[rows, K] of any wire dtype -> bf16 (hi, lo) [rows, Kp] with zero columns behind K: the A operand of a tcgen05 GEMM whose
+    reduction length is not a tile multiple, or whose input is still an integer observation (no .float() copy)."""
+    rows, K = x2.shape
+    assert x2.dtype in _PACK_DTYPE and x2.stride(1) == 1, (x2.dtype, x2.stride())
+    hi = torch.empty((rows, Kp), dtype=torch.bfloat16, device=x2.device)
+    lo = torch.empty((rows, Kp), dtype=torch.bfloat16, device=x2.device) if want_lo else None
+    lib.call('dsb_pack_pair', x2, _PACK_DTYPE[x2.dtype], rows, K, x2.stride(0), hi, lo, Kp)
+    return hi, lo
+
+
+def _padded_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], Np: int, Kp: int):
+    w = F.pad(weight.detach(), (0, Kp - weight.shape[1], 0, Np - weight.shape[0]))
+    hi, lo = split_bf16(w)
+    b = F.pad(bias.detach(), (0, Np - bias.shape[0])).contiguous() if bias is not None else None
+    return hi, lo, b
+
+
+class _PaddedLinear(torch.autograd.Function):
+    """y = act(x W^T + b) for shapes the tile grid does not divide: N is padded to a multiple of 64 and K to a multiple of 64
+    with zeros (weights once per optimiser step, the activation by the packing kernel); forward, dX and dW all run on the
+    tcgen05 kernel.  Returns the PADDED result [rows, Np]; the caller slices (autograd then pads the gradient back)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu, terms, exact_input):
+        N, K = weight.shape
+        Kp = _pad_to(K, 64)
+        Np = _pad_to(N, 64) if N <= 64 else _pad_to(N, 128)
+        x2 = x.reshape(-1, K)
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        a_hi, a_lo = pack_pair(x2, Kp, want_lo=not exact_input)
+        w_hi, w_lo, b_pad = weight_cached(weight, 'padded_%d_%d' % (Np, Kp), lambda: _padded_weight(weight, bias, Np, Kp))
+        if bias is not None and not bias.is_leaf:
+            b_pad = F.pad(bias.detach(), (0, Np - N)).contiguous()
+        y = torch.empty((M, Np), dtype=torch.float32, device=x.device)
+        _gemm_ex(a_hi=a_hi, a_lo=a_lo, b_hi=w_hi, b_lo=w_lo, bias=b_pad, alpha=1.0, relu=1 if relu else 0, terms=terms, c=y,
+                 m=M, n=Np, k=Kp, batch=1, inner=1, splits=1, a_exact=1 if exact_input else 0)
+        ctx.save_for_backward(a_hi, a_lo, w_hi, w_lo, y if relu else None)
+        ctx.meta = (N, K, Np, Kp, M, relu, terms, bias is not None, tuple(x.shape), exact_input)
+        ctx.weight_ref, ctx.bias_ref = weight, bias
+        ctx.set_materialize_grads(False)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        a_hi, a_lo, w_hi, w_lo, y = ctx.saved_tensors
+        N, K, Np, Kp, M, relu, terms, has_bias, xshape, exact_input = ctx.meta
+        if gy is None:
+            return (None,) * 6
+        gy2 = gy.reshape(M, Np).contiguous()
+        want_b = has_bias and ctx.needs_input_grad[2]
+        g_hi, g_lo, gb, _ = relu_bwd_split(gy2, y if relu else None, want_b, need_g=False)
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            # dX = dY W: written straight into [M, K] when the row pitch allows a tensor map (the copy engine drops the
+            # columns behind K), else into a padded buffer that is sliced
+            direct = K % 4 == 0
+            gx = torch.empty((M, K if direct else Kp), dtype=torch.float32, device=gy2.device)
+            _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=w_hi, b_lo=w_lo, b_mn=1, alpha=1.0, terms=terms, c=gx, m=M, n=Kp, k=Np, batch=1,
+                     inner=1, splits=1, bn=64 if Kp % 128 else 0)
+            gx = (gx if direct else gx[:, :K]).reshape(xshape)
+        if ctx.needs_input_grad[1]:
+            # dW = dY^T X over the rows (reduction padded to 64: rows behind M are TMA zero fill on both operands)
+            slot = _grad_slot(ctx.weight_ref)
+            kk = _pad_to(M, 64)
+            tiles = (_pad_to(Np, 128) // 128) * (Kp // 64)
+            splits = _pick_splits(tiles, kk)
+            common = dict(a_hi=g_hi, a_lo=g_lo, b_hi=a_hi, b_lo=a_lo, a_mn=1, b_mn=1, alpha=1.0, terms=terms, m=Np, n=Kp, k=kk,
+                          batch=1, inner=1, splits=splits, c_row_split=0, c_accumulate=1, bn=64 if Kp % 128 else 0,
+                          b_exact=1 if exact_input else 0)
+            if slot is not None and K % 4 == 0:
+                _gemm_ex(c=slot, **common)               # rows >= N and columns >= K fall outside the tensor map: dropped
+            else:
+                part = torch.zeros((Np, Kp), dtype=torch.float32, device=gy2.device)
+                _gemm_ex(c=part, **common)
+                gw = part[:N, :K]
+                if slot is not None:
+                    slot.add_(gw)
+                    gw = None
+        if want_b and gb is not None:
+            gb = gb[:N]
+            bslot = _grad_slot(ctx.bias_ref)
+            if bslot is not None:
+                bslot.add_(gb)
+                gb = None
+        return gx, gw, gb, None, None, None
+
+
+def linear_any(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = False, terms: int = 3,
+               exact_input: bool = False) -> torch.Tensor:
+    """fc_block of any shape on the tensor cores (see _PaddedLinear).  x may still be an integer / fp16 observation tensor;
+    exact_input: its values are exactly representable in bf16 (0/1 flags, counts <= 256): one product less, no lo operand."""
+    N = weight.shape[0]
+    y = _PaddedLinear.apply(x, weight, bias, relu, terms, exact_input)
+    return y[:, :N].reshape(*x.shape[:-1], N)
+
+
+class _GluGate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gate, x):
+        gate, x = gate.contiguous(), x.contiguous()
+        out = torch.empty_like(x)
+        lib.call('dsb_glu_gate_fwd', gate, x, out, x.numel())
+        ctx.save_for_backward(gate, x)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        gate, x = ctx.saved_tensors
+        dg, dx = torch.empty_like(gate), torch.empty_like(x)
+        lib.call('dsb_glu_gate_bwd', go.contiguous(), gate, x, dg, dx, x.numel())
+        return dg, dx
+
+
+def glu_gate(gate: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """sigmoid(gate) * x, the gate of GLU (module_utils.py:508-524), one kernel each way."""
+    if _use_kernel(x) and x.numel() % 4 == 0 and gate.shape == x.shape:
+        return _GluGate.apply(gate.float(), x.float())
+    return torch.sigmoid(gate) * x
+
+
+class _OneHotLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weight, bias, idx, relu, embedding, clamp_max, flag):
+        if embedding:
+            C, N = weight.shape
+            so, sc = 1, N
+        else:
+            N, C = weight.shape
+            so, sc = C, 1
+        P = idx.numel()
+        out = torch.empty((P, N), dtype=torch.float32, device=weight.device)
+        lib.call('dsb_onehot_linear_fwd', weight, bias, idx, out, P, N, C, so, sc, 1 if relu else 0, 1 if clamp_max else 0, flag)
+        ctx.save_for_backward(idx, out if relu else None)
+        ctx.meta = (P, N, C, so, sc, relu, tuple(weight.shape), bias is not None)
+        ctx.refs = (weight, bias)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        idx, out = ctx.saved_tensors
+        P, N, C, so, sc, relu, wshape, has_bias = ctx.meta
+        w_ref, b_ref = ctx.refs
+        wslot, bslot = _grad_slot(w_ref), (_grad_slot(b_ref) if has_bias else None)
+        gw = wslot if wslot is not None else torch.zeros(wshape, dtype=torch.float32, device=go.device)
+        gb = None
+        if has_bias:
+            gb = bslot if bslot is not None else torch.zeros(N, dtype=torch.float32, device=go.device)
+        lib.call('dsb_onehot_linear_bwd', go.contiguous(), out, idx, gw, gb, P, N, C, so, sc, 1 if relu else 0)
+        return (None if wslot is not None else gw), (None if (bslot is not None or not has_bias) else gb), None, None, None, None, None
+
+
+def onehot_linear(weight: torch.Tensor, bias: Optional[torch.Tensor], idx: torch.Tensor, relu: bool = True,
+                  embedding: bool = False, clamp_max: bool = False, flag: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """act(fc(one_hot(idx))) without the one-hot: a gather of weight columns (fc weight [N, C]) or rows (``embedding``:
+    table [C, N]) + bias + ReLU (action_type_head.py:61-63, action_arg_head.py:49-52, scalar_encoder.py:105-116); the
+    backward scatters into the weight gradient.  Ids outside [0, C) are clamped; bit 4 of ``flag`` records them unless
+    ``clamp_max`` (the scalar encoder clamps too-large ids on purpose, scalar_encoder.py:110-114)."""
+    shape = idx.shape
+    i64 = idx.reshape(-1).to(torch.int64).contiguous()
+    if _use_kernel(weight):
+        out = _OneHotLinear.apply(weight, bias, i64, relu, embedding, clamp_max, flag)
+    else:
+        C = weight.shape[0] if embedding else weight.shape[1]
+        if flag is not None:
+            flag |= 4 * int(((i64 < 0) | ((i64 >= C) & (not clamp_max))).any())
+        i64 = i64.clamp(0, C - 1)
+        out = weight[i64] if embedding else weight.t()[i64]
+        if bias is not None:
+            out = out + bias
+        out = torch.relu(out) if relu else out
+    return out.view(*shape, out.shape[-1])
+
+
+class _TargetUnit(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kfull, col, query, entity_num, temperature):
+        P, E, ld = kfull.shape
+        kfull, query = kfull.contiguous(), query.contiguous()
+        logits = torch.empty((P, E), dtype=torch.float32, device=kfull.device)
+        key = kfull.view(-1)[col:]                                  # the head's 32 columns inside the stacked key projection
+        lib.call('dsb_target_unit_fwd', key, ld, query, entity_num, logits, P, E, float(temperature))
+        ctx.save_for_backward(kfull, query, entity_num)
+        ctx.meta = (col, float(temperature))
+        return logits
+
+    @staticmethod
+    def backward(ctx, gl):
+        kfull, query, entity_num = ctx.saved_tensors
+        col, temperature = ctx.meta
+        P, E, ld = kfull.shape
+        gk = torch.zeros_like(kfull) if ld != 32 else torch.empty_like(kfull)
+        gq = torch.empty_like(query)
+        lib.call('dsb_target_unit_bwd', gl.contiguous(), kfull.view(-1)[col:], ld, query, entity_num, gk.view(-1)[col:], ld, gq,
+                 P, E, temperature)
+        return gk, None, gq, None, None
+
+
+def target_unit_logits(kfull: torch.Tensor, col: int, query: torch.Tensor, entity_num: torch.Tensor,
+                       temperature: float) -> torch.Tensor:
+    """TargetUnitHead (action_arg_head.py:357-361): logits[p, e] = key[p, e] . query[p] with key = kfull[..., col:col+32],
+    entities >= entity_num masked to -1e9, divided by the temperature; one warp-level kernel each way."""
+    P, E, ld = kfull.shape
+    if _use_kernel(kfull) and E % 4 == 0 and ld % 4 == 0 and query.shape[-1] == 32:
+        return _TargetUnit.apply(kfull, col, query.float(), entity_num.to(torch.int64).contiguous(), temperature)
+    key = kfull[..., col:col + 32]
+    logits = torch.matmul(key, query.unsqueeze(-1)).squeeze(-1)
+    valid = torch.arange(E, device=kfull.device).unsqueeze(0) < entity_num.unsqueeze(1)
+    return logits.masked_fill(~valid, -1e9) / temperature
 
 
 # ------------------------------------------------------------------------------------------------
@@ -960,13 +1182,11 @@ class _LstmCell(torch.autograd.Function):
 
 
 class _LstmLayer(torch.autograd.Function):
-    """One LayerNorm-LSTM layer over all timesteps (model/lstm.py:120-167) as ONE autograd node.
-
-    Per step the forward is a recurrent product h W_hh^T (library fp32 GEMM, M = batch) + the fused cell kernel; the backward
-    walks the steps in reverse with the cell-backward kernel and dh = d_hg W_hh.  What the per-cell formulation paid per
-    (layer, step) and this does once per layer: the W_hh gradient (one tensor-core GEMM over all L*B rows instead of L small
-    fp32 GEMMs + L accumulate adds), the LayerNorm parameter gradients (accumulated in place by the kernel's atomics instead of
-    4 zero-fills + 4 adds per step) and ~10 autograd nodes of Python bookkeeping."""
+    """One LayerNorm-LSTM layer over all timesteps (model/lstm.py:120-167) as ONE autograd node and ONE kernel launch each way
+    (csrc/lstm_seq.cu): a CTA keeps the h / c of its batch rows on chip for the whole sequence and streams W_hh from L2.
+    Outside the kernel remain the two things that are genuinely GEMM shaped: the input projection of all steps (policy_net) and
+    the W_hh gradient, one tensor-core GEMM over all L*B rows; LayerNorm parameter gradients are accumulated by the kernel
+    straight into the arena."""
 
     @staticmethod
     def forward(ctx, ig_all, h0, c0, w_hh, gam_h, bet_h, gam_c, bet_c):
@@ -978,13 +1198,9 @@ class _LstmLayer(torch.autograd.Function):
         hs, cs = torch.empty((L, B, H), **f32), torch.empty((L, B, H), **f32)
         gates, hg_all = torch.empty((L, B, G), **f32), torch.empty((L, B, G), **f32)
         pre_c, st_h, st_c = torch.empty((L, B, H), **f32), torch.empty((L, B, 2), **f32), torch.empty((L, B, 2), **f32)
-        w_t = w_hh.detach().t()
-        h, c = h0, c0
-        for t in range(L):
-            torch.mm(h, w_t, out=hg_all[t])
-            lib.call('dsb_lstm_cell_fwd', ig_all[t], hg_all[t], c, gam_h, bet_h, gam_c, bet_c, hs[t], cs[t], gates[t], st_h[t],
-                     pre_c[t], st_c[t], B, H, 1e-5)
-            h, c = hs[t], cs[t]
+        w_t = weight_cached(w_hh, 'hh_t', lambda: w_hh.detach().t().contiguous())
+        lib.call('dsb_lstm_seq_fwd', ig_all, h0, c0, w_t, gam_h, bet_h, gam_c, bet_c, hs, cs, gates, hg_all, st_h, pre_c, st_c,
+                 L, B, H, 1e-5)
         ctx.save_for_backward(gates, hg_all, st_h, pre_c, st_c, hs, cs, h0, c0, w_hh, gam_h, gam_c, bet_c)
         ctx.refs = (w_hh, gam_h, bet_h, gam_c, bet_c)
         ctx.set_materialize_grads(False)
@@ -998,6 +1214,7 @@ class _LstmLayer(torch.autograd.Function):
         dev = gates.device
         f32 = dict(dtype=torch.float32, device=dev)
         d_ig, d_hg = torch.empty((L, B, G), **f32), torch.empty((L, B, G), **f32)
+        dh0, dc0 = torch.empty((B, H), **f32), torch.empty((B, H), **f32)
         refs = ctx.refs
         slots = [_grad_slot(p) for p in refs[1:]]
         direct = all(s_ is not None for s_ in slots)
@@ -1006,21 +1223,9 @@ class _LstmLayer(torch.autograd.Function):
         else:
             dgh, dbh = torch.zeros(G, **f32), torch.zeros(G, **f32)
             dgc, dbc = torch.zeros(H, **f32), torch.zeros(H, **f32)
-        dh_next = None
-        dc_next = g_clast.contiguous() if g_clast is not None else None
-        w = w_hh.detach()
-        for t in range(L - 1, -1, -1):
-            if g_hs is not None:
-                gh = g_hs[t] if dh_next is None else g_hs[t] + dh_next
-            else:
-                gh = dh_next if dh_next is not None else torch.zeros((B, H), **f32)
-            gh = gh.contiguous()
-            c_in = cs[t - 1] if t > 0 else c0
-            d_cin = torch.empty((B, H), **f32)
-            lib.call('dsb_lstm_cell_bwd', gh, dc_next, gates[t], hg_all[t], st_h[t], c_in, pre_c[t], st_c[t], gam_h, gam_c, bet_c,
-                     d_ig[t], d_hg[t], d_cin, dgh, dbh, dgc, dbc, B, H)
-            dh_next = torch.mm(d_hg[t], w)
-            dc_next = d_cin
+        lib.call('dsb_lstm_seq_bwd', g_hs.contiguous() if g_hs is not None else None,
+                 g_clast.contiguous() if g_clast is not None else None, gates, hg_all, st_h, pre_c, st_c, cs, c0, w_hh.detach(),
+                 gam_h, gam_c, bet_c, d_ig, d_hg, dh0, dc0, dgh, dbh, dgc, dbc, L, B, H)
         gw = None
         if ctx.needs_input_grad[3]:
             h_prev = torch.cat([h0.unsqueeze(0), hs[:L - 1]], dim=0).reshape(L * B, H)
@@ -1031,7 +1236,7 @@ class _LstmLayer(torch.autograd.Function):
                 gw = weight_grad(g_hi, g_lo, x_hi, x_lo, 3, accumulate_into=_grad_slot(refs[0]))
             else:
                 gw = dg2.t() @ h_prev
-        return (d_ig, dh_next, dc_next, gw) + ((None,) * 4 if direct else (dgh, dbh, dgc, dbc))
+        return (d_ig, dh0, dc0, gw) + ((None,) * 4 if direct else (dgh, dbh, dgc, dbc))
 
 
 def lstm_layer(ig_all, h0, c0, w_hh, gam_h, bet_h, gam_c, bet_c):

@@ -66,6 +66,16 @@ def set_library_precision():
     torch.backends.cuda.matmul.allow_tf32 = False
 
 
+def bad_input_message(code: int) -> str:
+    """device error flag -> the message of the exception the reference raises at that point"""
+    what = []
+    if code & 1:
+        what.append('negative categorical id in an entity field')                    # entity_encoder.py:69-72
+    if code & 4:
+        what.append('action / scalar id outside its vocabulary (one-hot index out of range)')   # F.one_hot / nn.Embedding raise
+    return '; '.join(what) or 'invalid input (code %d)' % code
+
+
 class Net:
     """Functional network over a parameter mapping.  ``terms`` = products per tensor-core GEMM (3 = fp32-class)."""
 
@@ -78,15 +88,19 @@ class Net:
     def raise_on_bad_input(self) -> None:
         """entity_encoder.py:69-72 raises on a negative categorical id.  The kernels only record it (one device flag for
         the whole forward) so the check costs a single host read at the end instead of one pipeline drain per chunk."""
-        if self.bad_input_flag is not None and int(self.bad_input_flag.item()) != 0:
-            self.bad_input_flag.zero_()
-            raise RuntimeError('negative categorical id in an entity field')
+        if self.bad_input_flag is not None:
+            code = int(self.bad_input_flag.item())
+            if code != 0:
+                self.bad_input_flag.zero_()
+                raise RuntimeError(bad_input_message(code))
 
     # -------------------------------------------------------------------------------------- primitives
-    def fc(self, name: str, x: Tensor, relu: bool = False, split: bool = False) -> Tensor:
+    def fc(self, name: str, x: Tensor, relu: bool = False, split: bool = False, exact: bool = False) -> Tensor:
         """fc_block; split=True makes the GEMM epilogue also write the bf16 pair its consumer GEMM will read, split='only'
-        writes nothing but the pair (the consumer must be another tcgen05 GEMM; the fp32 result is a NaN placeholder)."""
-        return ops.linear(x, self.P[name + '.0.weight'], self.P[name + '.0.bias'], relu, self.terms, split)
+        writes nothing but the pair (the consumer must be another tcgen05 GEMM; the fp32 result is a NaN placeholder).
+        Shapes the tile grid does not divide (and integer-typed observation inputs) go through the zero-padded tensor-core
+        path (ops.linear_any); exact=True: the input values are exact in bf16 (0/1 flags, counts <= 256)."""
+        return ops.linear(x, self.P[name + '.0.weight'], self.P[name + '.0.bias'], relu, self.terms, split, exact_input=exact)
 
     def conv(self, name: str, x: Tensor, pad: int, relu: bool = False) -> Tensor:
         y = F.conv2d(x, self.P[name + '.0.weight'], self.P[name + '.0.bias'], padding=pad)
@@ -132,10 +146,13 @@ class Net:
         dev = s['time'].device
         outs, ctx, base = [], [], []
         for name, kind, din, is_ctx, is_base in SCALAR_FIELDS:
-            if kind == 'emb':
-                e = torch.relu(F.embedding(s[name].long().clamp(max=din - 1), P[pre + name + '.weight']))
-            elif kind == 'fc':
-                e = self.fc(pre + name, s[name].float(), relu=True)
+            if kind == 'emb':       # relu(nn.Embedding(clamp(id))) as one gather kernel (scalar_encoder.py:105-116)
+                e = ops.onehot_linear(P[pre + name + '.weight'], None, s[name], relu=True, embedding=True, clamp_max=True,
+                                      flag=self.bad_input_flag)
+            elif kind == 'fc':      # the observation goes to the GEMM in its wire dtype: 0/1 flags and counts are exact in bf16
+                x = s[name]
+                e = self.fc(pre + name, x if x.is_cuda else x.float(), relu=True,
+                            exact=x.dtype in (torch.uint8, torch.int8, torch.int16))
             else:
                 bo, loc = s['beginning_order'].long(), s['bo_location'].long()
                 B = bo.shape[0]
@@ -297,7 +314,8 @@ class Net:
 
     # -------------------------------------------------------------------------------------- heads
     def glu(self, name: str, x: Tensor, ctx: Tensor) -> Tensor:
-        return self.fc(name + '.layer2', torch.sigmoid(self.fc(name + '.layer1', ctx)) * x)
+        """GLU (module_utils.py:508-524): layer2(sigmoid(layer1(context)) * x)."""
+        return self.fc(name + '.layer2', ops.glu_gate(self.fc(name + '.layer1', ctx), x))
 
     def action_type_head(self, lstm_out, scalar_context, action_type=None):
         """head/action_type_head.py:48-67 (K10)."""
@@ -310,9 +328,9 @@ class Net:
         logits = self.glu(pre + 'action_fc', x, scalar_context) / self.T
         if action_type is None:
             action_type = self.sample(logits)
-        # one_hot(a) @ W^T == gather of weight columns
-        w1 = self.P[pre + 'action_map_fc1.0.weight']
-        e1 = torch.relu(w1.t()[action_type.long()] + self.P[pre + 'action_map_fc1.0.bias'])
+        # relu(fc(one_hot(a))) == gather of weight columns (+ bias, ReLU) in one kernel; an id outside the head is recorded
+        e1 = ops.onehot_linear(self.P[pre + 'action_map_fc1.0.weight'], self.P[pre + 'action_map_fc1.0.bias'], action_type,
+                               relu=True, flag=self.bad_input_flag)
         e1 = self.glu(pre + 'glu1', self.fc(pre + 'action_map_fc2', e1), scalar_context)
         return logits, action_type, e1 + self.glu(pre + 'glu2', lstm_out, scalar_context)
 
@@ -323,8 +341,8 @@ class Net:
             x = x / self.T
         if action is None:
             action = self.sample(x)
-        w1 = self.P[pre + 'embed_fc1.0.weight']
-        e = torch.relu(w1.t()[action.long()] + self.P[pre + 'embed_fc1.0.bias'])
+        e = ops.onehot_linear(self.P[pre + 'embed_fc1.0.weight'], self.P[pre + 'embed_fc1.0.bias'], action, relu=True,
+                              flag=self.bad_input_flag)
         return x, action, emb + self.fc(pre + 'embed_fc2', e)
 
     def head_keys(self, entity_embeddings):
@@ -336,15 +354,17 @@ class Net:
             return cached[1], cached[2]
         P = self.P
         a, b = 'policy.selected_units_head.key_fc.0.', 'policy.target_unit_head.key_fc.0.'
+        kfull = None
         if entity_embeddings.is_cuda:
             w = torch.cat([P[a + 'weight'], P[b + 'weight']], dim=0)
             bias = torch.cat([P[a + 'bias'], P[b + 'bias']], dim=0)
-            k = ops.linear(entity_embeddings, w, bias, False, self.terms, allow_n64=True)
-            ksu, ktu = k[..., :32], k[..., 32:]
+            kfull = ops.linear(entity_embeddings, w, bias, False, self.terms, allow_n64=True)
+            ksu, ktu = kfull[..., :32], kfull[..., 32:]
         else:
             ksu = self.fc('policy.selected_units_head.key_fc', entity_embeddings)
             ktu = self.fc('policy.target_unit_head.key_fc', entity_embeddings)
         self._head_keys = (entity_embeddings, ksu, ktu)
+        self._head_keys_full = kfull
         return ksu, ktu
 
     def su_keys(self, entity_embeddings, entity_num):
@@ -458,10 +478,10 @@ class Net:
         pre = 'policy.target_unit_head.'
         key = self.head_keys(entity_embeddings)[1]
         q = self.fc(pre + 'query_fc2', self.fc(pre + 'query_fc1', emb, relu=True))
-        logits = torch.matmul(key, q.unsqueeze(-1)).squeeze(-1)
-        E = entity_embeddings.shape[1]
-        valid = torch.arange(E, device=emb.device).unsqueeze(0) < entity_num.unsqueeze(1)
-        logits = logits.masked_fill(~valid, -1e9) / self.T
+        if self._head_keys_full is not None:      # K13: dot + mask + temperature as one warp-level kernel on the stacked keys
+            logits = ops.target_unit_logits(self._head_keys_full, 32, q, entity_num, self.T)
+        else:
+            logits = ops.target_unit_logits(key.contiguous(), 0, q, entity_num, self.T)
         if target_unit is None:
             target_unit = self.sample(logits)
         return logits, target_unit
@@ -507,7 +527,7 @@ class Net:
         for i in range(16):
             r = self.fc(pre + 'res.%d.fc2' % i, self.fc(pre + 'res.%d.fc1' % i, x, relu=True, split='only'))
             x = self.ln(pre + 'res.%d.norm' % i, r, residual=x, split=True)
-        v = F.linear(x, self.P[pre + 'value_fc.0.weight'], self.P[pre + 'value_fc.0.bias']).squeeze(1)
+        v = self.fc(pre + 'value_fc', x).squeeze(1)
         if BASELINE_ATAN[name]:
             v = (2.0 / math.pi) * torch.atan((math.pi / 2.0) * v)
         return v

@@ -178,6 +178,39 @@ int dsb_relu_bwd_split_blocks(int64_t rows, int N);
 int dsb_relu_bwd_split(const float* gy, const void* y, int y_is_bf16, float* g_out, void* hi, void* lo, float* colsum,
                        int colsum_atomic, int64_t rows, int N, dsb_stream_t stream);
 
+/* ---- operand packing for small / odd-shaped / integer-typed activations (scalar_encoder.py:99-132 `.float()` inputs; head MLPs
+ * whose K or N is not a tile multiple) ----
+ * x [rows, K] (row pitch ld_in elements) of dtype 0 u8, 1 i16, 2 i8, 3 f16, 4 f32, 5 i64 -> bf16 hi (and lo = bf16(x - hi),
+ * optional: 0/1 flags and counts <= 256 are exact in hi) [rows, Kp], columns >= K zero.  Kp % 8 == 0. */
+int dsb_pack_pair(const void* x, int dtype, int64_t rows, int K, int64_t ld_in, void* hi, void* lo, int Kp,
+                  dsb_stream_t stream);
+
+/* ---- GLU gate  out = sigmoid(gate) * x  (module_utils.py:508-524), fp32 [n], n % 4 == 0 ---- */
+int dsb_glu_gate_fwd(const float* gate, const float* x, float* out, int64_t n, dsb_stream_t stream);
+int dsb_glu_gate_bwd(const float* grad_out, const float* gate, const float* x, float* grad_gate, float* grad_x, int64_t n,
+                     dsb_stream_t stream);
+
+/* ---- act(W . one_hot(idx) + b) as a gather  (action_type_head.py:61-63, action_arg_head.py:49-52,82-85: the action
+ * embeddings fed back into the auto-regressive chain; scalar_encoder.py:105-116: nn.Embedding lookups) ----
+ * out[p, j] = act(W[j * stride_out + idx[p] * stride_class] + bias[j]), j < N, idx in [0, C).  fc weight [N, C]: stride_out = C,
+ * stride_class = 1; embedding table [C, N]: stride_out = 1, stride_class = N.  An id outside [0, C) is clamped; bit 4 of
+ * error_flag (optional) records it unless clamp_max != 0 and the id is too LARGE (scalar_encoder.py:110-114 clamps those).
+ * Backward ADDS into grad_W (same strides) and grad_bias [N] (optional) with atomics (rows of one class collide). */
+int dsb_onehot_linear_fwd(const float* W, const float* bias, const int64_t* idx, float* out, int64_t P, int N, int C,
+                          int64_t stride_out, int64_t stride_class, int relu, int clamp_max, int* error_flag,
+                          dsb_stream_t stream);
+int dsb_onehot_linear_bwd(const float* grad_out, const float* out, const int64_t* idx, float* grad_W, float* grad_bias,
+                          int64_t P, int N, int C, int64_t stride_out, int64_t stride_class, int relu, dsb_stream_t stream);
+
+/* ---- TargetUnitHead logits  (action_arg_head.py:343-363) ----
+ * logits[p, e] = (e < entity_num[p] ? key[p, e, 0:32] . query[p, 0:32] : -1e9) / temperature; key rows have pitch ldk floats
+ * (>= 32: the key projection shares its GEMM output with the selected-units head), E % 4 == 0.  One warp per 4 entities.
+ * Backward: grad_query [P, 32] and grad_key [P, E, 32] (row pitch ldgk; masked entities get zeros). */
+int dsb_target_unit_fwd(const float* key, int ldk, const float* query, const int64_t* entity_num, float* logits, int64_t P,
+                        int E, float temperature, dsb_stream_t stream);
+int dsb_target_unit_bwd(const float* grad_logits, const float* key, int ldk, const float* query, const int64_t* entity_num,
+                        float* grad_key, int ldgk, float* grad_query, int64_t P, int E, float temperature, dsb_stream_t stream);
+
 /* ---- tcgen05 GEMM family  (fc_block nn_module.py:231-270; attention module_utils.py:88-111; their backward) ----
  * dsb_gemm_bf16_split:  C[M,N] = act( A[M,K] . W[N,K]^T + bias[N] ),  A and W as bf16 (hi, lo) pairs, K contiguous,
  * K % 64 == 0, N % 128 == 0, M arbitrary.  terms = 1: hi*hi only (plain bf16); terms = 3: hi*hi + hi*lo + lo*hi
@@ -266,6 +299,23 @@ int dsb_lstm_cell_bwd(const float* gh, const float* gcy, const float* gates, con
                       const float* c_in, const float* pre_c, const float* stats_c, const float* gamma_h,
                       const float* gamma_c, const float* beta_c, float* d_ig, float* d_hg, float* d_cin, float* dgamma_h,
                       float* dbeta_h, float* dgamma_c, float* dbeta_c, int B, int H, dsb_stream_t stream);
+
+/* ---- persistent LayerNorm-LSTM layer: every time step of one layer in one launch each way  (LSTMLayer / LayerNormLSTMCell,
+ *      model/lstm.py:138-167; csrc/lstm_seq.cu) ----
+ * ig_all [L,B,4H] = LN_i(x W_ih^T) for all steps, (h0, c0) [B,H], w_hh_t [H,4H] = W_hh^T (forward) / w_hh [4H,H] (backward).
+ * Forward writes hs, cs [L,B,H] and the tensors the backward needs: gates [L,B,4H] (pre-activation), hg [L,B,4H] (raw
+ * h W_hh^T), stats_h / stats_c [L,B,2] (mean, rstd), pre_c [L,B,H].  Backward takes grad_hs [L,B,H] (may be NULL) and the
+ * gradient of the last cell state (may be NULL), writes d_ig (gradient of ig_all), d_hg (gradient of the raw recurrent
+ * product: the caller forms dW_hh = d_hg^T h_prev with one GEMM), dh0, dc0 and ADDS the LayerNorm parameter gradients into
+ * dgamma_h / dbeta_h [4H], dgamma_c / dbeta_c [H].  H = 128 or 384. */
+int dsb_lstm_seq_fwd(const float* ig_all, const float* h0, const float* c0, const float* w_hh_t, const float* gamma_h,
+                     const float* beta_h, const float* gamma_c, const float* beta_c, float* hs, float* cs, float* gates, float* hg,
+                     float* stats_h, float* pre_c, float* stats_c, int L, int B, int H, float eps, dsb_stream_t stream);
+int dsb_lstm_seq_bwd(const float* grad_hs, const float* grad_c_last, const float* gates, const float* hg, const float* stats_h,
+                     const float* pre_c, const float* stats_c, const float* cs, const float* c0, const float* w_hh,
+                     const float* gamma_h, const float* gamma_c, const float* beta_c, float* d_ig, float* d_hg, float* dh0,
+                     float* dc0, float* dgamma_h, float* dbeta_h, float* dgamma_c, float* dbeta_c, int L, int B, int H,
+                     dsb_stream_t stream);
 
 /* ---- fused grad-norm -> clip -> Adam over the flat arena  (rl_learner.py:73-80,125,132; grad_clip.py:141-144) ----
  * step 1: dsb_sumsq partial sums of grad^2 into `partial` [>= dsb_sumsq_partials()] then a finishing reduction

@@ -390,7 +390,7 @@ def test_max_pool2_nhwc_fwd_bwd(N, H, W, C):
     assert torch.allclose(win, go)
 
 
-@pytest.mark.parametrize('L,B,H', [(5, 64, 384), (1, 3, 384), (4, 128, 128)])
+@pytest.mark.parametrize('L,B,H', [(5, 64, 384), (1, 3, 384), (4, 128, 128), (33, 128, 384), (3, 5, 384)])
 def test_lstm_layer_matches_cell_loop(L, B, H):
     """the layer-level autograd node (one dW_hh GEMM, in-place LayerNorm gradients) against the per-cell formulation"""
     g = torch.Generator().manual_seed(L + B + H)
@@ -485,3 +485,118 @@ def test_flat_adam_weight_decay_schedule_and_skip_flag():
     grad.normal_()
     mine.step(skip_flag=torch.ones(4, device=DEV))
     assert torch.equal(p, before) and torch.equal(mine.exp_avg, m_before)
+
+
+@pytest.mark.parametrize('M,K,N,relu,dtype', [(264, 10, 64, True, torch.float32), (264, 90, 128, True, torch.int16),
+                                             (37, 260, 128, True, torch.uint8), (4096, 256, 327, False, torch.float32),
+                                             (1000, 256, 2, False, torch.float32), (513, 32, 256, True, torch.float32),
+                                             (300, 1024, 32, True, torch.float32), (77, 32, 32, False, torch.float32),
+                                             (4224, 256, 1, False, torch.float32), (1, 269, 64, True, torch.uint8)])
+def test_linear_any_shapes_fwd_bwd(M, K, N, relu, dtype):
+    """fc_block shapes the tile grid does not divide (scalar encoder, head MLPs, value_fc) on the tcgen05 kernel through
+    zero padding: forward, input gradient and weight / bias gradients against fp64."""
+    g = torch.Generator().manual_seed(M + K + N)
+    if dtype == torch.float32:
+        x = torch.randn(M, K, generator=g)
+    else:
+        x = torch.randint(0, 21 if dtype == torch.uint8 else 2, (M, K), generator=g).to(dtype)
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g)
+    go = torch.randn(M, N, generator=g)
+    xr = x.double().requires_grad_(dtype == torch.float32)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = F.linear(xr, wr, br)
+    ref = torch.relu(ref) if relu else ref
+    ref.backward(go.double())
+    xd = x.to(DEV).requires_grad_(dtype == torch.float32)
+    wd, bd = w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    out = ops.linear(xd, wd, bd, relu, 3, exact_input=dtype != torch.float32)
+    out.backward(go.to(DEV))
+    scale = ref.abs().max().item()
+    assert out.shape == (M, N)
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 2e-5 * max(scale, 1.0)
+    gs = wr.grad.abs().max().item()
+    assert (wd.grad.cpu().double() - wr.grad).abs().max().item() <= 1e-4 * max(gs, 1e-3)
+    assert (bd.grad.cpu().double() - br.grad).abs().max().item() <= 1e-4 * max(br.grad.abs().max().item(), 1e-3)
+    if dtype == torch.float32:
+        assert (xd.grad.cpu().double() - xr.grad).abs().max().item() <= 1e-4 * max(xr.grad.abs().max().item(), 1e-3)
+
+
+def test_linear_any_accumulates_into_arena_slots():
+    """when weight / bias are arena leaves their gradients are ADDED in place (TMA reduce-add clipped to [N, K])."""
+    g = torch.Generator().manual_seed(0)
+    M, K, N = 300, 32, 200
+    x = torch.randn(M, K, generator=g).to(DEV)
+    w = torch.nn.Parameter(torch.randn(N, K, generator=g).to(DEV))
+    b = torch.nn.Parameter(torch.randn(N, generator=g).to(DEV))
+    w.grad, b.grad = torch.ones_like(w), torch.ones_like(b)
+    go = torch.randn(M, N, generator=g).to(DEV)
+    ops.linear(x, w, b, False, 3).backward(go)
+    assert torch.allclose(w.grad, 1 + go.t() @ x, rtol=1e-4, atol=1e-3)
+    assert torch.allclose(b.grad, 1 + go.sum(0), rtol=1e-4, atol=1e-3)
+
+
+def test_glu_gate_fwd_bwd():
+    g = torch.Generator().manual_seed(4)
+    a, x, go = (torch.randn(777, 256, generator=g) for _ in range(3))
+    ar, xr = a.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    (torch.sigmoid(ar) * xr).backward(go)
+    ad, xd = a.to(DEV).requires_grad_(True), x.to(DEV).requires_grad_(True)
+    out = ops.glu_gate(ad, xd)
+    out.backward(go.to(DEV))
+    assert torch.allclose(out.cpu(), torch.sigmoid(a) * x, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(ad.grad.cpu(), ar.grad, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(xd.grad.cpu(), xr.grad, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('embedding', [False, True])
+def test_onehot_linear_fwd_bwd(embedding):
+    g = torch.Generator().manual_seed(6)
+    P, N, C = 500, 256, 327
+    w = torch.randn((C, N) if embedding else (N, C), generator=g)
+    b = None if embedding else torch.randn(N, generator=g)
+    idx = torch.randint(0, C, (P,), generator=g)
+    go = torch.randn(P, N, generator=g)
+    wr = w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True) if b is not None else None
+    ref = F.embedding(idx, wr) if embedding else F.linear(F.one_hot(idx, C).float(), wr, br)
+    ref = torch.relu(ref)
+    ref.backward(go)
+    wd = w.to(DEV).requires_grad_(True)
+    bd = b.to(DEV).requires_grad_(True) if b is not None else None
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out = ops.onehot_linear(wd, bd, idx.to(DEV), relu=True, embedding=embedding, flag=flag)
+    out.backward(go.to(DEV))
+    assert torch.equal(out.cpu(), ref.detach()) and int(flag.item()) == 0
+    assert torch.allclose(wd.grad.cpu(), wr.grad, rtol=1e-4, atol=1e-5)
+    if b is not None:
+        assert torch.allclose(bd.grad.cpu(), br.grad, rtol=1e-4, atol=1e-4)
+    # ids outside the vocabulary: clamped; recorded unless the caller asked for the scalar encoder's clamp-max semantics
+    bad = idx.clone()
+    bad[3] = C + 5
+    o2 = ops.onehot_linear(wd, bd, bad.to(DEV), relu=True, embedding=embedding, clamp_max=True, flag=flag)
+    assert int(flag.item()) == 0 and torch.equal(o2[3].cpu(), torch.relu((w[C - 1] if embedding else w[:, C - 1] + b)))
+    ops.onehot_linear(wd, bd, bad.to(DEV), relu=True, embedding=embedding, flag=flag)
+    assert int(flag.item()) == 4
+
+
+@pytest.mark.parametrize('P,E,ld,col', [(50, 512, 64, 32), (3, 512, 32, 0), (7, 64, 64, 0)])
+def test_target_unit_logits_fwd_bwd(P, E, ld, col):
+    g = torch.Generator().manual_seed(P + E)
+    kfull = torch.randn(P, E, ld, generator=g)
+    q = torch.randn(P, 32, generator=g)
+    en = torch.randint(1, E + 1, (P,), generator=g)
+    en[0] = E
+    T = 0.8
+    go = torch.randn(P, E, generator=g)
+    kr, qr = kfull.clone().requires_grad_(True), q.clone().requires_grad_(True)
+    valid = torch.arange(E).unsqueeze(0) < en.unsqueeze(1)
+    ref = torch.matmul(kr[..., col:col + 32], qr.unsqueeze(-1)).squeeze(-1).masked_fill(~valid, -1e9) / T
+    ref.backward(go)
+    kd, qd = kfull.to(DEV).requires_grad_(True), q.to(DEV).requires_grad_(True)
+    out = ops.target_unit_logits(kd, col, qd, en.to(DEV), T)
+    out.backward(go.to(DEV))
+    assert torch.allclose(out.cpu(), ref.detach(), rtol=1e-5, atol=1e-4)
+    assert torch.equal(out.cpu() < -1e8, ~valid)
+    assert torch.allclose(kd.grad.cpu(), kr.grad, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(qd.grad.cpu(), qr.grad, rtol=1e-4, atol=1e-3)

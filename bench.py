@@ -554,6 +554,26 @@ def run_b200(args, rank, world, local_rank):
         i1.record()
         torch.cuda.synchronize()
     infer_ms = i0.elapsed_time(i1) / 5
+    # the same call served from a captured CUDA graph (distar_b200.serving.InferenceServer): host batch in pinned memory ->
+    # static device buffers -> replay (64 fixed pointer steps) -> results; timed end to end per request
+    serve = None
+    try:
+        from distar_b200.serving import InferenceServer
+        host_obs = tree_map(lambda t: t.pin_memory(), synth_obs(32, seed=7))
+        server = InferenceServer(model, host_obs, su_steps=64)
+        for _ in range(2):
+            server.infer(host_obs)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for _ in range(10):
+            server.infer(host_obs)
+        torch.cuda.synchronize()
+        serve_ms = (time.time() - t0) * 1e3 / 10
+        serve = {'ms_per_request': serve_ms, 'obs_per_s': 32 / (serve_ms / 1e3), 'batch': 32,
+                 'note': 'CUDA-graph replay incl. H2D of the observation batch and the host read of the result'}
+        del server
+    except Exception as exc:                                    # the learner metric must not depend on the serving extra
+        serve = {'error': repr(exc)[:200]}
     peaks = load_peaks()
     roofs = kernel_rooflines(dev, peaks)
     workload = {
@@ -586,7 +606,7 @@ def run_b200(args, rank, world, local_rank):
         'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches),
         'peak_hbm_gib': round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
         'inference': {'workload': 'compute_logp_action, batch 32 (forward + sampling), 1 GPU', 'ms_per_call': infer_ms,
-                      'obs_per_s': 32 / (infer_ms / 1e3)},
+                      'obs_per_s': 32 / (infer_ms / 1e3), 'graph_server': serve},
         'roofline': main,
         'rooflines': roofs,
     }

@@ -246,10 +246,13 @@ class Model(nn.Module):
             return net.entity_encoder(en, num)
 
         outs = []
+        # the scalar encoder is tiny and launch-bound: one pass over all rows, sliced per chunk below
+        scalar_all = net.scalar_encoder(scalar_info)
         for s0 in range(0, N, chunk):
             state['i'] += 1
-            sp, en, sc, num = tree_map(lambda t: t[s0:s0 + chunk], (spatial_info, entity_info, scalar_info, entity_num))
-            li, ctx, bf, ee, ms = net.encoder(sp, en, sc, num, entity_fn=entity_fn)
+            sp, en, num = tree_map(lambda t: t[s0:s0 + chunk], (spatial_info, entity_info, entity_num))
+            li, ctx, bf, ee, ms = net.encoder(sp, en, None, num, entity_fn=entity_fn,
+                                              scalar_out=tuple(t[s0:s0 + chunk] for t in scalar_all))
             outs.append((li, ctx, bf, ee) + tuple(ms[3:]))        # only the 16x16 skips leave the encoder
         cat = [torch.cat([o[i] for o in outs], dim=0) for i in range(len(outs[0]))]
         return cat[0], cat[1], cat[2], cat[3], [None, None, None] + cat[4:]
@@ -259,31 +262,36 @@ class Model(nn.Module):
         out = self.compute_logp_action(spatial_info, entity_info, scalar_info, entity_num, hidden_state)
         return out['action_info'], out['selected_units_num'], out['hidden_state']
 
-    def compute_logp_action(self, spatial_info, entity_info, scalar_info, entity_num, hidden_state, **kwargs):
-        """model.py:56-74: encoder -> one LSTM step -> sampling policy -> per-head log-prob of the sample."""
+    def compute_logp_action(self, spatial_info, entity_info, scalar_info, entity_num, hidden_state, su_fixed_steps=None,
+                            defer_input_check: bool = False, **kwargs):
+        """model.py:56-74: encoder -> one LSTM step -> sampling policy -> per-head log-prob of the sample.
+        su_fixed_steps / defer_input_check: the host-read-free form serving.InferenceServer captures in a CUDA graph (a fixed
+        number of pointer steps; the invalid-input flag is left in ``_bad_input_flag`` for the caller)."""
         net = self._net()
         lstm_input, scalar_context, _bf, entity_embeddings, map_skip = self._encode(
             net, spatial_info, entity_info, scalar_info, entity_num)
         lstm_out, out_state = net.lstm('core_lstm', lstm_input.unsqueeze(0), hidden_state, 3)
         action, su_num, logit, extra = net.policy_sample(lstm_out.squeeze(0), entity_embeddings, map_skip,
-                                                        scalar_context, entity_num, self._su_mask)
+                                                        scalar_context, entity_num, self._su_mask, su_fixed_steps)
         logp = {}
         for k, a in action.items():
             logp[k] = torch.log_softmax(logit[k], dim=-1).gather(-1, a.unsqueeze(-1)).squeeze(-1)
-        net.raise_on_bad_input()
+        if not defer_input_check:
+            net.raise_on_bad_input()
         return {'action_info': action, 'action_logp': logp, 'selected_units_num': su_num, 'entity_num': entity_num,
                 'hidden_state': out_state, 'logit': logit, 'extra_units': extra}
 
     def compute_teacher_logit(self, spatial_info, entity_info, scalar_info, entity_num, hidden_state,
-                              selected_units_num, action_info, **kwargs):
-        """model.py:76-93."""
+                              selected_units_num, action_info, su_fixed_steps=None, defer_input_check: bool = False, **kwargs):
+        """model.py:76-93.  su_fixed_steps / defer_input_check: see compute_logp_action."""
         net = self._net()
         lstm_input, scalar_context, _bf, entity_embeddings, map_skip = self._encode(
             net, spatial_info, entity_info, scalar_info, entity_num)
         lstm_out, out_state = net.lstm('core_lstm', lstm_input.unsqueeze(0), hidden_state, 3)
         _a, su_num, logit = net.policy_train(lstm_out.squeeze(0), entity_embeddings, map_skip, scalar_context,
-                                             entity_num, action_info, selected_units_num)
-        net.raise_on_bad_input()
+                                             entity_num, action_info, selected_units_num, su_steps=su_fixed_steps)
+        if not defer_input_check:
+            net.raise_on_bad_input()
         return {'logit': logit, 'hidden_state': out_state, 'entity_num': entity_num, 'selected_units_num': su_num}
 
     def rl_learner_forward(self, spatial_info, entity_info, scalar_info, entity_num, hidden_state, action_info,

@@ -354,7 +354,7 @@ def sample_categorical(logits: torch.Tensor, generator: Optional[torch.Generator
 # selected-units pointer network, sampling path (K12)
 # ------------------------------------------------------------------------------------------------
 def su_sample(weights16, emb0, key, valid_mask, entity_num, su_mask, temperature: float, rng: str = 'cuda',
-              max_steps: int = 64):
+              max_steps: int = 64, poll: bool = True):
     """The sampling loop of SelectedUnitsHead._query (action_arg_head.py:262-314) with ONE kernel per step.
 
     key [N,S,32] (end token at slot entity_num), valid_mask [N,S] bool (slots < entity_num + 1), su_mask [N] bool (rows
@@ -396,7 +396,8 @@ def su_sample(weights16, emb0, key, valid_mask, entity_num, su_mask, temperature
             if int(ended[i].item()) != 0:
                 steps = i + 1
                 break
-        elif (i & 7) == 7 or i == max_steps - 1:
+        elif poll and ((i & 7) == 7 or i == max_steps - 1):
+            # (poll=False: fixed step count, no host read - the form a CUDA graph can capture; the caller trims)
             flags = ended[:i + 1].tolist()
             if 1 in flags:
                 steps = flags.index(1) + 1
@@ -432,8 +433,36 @@ def weight_cached(w: torch.Tensor, key: str, build):
     if hit is not None and hit[0] == stamp:
         return hit[1]
     val = build()
-    cache[key] = (stamp, val)
+    cache[key] = (stamp, val, build)
     return val
+
+
+def _flat_tensors(v):
+    if torch.is_tensor(v):
+        return [v]
+    if isinstance(v, (tuple, list)):
+        return [t for x in v for t in _flat_tensors(x)]
+    return []
+
+
+def refresh_weight_cache(params) -> int:
+    """Recompute every cached derived weight form of `params` INTO THE SAME BUFFERS.  A captured CUDA graph (serving.py) has
+    the addresses of those buffers baked into its launches, so after new weights arrive they must be rewritten in place rather
+    than replaced.  Returns the number of refreshed entries."""
+    n = 0
+    for p in params:
+        cache = p.__dict__.get('_dsb_wcache')
+        if not cache:
+            continue
+        for key, entry in list(cache.items()):
+            if len(entry) < 3:
+                continue
+            _, old, build = entry
+            for dst, src in zip(_flat_tensors(old), _flat_tensors(build())):
+                dst.copy_(src)
+            cache[key] = ((p._version, WEIGHT_EPOCH[0], p.data_ptr()), old, build)
+            n += 1
+    return n
 
 
 def invalidate_weight_cache() -> None:
@@ -873,10 +902,11 @@ def pack_pair(x2: torch.Tensor, Kp: int, want_lo: bool = True):
     """[rows, K] of any wire dtype -> bf16 (hi, lo) [rows, Kp] with zero columns behind K: the A operand of a tcgen05 GEMM whose
     reduction length is not a tile multiple, or whose input is still an integer observation (no .float() copy)."""
     rows, K = x2.shape
-    assert x2.dtype in _PACK_DTYPE and x2.stride(1) == 1, (x2.dtype, x2.stride())
+    assert x2.is_cuda and x2.dtype in _PACK_DTYPE and x2.stride(1) == 1, (x2.dtype, x2.stride())
     hi = torch.empty((rows, Kp), dtype=torch.bfloat16, device=x2.device)
     lo = torch.empty((rows, Kp), dtype=torch.bfloat16, device=x2.device) if want_lo else None
-    lib.call('dsb_pack_pair', x2, _PACK_DTYPE[x2.dtype], rows, K, x2.stride(0), hi, lo, Kp)
+    # rows may be strided (a column slice of a wider GEMM output): the kernel takes the row pitch, so pass the raw address
+    lib.call('dsb_pack_pair', x2.data_ptr(), _PACK_DTYPE[x2.dtype], rows, K, x2.stride(0), hi, lo, Kp)
     return hi, lo
 
 

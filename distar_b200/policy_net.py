@@ -259,10 +259,13 @@ class Net:
     def pool_nhwc(x: Tensor) -> Tensor:
         return ops.max_pool2_nhwc(x)
 
-    def encoder(self, spatial_info, entity_info, scalar_info, entity_num, entity_fn=None):
+    def encoder(self, spatial_info, entity_info, scalar_info, entity_num, entity_fn=None, scalar_out=None):
         """model/encoder.py:28-45.  entity_fn lets the caller wrap the entity transformer (the activation-memory hog)
-        in activation checkpointing while the rest of the encoder keeps its activations."""
-        embedded_scalar, scalar_context, baseline_feature = self.scalar_encoder(scalar_info)
+        in activation checkpointing while the rest of the encoder keeps its activations.  scalar_out: this chunk's rows of a
+        scalar encoder pass the caller already ran over ALL observation rows (its ~20 small layers are launch-bound: once
+        per step instead of once per encoder chunk)."""
+        embedded_scalar, scalar_context, baseline_feature = scalar_out if scalar_out is not None else \
+            self.scalar_encoder(scalar_info)
         run_entity = entity_fn or self.entity_encoder
         entity_embeddings, embedded_entity, _mask = run_entity(entity_info, entity_num)
         if entity_embeddings.is_cuda:
@@ -424,7 +427,7 @@ class Net:
         logits = logits.masked_fill(~step_mask, -1e9)
         return logits, emb_steps[:, -1], selected_units_num
 
-    def selected_units_sample(self, emb0, entity_embeddings, entity_num, su_mask):
+    def selected_units_sample(self, emb0, entity_embeddings, entity_num, su_mask, fixed_steps: Optional[int] = None):
         """Sampling pointer network, action_arg_head.py:262-314 (K12; sequential, early exit when all rows ended)."""
         pre = 'policy.selected_units_head.'
         N = emb0.shape[0]
@@ -440,7 +443,11 @@ class Net:
                    P[cp + '.layernorm_h.bias'], P[cp + '.layernorm_c.weight'], P[cp + '.layernorm_c.bias'],
                    P[pre + 'embed_fc1.0.weight'], P[pre + 'embed_fc1.0.bias'], P[pre + 'embed_fc2.0.weight'],
                    P[pre + 'embed_fc2.0.bias']]
-            logits, units, ae, num = ops.su_sample(w16, emb0, key, valid, entity_num, su_mask, self.T, self.rng)
+            if fixed_steps:          # graph-capturable form: a fixed number of pointer steps, no host reads
+                logits, units, ae, num = ops.su_sample(w16, emb0, key, valid, entity_num, su_mask, self.T, self.rng,
+                                                       max_steps=fixed_steps, poll=False)
+            else:
+                logits, units, ae, num = ops.su_sample(w16, emb0, key, valid, entity_num, su_mask, self.T, self.rng)
             return logits, units, ae, num, torch.zeros(N, MAX_ENTITY_NUM + 1, device=dev)
         step_mask = valid & (slot != entity_num.unsqueeze(1))
         num = torch.full((N,), MAX_SELECTED_UNITS_NUM, dtype=torch.long, device=dev)
@@ -533,7 +540,8 @@ class Net:
         return v
 
     # -------------------------------------------------------------------------------------- policy
-    def policy_sample(self, lstm_out, entity_embeddings, map_skip, scalar_context, entity_num, su_action_mask):
+    def policy_sample(self, lstm_out, entity_embeddings, map_skip, scalar_context, entity_num, su_action_mask,
+                      su_fixed_steps: Optional[int] = None):
         """model/policy.py:22-48."""
         logit, action = {}, {}
         logit['action_type'], action['action_type'], emb = self.action_type_head(lstm_out, scalar_context)
@@ -541,7 +549,7 @@ class Net:
         logit['queued'], action['queued'], emb = self.arg_head('policy.queued_head.', emb, 2, True)
         su_mask = su_action_mask.to(emb.device)[action['action_type']]
         logit['selected_units'], action['selected_units'], emb, su_num, extra = self.selected_units_sample(
-            emb, entity_embeddings, entity_num, su_mask)
+            emb, entity_embeddings, entity_num, su_mask, su_fixed_steps)
         logit['target_unit'], action['target_unit'] = self.target_unit_head(emb, entity_embeddings, entity_num)
         logit['target_location'], action['target_location'] = self.location_head(emb, map_skip)
         return action, su_num, logit, extra

@@ -323,3 +323,20 @@ def test_sl_learner_steps(sd):
     assert float(log['total_loss']) == float(log['total_loss']) and 'selected_units_iou' in log
     assert l.hidden_state[0][0].shape == (B, 384) and not l.hidden_state[0][0].requires_grad
     assert float(h0[0].abs().sum()) > 0
+
+
+def test_weight_publication_maps_between_arena_layouts(sd):
+    """WeightPublisher / WeightSubscriber on CPU tensors: a learner arena (with value networks) into an actor arena (without)."""
+    from distar_b200.serving import WeightPublisher, WeightSubscriber
+    learner_model = _model(sd)
+    actor = Model({'model': {'spatial_x': 128, 'spatial_y': 128}}, use_value_network=False, seed=1)
+    pub, sub = WeightPublisher(learner_model), WeightSubscriber(actor)
+    assert len(pub.ranges) <= 4 and not any(n.startswith('value_networks') for n in pub.names)
+    with torch.no_grad():
+        learner_model.flat_param.add_(0.5)
+    assert pub.publish() == 1
+    sub.update(pub)
+    lp = dict(learner_model.named_parameters())
+    for n, p in actor.named_parameters():
+        if p.requires_grad:
+            assert torch.equal(p, lp[n]), n

@@ -118,6 +118,9 @@ def entity_features_split(entity_info: dict, fields, check_negative: bool = True
     return hi, lo
 
 
+_CONST_IDX = {}
+
+
 def entity_exact_weight(w: torch.Tensor, fields) -> torch.Tensor:
     """[out, 997] embedding weight -> [out, 1024] for the exact-operand feature rows of entity_features_split(exact=True):
     the columns of the scalar ('u') fields are repeated after the row (they multiply the bf16 residuals), zeros after."""
@@ -126,7 +129,10 @@ def entity_exact_weight(w: torch.Tensor, fields) -> torch.Tensor:
         if kind == 'u':
             ucols.append(off)
         off += wd
-    idx = torch.tensor(ucols, device=w.device)
+    key = (w.device, tuple(ucols))
+    idx = _CONST_IDX.get(key)          # built once per device: a host -> device copy here would be illegal under CUDA-graph capture
+    if idx is None:
+        idx = _CONST_IDX[key] = torch.tensor(ucols, device=w.device)
     return torch.cat([w, w.index_select(1, idx), w.new_zeros(w.shape[0], 1024 - off - len(ucols))], dim=1)
 
 
@@ -364,9 +370,9 @@ def su_sample(weights16, emb0, key, valid_mask, entity_num, su_mask, temperature
     Returns (logits [N,steps,S], units [N,steps], ae [N,1024], selected_units_num [N])."""
     N, S, _ = key.shape
     dev = key.device
-    rows = torch.arange(N, device=dev)
-    mask = valid_mask.clone()
-    mask[rows, entity_num] = False                       # end flag is not available at the first selection
+    # end flag is not available at the first selection (pure device ops: an indexed assignment of a Python scalar would be
+    # a host -> device copy, which CUDA-graph capture forbids)
+    mask = valid_mask & (torch.arange(S, device=dev).unsqueeze(0) != entity_num.unsqueeze(1))
     mask = mask.to(torch.uint8).contiguous()
     ae = emb0.detach().clone().contiguous()
     emb0c = emb0.detach().contiguous()

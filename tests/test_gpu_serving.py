@@ -39,7 +39,7 @@ def test_graph_replay_matches_eager_calls():
     server = InferenceServer(actor, obs, teacher=teacher, su_steps=16)
     for seed in (9, 10):                                   # the second request reuses the captured graph with new inputs
         obs = synth_obs(4, seed=seed, entity_num=torch.tensor([512, 77, 300, 5]))
-        out = server.infer(tree_map(lambda t: t.pin_memory(), obs))
+        out = server.infer(tree_map(lambda t: t.pin_memory(), obs), teacher_hidden=obs['hidden_state'])
         steps = out['action_info']['selected_units'].shape[1]
         assert steps == max(1, int(out['selected_units_num'].max())) and out['logit']['selected_units'].shape[1] == steps
         with torch.no_grad():

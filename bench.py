@@ -45,6 +45,9 @@ def parse():
                     help='number of encoder chunks whose entity-transformer activations are kept (not recomputed)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--e2e-format', default='compact', choices=['compact', 'padded'],
+                    help='what crosses PCIe every step of the e2e measurement: compact = un-padded trajectories expanded on the '
+                         'GPU (distar_b200.batch, the product path); padded = the reference collate layout (1.47 GB / step)')
     ap.add_argument('--cpu-batch', type=int, default=4)
     ap.add_argument('--cpu-unroll', type=int, default=8)
     ap.add_argument('--cpu-all-cores', action='store_true',
@@ -409,8 +412,15 @@ def run_b200(args, rank, world, local_rank):
                               'data': {'batch_size': B}}}
         learner = SLLearner(model, sl_cfg, ignore_steps=-1)       # the reference's 6 no-update iterations are start-up only
         host = synth_sl_batch(B, T, seed=1000 * rank)
+    compact = rl and args.e2e_format == 'compact'
+    padded_bytes = tree_bytes(host)
+    if compact:
+        from distar_b200.batch import compact_rl_batch, expand_rl_batch
+        wire = tree_map(lambda t: t.pin_memory(), compact_rl_batch(host))      # what an actor-side sender would ship
     host = tree_map(lambda t: t.pin_memory(), host)
-    h2d = tree_bytes(host)
+    if not compact:
+        wire = host
+    h2d = tree_bytes(wire)
     resident = tree_map(lambda t: t.to(dev, non_blocking=True), host)
 
     def barrier():
@@ -444,7 +454,7 @@ def run_b200(args, rank, world, local_rank):
     copy_stream = torch.cuda.Stream(device=dev)
     # two persistent device staging batches (double buffering): allocating 1.5 GB of fresh device tensors per step on a side
     # stream made the caching allocator fall back to cudaMalloc / cudaFree under a 150 GiB working set (+46 ms per step)
-    stage = [tree_map(lambda t: torch.empty(t.shape, dtype=t.dtype, device=dev), host) for _ in range(2)]
+    stage = [tree_map(lambda t: torch.empty(t.shape, dtype=t.dtype, device=dev), wire) for _ in range(2)]
     ready = [None, None]      # copy-stream event: staging batch i holds the next batch
     consumed = [None, None]   # main-stream event: the step that read staging batch i is completely queued behind it
     counter = [0]
@@ -469,7 +479,7 @@ def run_b200(args, rank, world, local_rank):
             t0 = torch.cuda.Event(enable_timing=True) if os.environ.get('DSB_E2E_TIMECOPY') == '1' else None
             if t0 is not None:
                 t0.record(copy_stream)
-            _copy_tree(stage[i], host)
+            _copy_tree(stage[i], wire)
             ready[i] = torch.cuda.Event(enable_timing=t0 is not None)
             ready[i].record(copy_stream)
             if t0 is not None:
@@ -488,7 +498,8 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.current_stream().wait_event(ready[i])
         ready[i] = None
         prefetch(1 - i)                                     # next step's batch; overlaps with this step's compute
-        info = learner._train(stage[i])
+        # compact wire format: the padded reference layout is assembled in HBM by three kernels (inside the timed region)
+        info = learner._train(expand_rl_batch(wire, staged=stage[i]) if compact else stage[i])
         consumed[i] = torch.cuda.Event()
         consumed[i].record(torch.cuda.current_stream())
         # device -> host read of the step result: the loss and the ~45 logged scalars arrive in ONE asynchronous copy queued
@@ -520,7 +531,9 @@ def run_b200(args, rank, world, local_rank):
             print('H2D batch copy durations (ms):', ['%.1f' % a.elapsed_time(b) for a, b in copy_times], file=sys.stderr)
         n_scalars = len(last_info[0]) if last_info[0] is not None else 0
         e2e = {'value': world * B * T / (ms_e2e / 1e3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d,
-               'd2h_bytes_per_step': 4 * n_scalars, 'ms_per_step': ms_e2e}
+               'd2h_bytes_per_step': 4 * n_scalars, 'ms_per_step': ms_e2e,
+               'wire_format': 'compact trajectories, expanded on the GPU (distar_b200.batch)' if compact else
+                              'padded reference collate layout', 'padded_layout_bytes': padded_bytes}
     per_player = None
     if args.workload == 'league':
         # every player's learners report their own step time (max within the group); a player's rate = its GPUs * B * T / that

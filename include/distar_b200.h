@@ -300,6 +300,22 @@ int dsb_lstm_cell_bwd(const float* gh, const float* gcy, const float* gates, con
                       const float* gamma_c, const float* beta_c, float* d_ig, float* d_hg, float* d_cin, float* dgamma_h,
                       float* dbeta_h, float* dgamma_c, float* dbeta_c, int B, int H, dsb_stream_t stream);
 
+/* ---- on-device learner-batch assembly from compact trajectories  (collate_fn / padding_entity_info,
+ *      rl_training/rl_dataloader.py:45-76,206-245; csrc/batch_expand.cu) ----
+ * dsb_expand_ragged: dst[r, s, e] = (s < steps[r] && e < width[r]) ? src[row_offset[r] + s * width[r] + e] : fill for r < rows,
+ * s < S, e < W; steps may be NULL (one step per row).  elem_bytes 1 / 2 / 4 (4: float when fill_is_float, else int32).  Pads
+ * entity fields with 0 to [rows, 512], the target-unit teacher logits with -1e9 to [rows, 512], the selected-units teacher
+ * logits with -1e9 to [rows, 64, 513] and the selected-units behaviour log-probs / labels to [rows, 64].
+ * dsb_sequence_mask: dst[r, j] = j < lengths[r] + add (uint8 0 / 1): selected_units_mask (add 0, W 64),
+ * selected_units_logits_mask (add 1, W 513), target_units_logits_mask (add 0, W 512).
+ * dsb_unpack_planes: one uint16 per pixel (bits [0,2) visibility_map, [2] creep, [3,6) player_relative, [6] alerts, [7] pathable,
+ * [8] buildable) -> the six uint8 planes spatial_encoder.py:51-71 reads. */
+int dsb_expand_ragged(const void* src, const int64_t* row_offset, const int* steps, const int* width, void* dst, int64_t rows,
+                      int S, int W, int elem_bytes, double fill, int fill_is_float, dsb_stream_t stream);
+int dsb_sequence_mask(const int64_t* lengths, int add, uint8_t* dst, int64_t rows, int W, dsb_stream_t stream);
+int dsb_unpack_planes(const uint16_t* packed, uint8_t* visibility, uint8_t* creep, uint8_t* player_relative, uint8_t* alerts,
+                      uint8_t* pathable, uint8_t* buildable, int64_t n, dsb_stream_t stream);
+
 /* ---- persistent LayerNorm-LSTM layer: every time step of one layer in one launch each way  (LSTMLayer / LayerNormLSTMCell,
  *      model/lstm.py:138-167; csrc/lstm_seq.cu) ----
  * ig_all [L,B,4H] = LN_i(x W_ih^T) for all steps, (h0, c0) [B,H], w_hh_t [H,4H] = W_hh^T (forward) / w_hh [4H,H] (backward).

@@ -1,0 +1,78 @@
+"""The drop-in boundary exercised for real: the ``distar/agent/b200`` pipeline (distar_b200/plugin) is found by the
+reference's OWN import_helper, instantiated under the reference's OWN BaseLearner (hooks, logger, checkpoint helper, lr
+scheduler unmodified) and run for a few iterations on CPU with the kernel stand-ins; the checkpoint the framework's SaveCkptHook
+writes is then loaded back by its LoadCkptHook into a second learner.  Runs only where /root/reference exists."""
+import os
+
+import pytest
+import torch
+
+import ref_import
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not ref_import.reference_available(), reason='reference tree not mounted')]
+
+
+@pytest.fixture()
+def pipeline(tmp_path, monkeypatch):
+    ref_import.install_shims()
+    from distar_b200 import ops, plugin
+    plugin.register('b200')
+    monkeypatch.chdir(tmp_path)                       # the framework writes ./experiments/<name>/...
+    ops.enable_host_logic_testing(True)
+    yield
+    ops.enable_host_logic_testing(False)
+
+
+def _cfg(name, load_path=''):
+    from distar.ctools.utils import read_config
+    cfg = read_config(os.path.join(ref_import.REFERENCE_ROOT, 'distar/bin/rl_user_config.yaml'))
+    cfg.common.experiment_name = name
+    cfg.common.type = 'rl'
+    cfg.learner.agent = 'b200'
+    cfg.learner.job_type = 'eval'                     # no league / coordinator in a unit test: synthetic batches
+    cfg.learner.use_cuda = False
+    cfg.learner.use_distributed = False
+    cfg.learner.use_value_feature = False             # as `rl_train.py --task bot` sets it (rl_train.py:134-136)
+    cfg.learner.player_id = 'MP0'
+    cfg.learner.load_path = load_path
+    cfg.learner.load_optimizer = True                 # (bin/rl_user_config.yaml ships it off; the hook default is on)
+    cfg.learner.data.batch_size = 1
+    cfg.actor.traj_len = 2
+    cfg.model.spatial_x = cfg.model.spatial_y = 128
+    cfg.model.enable_baselines = ['winloss']
+    return cfg
+
+
+def test_b200_pipeline_runs_under_the_reference_learner_framework(pipeline):
+    from distar.agent.import_helper import import_module
+    from distar.ctools.worker.learner.base_learner import BaseLearner
+    RLLearner = import_module('b200', 'RLLearner')            # how rl_train.py:43 picks the class
+    assert issubclass(RLLearner, BaseLearner)
+    assert import_module('b200', 'Agent').__name__ == 'Agent' and import_module('b200', 'SLLearner').__name__ == 'SLLearner'
+    learner = RLLearner(_cfg('plug_a'))
+    from distar_b200.model import Model
+    from distar_b200.ops import FlatAdam
+    assert isinstance(learner.model, Model) and isinstance(learner.optimizer, FlatAdam)
+    assert isinstance(learner.lr_scheduler, torch.optim.lr_scheduler.MultiStepLR)
+    w0 = learner.model.flat_param.clone()
+    learner.run(max_iterations=2)                             # before_run / after_iter / after_run hooks of the framework
+    assert learner.last_iter.val == 2 and not torch.equal(w0, learner.model.flat_param)
+    ckpt_dir = os.path.join('experiments', 'plug_a', 'MP0', 'checkpoint')
+    files = sorted(os.listdir(ckpt_dir))
+    assert files, 'SaveCkptHook (after_run) wrote nothing'
+    ck = torch.load(os.path.join(ckpt_dir, files[-1]), map_location='cpu', weights_only=False)
+    assert set(ck.keys()) >= {'model', 'optimizer', 'last_iter'} and ck['last_iter'] == 2
+    assert set(ck['optimizer'].keys()) == {'state', 'param_groups'}
+    # resume through the framework's LoadCkptHook (learner_hook.py:136-166: model + optimizer + last_iter)
+    resumed = RLLearner(_cfg('plug_b', load_path=os.path.abspath(os.path.join(ckpt_dir, files[-1]))))
+    resumed.call_hook('before_run')
+    assert resumed.last_iter.val == 2 and resumed.optimizer.t == learner.optimizer.t == 2
+    assert torch.equal(resumed.model.flat_param, learner.model.flat_param)
+    assert torch.equal(resumed.optimizer.exp_avg_sq, learner.optimizer.exp_avg_sq)
+    # the reference's torch.optim.Adam accepts the optimizer entry of OUR checkpoint (same per-parameter layout)
+    ref_model, _cfg_ref, _mods = ref_import.load_reference(spatial=128, enable_baselines=('winloss',))
+    ref_model.load_state_dict(ck['model'], strict=True)
+    ref_opt = torch.optim.Adam(ref_model.parameters(), lr=1e-5, betas=(0.0, 0.99), eps=1e-5)
+    ref_opt.load_state_dict(ck['optimizer'])
+    assert len(ref_opt.state_dict()['state']) == len(ck['optimizer']['state'])

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libdistar_b200.so')
-SOURCES = ['api.cu', 'scatter_connection.cu', 'return_scan.cu', 'categorical.cu', 'optim.cu', 'upsample.cu', 'attention.cu', 'layernorm.cu', 'spatial_stem.cu', 'entity_features.cu', 'pointer_head.cu', 'small_ops.cu', 'lstm_seq.cu', 'batch_expand.cu', 'gemm_tcgen05.cu']
+SOURCES = ['api.cu', 'scatter_connection.cu', 'return_scan.cu', 'categorical.cu', 'optim.cu', 'upsample.cu', 'attention.cu', 'layernorm.cu', 'spatial_stem.cu', 'entity_features.cu', 'pointer_head.cu', 'small_ops.cu', 'lstm_seq.cu', 'batch_expand.cu', 'su_train.cu', 'gemm_tcgen05.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC']
 
 

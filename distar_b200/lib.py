@@ -54,6 +54,12 @@ _SIGNATURES = {
     'dsb_gate_update_bwd': (_i, [_vp] * 9 + [_i64, _vp]),
     'dsb_relu_bwd_split_blocks': (_i, [_i64, _i]),
     'dsb_relu_bwd_split': (_i, [_vp, _vp, _i] + [_vp] * 4 + [_i, _i64, _i, _vp]),
+    'dsb_su_prefix_mean_fwd': (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
+    'dsb_su_prefix_mean_bwd': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp]),
+    'dsb_su_lstm_fwd': (_i, [_vp] * 12 + [_i64, _i, _vp]),
+    'dsb_su_lstm_bwd': (_i, [_vp] * 16 + [_i64, _i, _vp]),
+    'dsb_su_logits_fwd': (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i64, _i, _i, _vp]),
+    'dsb_su_logits_bwd': (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     'dsb_expand_ragged': (_i, [_vp] * 5 + [_i64, _i, _i, _i, _c.c_double, _i, _vp]),
     'dsb_sequence_mask': (_i, [_vp, _i, _vp, _i64, _i, _vp]),
     'dsb_unpack_planes': (_i, [_vp] * 7 + [_i64, _vp]),

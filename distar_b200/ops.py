@@ -1081,9 +1081,48 @@ def onehot_linear(weight: torch.Tensor, bias: Optional[torch.Tensor], idx: torch
     return out.view(*shape, out.shape[-1])
 
 
+class KeyGradSink:
+    """Gradient accumulator of the stacked key projection [P, E, 64] of the two pointer heads.  Its three consumers
+    (su_prefix_mean, su_logits, target_unit_logits) each touch only some rows / columns; instead of every one of them
+    returning a full zero-padded [P, E, 64] tensor for autograd to add up (three 0.5 GB fills + two adds at P = 4096) their
+    backward kernels write into ONE zero-initialised buffer and hand autograd None; ``fork_keys`` returns the buffer as the
+    gradient of the projection once all of them have run (autograd runs a node only after every consumer's backward)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, like: torch.Tensor) -> torch.Tensor:
+        if self.buf is None:
+            self.buf = torch.zeros_like(like)
+        return self.buf
+
+
+class _KeyFork(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kfull, sink):
+        ctx.sink = sink
+        ctx.set_materialize_grads(False)
+        return kfull.view_as(kfull)
+
+    @staticmethod
+    def backward(ctx, g):
+        buf, ctx.sink.buf = ctx.sink.buf, None
+        if buf is None:
+            return g, None
+        if g is not None:
+            buf.add_(g)
+        return buf, None
+
+
+def fork_keys(kfull: torch.Tensor):
+    """-> (kfull', sink): pass both to the pointer-head operators."""
+    sink = KeyGradSink()
+    return _KeyFork.apply(kfull, sink), sink
+
+
 class _TargetUnit(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, kfull, col, query, entity_num, temperature):
+    def forward(ctx, kfull, col, query, entity_num, temperature, sink):
         P, E, ld = kfull.shape
         kfull, query = kfull.contiguous(), query.contiguous()
         logits = torch.empty((P, E), dtype=torch.float32, device=kfull.device)
@@ -1091,6 +1130,7 @@ class _TargetUnit(torch.autograd.Function):
         lib.call('dsb_target_unit_fwd', key, ld, query, entity_num, logits, P, E, float(temperature))
         ctx.save_for_backward(kfull, query, entity_num)
         ctx.meta = (col, float(temperature))
+        ctx.sink = sink
         return logits
 
     @staticmethod
@@ -1098,24 +1138,151 @@ class _TargetUnit(torch.autograd.Function):
         kfull, query, entity_num = ctx.saved_tensors
         col, temperature = ctx.meta
         P, E, ld = kfull.shape
-        gk = torch.zeros_like(kfull) if ld != 32 else torch.empty_like(kfull)
+        if ctx.sink is not None:
+            gk = ctx.sink.get(kfull)                                # shared buffer: this head owns columns [col, col + 32)
+        else:
+            gk = torch.zeros_like(kfull) if ld != 32 else torch.empty_like(kfull)
         gq = torch.empty_like(query)
         lib.call('dsb_target_unit_bwd', gl.contiguous(), kfull.view(-1)[col:], ld, query, entity_num, gk.view(-1)[col:], ld, gq,
                  P, E, temperature)
-        return gk, None, gq, None, None
+        return (None if ctx.sink is not None else gk), None, gq, None, None, None
 
 
 def target_unit_logits(kfull: torch.Tensor, col: int, query: torch.Tensor, entity_num: torch.Tensor,
-                       temperature: float) -> torch.Tensor:
+                       temperature: float, sink: Optional[KeyGradSink] = None) -> torch.Tensor:
     """TargetUnitHead (action_arg_head.py:357-361): logits[p, e] = key[p, e] . query[p] with key = kfull[..., col:col+32],
     entities >= entity_num masked to -1e9, divided by the temperature; one warp-level kernel each way."""
     P, E, ld = kfull.shape
     if _use_kernel(kfull) and E % 4 == 0 and ld % 4 == 0 and query.shape[-1] == 32:
-        return _TargetUnit.apply(kfull, col, query.float(), entity_num.to(torch.int64).contiguous(), temperature)
+        return _TargetUnit.apply(kfull, col, query.float(), entity_num.to(torch.int64).contiguous(), temperature, sink)
     key = kfull[..., col:col + 32]
     logits = torch.matmul(key, query.unsqueeze(-1)).squeeze(-1)
     valid = torch.arange(E, device=kfull.device).unsqueeze(0) < entity_num.unsqueeze(1)
     return logits.masked_fill(~valid, -1e9) / temperature
+
+
+# ------------------------------------------------------------------------------------------------
+# teacher-forced selected-units pointer network (K12 training path, csrc/su_train.cu)
+# ------------------------------------------------------------------------------------------------
+class _SuPrefixMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kfull, su, entity_num, num, S, sink):
+        P, E, ld = kfull.shape
+        mean = torch.empty((P, S, 32), dtype=torch.float32, device=kfull.device)
+        cnt = torch.empty((P, S), dtype=torch.int32, device=kfull.device)
+        lib.call('dsb_su_prefix_mean_fwd', kfull, ld, su, su.shape[1], entity_num, num, mean, cnt, P, E, S)
+        ctx.save_for_backward(kfull, su, entity_num, num, cnt)
+        ctx.sink, ctx.S = sink, S
+        return mean
+
+    @staticmethod
+    def backward(ctx, g):
+        kfull, su, entity_num, num, cnt = ctx.saved_tensors
+        P, E, ld = kfull.shape
+        gk = ctx.sink.get(kfull) if ctx.sink is not None else torch.zeros_like(kfull)
+        lib.call('dsb_su_prefix_mean_bwd', g.contiguous(), su, su.shape[1], entity_num, num, cnt, gk, ld, P, E, ctx.S)
+        return (None if ctx.sink is not None else gk), None, None, None, None, None
+
+
+class _SuLstm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ig, w_hh, gam_h, bet_h, gam_c, bet_c):
+        P, S, _ = ig.shape
+        ig = ig.contiguous()
+        f32 = dict(dtype=torch.float32, device=ig.device)
+        hs, cs = torch.empty((P, S, 32), **f32), torch.empty((P, S, 32), **f32)
+        gates, hg = torch.empty((P, S, 128), **f32), torch.empty((P, S, 128), **f32)
+        pre_c, st = torch.empty((P, S, 32), **f32), torch.empty((P, S, 4), **f32)
+        w = w_hh.detach().contiguous()
+        lib.call('dsb_su_lstm_fwd', ig, w, gam_h, bet_h, gam_c, bet_c, hs, cs, gates, hg, pre_c, st, P, S)
+        ctx.save_for_backward(w, gam_h, gam_c, bet_c, hs, cs, gates, hg, pre_c, st)
+        ctx.refs = (w_hh, gam_h, bet_h, gam_c, bet_c)
+        return hs
+
+    @staticmethod
+    def backward(ctx, g_hs):
+        w, gam_h, gam_c, bet_c, hs, cs, gates, hg, pre_c, st = ctx.saved_tensors
+        P, S, _ = hs.shape
+        f32 = dict(dtype=torch.float32, device=hs.device)
+        d_ig, d_hg = torch.empty((P, S, 128), **f32), torch.empty((P, S, 128), **f32)
+        refs = ctx.refs
+        slots = [_grad_slot(p) for p in refs[1:]]
+        direct = all(s_ is not None for s_ in slots)
+        dgh, dbh, dgc, dbc = slots if direct else (torch.zeros(128, **f32), torch.zeros(128, **f32), torch.zeros(32, **f32),
+                                                   torch.zeros(32, **f32))
+        lib.call('dsb_su_lstm_bwd', g_hs.contiguous(), w, gam_h, gam_c, bet_c, cs, gates, hg, pre_c, st, d_ig, d_hg, dgh, dbh, dgc,
+                 dbc, P, S)
+        gw = None
+        if ctx.needs_input_grad[1]:
+            # dW_hh = d_hg^T h_prev over all (row, step) pairs: one (zero-padded) tensor-core GEMM
+            h_prev = torch.cat([torch.zeros((P, 1, 32), **f32), hs[:, :-1]], dim=1).reshape(P * S, 32)
+            gw = small_weight_grad(d_hg.reshape(P * S, 128), h_prev, accumulate_into=_grad_slot(refs[0]))
+        return (d_ig, gw) + ((None,) * 4 if direct else (dgh, dbh, dgc, dbc))
+
+
+def small_weight_grad(g: torch.Tensor, x: torch.Tensor, accumulate_into: Optional[torch.Tensor] = None):
+    """dW [N, K] = g^T x for a skinny layer (N, K small, many rows) on the tcgen05 kernel: both operands packed to zero-padded
+    bf16 pairs, reduction split over the rows.  Adds into ``accumulate_into`` ([N, K], K % 4 == 0) when given."""
+    M, N = g.shape
+    K = x.shape[1]
+    Np, Kp = _pad_to(N, 64), _pad_to(K, 64)
+    g_hi, g_lo = pack_pair(g, Np)
+    x_hi, x_lo = pack_pair(x, Kp)
+    kk = _pad_to(M, 64)
+    splits = _pick_splits((_pad_to(Np, 128) // 128) * (Kp // 64), kk)
+    common = dict(a_hi=g_hi, a_lo=g_lo, b_hi=x_hi, b_lo=x_lo, a_mn=1, b_mn=1, alpha=1.0, terms=3, m=Np, n=Kp, k=kk, batch=1, inner=1,
+                  splits=splits, c_row_split=0, c_accumulate=1, bn=64 if Kp % 128 else 0)
+    if accumulate_into is not None and K % 4 == 0:
+        _gemm_ex(c=accumulate_into, **common)
+        return None
+    part = torch.zeros((Np, Kp), dtype=torch.float32, device=g.device)
+    _gemm_ex(c=part, **common)
+    if accumulate_into is not None:
+        accumulate_into.add_(part[:N, :K])
+        return None
+    return part[:N, :K]
+
+
+class _SuLogits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hs, kfull, end_emb, su, entity_num, sink):
+        P, S, _ = hs.shape
+        _, E, ld = kfull.shape
+        hs = hs.contiguous()
+        end = end_emb.detach().reshape(-1).contiguous()
+        logits = torch.empty((P, S, E + 1), dtype=torch.float32, device=hs.device)
+        lib.call('dsb_su_logits_fwd', hs, kfull, ld, end, su, su.shape[1], entity_num, logits, P, E, S)
+        ctx.save_for_backward(hs, kfull, end, su, entity_num)
+        ctx.sink, ctx.end_ref = sink, end_emb
+        return logits
+
+    @staticmethod
+    def backward(ctx, gl):
+        hs, kfull, end, su, entity_num = ctx.saved_tensors
+        P, S, _ = hs.shape
+        _, E, ld = kfull.shape
+        gk = ctx.sink.get(kfull) if ctx.sink is not None else torch.zeros_like(kfull)
+        dhs = torch.empty_like(hs)
+        slot = _grad_slot(ctx.end_ref)
+        d_end = slot.view(-1) if slot is not None else torch.zeros(32, dtype=torch.float32, device=hs.device)
+        lib.call('dsb_su_logits_bwd', gl.contiguous(), hs, kfull, ld, end, su, su.shape[1], entity_num, dhs, gk, d_end, P, E, S)
+        return dhs, (None if ctx.sink is not None else gk), (None if slot is not None else d_end.view(ctx.end_ref.shape)), None, \
+            None, None
+
+
+def su_prefix_mean(kfull, selected_units, entity_num, selected_units_num, S: int, sink=None):
+    """mean / sum of the keys of the units labelled up to each step (action_arg_head.py:196-199) -> [P, S, 32]."""
+    return _SuPrefixMean.apply(kfull, selected_units, entity_num, selected_units_num, S, sink)
+
+
+def su_lstm(ig, w_hh, gam_h, bet_h, gam_c, bet_c):
+    """32-wide LayerNorm-LSTM over the S pointer steps from zero state; ig [P, S, 128] = LN_i(q W_ih^T) -> h [P, S, 32]."""
+    return _SuLstm.apply(ig, w_hh, gam_h, bet_h, gam_c, bet_c)
+
+
+def su_logits(hs, kfull, end_embedding, selected_units, entity_num, sink=None):
+    """pointer logits [P, S, E + 1] with the reference's mask recurrence (action_arg_head.py:179-195)."""
+    return _SuLogits.apply(hs, kfull, end_embedding, selected_units, entity_num, sink)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -362,12 +362,16 @@ class Net:
             w = torch.cat([P[a + 'weight'], P[b + 'weight']], dim=0)
             bias = torch.cat([P[a + 'bias'], P[b + 'bias']], dim=0)
             kfull = ops.linear(entity_embeddings, w, bias, False, self.terms, allow_n64=True)
+            # the three consumers of the stacked keys accumulate their gradients into one shared buffer (ops.KeyGradSink)
+            kfull, self._head_keys_sink = ops.fork_keys(kfull)
             ksu, ktu = kfull[..., :32], kfull[..., 32:]
         else:
             ksu = self.fc('policy.selected_units_head.key_fc', entity_embeddings)
             ktu = self.fc('policy.target_unit_head.key_fc', entity_embeddings)
         self._head_keys = (entity_embeddings, ksu, ktu)
         self._head_keys_full = kfull
+        if kfull is None:
+            self._head_keys_sink = None
         return ksu, ktu
 
     def su_keys(self, entity_embeddings, entity_num):
@@ -400,8 +404,25 @@ class Net:
         drain the launch queue); otherwise it is read back now."""
         pre = 'policy.selected_units_head.'
         N = emb0.shape[0]
-        key, valid, slot = self.su_keys(entity_embeddings, entity_num)
         S = max(int(selected_units_num.max()) if steps is None else int(steps), 1)
+        if emb0.is_cuda:
+            # K12, training path: the three non-GEMM pieces are one kernel each (csrc/su_train.cu), the four small MLP layers
+            # run on the tensor cores over all (row, step) pairs; keys are read in place from the stacked key projection
+            P_, cp = self.P, pre + 'lstm.layers.0.cell'
+            self.head_keys(entity_embeddings)
+            kfull, sink = self._head_keys_full, self._head_keys_sink
+            su = selected_units.long().contiguous()
+            en, num = entity_num.to(torch.int64).contiguous(), selected_units_num.to(torch.int64).contiguous()
+            mean = ops.su_prefix_mean(kfull, su, en, num, S, sink)                                 # [N,S,32]
+            emb_steps = emb0.unsqueeze(1) + self.fc(pre + 'embed_fc2', self.fc(pre + 'embed_fc1', mean, relu=True))
+            ae = torch.cat([emb0.unsqueeze(1), emb_steps[:, :-1]], dim=1)
+            q = self.fc(pre + 'query_fc2', self.fc(pre + 'query_fc1', ae, relu=True))              # [N,S,32]
+            ig = self.ln(cp + '.layernorm_i', ops.linear(q, P_[cp + '.weight_ih'], None, False, self.terms))
+            hs = ops.su_lstm(ig, P_[cp + '.weight_hh'], P_[cp + '.layernorm_h.weight'], P_[cp + '.layernorm_h.bias'],
+                             P_[cp + '.layernorm_c.weight'], P_[cp + '.layernorm_c.bias'])
+            logits = ops.su_logits(hs, kfull, P_[pre + 'end_embedding'], su, en, sink)
+            return logits, emb_steps[:, -1], selected_units_num
+        key, valid, slot = self.su_keys(entity_embeddings, entity_num)
         su = selected_units[:, :S].long()
         onehot = su.unsqueeze(-1) == slot.unsqueeze(1)                               # [N,S,E+1]
         ended = torch.cummax((su == entity_num.unsqueeze(1)).long(), dim=1)[0].bool()  # end_flag after step i
@@ -486,7 +507,7 @@ class Net:
         key = self.head_keys(entity_embeddings)[1]
         q = self.fc(pre + 'query_fc2', self.fc(pre + 'query_fc1', emb, relu=True))
         if self._head_keys_full is not None:      # K13: dot + mask + temperature as one warp-level kernel on the stacked keys
-            logits = ops.target_unit_logits(self._head_keys_full, 32, q, entity_num, self.T)
+            logits = ops.target_unit_logits(self._head_keys_full, 32, q, entity_num, self.T, self._head_keys_sink)
         else:
             logits = ops.target_unit_logits(key.contiguous(), 0, q, entity_num, self.T)
         if target_unit is None:

@@ -110,6 +110,38 @@ int dsb_su_sample_step(const void* const* weights16, const float* emb0, float* a
                        const int64_t* prev, const float* q, float* logits_out, int64_t* result, int* all_ended, int N,
                        int S, int step, float temperature, dsb_stream_t stream);
 
+/* ---- selected-units pointer network, teacher-forced (training) path  (SelectedUnitsHead._train_query,
+ *      head/action_arg_head.py:168-216; csrc/su_train.cu) ----
+ * kfull [P, E, ld] fp32: the stacked key projection, this head's 32 key columns first; end_embedding [32] is the learned end
+ * token that occupies slot entity_num (:118-129); selected_units [P, su_ld] int64 labels, S <= 64 steps are processed.
+ * su_prefix_mean: mean[p, i, :] = mean (selected_units_num[p] != 0) or sum of the keys of the distinct units labelled at steps
+ *   <= i, the end token and everything after it excluded (:196-199); count [P, S] is kept for the backward, which ADDS the key
+ *   gradients into grad_kfull (same [P, E, ld] layout, zeroed by the caller, shared with su_logits and the target-unit head).
+ * su_lstm: the 32-wide LayerNorm-LSTM over the S steps from zero state; ig [P, S, 128] = LN_i(q W_ih^T); one warp per row.
+ *   Saves gates / hg [P,S,128], pre_c [P,S,32], stats [P,S,4] = (mean_h, rstd_h, mean_c, rstd_c).  Backward returns d_ig and
+ *   d_hg (gradient of the raw h W_hh^T: the caller forms dW_hh = d_hg^T h_prev) and ADDS the LayerNorm parameter gradients.
+ * su_logits: logits[p, i, e] = h[p, i] . key_e for the E + 1 slots, -1e9 where the reference masks: slot > entity_num, slot
+ *   chosen at an earlier step, end token at step 0 (:179-186).  Backward: grad_hs, key gradients ADDED into grad_kfull, the end
+ *   token's gradient ADDED into grad_end_embedding [32]. */
+int dsb_su_prefix_mean_fwd(const float* kfull, int ld, const int64_t* selected_units, int su_ld, const int64_t* entity_num,
+                           const int64_t* selected_units_num, float* mean, int* count, int64_t P, int E, int S,
+                           dsb_stream_t stream);
+int dsb_su_prefix_mean_bwd(const float* grad_mean, const int64_t* selected_units, int su_ld, const int64_t* entity_num,
+                           const int64_t* selected_units_num, const int* count, float* grad_kfull, int ld, int64_t P, int E, int S,
+                           dsb_stream_t stream);
+int dsb_su_lstm_fwd(const float* ig, const float* w_hh, const float* gamma_h, const float* beta_h, const float* gamma_c,
+                    const float* beta_c, float* hs, float* cs, float* gates, float* hg, float* pre_c, float* stats, int64_t P,
+                    int S, dsb_stream_t stream);
+int dsb_su_lstm_bwd(const float* grad_hs, const float* w_hh, const float* gamma_h, const float* gamma_c, const float* beta_c,
+                    const float* cs, const float* gates, const float* hg, const float* pre_c, const float* stats, float* d_ig,
+                    float* d_hg, float* dgamma_h, float* dbeta_h, float* dgamma_c, float* dbeta_c, int64_t P, int S,
+                    dsb_stream_t stream);
+int dsb_su_logits_fwd(const float* hs, const float* kfull, int ld, const float* end_embedding, const int64_t* selected_units,
+                      int su_ld, const int64_t* entity_num, float* logits, int64_t P, int E, int S, dsb_stream_t stream);
+int dsb_su_logits_bwd(const float* grad_logits, const float* hs, const float* kfull, int ld, const float* end_embedding,
+                      const int64_t* selected_units, int su_ld, const int64_t* entity_num, float* grad_hs, float* grad_kfull,
+                      float* grad_end_embedding, int64_t P, int E, int S, dsb_stream_t stream);
+
 /* ---- masked categorical sampling  (torch.multinomial(softmax(x),1) sites: head/action_type_head.py:57-58,
  *      head/action_arg_head.py:46-47,79-80,147-148,361-362,448-449) ----
  * index[r] = argmax_j softmax(logits[r])_j / q[r,j]  (first max wins), q ~ Exp(1) supplied by the caller so the

@@ -64,19 +64,23 @@ def test_expand_on_device_is_bit_exact(B, T, entities):
 
 @pytest.mark.gpu
 def test_learner_step_from_compact_batch_matches_padded():
-    from distar_b200.learner import RLLearner
+    """forward + loss + backward on the device-assembled batch equals the same on the padded batch (loss and the whole gradient
+    arena; compared before the optimiser: Adam's first step is sign-like, so fp32 reassociation noise on near-zero gradient
+    entries - split-K partial sums meet through the copy engine in arrival order - would be amplified to +-lr)."""
     from distar_b200.model import Model
     from distar_b200.params import init_state_dict
+    from distar_b200.rl_loss import ReinforcementLoss
     cfg = {'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': ['winloss']}}
     batch = synth_rl_batch(2, 3, seed=4, entity_num='random', max_su=6)
-    losses = []
+    m = Model(cfg, use_value_network=True, seed=0)
+    m.load_state_dict(init_state_dict(seed=3))
+    m = m.cuda()
+    res = []
     for use_compact in (False, True):
-        m = Model(cfg, use_value_network=True, seed=0)
-        m.load_state_dict(init_state_dict(seed=3))
-        learner = RLLearner(m.cuda(), 'MP0', lr=1e-3)
         data = expand_rl_batch(compact_rl_batch(batch), 'cuda') if use_compact else tree_map(lambda t: t.cuda(), _reference_view(batch))
-        info = learner._train(data)
-        losses.append((float(info['total_loss']), m.flat_param.clone()))
-    assert abs(losses[0][0] - losses[1][0]) <= 1e-6 * max(1.0, abs(losses[0][0]))
-    # (split-K partial sums meet through the copy engine in arrival order: two runs agree to fp32 reassociation, not bit for bit)
-    assert torch.allclose(losses[0][1], losses[1][1], rtol=1e-5, atol=1e-7)
+        m.zero_grad()
+        info = ReinforcementLoss(None, 'MP0').compute_loss(m.rl_learner_forward(**data))
+        info['total_loss'].backward()
+        res.append((float(info['total_loss']), m.flat_grad.clone()))
+    assert abs(res[0][0] - res[1][0]) <= 1e-6 * max(1.0, abs(res[0][0]))
+    assert (res[0][1] - res[1][1]).norm().item() <= 1e-4 * res[0][1].norm().item()

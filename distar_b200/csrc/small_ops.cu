@@ -161,6 +161,221 @@ target_unit_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ k
     }
 }
 
+// ---- LayerNorm over narrow rows (D = 32 * NPL <= 128): the 64-wide pre-LN transformer of the beginning-build-order encoder
+// (scalar_encoder.py:19-57, module_utils.py:130-151).  One warp per row.  Backward adds gamma / beta gradients with atomics.
+template <int NPL>
+__global__ void ln_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    float* __restrict__ y, float* __restrict__ stats, int64_t rows, float eps) {
+    constexpr int D = 32 * NPL;
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows) return;
+    float v[NPL], s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) { v[i] = x[r * D + i * 32 + lane]; s += v[i]; }
+    const float mean = dsb::warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) { const float d = v[i] - mean; q += d * d; }
+    const float rstd = rsqrtf(dsb::warp_sum(q) * (1.0f / D) + eps);
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) y[r * D + i * 32 + lane] = (v[i] - mean) * rstd * gamma[i * 32 + lane] + beta[i * 32 + lane];
+    if (lane == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
+}
+template <int NPL>
+__global__ void ln_small_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ gamma,
+                                    const float* __restrict__ stats, float* __restrict__ gx, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int64_t rows, int rows_per_warp) {
+    constexpr int D = 32 * NPL;
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float ag[NPL], ab[NPL];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+    for (int64_t r = w * rows_per_warp; r < (w + 1) * rows_per_warp && r < rows; ++r) {
+        const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+        float g[NPL], xh[NPL], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+            const float go = gy[r * D + i * 32 + lane];
+            xh[i] = (x[r * D + i * 32 + lane] - mean) * rstd;
+            ag[i] += go * xh[i];
+            ab[i] += go;
+            g[i] = go * gamma[i * 32 + lane];
+            s1 += g[i];
+            s2 += g[i] * xh[i];
+        }
+        s1 = dsb::warp_sum(s1) * (1.0f / D);
+        s2 = dsb::warp_sum(s2) * (1.0f / D);
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) gx[r * D + i * 32 + lane] = rstd * (g[i] - s1 - xh[i] * s2);
+    }
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) { atomicAdd(dgamma + i * 32 + lane, ag[i]); atomicAdd(dbeta + i * 32 + lane, ab[i]); }
+}
+
+// ---- unmasked multi-head self-attention over short sequences (S <= 32 tokens, head_dim <= 16): the 20-token transformer of
+// the beginning-build-order encoder (module_utils.py:88-111 with heads = 2, head_dim = 8).  qkv [B, S, 3 * H * HD] (q | k | v,
+// each head-major), out [B, S, H * HD].  One warp per (sequence, head); lane = query token; K and V of the head in shared memory.
+template <int HD>
+__global__ void attn_small_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, int64_t B, int S, int H) {
+    extern __shared__ float sm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    float* ks = sm + wib * 2 * 32 * HD;
+    float* vs = ks + 32 * HD;
+    if (w >= B * H) return;
+    const int64_t b = w / H;
+    const int h = (int)(w - b * H);
+    const int ld = 3 * H * HD;
+    const float scale = rsqrtf((float)HD);
+    float q[HD];
+    if (lane < S) {
+        const float* row = qkv + (b * S + lane) * ld;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) {
+            q[d] = row[h * HD + d];
+            ks[lane * HD + d] = row[H * HD + h * HD + d];
+            vs[lane * HD + d] = row[2 * H * HD + h * HD + d];
+        }
+    }
+    __syncwarp();
+    if (lane >= S) return;
+    float sc[32], mx = -CUDART_INF_F;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (j < S) {
+            float a = 0.f;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) a = fmaf(q[d], ks[j * HD + d], a);
+            sc[j] = a * scale;
+            mx = fmaxf(mx, sc[j]);
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (j < S) { sc[j] = __expf(sc[j] - mx); sum += sc[j]; }
+    const float inv = 1.0f / sum;
+    float o[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (j < S) {
+        const float pj = sc[j] * inv;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) o[d] = fmaf(pj, vs[j * HD + d], o[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < HD; ++d) out[(b * S + lane) * (H * HD) + h * HD + d] = o[d];
+}
+template <int HD>
+__global__ void attn_small_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ gout, float* __restrict__ gqkv,
+                                      int64_t B, int S, int H) {
+    extern __shared__ float sm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    float* ks = sm + wib * 2 * 32 * HD;
+    float* vs = ks + 32 * HD;
+    if (w >= B * H) return;
+    const int64_t b = w / H;
+    const int h = (int)(w - b * H);
+    const int ld = 3 * H * HD;
+    const float scale = rsqrtf((float)HD);
+    const bool live = lane < S;
+    float q[HD], go[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) { q[d] = 0.f; go[d] = 0.f; }
+    if (live) {
+        const float* row = qkv + (b * S + lane) * ld;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) {
+            q[d] = row[h * HD + d];
+            ks[lane * HD + d] = row[H * HD + h * HD + d];
+            vs[lane * HD + d] = row[2 * H * HD + h * HD + d];
+            go[d] = gout[(b * S + lane) * (H * HD) + h * HD + d];
+        }
+    }
+    __syncwarp();
+    float p[32], mx = -CUDART_INF_F, sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        p[j] = 0.f;
+        if (j < S) {
+            float a = 0.f;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) a = fmaf(q[d], ks[j * HD + d], a);
+            p[j] = a * scale;
+            mx = fmaxf(mx, p[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (j < S) { p[j] = __expf(p[j] - mx); sum += p[j]; }
+    const float inv = live ? 1.0f / sum : 0.f;
+    float dsum = 0.f, dp[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        dp[j] = 0.f;
+        if (j < S) {
+            p[j] *= inv;
+            float a = 0.f;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) a = fmaf(go[d], vs[j * HD + d], a);
+            dp[j] = a;
+            dsum = fmaf(p[j], a, dsum);
+        }
+    }
+    float dq[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) dq[d] = 0.f;
+    // per key j: ds_ij for this lane's query; dk_j / dv_j are sums over the queries (= lanes)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (j >= S) continue;                                   // (S is warp-uniform)
+        const float ds = live ? p[j] * (dp[j] - dsum) * scale : 0.f;
+        const float pj = live ? p[j] : 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) {
+            dq[d] = fmaf(ds, ks[j * HD + d], dq[d]);
+            const float dk = dsb::warp_sum(ds * q[d]);
+            const float dv = dsb::warp_sum(pj * go[d]);
+            if (lane == 0) {
+                gqkv[(b * S + j) * ld + H * HD + h * HD + d] = dk;
+                gqkv[(b * S + j) * ld + 2 * H * HD + h * HD + d] = dv;
+            }
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int d = 0; d < HD; ++d) gqkv[(b * S + lane) * ld + h * HD + d] = dq[d];
+    }
+}
+
+// ---- token features of the beginning-build-order encoder (scalar_encoder.py:33-45): one-hot(action, 174) | one-hot(position, 20) |
+// 10-bit binary x | 10-bit binary y of the build location, written as the EXACT bf16 A operand [B * 20, Kp] of the embedding GEMM
+__global__ void bo_tokens_kernel(const int16_t* __restrict__ order, const int16_t* __restrict__ loc, int spatial_x,
+                                 __nv_bfloat16* __restrict__ hi, int64_t B, int L, int A, int Kp) {
+    const int64_t total = B * L * Kp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t tok = i / Kp;
+        const int c = (int)(i - tok * Kp);
+        const int pos = (int)(tok % L);
+        float v = 0.f;
+        if (c < A) {
+            int a = order[tok];
+            a = a < 0 ? 0 : (a >= A ? A - 1 : a);
+            v = c == a ? 1.f : 0.f;
+        } else if (c < A + L) {
+            v = (c - A) == pos ? 1.f : 0.f;
+        } else if (c < A + L + 20) {
+            const int l = loc[tok];
+            const int bit = c - A - L;
+            const int val = bit < 10 ? l % spatial_x : l / spatial_x;
+            v = (float)((val >> (9 - (bit % 10))) & 1);
+        }
+        hi[i] = __float2bfloat16_rn(v);
+    }
+}
+
 inline unsigned grid_for(int64_t n) {
     int64_t blocks = (n + kThreads - 1) / kThreads;
     const int64_t cap = 148 * 16;
@@ -232,4 +447,66 @@ extern "C" int dsb_target_unit_bwd(const float* grad_logits, const float* key, i
     target_unit_bwd_kernel<<<(unsigned)P, kThreads, 0, (cudaStream_t)stream>>>(grad_logits, key, ldk, query, entity_num, grad_key,
                                                                              ldgk, grad_query, E, 1.0f / temperature);
     return dsb::check_launch("target_unit_bwd");
+}
+
+extern "C" int dsb_ln_small_supported(int D) { return (D == 32 || D == 64 || D == 96) ? 1 : 0; }
+
+extern "C" int dsb_ln_small_fwd(const float* x, const float* gamma, const float* beta, float* y, float* stats, int64_t rows, int D,
+                                float eps, dsb_stream_t stream) {
+    DSB_REQUIRE(x && gamma && beta && y && stats && rows >= 0 && dsb_ln_small_supported(D), "ln_small_fwd: bad argument (D %d)", D);
+    if (rows == 0) return DSB_OK;
+    const unsigned grid = (unsigned)((rows * 32 + kThreads - 1) / kThreads);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (D == 32) ln_small_fwd_kernel<1><<<grid, kThreads, 0, s>>>(x, gamma, beta, y, stats, rows, eps);
+    else if (D == 64) ln_small_fwd_kernel<2><<<grid, kThreads, 0, s>>>(x, gamma, beta, y, stats, rows, eps);
+    else ln_small_fwd_kernel<3><<<grid, kThreads, 0, s>>>(x, gamma, beta, y, stats, rows, eps);
+    return dsb::check_launch("ln_small_fwd");
+}
+extern "C" int dsb_ln_small_bwd(const float* gy, const float* x, const float* gamma, const float* stats, float* gx, float* dgamma,
+                                float* dbeta, int64_t rows, int D, dsb_stream_t stream) {
+    DSB_REQUIRE(gy && x && gamma && stats && gx && dgamma && dbeta && rows >= 0 && dsb_ln_small_supported(D),
+                "ln_small_bwd: bad argument (D %d)", D);
+    if (rows == 0) return DSB_OK;
+    const int64_t warps = rows < 148 * 32 ? rows : 148 * 32;
+    const int rpw = (int)((rows + warps - 1) / warps);
+    const unsigned grid = (unsigned)((warps * 32 + kThreads - 1) / kThreads);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (D == 32) ln_small_bwd_kernel<1><<<grid, kThreads, 0, s>>>(gy, x, gamma, stats, gx, dgamma, dbeta, rows, rpw);
+    else if (D == 64) ln_small_bwd_kernel<2><<<grid, kThreads, 0, s>>>(gy, x, gamma, stats, gx, dgamma, dbeta, rows, rpw);
+    else ln_small_bwd_kernel<3><<<grid, kThreads, 0, s>>>(gy, x, gamma, stats, gx, dgamma, dbeta, rows, rpw);
+    return dsb::check_launch("ln_small_bwd");
+}
+
+extern "C" int dsb_attn_small_fwd(const float* qkv, float* out, int64_t B, int S, int H, int HD, dsb_stream_t stream) {
+    DSB_REQUIRE(qkv && out && B >= 0 && S > 0 && S <= 32 && H > 0 && (HD == 8 || HD == 16), "attn_small_fwd: bad argument");
+    if (B == 0) return DSB_OK;
+    const int wpb = kThreads / 32;
+    const unsigned grid = (unsigned)((B * H + wpb - 1) / wpb);
+    const size_t smem = (size_t)wpb * 2 * 32 * HD * sizeof(float);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (HD == 8) attn_small_fwd_kernel<8><<<grid, kThreads, smem, s>>>(qkv, out, B, S, H);
+    else attn_small_fwd_kernel<16><<<grid, kThreads, smem, s>>>(qkv, out, B, S, H);
+    return dsb::check_launch("attn_small_fwd");
+}
+extern "C" int dsb_attn_small_bwd(const float* qkv, const float* grad_out, float* grad_qkv, int64_t B, int S, int H, int HD,
+                                  dsb_stream_t stream) {
+    DSB_REQUIRE(qkv && grad_out && grad_qkv && B >= 0 && S > 0 && S <= 32 && H > 0 && (HD == 8 || HD == 16), "attn_small_bwd: bad argument");
+    if (B == 0) return DSB_OK;
+    const int wpb = kThreads / 32;
+    const unsigned grid = (unsigned)((B * H + wpb - 1) / wpb);
+    const size_t smem = (size_t)wpb * 2 * 32 * HD * sizeof(float);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (HD == 8) attn_small_bwd_kernel<8><<<grid, kThreads, smem, s>>>(qkv, grad_out, grad_qkv, B, S, H);
+    else attn_small_bwd_kernel<16><<<grid, kThreads, smem, s>>>(qkv, grad_out, grad_qkv, B, S, H);
+    return dsb::check_launch("attn_small_bwd");
+}
+
+extern "C" int dsb_bo_tokens(const int16_t* beginning_order, const int16_t* bo_location, int spatial_x, void* hi, int64_t B, int L,
+                             int num_actions, int Kp, dsb_stream_t stream) {
+    DSB_REQUIRE(beginning_order && bo_location && hi && B >= 0 && L > 0 && spatial_x > 0 && Kp >= num_actions + L + 20,
+                "bo_tokens: bad argument");
+    if (B == 0) return DSB_OK;
+    bo_tokens_kernel<<<grid_for(B * L * Kp), kThreads, 0, (cudaStream_t)stream>>>(beginning_order, bo_location, spatial_x,
+                                                                                  (__nv_bfloat16*)hi, B, L, num_actions, Kp);
+    return dsb::check_launch("bo_tokens");
 }

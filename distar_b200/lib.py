@@ -65,6 +65,12 @@ _SIGNATURES = {
     'dsb_unpack_planes': (_i, [_vp] * 7 + [_i64, _vp]),
     'dsb_lstm_seq_fwd': (_i, [_vp] * 15 + [_i, _i, _i, _f, _vp]),
     'dsb_lstm_seq_bwd': (_i, [_vp] * 21 + [_i, _i, _i, _vp]),
+    'dsb_bo_tokens': (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _i, _vp]),
+    'dsb_ln_small_supported': (_i, [_i]),
+    'dsb_ln_small_fwd': (_i, [_vp] * 5 + [_i64, _i, _f, _vp]),
+    'dsb_ln_small_bwd': (_i, [_vp] * 7 + [_i64, _i, _vp]),
+    'dsb_attn_small_fwd': (_i, [_vp, _vp, _i64, _i, _i, _i, _vp]),
+    'dsb_attn_small_bwd': (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp]),
     'dsb_pack_pair': (_i, [_vp, _i, _i64, _i, _i64, _vp, _vp, _i, _vp]),
     'dsb_glu_gate_fwd': (_i, [_vp, _vp, _vp, _i64, _vp]),
     'dsb_glu_gate_bwd': (_i, [_vp] * 5 + [_i64, _vp]),

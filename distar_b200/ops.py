@@ -1343,8 +1343,79 @@ def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, residu
     if _use_kernel(x) and lib.load().dsb_layernorm_supported(D):
         y, hi, lo = _LayerNorm.apply(x.float(), residual, weight, bias, want_split)
         return attach_split(y, hi, lo) if want_split else y
+    if x.is_cuda and residual is None and not want_split and lib.load().dsb_ln_small_supported(D):
+        return _LayerNormSmall.apply(x.float(), weight, bias)
     s = x if residual is None else x + residual
     return F.layer_norm(s, (D,), weight, bias, 1e-5)
+
+
+class _LayerNormSmall(torch.autograd.Function):
+    """LayerNorm over narrow rows (D = 32 / 64 / 96): the beginning-build-order transformer (csrc/small_ops.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D).contiguous()
+        y = torch.empty_like(x2)
+        stats = torch.empty((x2.shape[0], 2), dtype=torch.float32, device=x.device)
+        lib.call('dsb_ln_small_fwd', x2, weight, bias, y, stats, x2.shape[0], D, 1e-5)
+        ctx.save_for_backward(x2, weight, stats)
+        ctx.refs, ctx.shape = (weight, bias), x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, weight, stats = ctx.saved_tensors
+        rows, D = x2.shape
+        gx = torch.empty_like(x2)
+        gslot, bslot = _grad_slot(ctx.refs[0]), _grad_slot(ctx.refs[1])
+        direct = gslot is not None and bslot is not None
+        dg = gslot if direct else torch.zeros(D, dtype=torch.float32, device=x2.device)
+        db = bslot if direct else torch.zeros(D, dtype=torch.float32, device=x2.device)
+        lib.call('dsb_ln_small_bwd', gy.reshape(rows, D).contiguous(), x2, weight, stats, gx, dg, db, rows, D)
+        return gx.view(ctx.shape), (None if direct else dg), (None if direct else db)
+
+
+class _AttnSmall(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, heads, hd):
+        B, S, _ = qkv.shape
+        qkv = qkv.contiguous()
+        out = torch.empty((B, S, heads * hd), dtype=torch.float32, device=qkv.device)
+        lib.call('dsb_attn_small_fwd', qkv, out, B, S, heads, hd)
+        ctx.save_for_backward(qkv)
+        ctx.meta = (heads, hd)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        (qkv,) = ctx.saved_tensors
+        heads, hd = ctx.meta
+        B, S, _ = qkv.shape
+        g = torch.empty_like(qkv)
+        lib.call('dsb_attn_small_bwd', qkv, go.contiguous(), g, B, S, heads, hd)
+        return g, None, None
+
+
+def small_attention(qkv: torch.Tensor, heads: int, hd: int) -> torch.Tensor:
+    """Unmasked multi-head self-attention over short sequences (module_utils.py:88-111 at S = 20, 2 heads of 8: the
+    beginning-build-order transformer): qkv [B, S, 3 * heads * hd] -> [B, S, heads * hd], one warp per (sequence, head)."""
+    B, S, _ = qkv.shape
+    if _use_kernel(qkv) and S <= 32 and hd in (8, 16):
+        return _AttnSmall.apply(qkv.float(), heads, hd)
+    q, k, v = qkv.view(B, S, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    p = torch.softmax(torch.matmul(q, k.transpose(2, 3)) / math.sqrt(hd), dim=-1)
+    return torch.matmul(p, v).permute(0, 2, 1, 3).reshape(B, S, heads * hd)
+
+
+def bo_tokens(order: torch.Tensor, location: torch.Tensor, spatial_x: int, num_actions: int = 174, Kp: int = 256) -> torch.Tensor:
+    """Token features of the beginning-build-order encoder (scalar_encoder.py:33-45) as the exact bf16 operand
+    [B * 20, Kp] of its embedding GEMM (every feature is 0 / 1)."""
+    B, L = order.shape
+    hi = torch.empty((B * L, Kp), dtype=torch.bfloat16, device=order.device)
+    lib.call('dsb_bo_tokens', order.to(torch.int16).contiguous(), location.to(torch.int16).contiguous(), spatial_x, hi, B, L,
+             num_actions, Kp)
+    return hi
 
 
 class _LstmCell(torch.autograd.Function):

@@ -117,6 +117,8 @@ class Net:
     def attention(self, pre: str, x: Tensor, key_mask: Optional[Tensor], heads: int, hd: int) -> Tensor:
         """module_utils.py:88-111."""
         B, N, _ = x.shape
+        if key_mask is None and x.is_cuda:          # the 20-token beginning-build-order transformer: one warp per (row, head)
+            return self.fc(pre + '.project', ops.small_attention(self.fc(pre + '.attention_pre', x), heads, hd))
         q, k, v = self.fc(pre + '.attention_pre', x).view(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
         score = torch.matmul(q, k.transpose(2, 3)) / math.sqrt(hd)
         if key_mask is not None:
@@ -124,9 +126,10 @@ class Net:
         a = torch.matmul(torch.softmax(score, dim=-1), v).permute(0, 2, 1, 3).reshape(B, N, heads * hd)
         return self.fc(pre + '.project', a)
 
-    def transformer(self, pre: str, x: Tensor, key_mask, heads: int, hd: int, post_ln: bool) -> Tensor:
-        """module_utils.py:130-151,191-199."""
-        x = self.fc(pre + '.embedding', x, relu=True)
+    def transformer(self, pre: str, x: Tensor, key_mask, heads: int, hd: int, post_ln: bool, embedded: bool = False) -> Tensor:
+        """module_utils.py:130-151,191-199.  embedded: x already went through the embedding layer."""
+        if not embedded:
+            x = self.fc(pre + '.embedding', x, relu=True)
         for i in range(3):
             lp = '%s.layers.%d' % (pre, i)
             if post_ln:
@@ -154,6 +157,20 @@ class Net:
                 e = self.fc(pre + name, x if x.is_cuda else x.float(), relu=True,
                             exact=x.dtype in (torch.uint8, torch.int8, torch.int16))
             else:
+                if s['beginning_order'].is_cuda:
+                    # token features straight into the embedding GEMM's exact bf16 operand (all of them are 0 / 1)
+                    bo = s['beginning_order']
+                    tp = pre + 'beginning_order.transformer'
+                    hi = ops.bo_tokens(bo, s['bo_location'], self.W)
+                    w = P[tp + '.embedding.0.weight']
+                    x0 = ops.linear_presplit(hi, None, F.pad(w, (0, hi.shape[1] - w.shape[1])), P[tp + '.embedding.0.bias'], True,
+                                             self.terms).view(bo.shape[0], bo.shape[1], -1)
+                    t = self.transformer(tp, x0, None, 2, 8, post_ln=False, embedded=True)
+                    e = self.fc(pre + 'beginning_order.embedd_fc', t.mean(dim=1), relu=True)
+                    outs.append(e)
+                    ctx.append(e)
+                    base.append(e)
+                    continue
                 bo, loc = s['beginning_order'].long(), s['bo_location'].long()
                 B = bo.shape[0]
                 bits = torch.arange(9, -1, -1, device=dev)

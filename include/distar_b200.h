@@ -243,6 +243,24 @@ int dsb_target_unit_fwd(const float* key, int ldk, const float* query, const int
 int dsb_target_unit_bwd(const float* grad_logits, const float* key, int ldk, const float* query, const int64_t* entity_num,
                         float* grad_key, int ldgk, float* grad_query, int64_t P, int E, float temperature, dsb_stream_t stream);
 
+/* ---- beginning-build-order encoder pieces  (BeginningBuildOrderEncoder, obs_encoder/scalar_encoder.py:19-57: a 3-layer
+ *      pre-LN transformer over 20 tokens of width 64, 2 heads of 8) ----
+ * dsb_bo_tokens: token features one-hot(action, num_actions) | one-hot(position, L) | 10-bit x | 10-bit y of bo_location
+ *   (MSB first, x = loc % spatial_x, y = loc / spatial_x) written as the exact bf16 A operand hi [B * L, Kp] of the embedding GEMM.
+ * dsb_ln_small_*: LayerNorm over rows of D = 32 / 64 / 96 (one warp per row); backward ADDS dgamma / dbeta.
+ * dsb_attn_small_*: unmasked softmax(Q K^T / sqrt(HD)) V for S <= 32 tokens, HD = 8 or 16; qkv [B, S, 3 * H * HD] (q | k | v,
+ *   head-major), out [B, S, H * HD]; one warp per (sequence, head); the backward recomputes the probabilities. */
+int dsb_bo_tokens(const int16_t* beginning_order, const int16_t* bo_location, int spatial_x, void* hi, int64_t B, int L,
+                  int num_actions, int Kp, dsb_stream_t stream);
+int dsb_ln_small_supported(int D);
+int dsb_ln_small_fwd(const float* x, const float* gamma, const float* beta, float* y, float* stats, int64_t rows, int D, float eps,
+                     dsb_stream_t stream);
+int dsb_ln_small_bwd(const float* gy, const float* x, const float* gamma, const float* stats, float* gx, float* dgamma,
+                     float* dbeta, int64_t rows, int D, dsb_stream_t stream);
+int dsb_attn_small_fwd(const float* qkv, float* out, int64_t B, int S, int H, int HD, dsb_stream_t stream);
+int dsb_attn_small_bwd(const float* qkv, const float* grad_out, float* grad_qkv, int64_t B, int S, int H, int HD,
+                       dsb_stream_t stream);
+
 /* ---- tcgen05 GEMM family  (fc_block nn_module.py:231-270; attention module_utils.py:88-111; their backward) ----
  * dsb_gemm_bf16_split:  C[M,N] = act( A[M,K] . W[N,K]^T + bias[N] ),  A and W as bf16 (hi, lo) pairs, K contiguous,
  * K % 64 == 0, N % 128 == 0, M arbitrary.  terms = 1: hi*hi only (plain bf16); terms = 3: hi*hi + hi*lo + lo*hi

@@ -606,3 +606,130 @@ def test_target_unit_logits_fwd_bwd(P, E, ld, col):
     assert torch.equal(out.cpu() < -1e8, ~valid)
     assert torch.allclose(kd.grad.cpu(), kr.grad, rtol=1e-5, atol=1e-5)
     assert torch.allclose(qd.grad.cpu(), qr.grad, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize('rows,D', [(1000, 64), (37, 32), (5, 96), (84480, 64)])
+def test_layernorm_small_fwd_bwd(rows, D):
+    g = torch.Generator().manual_seed(rows + D)
+    x, go = torch.randn(rows, D, generator=g), torch.randn(rows, D, generator=g)
+    w, b = 1 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g)
+    xr, wr, br = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    F.layer_norm(xr, (D,), wr, br, 1e-5).backward(go.double())
+    xd, wd, bd = x.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    y = ops.layer_norm(xd, wd, bd)
+    y.backward(go.to(DEV))
+    assert torch.allclose(y.detach().cpu().double(), F.layer_norm(x.double(), (D,), w.double(), b.double(), 1e-5), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(xd.grad.cpu().double(), xr.grad, rtol=1e-4, atol=1e-5)
+    assert (wd.grad.cpu().double() - wr.grad).abs().max().item() <= 1e-4 * wr.grad.abs().max().item()
+    assert (bd.grad.cpu().double() - br.grad).abs().max().item() <= 1e-4 * br.grad.abs().max().item()
+
+
+@pytest.mark.parametrize('B,S,H,hd', [(50, 20, 2, 8), (3, 32, 2, 8), (7, 5, 1, 16)])
+def test_small_attention_fwd_bwd(B, S, H, hd):
+    g = torch.Generator().manual_seed(B + S)
+    qkv, go = torch.randn(B, S, 3 * H * hd, generator=g), torch.randn(B, S, H * hd, generator=g)
+    qr = qkv.double().requires_grad_(True)
+    q, k, v = qr.view(B, S, 3, H, hd).permute(2, 0, 3, 1, 4)
+    ref = torch.matmul(torch.softmax(torch.matmul(q, k.transpose(2, 3)) / math.sqrt(hd), dim=-1), v).permute(0, 2, 1, 3).reshape(B, S, H * hd)
+    ref.backward(go.double())
+    qd = qkv.to(DEV).requires_grad_(True)
+    out = ops.small_attention(qd, H, hd)
+    out.backward(go.to(DEV))
+    assert torch.allclose(out.detach().cpu().double(), ref.detach(), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(qd.grad.cpu().double(), qr.grad, rtol=1e-3, atol=1e-5)
+
+
+def test_bo_tokens_match_reference_features():
+    g = torch.Generator().manual_seed(2)
+    B, L, W = 9, 20, 128
+    bo = torch.randint(0, 174, (B, L), generator=g).to(torch.int16)
+    loc = torch.randint(0, W * W, (B, L), generator=g).to(torch.int16)
+    bits = torch.arange(9, -1, -1)
+    want = torch.cat([F.one_hot(bo.long(), 174).float(), torch.eye(L).unsqueeze(0).expand(B, -1, -1),
+                      (((loc.long() % W).unsqueeze(-1) >> bits) & 1).float(), (((loc.long() // W).unsqueeze(-1) >> bits) & 1).float()], dim=2)
+    hi = ops.bo_tokens(bo.to(DEV), loc.to(DEV), W)
+    assert hi.shape == (B * L, 256)
+    assert torch.equal(hi.float().cpu()[:, :214], want.reshape(B * L, 214)) and float(hi.float()[:, 214:].abs().sum()) == 0
+
+
+def test_pointer_training_kernels_match_torch_formulation():
+    """su_prefix_mean / su_lstm / su_logits (csrc/su_train.cu) against the one-hot / cummax formulation of round 1, including
+    repeated labels, rows without a selection and the shared key-gradient buffer."""
+    g = torch.Generator().manual_seed(11)
+    P, E, S = 7, 512, 6
+    en = torch.tensor([512, 40, 300, 5, 64, 512, 9])
+    num = torch.tensor([6, 3, 0, 2, 5, 4, 3])
+    su = torch.zeros(P, 64, dtype=torch.long)
+    for p in range(P):
+        k = int(num[p])
+        if k:
+            units = torch.randperm(int(en[p]), generator=g)[:k - 1]
+            su[p, :k - 1] = units
+            su[p, k - 1] = en[p]
+    su[4, 2] = su[4, 0]                                           # a repeated label
+    kfull = torch.randn(P, E, 64, generator=g)
+    end = torch.randn(1, 32, generator=g)
+    hs = torch.randn(P, S, 32, generator=g)
+    gm, gl = torch.randn(P, S, 32, generator=g), torch.randn(P, S, E + 1, generator=g)
+    # ---- torch formulation (policy_net CPU path)
+    kr, er, hr = kfull.clone().requires_grad_(True), end.clone().requires_grad_(True), hs.clone().requires_grad_(True)
+    slot = torch.arange(E + 1).unsqueeze(0)
+    key = torch.where((slot == en.unsqueeze(1)).unsqueeze(-1), er.view(1, 1, -1), F.pad(kr[..., :32], (0, 0, 0, 1)))
+    valid = slot < (en + 1).unsqueeze(1)
+    sus = su[:, :S]
+    onehot = sus.unsqueeze(-1) == slot.unsqueeze(1)
+    ended = torch.cummax((sus == en.unsqueeze(1)).long(), dim=1)[0].bool()
+    picked = torch.cummax((onehot & ~ended.unsqueeze(-1)).long(), dim=1)[0].float()
+    ssum = torch.matmul(picked, key)
+    mean_ref = torch.where((num != 0).view(P, 1, 1), ssum / picked.sum(-1, keepdim=True), ssum)
+    chosen = torch.cummax(onehot.long(), dim=1)[0].bool()
+    chosen = torch.cat([torch.zeros_like(chosen[:, :1]), chosen[:, :-1]], dim=1)
+    mask = valid.unsqueeze(1) & ~chosen
+    mask[:, 0] = valid & (slot != en.unsqueeze(1))
+    logits_ref = torch.matmul(hr, key.transpose(1, 2)).masked_fill(~mask, -1e9)
+    fin = torch.isfinite(mean_ref)
+    ((mean_ref * gm)[fin].sum() + (logits_ref * gl * mask).sum()).backward()
+    # ---- kernels
+    kd, ed, hd_ = kfull.to(DEV).requires_grad_(True), end.to(DEV).requires_grad_(True), hs.to(DEV).requires_grad_(True)
+    kf, sink = ops.fork_keys(kd)
+    mean = ops.su_prefix_mean(kf, su.to(DEV), en.to(DEV), num.to(DEV), S, sink)
+    logits = ops.su_logits(hd_, kf, ed, su.to(DEV), en.to(DEV), sink)
+    assert torch.equal(torch.isfinite(mean).cpu(), fin)
+    assert torch.allclose(mean.detach().cpu()[fin], mean_ref.detach()[fin], rtol=1e-5, atol=1e-6)
+    assert torch.equal(logits.detach().cpu() < -1e8, ~mask)
+    assert torch.allclose(logits.detach().cpu()[mask], logits_ref.detach()[mask], rtol=1e-5, atol=1e-4)
+    ((mean * gm.to(DEV))[fin.to(DEV)].sum() + (logits * gl.to(DEV) * mask.to(DEV)).sum()).backward()
+    assert torch.allclose(kd.grad.cpu(), kr.grad, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(ed.grad.cpu(), er.grad, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(hd_.grad.cpu(), hr.grad, rtol=1e-4, atol=1e-4)
+    # ---- the 32-wide LN-LSTM against a loop of the fused cell
+    ig = torch.randn(P, S, 128, generator=g)
+    w = torch.randn(128, 32, generator=g) / 6
+    gh, bh = 1 + 0.1 * torch.randn(128, generator=g), 0.1 * torch.randn(128, generator=g)
+    gc, bc = 1 + 0.1 * torch.randn(32, generator=g), 0.1 * torch.randn(32, generator=g)
+    go = torch.randn(P, S, 32, generator=g)
+
+    def run(kernel):
+        leaves = [t.clone().double().requires_grad_(True) if not kernel else t.to(DEV).requires_grad_(True) for t in (ig, w, gh, bh, gc, bc)]
+        a_ig, a_w, a_gh, a_bh, a_gc, a_bc = leaves
+        if kernel:
+            out = ops.su_lstm(a_ig, a_w, a_gh, a_bh, a_gc, a_bc)
+            out.backward(go.to(DEV))
+        else:
+            h = torch.zeros(P, 32, dtype=torch.double)
+            c = torch.zeros(P, 32, dtype=torch.double)
+            ys = []
+            for i in range(S):
+                gates = a_ig[:, i] + F.layer_norm(h @ a_w.t(), (128,), a_gh, a_bh, 1e-5)
+                gi, gf, gg, g_o = gates.chunk(4, 1)
+                c = F.layer_norm(torch.sigmoid(gf) * c + torch.sigmoid(gi) * torch.tanh(gg), (32,), a_gc, a_bc, 1e-5)
+                h = torch.sigmoid(g_o) * torch.tanh(c)
+                ys.append(h)
+            out = torch.stack(ys, dim=1)
+            out.backward(go.double())
+        return out.detach().cpu().double(), [t.grad.cpu().double() for t in leaves]
+    oa, ga = run(True)
+    ob, gb = run(False)
+    assert torch.allclose(oa, ob, rtol=1e-4, atol=1e-5)
+    for a, b, n in zip(ga, gb, ['ig', 'w_hh', 'gam_h', 'bet_h', 'gam_c', 'bet_c']):
+        assert (a - b).abs().max().item() <= 2e-4 * max(b.abs().max().item(), 1e-6), n

@@ -3,7 +3,7 @@
 // Replaces, for the training/inference path, the chain  scatter_connection (module_utils.py:11-34) -> 6 one-hot
 // embeddings + 6 effect-index scatters + cat (spatial_encoder.py:51-71) -> project conv + ReLU (:72) -> first
 // max_pool2d (:75-79).  The 56-channel fp32 input (3.7 MB / obs) and the 2 MiB scatter map are never materialised:
-//   pre[p, o] = b[o] + W[o,0] * height/256 + sum_k W[o, base_k + plane_k[p]]        (one-hot planes are LUT adds)
+//   pre[p, o] = b[o] + W[o,0] * height/256 + sum_k W[o, base_k + plane_k[p]]        (one-hot planes: ONE combined-table lookup)
 //             + sum_j [p in effect_j] W[o, 18+j]                                     (zero padding makes pixel 0 always set)
 //             + sum_{entities e at p} sum_c W[o, 24+c] * project[e, c]               (the scatter, pushed through the conv)
 //   out[pooled p, o] = max over the 2x2 window of relu(pre)
@@ -27,6 +27,14 @@ constexpr int kEffLen = 100;
 
 __device__ __constant__ int kPlaneBase[kPlanes] = {0, 1, 5, 7, 12, 14, 16};
 __device__ __constant__ int kPlaneVocab[kPlanes] = {0, 4, 2, 5, 2, 2, 2};
+// The six categorical planes of a pixel select one of 4*2*5*2*2*2 = 320 combinations; the sum of their six weight columns is
+// looked up in ONE table row (lut [320][32], rebuilt from the current weights by stem_lut_kernel at every launch) instead of six
+// shared-memory lookups + adds per pixel and lane: the stem is instruction-issue bound (ncu: 66 % issue-slot utilisation,
+// 129 warp instructions per pixel before this change), not bandwidth bound.
+constexpr int kCombos = 320;
+__host__ __device__ constexpr int combo_stride(int k) {   // k = 1..6 -> multiplier of plane k's digit
+    return k == 1 ? 1 : (k == 2 ? 4 : (k == 3 ? 8 : (k == 4 ? 40 : (k == 5 ? 80 : 160))));
+}
 __host__ __device__ constexpr int vocab_c(int k) { return k == 1 ? 4 : (k == 3 ? 5 : (k == 0 ? 0 : 2)); }   // compile-time vocab
 
 struct StemArgs {
@@ -38,6 +46,7 @@ struct StemArgs {
     const int64_t* entity_num;
     const float* weight;                // [32, 56]
     const float* bias;                  // [32]
+    const float* lut;                   // [320, 32] combined categorical table (workspace, written by stem_lut_kernel)
     int N, E, H, W;
 };
 
@@ -45,8 +54,9 @@ struct Smem {
     float* pre;        // [npix][32]
     float* wt;         // [56][32]  (transposed weight)
     float* wo;         // [32][56]  (original layout, for the d_project product)
-    uint8_t* pl;       // [7][npix]
-    uint32_t* eff;     // [6][npix/32]
+    uint16_t* cidx;    // [npix] combined index of the six categorical planes
+    uint8_t* hgt;      // [npix] height_map
+    uint32_t* eff;     // [npix/4] one byte per pixel: bit j = pixel is in effect list j
     uint32_t* list;    // [E] (e << 16) | pix
     int* counters;     // [kWarps + 1]
 };
@@ -56,15 +66,16 @@ __device__ __forceinline__ Smem carve(unsigned char* raw, int npix, int E) {
     s.pre = reinterpret_cast<float*>(raw);
     s.wt = s.pre + npix * kOC;
     s.wo = s.wt + kIC * kOC;
-    s.pl = reinterpret_cast<uint8_t*>(s.wo + kIC * kOC);
-    s.eff = reinterpret_cast<uint32_t*>(s.pl + kPlanes * npix);
-    s.list = s.eff + kEffects * (npix / 32);
+    s.cidx = reinterpret_cast<uint16_t*>(s.wo + kIC * kOC);
+    s.hgt = reinterpret_cast<uint8_t*>(s.cidx + npix);
+    s.eff = reinterpret_cast<uint32_t*>(s.hgt + npix);
+    s.list = s.eff + npix / 4;
     s.counters = reinterpret_cast<int*>(s.list + E);
     return s;
 }
 
 __host__ __device__ inline size_t stem_smem_bytes(int npix, int E) {
-    return (size_t)npix * kOC * 4 + (size_t)2 * kIC * kOC * 4 + (size_t)kPlanes * npix + (size_t)kEffects * (npix / 32) * 4 +
+    return (size_t)npix * kOC * 4 + (size_t)2 * kIC * kOC * 4 + (size_t)npix * 2 + (size_t)npix + (size_t)npix +
            (size_t)E * 4 + (kWarps + 1) * 4;
 }
 
@@ -73,12 +84,19 @@ __host__ __device__ inline size_t stem_smem_bytes(int npix, int E) {
 __device__ __forceinline__ int build_pre_tile(const StemArgs& a, const Smem& s, int n, int y0) {
     const int W = a.W, H = a.H, E = a.E, npix = kRows * W;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // stage the category planes of this tile and clear the effect bitmaps
-    for (int k = 0; k < kPlanes; ++k) {
-        const uint8_t* src = a.planes[k] + ((size_t)n * H + y0) * W;
-        for (int i = tid; i < npix; i += kThreads) s.pl[k * npix + i] = src[i];
+    // stage this tile: the six categorical planes collapse into one combined index per pixel (ids clamped into their
+    // vocabulary as before), the height byte is kept, the effect bytes are cleared
+    {
+        const size_t base = ((size_t)n * H + y0) * W;
+        for (int i = tid; i < npix; i += kThreads) {
+            int c = 0;
+#pragma unroll
+            for (int k = 1; k < kPlanes; ++k) c += min((int)a.planes[k][base + i], vocab_c(k) - 1) * combo_stride(k);
+            s.cidx[i] = (uint16_t)c;
+            s.hgt[i] = a.planes[0][base + i];
+        }
     }
-    for (int i = tid; i < kEffects * (npix / 32); i += kThreads) s.eff[i] = 0u;
+    for (int i = tid; i < npix / 4; i += kThreads) s.eff[i] = 0u;
     if (tid == 0) s.counters[kWarps] = 0;
     __syncthreads();
     // effect lists: every entry (including the zero padding) lights its pixel
@@ -86,7 +104,7 @@ __device__ __forceinline__ int build_pre_tile(const StemArgs& a, const Smem& s, 
         const int j = i / kEffLen;
         const int idx = (int)a.effects[j][(size_t)n * kEffLen + (i - j * kEffLen)];
         const int p = idx - y0 * W;
-        if (p >= 0 && p < npix) atomicOr(&s.eff[j * (npix / 32) + (p >> 5)], 1u << (p & 31));
+        if (p >= 0 && p < npix) atomicOr(&s.eff[p >> 2], 1u << ((p & 3) * 8 + j));
     }
     // ordered list of the entities inside this tile (same ballot compaction as scatter_connection)
     const int en = a.entity_num ? min((int)a.entity_num[n], E) : E;
@@ -112,17 +130,16 @@ __device__ __forceinline__ int build_pre_tile(const StemArgs& a, const Smem& s, 
         __syncthreads();
     }
     // dense part: lane = output channel, each warp walks its pixels
-    const float b = a.bias[lane];
+    const float b = a.bias[lane], wh = s.wt[lane] * (1.0f / 256.0f);
+    const uint8_t* effb = reinterpret_cast<const uint8_t*>(s.eff);
     for (int p = warp; p < npix; p += kWarps) {
-        float v = b + s.wt[lane] * ((float)s.pl[p] * (1.0f / 256.0f));
-#pragma unroll
-        for (int k = 1; k < kPlanes; ++k) {
-            const int idx = min((int)s.pl[k * npix + p], kPlaneVocab[k] - 1);
-            v += s.wt[(kPlaneBase[k] + idx) * kOC + lane];
+        float v = fmaf(wh, (float)s.hgt[p], b) + __ldg(a.lut + (int)s.cidx[p] * kOC + lane);
+        unsigned e = effb[p];                                  // almost always 0: <= 600 list entries per observation
+        while (e) {
+            const int j = __ffs(e) - 1;
+            v += s.wt[(18 + j) * kOC + lane];
+            e &= e - 1;
         }
-#pragma unroll
-        for (int j = 0; j < kEffects; ++j)
-            if ((s.eff[j * (npix / 32) + (p >> 5)] >> (p & 31)) & 1u) v += s.wt[(18 + j) * kOC + lane];
         s.pre[p * kOC + lane] = v;
     }
     __syncthreads();
@@ -202,7 +219,11 @@ stem_bwd_kernel(const StemArgs a, const float* __restrict__ gout, int out_c, flo
     for (int tile = blockIdx.x; tile < a.N * bands; tile += gridDim.x) {
         const int n = tile / bands, y0 = (tile - n * bands) * kRows;
         const int len = build_pre_tile(a, s, n, y0);
-        // route dOut through max-pool (first maximum in window scan order) and ReLU; overwrite pre with dpre
+        // route dOut through max-pool (first maximum in window scan order) and ReLU; overwrite pre with dpre.  Only the winning
+        // pixel of a window receives a gradient, so the parameter gradients of the dense part are accumulated right here, once
+        // per POOLED pixel and lane (25 register accumulators: bias, height, 17 one-hot columns, 6 effect planes; predicated adds,
+        // no atomics) instead of in a second pass over all 4x as many input pixels.
+        const uint8_t* effb = reinterpret_cast<const uint8_t*>(s.eff);
         for (int pp = warp; pp < (kRows / 2) * PW; pp += kWarps) {
             const int py = pp / PW, px = pp - py * PW;
             const int p00 = (2 * py) * W + 2 * px;
@@ -217,27 +238,26 @@ stem_bwd_kernel(const StemArgs a, const float* __restrict__ gout, int out_c, flo
             const float g = (best > 0.f) ? gout[((((size_t)n * PH + y0 / 2 + py) * PW + px) * out_c) + lane] : 0.f;
 #pragma unroll
             for (int k = 0; k < 4; ++k) s.pre[cand[k] * kOC + lane] = (k == bi) ? g : 0.f;
-        }
-        __syncthreads();
-        // parameter gradients of the dense part: 25 register accumulators per lane (bias, height, 17 one-hot columns,
-        // 6 effect planes) selected with predicated adds — no atomics in the per-pixel loop
-        for (int p = warp; p < npix; p += kWarps) {
-            const float d = s.pre[p * kOC + lane];
-            if (__ballot_sync(0xffffffffu, d != 0.f) == 0u) continue;
-            racc[0] += d;
-            racc[1] += d * ((float)s.pl[p] * (1.0f / 256.0f));
-            int slot = 2;
+            if (__ballot_sync(0xffffffffu, g != 0.f) == 0u) continue;
+            const int pw = p00 + (bi & 1) + (bi >> 1) * W;           // this lane's winning pixel
+            racc[0] += g;
+            racc[1] += g * ((float)s.hgt[pw] * (1.0f / 256.0f));
+            int slot = 2, c = (int)s.cidx[pw];
 #pragma unroll
             for (int k = 1; k < kPlanes; ++k) {
-                const int idx = min((int)s.pl[k * npix + p], vocab_c(k) - 1);
+                const int idx = c % vocab_c(k);                     // digits of the combined index, least significant plane first
+                c /= vocab_c(k);
 #pragma unroll
-                for (int v = 0; v < vocab_c(k); ++v) racc[slot + v] += (idx == v) ? d : 0.f;
+                for (int v = 0; v < vocab_c(k); ++v) racc[slot + v] += (idx == v) ? g : 0.f;
                 slot += vocab_c(k);
             }
+            const unsigned e = effb[pw];
+            if (__ballot_sync(0xffffffffu, e != 0u) != 0u) {
 #pragma unroll
-            for (int j = 0; j < kEffects; ++j)
-                racc[19 + j] += ((s.eff[j * (npix / 32) + (p >> 5)] >> (p & 31)) & 1u) ? d : 0.f;
+                for (int j = 0; j < kEffects; ++j) racc[19 + j] += ((e >> j) & 1u) ? g : 0.f;
+            }
         }
+        __syncthreads();
         // entities: d_project[e, c] = sum_o W[o, 24+c] dpre[pix, o];  dW[o, 24+c] += dpre[pix, o] * project[e, c]
         const float* prow = a.project + (size_t)n * a.E * kOC;
         for (int i = warp; i < len; i += kWarps) {
@@ -270,16 +290,36 @@ stem_bwd_kernel(const StemArgs a, const float* __restrict__ gout, int out_c, flo
     if (threadIdx.x < kOC) atomicAdd(&gbias[threadIdx.x], gw[kIC * kOC + threadIdx.x]);
 }
 
+// lut[combo][o] = sum over the six categorical planes of W[o, base_k + digit_k(combo)]
+__global__ void stem_lut_kernel(const float* __restrict__ weight, float* __restrict__ lut) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kCombos * kOC) return;
+    const int o = i % kOC;
+    int c = i / kOC;
+    float v = 0.f;
+#pragma unroll
+    for (int k = 1; k < kPlanes; ++k) {
+        const int digit = c % vocab_c(k);
+        c /= vocab_c(k);
+        v += weight[o * kIC + kPlaneBase[k] + digit];
+    }
+    lut[i] = v;
+}
+
 int fill_args(StemArgs& a, const void* const* planes, const void* const* effects, const float* project,
               const uint8_t* ex, const uint8_t* ey, const int64_t* entity_num, const float* weight, const float* bias,
-              int N, int E, int H, int W) {
-    DSB_REQUIRE(planes && effects && project && ex && ey && weight && bias, "spatial_stem: null pointer");
+              float* lut, int N, int E, int H, int W, cudaStream_t stream) {
+    DSB_REQUIRE(planes && effects && project && ex && ey && weight && bias && lut, "spatial_stem: null pointer");
     DSB_REQUIRE(N >= 0 && E > 0 && E <= 65535 && H % kRows == 0 && W % 32 == 0 && W % 2 == 0 && kRows * W <= 65535,
                 "spatial_stem: need H %% %d == 0 and W %% 32 == 0 (H=%d W=%d)", kRows, H, W);
     for (int k = 0; k < kPlanes; ++k) { DSB_REQUIRE(planes[k], "spatial_stem: null plane"); a.planes[k] = (const uint8_t*)planes[k]; }
     for (int j = 0; j < kEffects; ++j) { DSB_REQUIRE(effects[j], "spatial_stem: null effect list"); a.effects[j] = (const int16_t*)effects[j]; }
-    a.project = project; a.ex = ex; a.ey = ey; a.entity_num = entity_num; a.weight = weight; a.bias = bias;
+    a.project = project; a.ex = ex; a.ey = ey; a.entity_num = entity_num; a.weight = weight; a.bias = bias; a.lut = lut;
     a.N = N; a.E = E; a.H = H; a.W = W;
+    if (N > 0) {
+        stem_lut_kernel<<<(kCombos * kOC + 255) / 256, 256, 0, stream>>>(weight, lut);
+        return dsb::check_launch("spatial_stem_lut");
+    }
     return DSB_OK;
 }
 
@@ -287,10 +327,11 @@ int fill_args(StemArgs& a, const void* const* planes, const void* const* effects
 
 extern "C" int dsb_spatial_stem_fwd(const void* const* planes, const void* const* effects, const float* project,
                                     const uint8_t* ex, const uint8_t* ey, const int64_t* entity_num, const float* weight,
-                                    const float* bias, float* out, void* out_hi, void* out_lo, int out_c, int N, int E,
-                                    int H, int W, dsb_stream_t stream) {
+                                    const float* bias, float* lut_workspace, float* out, void* out_hi, void* out_lo, int out_c,
+                                    int N, int E, int H, int W, dsb_stream_t stream) {
     StemArgs a;
-    int rc = fill_args(a, planes, effects, project, ex, ey, entity_num, weight, bias, N, E, H, W);
+    int rc = fill_args(a, planes, effects, project, ex, ey, entity_num, weight, bias, lut_workspace, N, E, H, W,
+                       (cudaStream_t)stream);
     if (rc) return rc;
     DSB_REQUIRE(out && (out_c == 32 || out_c == 64) && (!out_hi == !out_lo), "spatial_stem_fwd: bad output arguments");
     if (N == 0) return DSB_OK;
@@ -309,11 +350,12 @@ extern "C" int dsb_spatial_stem_fwd(const void* const* planes, const void* const
 
 extern "C" int dsb_spatial_stem_bwd(const void* const* planes, const void* const* effects, const float* project,
                                     const uint8_t* ex, const uint8_t* ey, const int64_t* entity_num, const float* weight,
-                                    const float* bias, const float* grad_out, int out_c, float* grad_weight,
-                                    float* grad_bias, float* grad_project, int N, int E, int H, int W,
+                                    const float* bias, float* lut_workspace, const float* grad_out, int out_c,
+                                    float* grad_weight, float* grad_bias, float* grad_project, int N, int E, int H, int W,
                                     dsb_stream_t stream) {
     StemArgs a;
-    int rc = fill_args(a, planes, effects, project, ex, ey, entity_num, weight, bias, N, E, H, W);
+    int rc = fill_args(a, planes, effects, project, ex, ey, entity_num, weight, bias, lut_workspace, N, E, H, W,
+                       (cudaStream_t)stream);
     if (rc) return rc;
     DSB_REQUIRE(grad_out && grad_weight && grad_bias && grad_project && (out_c == 32 || out_c == 64),
                 "spatial_stem_bwd: bad arguments (grad_weight/grad_bias/grad_project must be zero-initialised by the caller)");

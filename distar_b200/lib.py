@@ -21,8 +21,8 @@ _SIGNATURES = {
     'dsb_scatter_connection_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'dsb_scatter_connection_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'dsb_entity_features': (_i, [_vp] * 5 + [_i, _vp, _vp, _i, _i64, _vp, _vp]),
-    'dsb_spatial_stem_fwd': (_i, [_vp] * 11 + [_i] * 5 + [_vp]),
-    'dsb_spatial_stem_bwd': (_i, [_vp] * 9 + [_i] + [_vp] * 3 + [_i] * 4 + [_vp]),
+    'dsb_spatial_stem_fwd': (_i, [_vp] * 12 + [_i] * 5 + [_vp]),
+    'dsb_spatial_stem_bwd': (_i, [_vp] * 10 + [_i] + [_vp] * 3 + [_i] * 4 + [_vp]),
     'dsb_return_scan': (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'dsb_categorical_stats_fwd': (_i, [_vp] * 10 + [_i64, _i, _vp]),
     'dsb_categorical_stats_bwd': (_i, [_vp] * 11 + [_i64, _i, _vp]),

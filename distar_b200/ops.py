@@ -165,7 +165,8 @@ class _SpatialStem(torch.autograd.Function):
         hi = torch.empty(out.shape, dtype=torch.bfloat16, device=dev)
         lo = torch.empty(out.shape, dtype=torch.bfloat16, device=dev)
         pa, ea = lib.ptr_array(planes), lib.ptr_array(effects)
-        lib.call('dsb_spatial_stem_fwd', pa, ea, project, ex, ey, entity_num, w2, bias, out, hi, lo, out_c, N, E, H, W)
+        lut = torch.empty(320 * 32, dtype=torch.float32, device=dev)       # scratch: combined table of the categorical planes
+        lib.call('dsb_spatial_stem_fwd', pa, ea, project, ex, ey, entity_num, w2, bias, lut, out, hi, lo, out_c, N, E, H, W)
         ctx.save_for_backward(project, w2, bias, ex, ey, entity_num, *planes, *effects)
         ctx.dims = (N, E, H, W, out_c, tuple(weight.shape))
         ctx.set_materialize_grads(False)
@@ -184,7 +185,8 @@ class _SpatialStem(torch.autograd.Function):
         gb = torch.zeros(32, dtype=torch.float32, device=dev)
         gp = torch.zeros((N, E, 32), dtype=torch.float32, device=dev)
         pa, ea = lib.ptr_array(planes), lib.ptr_array(effects)
-        lib.call('dsb_spatial_stem_bwd', pa, ea, project, ex, ey, entity_num, w2, bias, gout.contiguous(), out_c, gw, gb, gp,
+        lut = torch.empty(320 * 32, dtype=torch.float32, device=dev)
+        lib.call('dsb_spatial_stem_bwd', pa, ea, project, ex, ey, entity_num, w2, bias, lut, gout.contiguous(), out_c, gw, gb, gp,
                  N, E, H, W)
         return (gp, gw.view(wshape), gb, None, None, None, None) + (None,) * 13
 

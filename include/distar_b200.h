@@ -59,17 +59,19 @@ int dsb_entity_features(const void* const* fields, const int* kind, const int* o
  * planes: host array of 7 device pointers (height_map, visibility_map, creep, player_relative, alerts, pathable,
  * buildable; each u8 [N,H,W]); effects: host array of 6 device pointers (int16 [N,100] flat pixel lists, zero padded);
  * project [N,E,32] f32 (masked scatter_project output), ex/ey u8 [N,E], entity_num i64 [N] (NULL = E),
- * weight [32,56], bias [32] of the 1x1 project conv.
+ * weight [32,56], bias [32] of the 1x1 project conv; lut_workspace: 320 * 32 floats of scratch (the kernel rebuilds the combined
+ * lookup table of the six categorical planes from the current weights there at every call).
  * out [N, H/2, W/2, out_c] f32 channels-last, out_c = 32 or 64 (channels >= 32 written as 0); out_hi/out_lo optional bf16
  * split of out.  Backward: grad_weight [32,56], grad_bias [32], grad_project [N,E,32] must be ZEROED by the caller; the
  * kernel accumulates into the first two and writes each valid entity row of the third. */
 int dsb_spatial_stem_fwd(const void* const* planes, const void* const* effects, const float* project, const uint8_t* ex,
-                         const uint8_t* ey, const int64_t* entity_num, const float* weight, const float* bias, float* out,
-                         void* out_hi, void* out_lo, int out_c, int N, int E, int H, int W, dsb_stream_t stream);
+                         const uint8_t* ey, const int64_t* entity_num, const float* weight, const float* bias,
+                         float* lut_workspace, float* out, void* out_hi, void* out_lo, int out_c, int N, int E, int H, int W,
+                         dsb_stream_t stream);
 int dsb_spatial_stem_bwd(const void* const* planes, const void* const* effects, const float* project, const uint8_t* ex,
                          const uint8_t* ey, const int64_t* entity_num, const float* weight, const float* bias,
-                         const float* grad_out, int out_c, float* grad_weight, float* grad_bias, float* grad_project, int N,
-                         int E, int H, int W, dsb_stream_t stream);
+                         float* lut_workspace, const float* grad_out, int out_c, float* grad_weight, float* grad_bias,
+                         float* grad_project, int N, int E, int H, int W, dsb_stream_t stream);
 
 /* ---- V-trace / UPGO / TD(lambda) return scans  (rl_training/as_rl_utils.py:157-218,265-312; call sites :15,:40,:238) ----
  * reward [F,T,B], value [F,T+1,B] (bootstrap row already zeroed where terminal, rl_loss.py:47-49),

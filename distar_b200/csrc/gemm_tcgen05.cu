@@ -256,6 +256,8 @@ struct OperandMap {       // tile origin = (col_base + bi*col_inner, row_outer*b
 struct GemmParams {
     const float* bias;
     const float* residual;   // optional fp32 [c_rows, ldc] added before the ReLU
+    const __nv_bfloat16* mask;   // optional bf16 [c_rows, ldc]: result zeroed where mask == 0 (ReLU backward through a saved output)
+    float* colsum;               // optional fp32 [N]: column sums of the (masked) result are ADDED here (a bias gradient)
     __nv_bfloat16* c_hi;
     __nv_bfloat16* c_lo;
     float alpha;
@@ -620,6 +622,42 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 const float floor_v = p.relu ? 0.f : -3.402823466e38f;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(fmaf(__uint_as_float(r[j]), p.alpha, v[j]), floor_v);
+                if (p.mask && row_ok) {
+                    // dX of a layer whose input is another layer's ReLU output: multiply by that ReLU's derivative here (the
+                    // sign of the saved bf16 output) instead of in a separate pass over the gradient
+                    const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + (int64_t)(c_row0 + lane) * p.ldc + c_col0 + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 mm = __ldg(m4 + j);
+                        const uint32_t w[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (!(w[e] & 0x00007fffu)) v[8 * j + 2 * e] = 0.f;
+                            if (!(w[e] & 0x7fff0000u)) v[8 * j + 2 * e + 1] = 0.f;
+                        }
+                    }
+                }
+                if (p.colsum) {
+                    // column sums of this 32 x 32 block without leaving the register file: a 5-stage butterfly in which every
+                    // lane keeps the half of the columns that matches its lane bit and ships the other half (16 + 8 + 4 + 2 + 1 =
+                    // 31 shuffles); lane l ends up with the sum of column l over the warp's 32 rows
+                    float cs[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float lo_h = row_ok ? v[j] : 0.f, hi_h = row_ok ? v[j + 16] : 0.f;
+                        const bool up = lane & 16;
+                        cs[j] = (up ? hi_h : lo_h) + __shfl_xor_sync(0xffffffffu, up ? lo_h : hi_h, 16);
+                    }
+#define DSB_COLSUM_STAGE(W)                                                                           \
+                    _Pragma("unroll") for (int j = 0; j < (W); ++j) {                                 \
+                        const bool up = lane & (W);                                                   \
+                        const float keep = up ? cs[j + (W)] : cs[j], send = up ? cs[j] : cs[j + (W)]; \
+                        cs[j] = keep + __shfl_xor_sync(0xffffffffu, send, (W));                       \
+                    }
+                    DSB_COLSUM_STAGE(8) DSB_COLSUM_STAGE(4) DSB_COLSUM_STAGE(2) DSB_COLSUM_STAGE(1)
+#undef DSB_COLSUM_STAGE
+                    if (t.valid) atomicAdd(p.colsum + c_col0 + c0 + lane, cs[0]);
+                }
                 if (p.store_c) {
                     unsigned char* buf = my_buf + buf_sel * kStoreBufBytes;
                     buf_sel = (buf_sel + 1) % kStoreBufs;
@@ -820,7 +858,7 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
         configured = true;
     }
     GemmParams p;
-    p.bias = g.bias; p.residual = g.residual; p.c_hi = (__nv_bfloat16*)g.c_hi; p.c_lo = (__nv_bfloat16*)g.c_lo;
+    p.bias = g.bias; p.residual = g.residual; p.mask = (const __nv_bfloat16*)g.relu_mask; p.colsum = g.colsum; p.c_hi = (__nv_bfloat16*)g.c_hi; p.c_lo = (__nv_bfloat16*)g.c_lo;
     p.alpha = g.alpha; p.M = g.m; p.ldc = g.c_cols; p.N = g.n; p.terms = g.terms; p.relu = g.relu;
     p.accumulate = g.c_accumulate; p.store_c = g.c != nullptr;
     p.a_exact = g.a_exact; p.b_exact = g.b_exact;

@@ -99,6 +99,25 @@ __global__ void split_kernel(const float* __restrict__ x, __nv_bfloat16* __restr
         split_store(x[i], hi, lo, i);
 }
 
+// column sums of (hi + lo) over a band of rows per block, added atomically into out[N]; thread = 4 consecutive columns
+__global__ void colsum_pair_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                   float* __restrict__ out, int64_t rows, int N, int rows_per_block) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (c >= N) return;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int64_t r = r0; r < r1; ++r) {
+        const uint2 h = *reinterpret_cast<const uint2*>(hi + r * N + c), l = *reinterpret_cast<const uint2*>(lo + r * N + c);
+        const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h.x));
+        const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h.y));
+        const float2 l0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&l.x));
+        const float2 l1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&l.y));
+        a0 += h0.x + l0.x; a1 += h0.y + l0.y; a2 += h1.x + l1.x; a3 += h1.y + l1.y;
+    }
+    atomicAdd(out + c, a0); atomicAdd(out + c + 1, a1); atomicAdd(out + c + 2, a2); atomicAdd(out + c + 3, a3);
+}
+
 inline unsigned grid_for(int64_t n, int per_thread) {
     int64_t blocks = (n / per_thread + kThreads - 1) / kThreads;
     const int64_t cap = 148 * 8;
@@ -356,4 +375,18 @@ extern "C" int dsb_gate_update_bwd(const float* grad_out, const float* r, const 
         (const float4*)grad_out, (const float4*)r, (const float4*)g, (const float4*)x, sp, (float4*)grad_r, (float4*)grad_g,
         (float4*)grad_x, grad_sp, n4);
     return dsb::check_launch("gate_update_bwd");
+}
+
+extern "C" int dsb_colsum_pair(const void* hi, const void* lo, float* out, int64_t rows, int N, dsb_stream_t stream) {
+    DSB_REQUIRE(hi && lo && out && rows >= 0 && N > 0 && N % 4 == 0, "colsum_pair: bad argument (N %% 4)");
+    if (rows == 0) return DSB_OK;
+    const int threads = 128;
+    const int bx = (N / 4 + threads - 1) / threads;
+    int by = (int)((148 * 8 + bx - 1) / bx);
+    if (by > rows) by = (int)rows;
+    const int rpb = (int)((rows + by - 1) / by);
+    by = (int)((rows + rpb - 1) / rpb);
+    colsum_pair_kernel<<<dim3(bx, by), threads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo, out,
+                                                                        rows, N, rpb);
+    return dsb::check_launch("colsum_pair");
 }

@@ -78,6 +78,7 @@ _SIGNATURES = {
     'dsb_onehot_linear_bwd': (_i, [_vp] * 5 + [_i64, _i, _i, _i64, _i64, _i, _vp]),
     'dsb_target_unit_fwd': (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _f, _vp]),
     'dsb_target_unit_bwd': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i64, _i, _f, _vp]),
+    'dsb_colsum_pair': (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
     'dsb_sumsq_partials': (_i, []),
     'dsb_grad_norm': (_i, [_vp, _i64, _vp, _vp, _f, _vp]),
     'dsb_adam_step': (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp, _vp]),
@@ -103,7 +104,7 @@ class GemmArgs(ctypes.Structure):
                 ('residual', _vp), ('bn', _c.c_int32),
                 ('a_conv', _c.c_int32), ('b_conv', _c.c_int32), ('conv_h', _c.c_int32), ('conv_w', _c.c_int32),
                 ('conv_c', _c.c_int32), ('conv_taps', _c.c_int32), ('conv_imgs', _i64), ('c_accumulate', _c.c_int32), ('mc', _c.c_int32),
-                ('a_exact', _c.c_int32), ('b_exact', _c.c_int32)]
+                ('a_exact', _c.c_int32), ('b_exact', _c.c_int32), ('relu_mask', _vp), ('colsum', _vp)]
 
 
 _SIGNATURES['dsb_gemm_ex'] = (_i, [ctypes.POINTER(GemmArgs), _vp])

@@ -753,13 +753,21 @@ class _FFN(torch.autograd.Function):
         g2_hi, g2_lo, gb2, _ = relu_bwd_split(gy2, m, ctx.needs_input_grad[4], bias_grad_out=_grad_slot(b2))
         _, h_hi, h_lo = gemm_split(a_hi, a_lo, w1_hi, w1_lo, b1, True, terms, want_split='only')      # rebuild h
         gw2 = weight_grad(g2_hi, g2_lo, h_hi, h_lo, terms, accumulate_into=_grad_slot(w2)) if ctx.needs_input_grad[3] else None
-        dh = torch.empty((M, H), dtype=torch.float32, device=dev)
-        _gemm_ex(a_hi=g2_hi, a_lo=g2_lo, b_hi=w2_hi, b_lo=w2_lo, b_mn=1, alpha=1.0, terms=terms, c=dh, m=M, n=H, k=w2_hi.shape[0],
-                 batch=1, inner=1, splits=1)
+        # dh = g2 W2 through the first layer's ReLU: the mask (sign of the rebuilt bf16 hidden) is applied in the GEMM epilogue and
+        # only the (hi, lo) pair the next two GEMMs read is written - the fp32 dh and its separate masking pass do not exist
+        g1_hi = torch.empty((M, H), dtype=torch.bfloat16, device=dev)
+        g1_lo = torch.empty((M, H), dtype=torch.bfloat16, device=dev)
+        # (and the column sums of the masked gradient = the first layer's bias gradient are formed in the same epilogue)
+        gb1 = acc1 = None
+        if ctx.needs_input_grad[2]:
+            slot1 = _grad_slot(b1)
+            acc1 = slot1 if slot1 is not None else torch.zeros(H, dtype=torch.float32, device=dev)
+            gb1 = None if slot1 is not None else acc1
+        _gemm_ex(a_hi=g2_hi, a_lo=g2_lo, b_hi=w2_hi, b_lo=w2_lo, b_mn=1, alpha=1.0, terms=terms, c=None, c_hi=g1_hi, c_lo=g1_lo,
+                 m=M, n=H, k=w2_hi.shape[0], batch=1, inner=1, splits=1, relu_mask=h_hi, colsum=acc1)
         del g2_hi, g2_lo
         # first layer
-        g1_hi, g1_lo, gb1, _ = relu_bwd_split(dh, h_hi, ctx.needs_input_grad[2], bias_grad_out=_grad_slot(b1))
-        del dh, h_hi, h_lo
+        del h_hi, h_lo
         gw1 = weight_grad(g1_hi, g1_lo, a_hi, a_lo, terms, accumulate_into=_grad_slot(w1)) if ctx.needs_input_grad[1] else None
         gx = None
         if ctx.needs_input_grad[0]:

@@ -200,6 +200,10 @@ int dsb_gate_update_fwd(const float* r, const float* g, const float* x, const fl
 int dsb_gate_update_bwd(const float* grad_out, const float* r, const float* g, const float* x, const float* sp, float* grad_r,
                         float* grad_g, float* grad_x, float* grad_sp, int64_t n, dsb_stream_t stream);
 
+/* ---- column sums of a bf16 (hi, lo) pair [rows, N] ADDED into out [N]: the bias gradient of a layer whose masked gradient only
+ * exists as the pair a dX GEMM epilogue emitted (dsb_gemm_args.relu_mask) ---- */
+int dsb_colsum_pair(const void* hi, const void* lo, float* out, int64_t rows, int N, dsb_stream_t stream);
+
 /* ---- fp32 -> (hi, lo) bf16 split used by the split-precision tensor-core GEMM ---- */
 int dsb_split_bf16(const float* x, void* hi, void* lo, int64_t n, dsb_stream_t stream);
 
@@ -314,6 +318,10 @@ typedef struct dsb_gemm_args {
     int32_t a_exact;        /* terms == 3 only: A is exactly representable in bf16 (a_lo may be NULL): the a_lo x b_hi product
                                and the a_lo loads are skipped */
     int32_t b_exact;        /* same for B */
+    const void* relu_mask;  /* optional bf16 [c_rows, c_cols] (the saved bf16 output of a ReLU layer): the result is zeroed where it
+                               is 0 - the ReLU derivative applied in the epilogue of the dX GEMM that produces the gradient */
+    float* colsum;          /* optional fp32 [c_cols]: the column sums of the (masked) result are ADDED here - the bias gradient of
+                               the layer the gradient flows into, formed in the epilogue (warp butterfly + one atomic per column) */
 } dsb_gemm_args;
 int dsb_gemm_ex(const dsb_gemm_args* args, dsb_stream_t stream);
 

@@ -682,13 +682,27 @@ class _SplitLinear(torch.autograd.Function):
         a_hi, a_lo, w_hi, w_lo, y = ctx.saved_tensors
         if gy is None:
             return (g_pass,) + (None,) * 8
-        gy2 = gy.reshape(-1, gy.shape[-1]).contiguous()
-        M, N = gy2.shape
+        pre = getattr(gy, '_dsb_grad_pair', None)
         K = a_hi.shape[1]
-        on_gpu = gy2.is_cuda
         gx = gw = gb = None
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
-        if on_gpu and N % 4 == 0:
+        if pre is not None and not ctx.relu:
+            # the producer of this gradient (attention backward, ...) already wrote it as the bf16 pair the GEMMs below read
+            g_hi, g_lo, bias_done = pre
+            M, N = g_hi.shape
+            on_gpu, gy2, g = True, None, None
+            if want_b and not bias_done:
+                slot = _grad_slot(ctx.bias_ref)
+                acc = slot if slot is not None else torch.zeros(N, dtype=torch.float32, device=g_hi.device)
+                lib.call('dsb_colsum_pair', g_hi, g_lo, acc, M, N)
+                gb = None if slot is not None else acc
+        else:
+            gy2 = gy.reshape(-1, gy.shape[-1]).contiguous()
+            M, N = gy2.shape
+            on_gpu = gy2.is_cuda
+        if pre is not None and not ctx.relu:
+            pass
+        elif on_gpu and N % 4 == 0:
             g_hi, g_lo, gb, g = relu_bwd_split(gy2, y if ctx.relu else None, want_b, need_g=False,
                                                bias_grad_out=_grad_slot(ctx.bias_ref) if want_b else None)
         else:
@@ -697,7 +711,7 @@ class _SplitLinear(torch.autograd.Function):
             gb = g.sum(0) if want_b else None
         if ctx.needs_input_grad[0]:
             if on_gpu and K % 128 == 0 and N % 64 == 0:
-                gx = torch.empty((M, K), dtype=torch.float32, device=gy2.device)
+                gx = torch.empty((M, K), dtype=torch.float32, device=g_hi.device)
                 res = g_pass.reshape(M, K).contiguous() if g_pass is not None else None
                 _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=w_hi, b_lo=w_lo, b_mn=1, alpha=1.0, terms=ctx.terms, c=gx, m=M, n=K,
                          k=N, batch=1, inner=1, splits=1, residual=res)
@@ -800,9 +814,12 @@ class _EntityAttention(torch.autograd.Function):
     QKV activation by coordinates (no split / permute / contiguous copies) plus two row-softmax kernels."""
 
     @staticmethod
-    def forward(ctx, qkv, entity_num, heads, hd, q_hi=None, q_lo=None):
+    def forward(ctx, qkv, entity_num, heads, hd, q_hi=None, q_lo=None, qkv_bias=None, pair_grad=False):
+        ctx.in_shape = qkv.shape
+        ctx.bias_ref = qkv_bias
+        ctx.pair_grad = pair_grad
+        qkv = qkv.reshape(-1, qkv.shape[-1])
         NS, W3 = qkv.shape
-        S = 512 if NS % 512 == 0 else None
         n_obs = entity_num.shape[0]
         S = NS // n_obs
         H, D = heads, hd
@@ -836,7 +853,19 @@ class _EntityAttention(torch.autograd.Function):
         dev = g_out.device
         alpha = 1.0 / math.sqrt(D)
         g_hi, g_lo = split_bf16(g_out.contiguous())
-        dqkv = torch.empty((n_obs * S, 3 * H * D), dtype=torch.float32, device=dev)
+        # the gradient of the QKV activation only feeds the QKV layer's dX / dW GEMMs: the three products below write it as the
+        # bf16 pair those GEMMs read (no fp32 tensor, no separate split pass) and add its column sums - the QKV bias gradient -
+        # from their epilogues
+        # (only when the consumer is known to be a tensor-core linear that reads the pair: ctx.pair_grad; otherwise plain fp32)
+        bslot = None
+        if ctx.pair_grad:
+            dq_hi = torch.empty((n_obs * S, 3 * H * D), dtype=torch.bfloat16, device=dev)
+            dq_lo = torch.empty_like(dq_hi)
+            bslot = _grad_slot(ctx.bias_ref) if ctx.bias_ref is not None else None
+            out = dict(c=None, c_hi=dq_hi, c_lo=dq_lo, colsum=bslot)
+        else:
+            dq32 = torch.empty((n_obs * S, 3 * H * D), dtype=torch.float32, device=dev)
+            out = dict(c=dq32)
         common = dict(terms=3, batch=n_obs * H, inner=H, splits=1)
         # dP[q,k] = sum_d dO[q,d] V[k,d]
         dp = torch.empty((n_obs * H * S, S), dtype=torch.float32, device=dev)
@@ -844,37 +873,45 @@ class _EntityAttention(torch.autograd.Function):
                  a_col_inner=D, a_row_outer=S, b_col_base=2 * H * D, b_col_inner=D, b_row_outer=S,
                  c_row_outer=H * S, c_row_inner=S, **common)
         # dV[k,d] = sum_q P[q,k] dO[q,d]          (both operands reduce over rows -> MN-major)
-        _gemm_ex(a_hi=p_hi, a_lo=p_lo, b_hi=g_hi, b_lo=g_lo, a_mn=1, b_mn=1, alpha=1.0, c=dqkv, m=S, n=D, k=S,
+        _gemm_ex(a_hi=p_hi, a_lo=p_lo, b_hi=g_hi, b_lo=g_lo, a_mn=1, b_mn=1, alpha=1.0, m=S, n=D, k=S,
                  a_row_outer=H * S, a_row_inner=S, b_col_inner=D, b_row_outer=S,
-                 c_row_outer=S, c_col_base=2 * H * D, c_col_inner=D, **common)
+                 c_row_outer=S, c_col_base=2 * H * D, c_col_inner=D, **out, **common)
         ds_hi = torch.empty_like(p_hi)
         ds_lo = torch.empty_like(p_lo)
         lib.call('dsb_attn_softmax_bwd', p_hi, p_lo, dp, entity_num, H * S, ds_hi, ds_lo, n_obs * H * S, S)
         del dp
         # dQ[q,d] = alpha * sum_k dS[q,k] K[k,d]
-        _gemm_ex(a_hi=ds_hi, a_lo=ds_lo, b_hi=q_hi, b_lo=q_lo, b_mn=1, alpha=alpha, c=dqkv, m=S, n=D, k=S,
+        _gemm_ex(a_hi=ds_hi, a_lo=ds_lo, b_hi=q_hi, b_lo=q_lo, b_mn=1, alpha=alpha, m=S, n=D, k=S,
                  a_row_outer=H * S, a_row_inner=S, b_col_base=H * D, b_col_inner=D, b_row_outer=S,
-                 c_row_outer=S, c_col_base=0, c_col_inner=D, **common)
+                 c_row_outer=S, c_col_base=0, c_col_inner=D, **out, **common)
         # dK[k,d] = alpha * sum_q dS[q,k] Q[q,d]
-        _gemm_ex(a_hi=ds_hi, a_lo=ds_lo, b_hi=q_hi, b_lo=q_lo, a_mn=1, b_mn=1, alpha=alpha, c=dqkv, m=S, n=D, k=S,
+        _gemm_ex(a_hi=ds_hi, a_lo=ds_lo, b_hi=q_hi, b_lo=q_lo, a_mn=1, b_mn=1, alpha=alpha, m=S, n=D, k=S,
                  a_row_outer=H * S, a_row_inner=S, b_col_base=0, b_col_inner=D, b_row_outer=S,
-                 c_row_outer=S, c_col_base=H * D, c_col_inner=D, **common)
-        return dqkv, None, None, None, None, None
+                 c_row_outer=S, c_col_base=H * D, c_col_inner=D, **out, **common)
+        if not ctx.pair_grad:
+            return dq32.view(ctx.in_shape), None, None, None, None, None, None, None
+        dqkv = pair_only_placeholder(ctx.in_shape, dev)
+        dqkv._dsb_grad_pair = (dq_hi, dq_lo, bslot is not None)       # (hi, lo, bias gradient already accumulated)
+        return dqkv, None, None, None, None, None, None, None
 
 
-def entity_attention(qkv: torch.Tensor, entity_num: torch.Tensor, heads: int, hd: int) -> torch.Tensor:
+def entity_attention(qkv: torch.Tensor, entity_num: torch.Tensor, heads: int, hd: int,
+                     qkv_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """qkv [N, S, 3*heads*hd] (q | k | v, each head-major) -> context [N, S, heads*hd]; keys >= entity_num masked.
     On the GPU the context is returned as a pair-only tensor (fp32 placeholder + attached bf16 (hi, lo) pair, see
     pair_only_placeholder): its one consumer is the projection GEMM."""
     N, S, W3 = qkv.shape
     if _use_kernel(qkv) and S % 128 == 0 and hd % 128 == 0:
         sp = getattr(qkv, '_dsb_split', None)
+        # (qkv goes in un-reshaped: no view node between this Function and the QKV linear, so the gradient object this backward
+        # returns - a placeholder carrying the bf16 pair - reaches the linear's backward as is)
         if sp is not None and sp[0].shape == qkv.shape:
-            out, o_hi, o_lo = _EntityAttention.apply(qkv.reshape(N * S, W3), entity_num.to(torch.int64).contiguous(), heads,
-                                                     hd, sp[0].reshape(N * S, W3), sp[1].reshape(N * S, W3))
+            out, o_hi, o_lo = _EntityAttention.apply(qkv, entity_num.to(torch.int64).contiguous(), heads,
+                                                     hd, sp[0].reshape(N * S, W3), sp[1].reshape(N * S, W3), qkv_bias,
+                                                     bool(getattr(qkv, '_dsb_reads_grad_pair', False)))
         else:
-            out, o_hi, o_lo = _EntityAttention.apply(qkv.reshape(N * S, W3).contiguous(),
-                                                     entity_num.to(torch.int64).contiguous(), heads, hd)
+            out, o_hi, o_lo = _EntityAttention.apply(qkv.contiguous(), entity_num.to(torch.int64).contiguous(), heads, hd,
+                                                     None, None, qkv_bias, False)
         shape = (N, S, heads * hd)
         return attach_split(out.view(shape), o_hi.view(shape), o_lo.view(shape))
     q, k, v = qkv.view(N, S, 3, heads, hd).permute(2, 0, 3, 1, 4)
@@ -899,6 +936,8 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
         emit = emit_split and x.is_cuda
         y, y_hi, y_lo, x_pass = _SplitLinear.apply(x, weight, bias, relu, terms, sp[0], sp[1], emit, fork and x.is_cuda)
         y = attach_split(y, y_hi, y_lo) if emit else y
+        if x.is_cuda and not relu:
+            y._dsb_reads_grad_pair = True      # this node's backward accepts its gradient as a bf16 pair (_dsb_grad_pair)
         return (y, x_pass if x_pass is not None else x) if fork else y
     if _use_kernel(x) and not _TCGEN05_OFF and x.numel() > 0:
         y = linear_any(x, weight, bias, relu, terms, exact_input)

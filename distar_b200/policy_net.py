@@ -235,7 +235,8 @@ class Net:
             # the GEMM's autograd node (fork=True): its dX epilogue adds the residual branch's gradient
             qkv, xr = ops.linear(x, P[lp + '.attention.attention_pre.0.weight'], P[lp + '.attention.attention_pre.0.bias'], False,
                                  self.terms, 'only' if x.is_cuda else False, fork=True)
-            a = self.fc(lp + '.attention.project', ops.entity_attention(qkv, entity_num, 2, 128))
+            a = self.fc(lp + '.attention.project', ops.entity_attention(qkv, entity_num, 2, 128,
+                                                                       P[lp + '.attention.attention_pre.0.bias']))
             x = self.ln(lp + '.layernorm1', xr, residual=a, split=True)
             m, xr = ops.ffn(x, P[lp + '.mlp.0.0.weight'], P[lp + '.mlp.0.0.bias'], P[lp + '.mlp.1.0.weight'],
                             P[lp + '.mlp.1.0.bias'], self.terms, fork=True)

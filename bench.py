@@ -203,8 +203,8 @@ def tree_bytes(tree):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the two kernels BASELINE.json names, from the committed
 # `ncu --set full --clock-control none` captures of exactly these launches (profiles/r01_summary.md)
-NCU_SOURCE = 'profiles/r01_ncu_raw_{scatter,gemm}_final.csv'
-NCU_DRAM_BYTES = {'scatter_connection': 70.4e6 + 2155e6, 'entity_mlp_gemm_terms3': 139.5e6 + 493.7e6}
+NCU_SOURCE = 'profiles/r02_ncu_raw_{scatter,gemm}.csv'
+NCU_DRAM_BYTES = {'scatter_connection': 70.4e6 + 2155.0e6, 'entity_mlp_gemm_terms3': 139.6e6 + 493.7e6}
 
 
 def kernel_rooflines(dev, peaks):
@@ -248,7 +248,7 @@ def kernel_rooflines(dev, peaks):
         a_hi, a_lo = ops.split_bf16(a)
         w_hi, w_lo = ops.split_bf16(w)
         c = torch.empty(M, Nn, device=dev)
-        for terms, bn, mc in ((3, 0, 1), (3, 128, 1), (1, 0, 1), (3, 256, 4), (3, 128, 4), (1, 256, 4)):
+        for terms, bn, mc in ((3, 0, 0), (3, 256, 1), (3, 128, 1), (1, 0, 1), (1, 256, 4)):
             def run():
                 _lib.gemm_ex(a_hi=a_hi, a_lo=a_lo, b_hi=w_hi, b_lo=w_lo, bias=b, alpha=1.0, relu=1, terms=terms, c=c, m=M,
                              n=Nn, k=K, batch=1, inner=1, splits=1, bn=bn, mc=mc)
@@ -270,7 +270,8 @@ def kernel_rooflines(dev, peaks):
             # product `terms` times on the tensor cores: that tensor work is reported beside it
             flops = 2.0 * M * K * Nn
             ach = flops / dt / 1e12
-            key = 'entity_mlp_gemm_terms%d' % terms + ('_bn%d' % bn if bn else '') + ('_pair' if mc == 4 else '') + tag
+            key = 'entity_mlp_gemm_terms%d' % terms + ('_bn%d' % bn if bn else '') + ('_pair' if mc == 4 else '') + \
+                ('_single' if (bn, mc) == (256, 1) else '') + tag
             out[key] = {
                 'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
                 'frac': ach / peaks['bf16_tflops'], 'achieved_tensor_work': ach * terms,
@@ -278,7 +279,8 @@ def kernel_rooflines(dev, peaks):
                 'traffic_source': NCU_SOURCE if NCU_DRAM_BYTES.get(key) else None, 'us_per_launch': dt * 1e6,
                 'algorithmic_flop': flops,
                 'shape': 'M=%d K=%d N=%d, %d bf16 MMA products per element, tile %sx%s' % (
-                    M, K, Nn, terms, '256(CTA pair)' if mc == 4 else '128', bn if bn else 'auto(256)'),
+                    M, K, Nn, terms, '256(CTA pair, cta_group::2)' if mc == 4 or (mc == 0 and terms == 3) else '128',
+                    bn if bn else 'auto(256)'),
                 'peak_source': peaks['source']}
         del a, a_hi, a_lo, c
     # the down-projection of the same MLP: [M,1024] x [256,1024]^T (16 k blocks per tile: the mainloop-bound shape)

@@ -29,9 +29,10 @@
 //               and / or of the bf16 (hi, lo) pair of C (SWIZZLE_64B boxes), or TMA reduce-add (split-K, accumulation
 //               into a gradient buffer)
 // Cluster variants (template MC): 2 = two CTAs share every B tile by TMA multicast; 4 = CTA pair issuing
-// tcgen05.mma.cta_group::2 (M = 256 across two SMs, each CTA stages half of B, barriers in the leader CTA).  Both are
-// correct and tested; neither beats the single-CTA kernel for 3-term products yet, so the automatic choice
-// uses them only for 1-term products (multicast).
+// tcgen05.mma.cta_group::2 (M = 256 across two SMs, each CTA stages half of B, barriers in the leader CTA; all cross-CTA
+// barrier arrivals are .relaxed.cluster - a .release.cluster arrive per stage cost the producer ~0.7 us and made the pair
+// slower than the single-CTA kernel).  The automatic choice (launch()) uses the pair for the plain 3-term products with
+// >= 74 tile pairs and multicast for 1-term products.
 #include <cuda.h>
 #include <cstdlib>
 #include "common.cuh"
@@ -44,15 +45,14 @@ constexpr int kTileBytes = BM * BK * 2;                 // 16 KiB: one 128x64 bf
 constexpr int kStoreBufBytes = 32 * 128;                // one 32-row x 32-col fp32 staging box (128 B rows, SWIZZLE_128B)
 constexpr int kStoreBytes = 8 * kStoreBufBytes;         // 8 epilogue warps x one staging box each (x2 in CTA-pair mode)
 // per-BN shared-memory plan: stage = A_hi | A_lo | B_hi | B_lo; B slots are 16 KiB (BN <= 128) or 32 KiB (BN = 256)
-// MC = 4 (CTA pair, cta_group::2 MMAs): each CTA stages only its half of every B tile, which leaves room for a deeper ring.
-// The shared memory that frees goes to a second staging box per epilogue warp: with one box every 32x32 block of the
-// epilogue waits for the previous TMA store to drain (the measured limiter of the single-CTA kernel: the 1-term product is
-// no faster than ~0.7x the 3-term one), with two the store of block i overlaps the conversion of block i+1.
+// MC = 4 (CTA pair, cta_group::2 MMAs): each CTA stages only its half of every B tile (64 KiB stages), which leaves room
+// for a third ring stage (measured: FFN down-projection 182 us with 2 stages + double-buffered staging boxes, 166 us with
+// 3 stages + one box; the epilogue alone is HBM-write bound either way).
 template <int BN, int MC = 1> struct Plan {
     static constexpr int kBSlot = MC == 4 ? BN * 64 : (BN > 128 ? BN * 128 : kTileBytes);
     static constexpr int kStageBytes = 2 * kTileBytes + 2 * kBSlot;
-    static constexpr int kStages = MC == 4 ? (BN > 128 ? 2 : 3) : (BN > 128 ? 2 : 3);
-    static constexpr int kStoreBufs = MC == 4 ? 2 : 1;
+    static constexpr int kStages = MC == 4 ? (BN > 128 ? 3 : 4) : (BN > 128 ? 2 : 3);
+    static constexpr int kStoreBufs = 1;
     static constexpr int kStoreTotal = kStoreBufs * kStoreBytes;
     static constexpr int kSmemBytes = kStages * kStageBytes + kStoreTotal + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -117,11 +117,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar_addr, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes)
+    asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes)
                  : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_addr, void* dst, int c0, int c1) {
     asm volatile(
@@ -267,7 +267,8 @@ struct GemmParams {
     int a_exact, b_exact;    // terms == 3: that operand has no lo half (exactly representable in bf16)
     int store_c;             // 0: only the bf16 (hi, lo) pair is written (no fp32 C)
     int prefetch;            // L2-prefetch the next tile's A operand
-    int debug;               // DEV ONLY (env DSB_GEMM_DEBUG): 1 = skip global stores, 2 = skip MMAs, 4 = skip operand loads
+    int debug;               // DEV ONLY (env DSB_GEMM_DEBUG, tools/gemm_ablate.sh): 1 = skip global stores, 2 = skip MMAs, 4 = skip
+                             // operand loads, 8 = all stores to the first tile (L2 resident), 16 = no staging / store, 32 = no TMEM read
     int num_m, num_n, num_k; // tiles per (batch, split); k blocks per split
     int batch, inner, splits;
     int c_row_outer, c_row_inner, c_row_split, c_col_base, c_col_inner;
@@ -582,12 +583,17 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             tc_fence_after();
             const int row_in_batch = t.m0 + q * 32 + lane;
             const bool row_ok = t.valid && row_in_batch < p.M;
-            const int c_row0 = t.bo * p.c_row_outer + t.bi * p.c_row_inner + t.s * p.c_row_split + t.m0 + q * 32;
-            const int c_col0 = p.c_col_base + t.bi * p.c_col_inner + t.n0;
+            const int c_row0 = (p.debug & 8) ? q * 32 : t.bo * p.c_row_outer + t.bi * p.c_row_inner + t.s * p.c_row_split + t.m0 + q * 32;
+            const int c_col0 = (p.debug & 8) ? 0 : p.c_col_base + t.bi * p.c_col_inner + t.n0;
 #pragma unroll 1
             for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
                 uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+                if (p.debug & 32) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = lane + j;
+                } else {
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+                }
                 if (c0 == (half + 1) * (BN / 2) - 32) {   // this warp's share fully read: hand TMEM back to the MMA warp early
                     tc_fence_before();
                     __syncwarp();
@@ -657,6 +663,13 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     DSB_COLSUM_STAGE(8) DSB_COLSUM_STAGE(4) DSB_COLSUM_STAGE(2) DSB_COLSUM_STAGE(1)
 #undef DSB_COLSUM_STAGE
                     if (t.valid) atomicAdd(p.colsum + c_col0 + c0 + lane, cs[0]);
+                }
+                if (p.debug & 16) {
+                    float acc_sink = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc_sink += v[j];
+                    if (acc_sink == 1.2345e-30f) p.c_hi[0] = __float2bfloat16(acc_sink);
+                    continue;
                 }
                 if (p.store_c) {
                     unsigned char* buf = my_buf + buf_sel * kStoreBufBytes;
@@ -912,16 +925,22 @@ int launch(const dsb_gemm_args& g, cudaStream_t stream) {
         bn = tiles256 >= 148 ? 256 : (g.n % 128 == 0 ? 128 : 64);
     }
     DSB_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: bn must be 64, 128 or 256");
-    // 2-CTA clusters halve the B-operand traffic out of L2 (each CTA fetches half of every B tile and multicasts it).
-    // Measured (M=135168, K=256, N=1024): +5 % for 1-term products, nothing for 3-term ones — those are bound by
-    // shared-memory bandwidth (MMA operand reads + TMA writes ~158 B/clk/SM against 128), which multicast does not
-    // reduce; that needs cta_group::2 MMAs (next round).  Auto-select only where it pays.
+    // Cluster modes.  mc = 2 (TMA multicast of the B tile to two CTAs) halves the B traffic out of L2: measured +5 % for 1-term
+    // products, nothing for 3-term ones.  mc = 4 (CTA pair, cta_group::2 MMAs, 256 x 256 tile over two SMs) cuts the operand
+    // bytes per SM and the shared-memory reads per MMA by a third: measured -10..-17 % on the plain 3-term products with one
+    // output form at M = 135168 (FFN up 19.0 -> 16.7 ms per step, FFN down 9.1 -> 7.5, the dX products 9.1 -> 8.0 / 7.4 -> 6.5),
+    // +19 % on the batched attention scores (two k blocks per tile: the pair's barrier round trips do not amortise) and +12 %
+    // on the dual-output QKV projection; implicit-GEMM convolutions have N <= 128.  DSB_GEMM_PAIR=0 (dev A/B) turns it off.
     int mcast = g.mc;
     if (!mcast) {
         const int64_t batch = g.batch > 0 ? g.batch : 1, splits = g.splits > 0 ? g.splits : 1;
         const int64_t num_m = (g.m + BM - 1) / BM;
         const int64_t pairs = batch * splits * ((num_m + 1) / 2) * (g.n / bn);
         mcast = (g.terms == 1 && bn >= 128 && num_m >= 2 && pairs >= 74) ? 2 : 1;
+        static const int pair_mode = getenv("DSB_GEMM_PAIR") ? atoi(getenv("DSB_GEMM_PAIR")) : 1;
+        if (pair_mode && g.terms == 3 && bn == 256 && batch == 1 && splits == 1 && pairs >= 74 && !g.a_conv && !g.b_conv &&
+            !(g.c && g.c_hi))
+            mcast = 4;
     }
     DSB_REQUIRE(mcast == 1 || ((mcast == 2 || mcast == 4) && bn >= 128), "gemm: mc must be 1, 2 or 4 (2 and 4 need bn >= 128)");
     if (mcast == 4) return bn == 256 ? launch_bn<256, 4>(g, stream) : launch_bn<128, 4>(g, stream);

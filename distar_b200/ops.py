@@ -629,15 +629,16 @@ def weight_grad(g_hi, g_lo, x_hi, x_lo, terms: int = 3, accumulate_into: Optiona
     result is added to that [N,K] tensor (the parameter's .grad) and None is returned."""
     M, N = g_hi.shape
     K = x_hi.shape[1]
-    splits = _pick_splits(((N + 127) // 128) * (K // 128), M)
+    kk = _pad_to(M, 64)                                 # rows behind M are TMA zero fill on both operands (any token count)
+    splits = _pick_splits(((N + 127) // 128) * (K // 128), kk)
     bx = 1 if x_lo is None else 0                       # the activation is exact in bf16: no dY_hi x X_lo product
     if accumulate_into is not None:
         _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=x_hi, b_lo=x_lo, a_mn=1, b_mn=1, alpha=1.0, terms=terms, c=accumulate_into, m=N,
-                 n=K, k=M, batch=1, inner=1, splits=splits, c_row_split=0, c_accumulate=1, b_exact=bx)
+                 n=K, k=kk, batch=1, inner=1, splits=splits, c_row_split=0, c_accumulate=1, b_exact=bx)
         return None
     gw = torch.zeros((N, K), dtype=torch.float32, device=g_hi.device) if splits > 1 else \
         torch.empty((N, K), dtype=torch.float32, device=g_hi.device)
-    _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=x_hi, b_lo=x_lo, a_mn=1, b_mn=1, alpha=1.0, terms=terms, c=gw, m=N, n=K, k=M,
+    _gemm_ex(a_hi=g_hi, a_lo=g_lo, b_hi=x_hi, b_lo=x_lo, a_mn=1, b_mn=1, alpha=1.0, terms=terms, c=gw, m=N, n=K, k=kk,
              batch=1, inner=1, splits=splits, c_row_split=0, c_accumulate=1 if splits > 1 else 0, b_exact=bx)
     return gw
 
@@ -724,7 +725,7 @@ class _SplitLinear(torch.autograd.Function):
         elif g_pass is not None:
             gx = g_pass
         if ctx.needs_input_grad[1]:
-            if on_gpu and N % 64 == 0 and K % 128 == 0 and M % 64 == 0 and M >= 128:
+            if on_gpu and N % 64 == 0 and K % 128 == 0:
                 gw = weight_grad(g_hi, g_lo, a_hi, a_lo, ctx.terms, accumulate_into=_grad_slot(ctx.weight_ref))
             else:
                 gfull = g if g is not None else (g_hi.float() + g_lo.float())

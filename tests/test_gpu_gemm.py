@@ -329,3 +329,36 @@ def test_linear_64_wide_output():
     for got, want, n in [(xd.grad, xr.grad, 'dx'), (wd.grad, wr.grad, 'dw'), (bd.grad, br.grad, 'db')]:
         err = (got.double().cpu() - want).abs().max().item()
         assert err <= 1e-4 * want.abs().max().item(), (n, err)
+
+
+@pytest.mark.parametrize('b_mn', [0, 1])
+def test_gemm_auto_pair_matches_single_cta(b_mn):
+    """M large enough for the automatic CTA-pair choice (>= 74 tile pairs): bit-identical to the single-CTA kernel, including
+    the ReLU-mask + column-sum epilogue of the FFN dH product (same k order, same term order, same epilogue arithmetic)."""
+    M, N, K = 74 * 256 + 100, 512, 256
+    g = torch.Generator().manual_seed(7 + b_mn)
+    a = torch.randn(M, K, generator=g)
+    w = (torch.randn(K, N, generator=g) if b_mn else torch.randn(N, K, generator=g)) / K ** 0.5
+    a_hi, a_lo = _split(a)
+    w_hi, w_lo = _split(w)
+    mask = torch.relu(torch.randn(M, N, generator=g)).to(DEV).bfloat16()
+    outs = []
+    for mc in (1, 0):
+        c_hi = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        c_lo = torch.empty_like(c_hi)
+        colsum = torch.zeros(N, device=DEV)
+        _lib.gemm_ex(a_hi=a_hi, a_lo=a_lo, b_hi=w_hi, b_lo=w_lo, alpha=1.0, terms=3, c=None, c_hi=c_hi, c_lo=c_lo, m=M, n=N, k=K,
+                     batch=1, inner=1, splits=1, b_mn=b_mn, relu_mask=mask, colsum=colsum, bn=256, mc=mc)
+        c = torch.empty(M, N, device=DEV)
+        _lib.gemm_ex(a_hi=a_hi, a_lo=a_lo, b_hi=w_hi, b_lo=w_lo, alpha=1.0, terms=3, c=c, m=M, n=N, k=K, batch=1, inner=1,
+                     splits=1, b_mn=b_mn, bn=256, mc=mc)
+        torch.cuda.synchronize()
+        outs.append((c_hi, c_lo, colsum, c))
+    (h1, l1, s1, c1), (h0, l0, s0, c0) = outs
+    assert torch.equal(c1, c0) and torch.equal(h1, h0) and torch.equal(l1, l0)
+    ref = a.double() @ (w.double() if b_mn else w.double().t())
+    _check(c0, ref)
+    masked = ref * (mask.cpu().double() > 0)
+    assert (h0.double().cpu() + l0.double().cpu() - masked).abs().max() <= 2e-5 * ref.abs().max()
+    assert (s0.double().cpu() - masked.sum(0)).abs().max() <= 1e-4 * masked.abs().sum(0).max()
+    assert (s1 - s0).abs().max() <= 1e-4 * s0.abs().max()          # atomics: order differs

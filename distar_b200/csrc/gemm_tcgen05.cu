@@ -878,7 +878,7 @@ int launch_bn(const dsb_gemm_args& g, cudaStream_t stream) {
     static const int debug_bits = getenv("DSB_GEMM_DEBUG") ? atoi(getenv("DSB_GEMM_DEBUG")) : 0;
     p.debug = debug_bits;
     static const int no_prefetch = getenv("DSB_GEMM_NO_PREFETCH") ? atoi(getenv("DSB_GEMM_NO_PREFETCH")) : 0;   // DEV ONLY (A/B)
-    p.prefetch = !no_prefetch && g.terms == 1;   // measured: -21 % time for 1-term products, nothing (or worse) for 3-term ones
+    p.prefetch = !no_prefetch && g.terms == 1;   // measured: -21 % time for 1-term products; 3-term ones get slower (CTA pair: FFN up 175 -> 184 us, FFN down 165 -> 208)
     p.num_m = num_m; p.num_n = num_n; p.num_k = g.k / (BK * splits);
     p.batch = batch; p.inner = inner; p.splits = splits;
     p.c_row_outer = g.c_row_outer; p.c_row_inner = g.c_row_inner; p.c_row_split = g.c_row_split;

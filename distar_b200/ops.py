@@ -934,7 +934,7 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
         sp = getattr(x, '_dsb_split', None)
         if sp is None or sp[0].shape != x.shape:
             sp = (None, None)
-        emit = emit_split and x.is_cuda
+        emit = emit_split if x.is_cuda else False       # True: fp32 + pair, 'only': pair only
         y, y_hi, y_lo, x_pass = _SplitLinear.apply(x, weight, bias, relu, terms, sp[0], sp[1], emit, fork and x.is_cuda)
         y = attach_split(y, y_hi, y_lo) if emit else y
         if x.is_cuda and not relu:

@@ -29,7 +29,7 @@ def timed(run):
 
 
 for (M, K, N, tag) in ((264 * 512, 256, 1024, 'ffn1'), (264 * 512, 1024, 256, 'ffn2'), (264 * 512, 256, 768, 'qkv'),
-                       (264 * 512, 256, 256, 'proj')):
+                       (264 * 512, 256, 256, 'proj'), (264 * 256, 1152, 128, 'conv16'), (1024 * 1024, 1152, 128, 'conv32')):
     if only and tag not in only:
         continue
     a = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) / 16; b = torch.randn(N, device=dev)

@@ -50,6 +50,8 @@ def compact_rl_batch(batch: Dict) -> Dict:
            'reward': {k: v.clone() for k, v in batch['reward'].items()}, 'step': batch['step'].clone(),
            'actions_mask': {k: v.clone() for k, v in batch['mask']['actions_mask'].items()},
            'frame_masks': {k: batch['mask'][k].clone() for k in ('cum_action_mask', 'build_order_mask', 'built_unit_mask', 'effect_mask')}}
+    if 'value_feature' in batch:                 # use_value_feature: already wire-sized (uint8 / bool / int16 fields), passed through
+        out['value_feature'] = {k: v.clone() for k, v in batch['value_feature'].items()}
     # ---- entity fields, un-padded, grouped by dtype
     keep = torch.arange(MAX_ENTITY_NUM).unsqueeze(0) < en_all.unsqueeze(1)              # [N, 512]
     groups: Dict[torch.dtype, list] = {}
@@ -161,7 +163,10 @@ def expand_rl_batch(compact: Dict, device=None, staged: Dict = None) -> Dict:
     mask['selected_units_mask'] = _seq_mask(num, 0, MAX_SELECTED_UNITS_NUM).view(T, B, -1)
     mask['selected_units_logits_mask'] = _seq_mask(en, 1, MAX_ENTITY_NUM + 1).view(T, B, -1)
     mask['target_units_logits_mask'] = _seq_mask(en, 0, MAX_ENTITY_NUM).view(T, B, -1)
-    return {'spatial_info': sp, 'entity_info': entity_info, 'scalar_info': c['scalar_info'], 'entity_num': en_all,
-            'hidden_state': c['hidden_state'], 'action_info': action_info, 'selected_units_num': c['selected_units_num'],
-            'behaviour_logp': behaviour_logp, 'teacher_logit': teacher, 'mask': mask, 'reward': c['reward'], 'step': c['step'],
-            'batch_size': B, 'unroll_len': T}
+    out = {'spatial_info': sp, 'entity_info': entity_info, 'scalar_info': c['scalar_info'], 'entity_num': en_all,
+           'hidden_state': c['hidden_state'], 'action_info': action_info, 'selected_units_num': c['selected_units_num'],
+           'behaviour_logp': behaviour_logp, 'teacher_logit': teacher, 'mask': mask, 'reward': c['reward'], 'step': c['step'],
+           'batch_size': B, 'unroll_len': T}
+    if 'value_feature' in c:
+        out['value_feature'] = c['value_feature']
+    return out

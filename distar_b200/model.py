@@ -75,10 +75,11 @@ class Model(nn.Module):
         sy = int(_cfg_get(cfg, 'model.spatial_y', 152))
         self.spatial_x, self.spatial_y = sx, sy
         self.temperature = float(temperature if temperature is not None else _cfg_get(cfg, 'model.temperature', 1.0))
-        if _cfg_get(cfg, 'learner.use_value_feature', False):
-            raise NotImplementedError('use_value_feature=True (ValueEncoder) is outside the hot-path scope')
         enabled = list(_cfg_get(cfg, 'model.enable_baselines', BASELINES)) if use_value_network else []
         self.baselines = [b for b in BASELINES if b in enabled]
+        # model.py:31-39: the ValueEncoder exists only next to a value network; every baseline then reads
+        # [lstm output | value feature | scalar-encoder baseline feature]
+        self.use_value_feature = bool(_cfg_get(cfg, 'learner.use_value_feature', False)) and len(self.baselines) > 0
         self.only_update_baseline = bool(_cfg_get(cfg, 'model.only_update_baseline', False))
         self.gemm_terms, self.sample_rng = gemm_terms, sample_rng
         # observation rows are independent in the encoder: process them in chunks (and, while training,
@@ -89,10 +90,10 @@ class Model(nn.Module):
         self.cfg = _to_cfg({'encoder': {'core_lstm': {'num_layers': 3, 'hidden_size': 384, 'input_size': 1536}},
                             'temperature': self.temperature, 'spatial_x': sx, 'spatial_y': sy,
                             'enable_baselines': self.baselines})
-        self._specs = param_specs(sx, sy, self.baselines)
+        self._specs = param_specs(sx, sy, self.baselines, self.use_value_feature)
         if seed is None:
             seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
-        sd = init_state_dict(seed, sx, sy, self.baselines, perturb=0.0)
+        sd = init_state_dict(seed, sx, sy, self.baselines, perturb=0.0, use_value_feature=self.use_value_feature)
         n_train = sum(int(torch.tensor(s).prod()) if len(s) else 1 for _, s, k in self._specs if is_trainable(k))
         self._offsets = {}
         flat = torch.empty(n_train, dtype=torch.float32)
@@ -257,6 +258,24 @@ class Model(nn.Module):
         cat = [torch.cat([o[i] for o in outs], dim=0) for i in range(len(outs[0]))]
         return cat[0], cat[1], cat[2], cat[3], [None, None, None] + cat[4:]
 
+    def _value_encode(self, net: Net, vf) -> torch.Tensor:
+        """ValueEncoder over all (T+1)*B rows.  Its spatial tower works at full map resolution (~4.5 MB of activations per
+        row): it runs in `encoder_chunk`-row chunks and, while training, is recomputed in backward."""
+        N = vf['total_unit_count'].shape[0]
+        chunk = self.encoder_chunk
+        if not chunk or N <= chunk:
+            return net.value_encoder(vf)
+        ckpt = self.checkpoint_encoder and torch.is_grad_enabled()
+
+        def spatial_fn(*args):
+            outs = []
+            for s0 in range(0, N, chunk):
+                part = tuple(a[s0:s0 + chunk] for a in args)
+                outs.append(torch_checkpoint(net.value_encoder_spatial, *part, use_reentrant=False) if ckpt
+                            else net.value_encoder_spatial(*part))
+            return torch.cat(outs, dim=0)
+        return net.value_encoder(vf, spatial_fn=spatial_fn)
+
     def forward(self, spatial_info, entity_info, scalar_info, entity_num, hidden_state):
         """model.py:46-54."""
         out = self.compute_logp_action(spatial_info, entity_info, scalar_info, entity_num, hidden_state)
@@ -315,6 +334,9 @@ class Model(nn.Module):
                                           scalar_context[:-B], entity_num[:-B], flat_action, flat_su_num,
                                           su_steps=su_steps() if su_steps is not None else None)
         critic_input = lstm_out.detach() if self.only_update_baseline else lstm_out
+        if self.use_value_feature:                                                  # model.py:141-144
+            bf = baseline_feature.detach() if self.only_update_baseline else baseline_feature
+            critic_input = torch.cat([critic_input, self._value_encode(net, kwargs['value_feature']), bf], dim=1)
         values = {k: net.value_baseline(k, critic_input).view(T + 1, B) for k in self.baselines}
         logits = {k: v.view(T, B, *v.shape[1:]) for k, v in logits.items()}
         su = logits['selected_units']

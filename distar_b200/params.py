@@ -29,9 +29,9 @@ def _binary_table(rows: int, bits: int) -> torch.Tensor:
 
 
 def init_state_dict(seed: int = 0, spatial_x: int = 128, spatial_y: int = 128, baselines=('winloss',),
-                    perturb: float = 0.1) -> Dict[str, torch.Tensor]:
+                    perturb: float = 0.1, use_value_feature: bool = False) -> Dict[str, torch.Tensor]:
     sd = {}
-    for name, shape, kind in param_specs(spatial_x, spatial_y, baselines):
+    for name, shape, kind in param_specs(spatial_x, spatial_y, baselines, use_value_feature):
         g = _gen(seed, name)
         if kind == 'xavier_normal':
             rf = 1

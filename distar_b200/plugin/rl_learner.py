@@ -24,9 +24,9 @@ class _SyntheticDataloader:
     """job_type != 'train' (no league to pull trajectories from): seeded synthetic learner batches, the role of the
     ``FakeDataloader`` the stock class refers to (rl_learner.py:192-196)."""
 
-    def __init__(self, batch_size, unroll_len, device):
+    def __init__(self, batch_size, unroll_len, device, value_feature=False):
         from distar_b200.synth import synth_rl_batch, tree_map
-        self._batch = tree_map(lambda t: t.to(device), synth_rl_batch(batch_size, unroll_len, seed=0))
+        self._batch = tree_map(lambda t: t.to(device), synth_rl_batch(batch_size, unroll_len, seed=0, value_feature=value_feature))
 
     def __iter__(self):
         return self
@@ -63,7 +63,8 @@ class RLLearner(_Base):
     def _setup_dataloader(self):
         if self._job_type != 'train':
             self._dataloader = _SyntheticDataloader(self._whole_cfg.learner.data.batch_size,
-                                                    self._whole_cfg.actor.get('traj_len', 2), self._device)
+                                                    self._whole_cfg.actor.get('traj_len', 2), self._device,
+                                                    bool(self._whole_cfg.learner.get('use_value_feature', False)))
 
     def _get_iter_data(self):
         return next(self._dataloader)

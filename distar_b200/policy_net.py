@@ -58,6 +58,9 @@ BASELINE_ATAN = {'winloss': True, 'build_order': False, 'built_unit': False, 'ef
                  'battle': False}
 
 
+VALUE_FC_FIELDS = ['enemy_unit_counts_bow', 'enemy_unit_type_bool', 'enemy_agent_statistics', 'enemy_upgrades', 'cumulative_stat']
+
+
 def set_library_precision():
     """The reference computes in fp32 end to end.  PyTorch lets cuDNN convolutions silently use TF32 (10-bit mantissa),
     which alone costs ~1e-3 on the location logits; the parts of the path that are still library calls must run in
@@ -143,6 +146,29 @@ class Net:
         return x
 
     # -------------------------------------------------------------------------------------- encoders
+    def bo_embedding(self, pre: str, bo: Tensor, loc: Tensor) -> Tensor:
+        """BeginningBuildOrderEncoder.forward (scalar_encoder.py:34-53); `pre` selects the scalar encoder's or the value
+        encoder's copy of the module."""
+        P = self.P
+        if bo.is_cuda:
+            # token features straight into the embedding GEMM's exact bf16 operand (all of them are 0 / 1)
+            tp = pre + 'transformer'
+            hi = ops.bo_tokens(bo, loc, self.W)
+            w = P[tp + '.embedding.0.weight']
+            x0 = ops.linear_presplit(hi, None, F.pad(w, (0, hi.shape[1] - w.shape[1])), P[tp + '.embedding.0.bias'], True,
+                                     self.terms).view(bo.shape[0], bo.shape[1], -1)
+            t = self.transformer(tp, x0, None, 2, 8, post_ln=False, embedded=True)
+            return self.fc(pre + 'embedd_fc', t.mean(dim=1), relu=True)
+        bo, loc = bo.long(), loc.long()
+        B, dev = bo.shape[0], bo.device
+        bits = torch.arange(9, -1, -1, device=dev)
+        tok = torch.cat([F.one_hot(bo, 174).float(),
+                         torch.eye(20, device=dev).unsqueeze(0).expand(B, -1, -1),
+                         (((loc % self.W).unsqueeze(-1) >> bits) & 1).float(),
+                         (((loc // self.W).unsqueeze(-1) >> bits) & 1).float()], dim=2)
+        t = self.transformer(pre + 'transformer', tok, None, 2, 8, post_ln=False)
+        return self.fc(pre + 'embedd_fc', t.mean(dim=1), relu=True)
+
     def scalar_encoder(self, s: Dict[str, Tensor]):
         """obs_encoder/scalar_encoder.py:99-132 (K8)."""
         P, pre = self.P, 'encoder.scalar_encoder.encode_modules.'
@@ -157,29 +183,7 @@ class Net:
                 e = self.fc(pre + name, x if x.is_cuda else x.float(), relu=True,
                             exact=x.dtype in (torch.uint8, torch.int8, torch.int16))
             else:
-                if s['beginning_order'].is_cuda:
-                    # token features straight into the embedding GEMM's exact bf16 operand (all of them are 0 / 1)
-                    bo = s['beginning_order']
-                    tp = pre + 'beginning_order.transformer'
-                    hi = ops.bo_tokens(bo, s['bo_location'], self.W)
-                    w = P[tp + '.embedding.0.weight']
-                    x0 = ops.linear_presplit(hi, None, F.pad(w, (0, hi.shape[1] - w.shape[1])), P[tp + '.embedding.0.bias'], True,
-                                             self.terms).view(bo.shape[0], bo.shape[1], -1)
-                    t = self.transformer(tp, x0, None, 2, 8, post_ln=False, embedded=True)
-                    e = self.fc(pre + 'beginning_order.embedd_fc', t.mean(dim=1), relu=True)
-                    outs.append(e)
-                    ctx.append(e)
-                    base.append(e)
-                    continue
-                bo, loc = s['beginning_order'].long(), s['bo_location'].long()
-                B = bo.shape[0]
-                bits = torch.arange(9, -1, -1, device=dev)
-                tok = torch.cat([F.one_hot(bo, 174).float(),
-                                 torch.eye(20, device=dev).unsqueeze(0).expand(B, -1, -1),
-                                 (((loc % self.W).unsqueeze(-1) >> bits) & 1).float(),
-                                 (((loc // self.W).unsqueeze(-1) >> bits) & 1).float()], dim=2)
-                t = self.transformer(pre + 'beginning_order.transformer', tok, None, 2, 8, post_ln=False)
-                e = self.fc(pre + 'beginning_order.embedd_fc', t.mean(dim=1), relu=True)
+                e = self.bo_embedding(pre + 'beginning_order.', s['beginning_order'], s['bo_location'])
             outs.append(e)
             if is_ctx:
                 ctx.append(e)
@@ -577,6 +581,50 @@ class Net:
         if BASELINE_ATAN[name]:
             v = (2.0 / math.pi) * torch.atan((math.pi / 2.0) * v)
         return v
+
+    # -------------------------------------------------------------------------------------- value encoder
+    def value_encoder_flat(self, vf: Dict[str, Tensor]):
+        """ValueEncoder.forward, obs_encoder/value_encoder.py:47-63,73: everything but the spatial tower, over all rows at once.
+        Returns (fc embeddings [N,352], beginning-order embedding [N,64], masked scatter projection [N,512,8])."""
+        P, pre = self.P, 'value_encoder.'
+        em = pre + 'encode_modules.'
+        fc = []
+        for k in VALUE_FC_FIELDS:                  # config order: actor_critic_default_config.yaml:29-64
+            x = vf[k]
+            fc.append(self.fc(em + k, x if x.is_cuda else x.float(), relu=True,
+                              exact=x.dtype in (torch.uint8, torch.int8, torch.int16)))
+        unit = torch.cat([F.embedding(vf['unit_alliance'].long(), P[em + 'unit_alliance.weight']),
+                          F.embedding(vf['unit_type'].long(), P[em + 'unit_type.weight'])], dim=-1)    # trainable nn.Embedding
+        bo = self.bo_embedding(em + 'beginning_order.', vf['beginning_order'], vf['bo_location'])
+        project = self.fc(pre + 'scatter_project', unit, relu=True)
+        E = project.shape[1]
+        valid = torch.arange(E, device=project.device).unsqueeze(0) < vf['total_unit_count'].unsqueeze(1)
+        return torch.cat(fc, dim=-1), bo, project * valid.unsqueeze(-1)
+
+    def value_encoder_spatial(self, project: Tensor, unit_x: Tensor, unit_y: Tensor, unit_count: Tensor, own: Tensor,
+                              enemy: Tensor) -> Tensor:
+        """value_encoder.py:64-72: scatter_connection of the 8-wide unit projection, + the two unit-presence planes, 1x1
+        project, (max-pool, 3x3 conv) x 3, four ResBlocks, spatial_fc -> [N,128].  The scatter runs on the 32-channel
+        scatter_connection kernel (channels 8..31 zero); the 16/32-channel convolutions are fp32 library calls (this tower
+        is 0.08 GFLOP per observation, outside the BASELINE hot path)."""
+        P, pre = self.P, 'value_encoder.'
+        N, _c, H, W = own.shape
+        smap = ops.scatter_connection(F.pad(project, (0, 32 - project.shape[-1])), unit_x, unit_y, unit_count, H, W)
+        x = torch.cat([smap[:, :project.shape[-1]], own.float(), enemy.float()], dim=1)
+        x = self.conv(pre + 'project', x, 0, relu=True)
+        for i in range(3):
+            x = self.conv(pre + 'downsample.%d' % (2 * i + 1), F.max_pool2d(x, 2, 2), 1, relu=True)
+        for i in range(4):
+            r = self.conv(pre + 'res.%d.conv1' % i, x, 1, relu=True)
+            x = torch.relu(self.conv(pre + 'res.%d.conv2' % i, r, 1) + x)
+        return self.fc(pre + 'spatial_fc', x.reshape(N, -1), relu=True)
+
+    def value_encoder(self, vf: Dict[str, Tensor], spatial_fn=None) -> Tensor:
+        """-> [N,544] = [fc embeddings | spatial | beginning order] (value_encoder.py:73)."""
+        fc, bo, project = self.value_encoder_flat(vf)
+        run = spatial_fn or self.value_encoder_spatial
+        sp = run(project, vf['unit_x'], vf['unit_y'], vf['total_unit_count'], vf['own_units_spatial'], vf['enemy_units_spatial'])
+        return torch.cat([fc, sp, bo], dim=-1)
 
     # -------------------------------------------------------------------------------------- policy
     def policy_sample(self, lstm_out, entity_embeddings, map_skip, scalar_context, entity_num, su_action_mask,

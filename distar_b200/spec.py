@@ -65,7 +65,36 @@ def _lnlstm(out: List[Spec], pre: str, din: int, hid: int, layers: int):
         _ln(out, cp + '.layernorm_c', hid)
 
 
-def param_specs(spatial_x: int = 128, spatial_y: int = 128, baselines=('winloss',)) -> List[Spec]:
+VALUE_FEATURE_DIM = 544          # ValueEncoder output: 352 (fc embeddings) + 128 (spatial_fc) + 64 (beginning order)
+
+
+def value_encoder_specs(o: List[Spec], spatial_x: int, spatial_y: int) -> None:
+    """ValueEncoder (obs_encoder/value_encoder.py:12-45; dims actor_critic_default_config.yaml:27-74), registration order."""
+    ve = 'value_encoder.'
+    em = ve + 'encode_modules.'
+    _fc(o, em + 'enemy_unit_counts_bow', 260, 64)
+    _fc(o, em + 'enemy_unit_type_bool', 260, 64)
+    _fc(o, em + 'enemy_agent_statistics', 10, 64)
+    _fc(o, em + 'enemy_upgrades', 90, 32)
+    o.append((em + 'unit_alliance.weight', (2, 16), 'randn'))            # nn.Embedding, trainable, N(0, 1)
+    o.append((em + 'unit_type.weight', (260, 48), 'randn'))
+    _fc(o, em + 'cumulative_stat', 167, 128)
+    _transformer(o, em + 'beginning_order.transformer', 214, 64, 128, 2, 8)
+    _fc(o, em + 'beginning_order.embedd_fc', 64, 64)
+    o.append((em + 'beginning_order.action_one_hot.weight', (174, 174), 'frozen_eye'))
+    o.append((em + 'beginning_order.order_one_hot.weight', (20, 20), 'frozen_eye'))
+    o.append((em + 'beginning_order.location_binary.weight', (1024, 10), 'frozen_binary'))
+    _fc(o, ve + 'scatter_project', 64, 8)
+    _conv(o, ve + 'project', 10, 16, 1)
+    for i, (a, b) in enumerate([(16, 16), (16, 32), (32, 32)]):
+        _conv(o, ve + 'downsample.%d' % (2 * i + 1), a, b, 3)            # nn.Sequential(pool, conv, pool, conv, pool, conv)
+    for i in range(4):
+        _conv(o, ve + 'res.%d.conv1' % i, 32, 32, 3)
+        _conv(o, ve + 'res.%d.conv2' % i, 32, 32, 3)
+    _fc(o, ve + 'spatial_fc', 32 * (spatial_y // 8) * (spatial_x // 8), 128)
+
+
+def param_specs(spatial_x: int = 128, spatial_y: int = 128, baselines=('winloss',), use_value_feature: bool = False) -> List[Spec]:
     """Ordered exactly like the reference's state_dict."""
     o: List[Spec] = []
     se = 'encoder.scalar_encoder.'
@@ -151,11 +180,14 @@ def param_specs(spatial_x: int = 128, spatial_y: int = 128, baselines=('winloss'
     _fc(o, lh + 'project_embed', 1024, (spatial_y // 8) * (spatial_x // 8) * 4)
     for i, (a, b) in enumerate([(128, 64), (64, 32), (32, 1)]):
         _conv(o, lh + 'upsample.%d' % i, a, b, 3)
+    if use_value_feature and len(baselines):          # model.py:31-34: only with a value network
+        value_encoder_specs(o, spatial_x, spatial_y)
     for b in BASELINES:
         if b not in baselines:
             continue
         vp = 'value_networks.%s.' % b
-        _fc(o, vp + 'project', 384, 256)
+        # value.py:20-23: + 1056 = value feature (544) + the scalar encoder's baseline feature (512)
+        _fc(o, vp + 'project', 384 + (VALUE_FEATURE_DIM + 512 if use_value_feature else 0), 256)
         for i in range(16):
             _fc(o, vp + 'res.%d.fc1' % i, 256, 256)
             _fc(o, vp + 'res.%d.fc2' % i, 256, 256)

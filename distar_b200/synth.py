@@ -117,7 +117,30 @@ def _masked_logits(shape, valid: torch.Tensor, g) -> torch.Tensor:
     return torch.randn(shape, generator=g).masked_fill(~valid, -1e9)
 
 
-def synth_rl_batch(batch_size: int, unroll_len: int, seed: int = 0, entity_num=None, max_su: int = 12) -> Dict:
+def synth_value_feature(rows: int, seed: int = 0) -> Dict:
+    """The `value_feature` entry of a learner batch (use_value_feature: True), dtypes as lib/features.py:690-765 builds them
+    plus the behaviour z the agent merges in (agent.py:562-564,609-613): opponent unit statistics, the positions / types of
+    all visible units (enemy first, padded to MAX_ENTITY_NUM) and two boolean unit-presence planes."""
+    g = torch.Generator(device='cpu')
+    g.manual_seed(seed + 15485863)
+    total = _ri(g, 1, E + 1, (rows,), torch.int64)
+    valid = torch.arange(E).unsqueeze(0) < total.unsqueeze(1)
+    bow = _ri(g, 0, 4, (rows, 260), torch.uint8) * (torch.rand((rows, 260), generator=g) < 0.1).to(torch.uint8)
+    return {'unit_type': (_ri(g, 0, 260, (rows, E), torch.int16) * valid).to(torch.int16),
+            'enemy_unit_counts_bow': bow, 'enemy_unit_type_bool': (bow > 0).to(torch.uint8),
+            'unit_x': (_ri(g, 0, W, (rows, E), torch.uint8) * valid).to(torch.uint8),
+            'unit_y': (_ri(g, 0, H, (rows, E), torch.uint8) * valid).to(torch.uint8),
+            'unit_alliance': (torch.rand((rows, E), generator=g) < 0.4) & valid, 'total_unit_count': total,
+            'enemy_agent_statistics': torch.log(_ri(g, 0, 2000, (rows, 10), torch.int64).float() + 1),
+            'enemy_upgrades': (torch.rand((rows, 90), generator=g) < 0.1).to(torch.uint8),
+            'own_units_spatial': torch.rand((rows, 1, H, W), generator=g) < 0.02,
+            'enemy_units_spatial': torch.rand((rows, 1, H, W), generator=g) < 0.02,
+            'beginning_order': _ri(g, 0, 174, (rows, 20), torch.int64), 'bo_location': _ri(g, 0, H * W, (rows, 20), torch.int64),
+            'cumulative_stat': (torch.rand((rows, 167), generator=g) < 0.2).long()}
+
+
+def synth_rl_batch(batch_size: int, unroll_len: int, seed: int = 0, entity_num=None, max_su: int = 12,
+                   value_feature: bool = False) -> Dict:
     """One learner batch in the reference's collate layout (see module docstring)."""
     B, T = batch_size, unroll_len
     obs = synth_obs((T + 1) * B, seed=seed, entity_num=entity_num)
@@ -157,6 +180,8 @@ def synth_rl_batch(batch_size: int, unroll_len: int, seed: int = 0, entity_num=N
     batch.update({'action_info': action_info, 'selected_units_num': selected_units_num,
                   'behaviour_logp': behaviour_logp, 'teacher_logit': teacher, 'mask': mask, 'reward': reward,
                   'step': step, 'batch_size': B, 'unroll_len': T})
+    if value_feature:
+        batch['value_feature'] = synth_value_feature((T + 1) * B, seed=seed)
     return batch
 
 

@@ -300,6 +300,41 @@ def encoder(P: Params, spatial_info, entity_info, scalar_info, entity_num):
     return lstm_input, scalar_context, baseline_feature, entity_embeddings, map_skip
 
 
+VALUE_FC_FIELDS = ['enemy_unit_counts_bow', 'enemy_unit_type_bool', 'enemy_agent_statistics', 'enemy_upgrades', 'cumulative_stat']
+
+
+def _bo_tokens(bo: Tensor, loc: Tensor, spatial_x: int) -> Tensor:
+    """BeginningBuildOrderEncoder.forward up to the transformer input, scalar_encoder.py:34-48."""
+    B = bo.shape[0]
+    return torch.cat([F.one_hot(bo.long(), BO_ACTIONS).float(), torch.eye(BO_LEN).unsqueeze(0).expand(B, -1, -1),
+                      binary_rows(loc.long() % spatial_x, 10), binary_rows(loc.long() // spatial_x, 10)], dim=2)
+
+
+def value_encoder(P: Params, vf: Dict[str, Tensor], spatial_x: int) -> Tensor:
+    """ValueEncoder.forward, obs_encoder/value_encoder.py:47-74 (module order: actor_critic_default_config.yaml:29-64)."""
+    pre = 'value_encoder.'
+    em = pre + 'encode_modules.'
+    fc = [_fc(P, em + k, vf[k].float(), relu=True) for k in VALUE_FC_FIELDS]                       # :50-53
+    unit = torch.cat([P[em + 'unit_alliance.weight'][vf['unit_alliance'].long()],
+                      P[em + 'unit_type.weight'][vf['unit_type'].long()]], dim=-1)                  # :54-56 (nn.Embedding)
+    t = transformer(P, em + 'beginning_order.transformer', _bo_tokens(vf['beginning_order'], vf['bo_location'], spatial_x),
+                    None, heads=2, head_dim=8, layers=3, ln_type='pre')
+    bo = _fc(P, em + 'beginning_order.embedd_fc', t.mean(dim=1), relu=True)                         # :58
+    project = _fc(P, pre + 'scatter_project', unit, relu=True)                                      # :61
+    project = project * sequence_mask(vf['total_unit_count'], project.shape[1]).unsqueeze(2)        # :62-63
+    N, _c, H, W = vf['own_units_spatial'].shape
+    scatter_map = scatter_connection(project, vf['unit_x'], vf['unit_y'], H, W)                     # :64-66
+    x = torch.cat([scatter_map, vf['own_units_spatial'].float(), vf['enemy_units_spatial'].float()], dim=1)
+    x = _conv(P, pre + 'project', x, 0, relu=True)                                                  # :68
+    for i in range(3):                                                                              # :69 nn.Sequential(pool, conv) x 3
+        x = _conv(P, pre + 'downsample.%d' % (2 * i + 1), F.max_pool2d(x, 2, 2), 1, relu=True)
+    for i in range(4):                                                                              # :70-71 ResBlock, res_block.py:56-65
+        r = _conv(P, pre + 'res.%d.conv1' % i, x, 1, relu=True)
+        x = torch.relu(_conv(P, pre + 'res.%d.conv2' % i, r, 1) + x)
+    x = _fc(P, pre + 'spatial_fc', x.reshape(N, -1), relu=True)                                     # :72
+    return torch.cat(fc + [x, bo], dim=-1)                                                          # :73
+
+
 # --------------------------------------------------------------------------------------------
 # LayerNorm LSTM (model/lstm.py:120-167,215-234)
 # --------------------------------------------------------------------------------------------
@@ -607,19 +642,24 @@ def enabled_baselines(P: Params) -> List[str]:
 
 def rl_learner_forward(P: Params, spatial_info, entity_info, scalar_info, entity_num, hidden_state, action_info,
                        selected_units_num, behaviour_logp, teacher_logit, mask, reward, step, batch_size,
-                       unroll_len, temperature: float = 1.0, **_):
-    """Model.rl_learner_forward, model/model.py:95-168 (use_value_feature False, only_update_baseline False)."""
+                       unroll_len, temperature: float = 1.0, value_feature=None, **_):
+    """Model.rl_learner_forward, model/model.py:95-168 (only_update_baseline False; use_value_feature when the weights hold
+    a value encoder: critic input = [lstm output | value feature | scalar encoder baseline feature], :141-144)."""
     B, T = batch_size, unroll_len
     flat_action = {k: v.flatten(0, 1) for k, v in action_info.items()}
     flat_su_num = selected_units_num.flatten(0, 1)
-    lstm_input, scalar_context, _b, entity_embeddings, map_skip = encoder(
+    lstm_input, scalar_context, baseline_feature, entity_embeddings, map_skip = encoder(
         P, spatial_info, entity_info, scalar_info, entity_num)
     state0 = [(h.view(-1, B, h.shape[-1])[0], c.view(-1, B, c.shape[-1])[0]) for h, c in hidden_state]
     lstm_out, _ = lnlstm(P, 'core_lstm', lstm_input.view(-1, B, lstm_input.shape[-1]), state0, 3)
     lstm_out = lstm_out.reshape(-1, lstm_out.shape[-1])
     _a, _n, logits = policy_train(P, lstm_out[:-B], entity_embeddings[:-B], [m[:-B] for m in map_skip],
                                   scalar_context[:-B], entity_num[:-B], flat_action, flat_su_num, temperature)
-    values = {k: value_baseline(P, k, lstm_out, BASELINE_ATAN[k]).view(T + 1, B) for k in enabled_baselines(P)}
+    critic_input = lstm_out
+    if 'value_encoder.project.0.weight' in P:
+        W = spatial_info['height_map'].shape[-1]
+        critic_input = torch.cat([lstm_out, value_encoder(P, value_feature, W), baseline_feature], dim=1)
+    values = {k: value_baseline(P, k, critic_input, BASELINE_ATAN[k]).view(T + 1, B) for k in enabled_baselines(P)}
     logits = {k: v.view(T, B, *v.shape[1:]) for k, v in logits.items()}
     su = logits['selected_units']
     logits['selected_units'] = F.pad(su, (0, 0, 0, MAX_SELECTED_UNITS_NUM - su.shape[2]), 'constant', -1e9)

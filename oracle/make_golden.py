@@ -67,7 +67,16 @@ def rl_chunk_case():
     return batch
 
 
-FULL_GRADS = ['policy.action_type_head.action_fc.layer2.0.bias', 'core_lstm.layers.2.cell.layernorm_c.weight',
+def rl_value_case():
+    """learner.use_value_feature: True (bin/rl_user_config.yaml self-play default): 8 rows with the ValueEncoder inputs."""
+    return synth_rl_batch(2, 3, seed=71, entity_num='random', max_su=6, value_feature=True)
+
+
+VALUE_BASELINES = ('winloss', 'battle')
+VALUE_WEIGHT_SEED = 4
+
+FULL_GRADS = ['value_encoder.encode_modules.unit_type.weight', 'value_encoder.project.0.weight',
+              'value_encoder.spatial_fc.0.bias', 'policy.action_type_head.action_fc.layer2.0.bias', 'core_lstm.layers.2.cell.layernorm_c.weight',
               'encoder.scatter_project.0.weight', 'value_networks.winloss.value_fc.0.weight',
               'policy.selected_units_head.end_embedding', 'encoder.spatial_encoder.project.0.weight']
 
@@ -92,8 +101,23 @@ def dump_rl(model, loss_fn, batch, meta, path, compact):
                 'grad_norm': grad_norm, 'grad_proj': proj, 'grads': grads}, path)
 
 
+def value_feature_golden():
+    model, cfg, mods = ref_import.load_reference(spatial=128, enable_baselines=VALUE_BASELINES, use_value_feature=True)
+    sd = init_state_dict(seed=VALUE_WEIGHT_SEED, baselines=VALUE_BASELINES, use_value_feature=True)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    meta = {'weight_seed': VALUE_WEIGHT_SEED, 'baselines': list(VALUE_BASELINES), 'use_value_feature': True,
+            'weights_checksum': checksum(sd), 'torch': str(torch.__version__)}
+    dump_rl(model, mods['ReinforcementLoss'](cfg.learner, 'MP0'), rl_value_case(), meta, os.path.join(OUT, 'rl_value_feature.pt'),
+            compact=True)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if '--only-value-feature' in sys.argv:
+        value_feature_golden()
+        print('rl_value_feature.pt', os.path.getsize(os.path.join(OUT, 'rl_value_feature.pt')))
+        return
     model, cfg, mods = ref_import.load_reference(spatial=128, enable_baselines=BASELINES)
     sd = init_state_dict(seed=WEIGHT_SEED, baselines=BASELINES)
     model.load_state_dict(sd, strict=True)
@@ -129,6 +153,7 @@ def main():
                 'selected_units_num': r['selected_units_num'],
                 'logit': {k: compact_logits(v) for k, v in r['logit'].items()},
                 'hidden_state': r['hidden_state']}, os.path.join(OUT, 'infer32.pt'))
+    value_feature_golden()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -50,7 +50,7 @@ def install_shims():
                 setattr(sys.modules['s2clientprotocol'], name.split('.')[1], sys.modules[name])
 
 
-def load_reference(spatial=128, enable_baselines=('winloss',), seed=0):
+def load_reference(spatial=128, enable_baselines=('winloss',), seed=0, use_value_feature=False):
     """Returns (model, cfg, modules) with modules = dict(F=features, ReinforcementLoss=..., SupervisedLoss=...)."""
     assert reference_available(), 'reference tree not mounted'
     install_shims()
@@ -62,7 +62,7 @@ def load_reference(spatial=128, enable_baselines=('winloss',), seed=0):
     from distar.ctools.utils import read_config
     cfg = read_config(os.path.join(REFERENCE_ROOT, 'distar/bin/rl_user_config.yaml'))
     cfg.common.type = 'rl'
-    cfg.learner.use_value_feature = False
+    cfg.learner.use_value_feature = bool(use_value_feature)
     cfg.learner.player_id = 'MP0'
     cfg.model.spatial_x = cfg.model.spatial_y = spatial
     cfg.model.enable_baselines = list(enable_baselines)

@@ -340,3 +340,38 @@ def test_weight_publication_maps_between_arena_layouts(sd):
     for n, p in actor.named_parameters():
         if p.requires_grad:
             assert torch.equal(p, lp[n]), n
+
+
+@pytest.mark.parametrize('chunk', [0, 2])
+def test_rl_step_with_value_feature_matches_oracle(monkeypatch, chunk):
+    """learner.use_value_feature: True - ValueEncoder (value_encoder.py:47-74) in front of every baseline (model.py:141-144),
+    with and without the chunked / recomputed spatial tower."""
+    monkeypatch.setattr(ops, 'split_bf16', lambda x: (x.contiguous(), torch.zeros_like(x)))
+    sd = init_state_dict(seed=4, baselines=('winloss', 'battle'), use_value_feature=True)
+    cfg = {'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': ['winloss', 'battle']},
+           'learner': {'use_value_feature': True}}
+    m = Model(cfg, use_value_network=True, seed=0, encoder_chunk=chunk)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd)
+    batch = synth_rl_batch(2, 2, seed=23, entity_num='random', max_su=5, value_feature=True)
+    P = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    o_out = O.rl_learner_forward(P, **tree_clone(batch))
+    o_info = O.rl_loss(o_out)
+    o_info['total_loss'].backward()
+    m.zero_grad()
+    out = m.rl_learner_forward(**tree_clone(batch))
+    info = ReinforcementLoss(None, 'MP0').compute_loss(out)
+    info['total_loss'].backward()
+    for k in o_out['value']:
+        _close(out['value'][k], o_out['value'][k], 'value/' + k)
+    gmax = max(P[n].grad.abs().max().item() for n, p in m.named_parameters() if p.requires_grad)
+    n_ve = 0
+    for n, p in m.named_parameters():
+        if p.requires_grad:
+            g = P[n].grad
+            assert (p.grad - g).abs().max().item() <= 2e-3 * max(g.abs().max().item(), 1e-3 * gmax), n
+            n_ve += n.startswith('value_encoder.')
+    assert n_ve > 60
+    # an actor-side model (no value network) has no value encoder even with the flag set (model.py:31-34)
+    actor = Model(cfg, use_value_network=False, seed=0)
+    assert not any(k.startswith('value_') for k in actor.state_dict())

@@ -33,7 +33,7 @@ def _cfg(name, load_path=''):
     cfg.learner.job_type = 'eval'                     # no league / coordinator in a unit test: synthetic batches
     cfg.learner.use_cuda = False
     cfg.learner.use_distributed = False
-    cfg.learner.use_value_feature = False             # as `rl_train.py --task bot` sets it (rl_train.py:134-136)
+    assert cfg.learner.use_value_feature              # the shipped self-play default: ValueEncoder in front of the baselines
     cfg.learner.player_id = 'MP0'
     cfg.learner.load_path = load_path
     cfg.learner.load_optimizer = True                 # (bin/rl_user_config.yaml ships it off; the hook default is on)
@@ -71,7 +71,7 @@ def test_b200_pipeline_runs_under_the_reference_learner_framework(pipeline):
     assert torch.equal(resumed.model.flat_param, learner.model.flat_param)
     assert torch.equal(resumed.optimizer.exp_avg_sq, learner.optimizer.exp_avg_sq)
     # the reference's torch.optim.Adam accepts the optimizer entry of OUR checkpoint (same per-parameter layout)
-    ref_model, _cfg_ref, _mods = ref_import.load_reference(spatial=128, enable_baselines=('winloss',))
+    ref_model, _cfg_ref, _mods = ref_import.load_reference(spatial=128, enable_baselines=('winloss',), use_value_feature=True)
     ref_model.load_state_dict(ck['model'], strict=True)
     ref_opt = torch.optim.Adam(ref_model.parameters(), lr=1e-5, betas=(0.0, 0.99), eps=1e-5)
     ref_opt.load_state_dict(ck['optimizer'])

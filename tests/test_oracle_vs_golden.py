@@ -110,3 +110,27 @@ def test_oracle_multi_chunk_rl_vs_golden(sd):
         assert abs(pr - g['grad_proj'][n]) <= 2e-3 * max(v, 1e-3 * gmax) * max(1.0, P[n].numel() ** 0.5 / 30), n
     for n, v in g['grads'].items():
         close(P[n].grad, v, 'grad/' + n, rtol=1e-3)
+
+
+def test_oracle_value_feature_rl_vs_golden():
+    """use_value_feature: True - the oracle's ValueEncoder restatement against what the reference produced."""
+    from golden_util import assert_compact_close
+    g = torch.load(os.path.join(GOLD, 'rl_value_feature.pt'))
+    sd = init_state_dict(seed=G.VALUE_WEIGHT_SEED, baselines=G.VALUE_BASELINES, use_value_feature=True)
+    assert G.checksum(sd) == g['meta']['weights_checksum'] and G.checksum(G.rl_value_case()) == g['input_checksum']
+    P = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    out = O.rl_learner_forward(P, **tree_clone(G.rl_value_case()))
+    info = O.rl_loss(out)
+    info['total_loss'].backward()
+    for k in O.HEADS:
+        assert_compact_close(out['target_logit'][k], g['target_logit'][k], 'target_logit/' + k, rtol=1e-4)
+    for k, v in g['value'].items():
+        close(out['value'][k], v, 'value/' + k)
+    for k, v in g['loss'].items():
+        assert abs(info[k].item() - v) <= 1e-4 * max(1.0, abs(v)), (k, info[k].item(), v)
+    gmax = max(g['grad_norm'].values())
+    for n, v in g['grad_norm'].items():
+        assert abs(P[n].grad.norm().item() - v) <= 1e-3 * max(v, 1e-3 * gmax), n
+    for n, v in g['grads'].items():
+        close(P[n].grad, v, 'grad/' + n, rtol=1e-3)
+    assert any(n.startswith('value_encoder.') for n in g['grads'])

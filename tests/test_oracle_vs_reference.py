@@ -242,3 +242,36 @@ def test_adam_state_interchanges_with_reference_optimizer(ref):
             assert torch.allclose(back['state'][i]['exp_avg'], st['exp_avg'], rtol=1e-5, atol=1e-9), i
     finally:
         ops.enable_host_logic_testing(False)
+
+
+def test_rl_step_with_value_feature_matches_reference():
+    """learner.use_value_feature: True (the bin/rl_user_config.yaml default for self-play): ValueEncoder
+    (obs_encoder/value_encoder.py) feeds every baseline (model.py:141-144, value.py:20-23)."""
+    model, cfg, mods = ref_import.load_reference(spatial=128, enable_baselines=('winloss', 'battle'), use_value_feature=True)
+    sd = init_state_dict(seed=4, baselines=('winloss', 'battle'), use_value_feature=True)
+    model.load_state_dict(sd, strict=True)
+    assert [k for k, _ in model.named_parameters()] == [k for k in sd if dict(model.named_parameters()).get(k) is not None]
+    batch = synth_rl_batch(2, 2, seed=23, entity_num='random', max_su=5, value_feature=True)
+    loss_fn = mods['ReinforcementLoss'](cfg.learner, 'MP0')
+    model.zero_grad()
+    r_out = model.rl_learner_forward(**tree_clone(batch))
+    r_info = loss_fn.compute_loss(r_out)
+    r_info['total_loss'].backward()
+    P = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    o_out = O.rl_learner_forward(P, **tree_clone(batch))
+    o_info = O.rl_loss(o_out)
+    o_info['total_loss'].backward()
+    for k in r_out['value']:
+        _close(o_out['value'][k], r_out['value'][k], name='value/' + k)
+    for k, v in r_info.items():
+        rv = v.item() if torch.is_tensor(v) else v
+        assert abs(o_info[k].item() - rv) <= 1e-4 * max(1.0, abs(rv)), (k, o_info[k].item(), rv)
+    gmax = max(p.grad.abs().max().item() for p in model.parameters() if p.requires_grad)
+    n_ve = 0
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        assert p.grad is not None, name
+        _close(P[name].grad, p.grad, rtol=1e-3, atol=1e-4 * max(p.grad.abs().max().item(), 1e-4 * gmax), name='grad/' + name)
+        n_ve += name.startswith('value_encoder.')
+    assert n_ve > 60

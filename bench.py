@@ -520,8 +520,10 @@ def run_b200(args, rank, world, local_rank):
     l0 = lib.launch_count()
     ms, ms_mine = timed(step_resident, args.steps)
     launches = lib.launch_count() - l0
-    # the dominant kernel family, timed live inside the step: CUDA events around every tcgen05 GEMM launch of ONE extra step
-    gemm_in_step = gemm_family_in_step(step_resident) if rank == 0 and os.environ.get('DSB_NO_GEMM_TIMING') != '1' else None
+    # the dominant kernel family, timed live inside the step: CUDA events around every tcgen05 GEMM launch of ONE extra step.
+    # EVERY rank runs that step (it contains the gradient all-reduce of the rank's group: a step on rank 0 alone would wait
+    # for its peers forever); rank 0's trace is the one reported.
+    gemm_in_step = gemm_family_in_step(step_resident) if os.environ.get('DSB_NO_GEMM_TIMING') != '1' else None
     clk = clocks.stop() if rank == 0 else None
     e2e = None
     ms_e2e_mine = None

@@ -1683,6 +1683,13 @@ class _ConvNHWC(torch.autograd.Function):
         return gx, gw, gb, gres, None, None, None
 
 
+def conv_geometry_supported(H: int, W: int, C: int) -> bool:
+    """Map sizes the implicit-GEMM convolution covers: its TMA boxes are whole image rows of a power-of-two width <= 64
+    (gemm_tcgen05.cu make_map_nhwc).  Other sizes (the reference default 160x152 gives 76x80 / 38x40 / 19x20 maps) take the
+    fp32 library convolution for 3x3 kernels and the fc path for 1x1 kernels."""
+    return C % 64 == 0 and W <= 64 and 64 % W == 0 and H % max(1, 128 // W) == 0
+
+
 def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = False,
               residual: Optional[torch.Tensor] = None, terms: int = 3, emit_split: bool = False) -> torch.Tensor:
     """conv2d_block (ctools/torch_utils/network/nn_module.py:119-174) on an NHWC activation [N,H,W,C] whose channel
@@ -1690,18 +1697,34 @@ def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
     Returns [N,H,W,pad64(Cout)] (padded output channels are exactly 0)."""
     N, H, W, C = x.shape
     kh = weight.shape[2]
-    if _use_kernel(x):
-        assert C % 64 == 0 and W <= 64 and 64 % W == 0 and H % max(1, 128 // W) == 0, (x.shape, weight.shape)
+    if _use_kernel(x) and conv_geometry_supported(H, W, C):
         if getattr(x, '_dsb_split', None) is None:
             x = x.contiguous()
         y, y_hi, y_lo = _ConvNHWC.apply(x, weight, bias, residual, relu, terms, emit_split)
         return attach_split(y, y_hi, y_lo) if emit_split else y
+    if _use_kernel(x) and kh == 1 and C % 64 == 0:
+        # a 1x1 convolution at a map size the implicit GEMM's TMA boxes do not cover (e.g. 19x20 at the 160x152 default):
+        # it is a plain fc over the pixels, so it stays on the tensor cores; the residual / ReLU are applied after it
+        Cout, Cin = weight.shape[:2]
+        cp = _pad_to(Cout, 64)
+        w2 = F.pad(weight.reshape(Cout, Cin), (0, C - Cin, 0, cp - Cout))
+        b2 = F.pad(bias, (0, cp - Cout)) if bias is not None else None
+        x2 = x.reshape(N * H * W, C)
+        sp = getattr(x, '_dsb_split', None)
+        if sp is not None and sp[0].shape == x.shape:
+            x2 = attach_split(x2, sp[0].reshape(x2.shape), sp[1].reshape(x2.shape))
+        y = linear(x2, w2, b2, relu and residual is None, terms, allow_n64=True).view(N, H, W, cp)
+        if residual is not None:
+            y = y + residual
+            y = torch.relu(y) if relu else y
+        return y
     Cout, Cin = weight.shape[:2]
     y = F.conv2d(x[..., :Cin].permute(0, 3, 1, 2), weight, bias, padding=kh // 2).permute(0, 2, 3, 1)
     y = F.pad(y, (0, _pad_to(Cout, 64) - Cout))
     if residual is not None:
         y = y + residual
-    return torch.relu(y) if relu else y
+    y = torch.relu(y) if relu else y
+    return y.contiguous()          # channels-last in memory, like the kernel path: downstream kernels take raw pointers
 
 
 # ------------------------------------------------------------------------------------------------
@@ -1969,8 +1992,7 @@ def upsample_conv3x3(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch
     [N,H,W,Cpad>=Cin] -> [N,2H,2W,C] (exactly C channels; C in {32, 64} on the GPU).  With pair_only the result exists only
     as the bf16 (hi, lo) pair the next tensor-core GEMM reads (see pair_only_placeholder)."""
     C, Cin = weight.shape[:2]
-    if _use_kernel(x):
-        assert C in (32, 64) and x.shape[-1] % 64 == 0 and x.shape[1] % 8 == 0 and x.shape[2] % 8 == 0, (x.shape, weight.shape)
+    if _use_kernel(x) and C in (32, 64) and x.shape[-1] % 64 == 0 and x.shape[1] % 8 == 0 and x.shape[2] % 8 == 0:
         sp = getattr(x, '_dsb_split', None)
         if sp is None or sp[0].shape != x.shape:
             sp = (None, None)
@@ -1978,7 +2000,7 @@ def upsample_conv3x3(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch
         return attach_split(y, y_hi, y_lo) if pair_only else y
     up = F.interpolate(x[..., :Cin].permute(0, 3, 1, 2), scale_factor=2., mode='bilinear')
     y = F.conv2d(up, weight, bias, padding=1).permute(0, 2, 3, 1)
-    return torch.relu(y) if relu else y
+    return (torch.relu(y) if relu else y).contiguous()
 
 
 def upsample_bilinear2x(x: torch.Tensor) -> torch.Tensor:

@@ -39,10 +39,12 @@ def _ri(g, lo, hi, shape, dtype):
     return torch.randint(lo, hi, shape, generator=g).to(dtype)
 
 
-def synth_obs(n: int, seed: int = 0, entity_num=None, hidden: bool = True) -> Dict:
-    """n observation rows. entity_num: None -> 512 for every row; 'random' -> U{64..512}; or a LongTensor."""
+def synth_obs(n: int, seed: int = 0, entity_num=None, hidden: bool = True, hw=None) -> Dict:
+    """n observation rows. entity_num: None -> 512 for every row; 'random' -> U{64..512}; or a LongTensor.
+    hw: (spatial_y, spatial_x) of the maps, default 128 x 128 (the reference's own default is (152, 160))."""
     g = torch.Generator(device='cpu')
     g.manual_seed(seed)
+    H, W = hw if hw is not None else (globals()['H'], globals()['W'])
     sp = {'height_map': _ri(g, 0, 256, (n, H, W), torch.uint8),
           'visibility_map': _ri(g, 0, 4, (n, H, W), torch.uint8),
           'creep': _ri(g, 0, 2, (n, H, W), torch.uint8),
@@ -89,7 +91,7 @@ def synth_obs(n: int, seed: int = 0, entity_num=None, hidden: bool = True) -> Di
     return out
 
 
-def synth_actions(rows: int, entity_num: torch.Tensor, g: torch.Generator, max_su: int = 12):
+def synth_actions(rows: int, entity_num: torch.Tensor, g: torch.Generator, max_su: int = 12, hw=None):
     """Teacher-forced labels for `rows` policy rows: selected_units_num in {0} U [2, max_su] (never 1:
     the reference's teacher-forced path divides 0/0 there, action_arg_head.py:196-198)."""
     en = entity_num.long()
@@ -97,7 +99,7 @@ def synth_actions(rows: int, entity_num: torch.Tensor, g: torch.Generator, max_s
          'delay': torch.randint(0, 128, (rows,), generator=g),
          'queued': torch.randint(0, 2, (rows,), generator=g),
          'target_unit': (torch.rand((rows,), generator=g) * en).long().clamp(max=E - 1),
-         'target_location': torch.randint(0, H * W, (rows,), generator=g)}
+         'target_location': torch.randint(0, (hw[0] * hw[1]) if hw is not None else H * W, (rows,), generator=g)}
     num = torch.randint(2, max_su + 1, (rows,), generator=g)
     num = torch.where(torch.rand((rows,), generator=g) < 0.2, torch.zeros_like(num), num)
     num = torch.minimum(num, en)          # need num-1 distinct units + end token

@@ -67,6 +67,33 @@ def rl_chunk_case():
     return batch
 
 
+DEFAULT_XY = (160, 152)          # the reference's own default map size (actor_critic_default_config.yaml: spatial_x / spatial_y)
+
+
+def teacher_default_size_case():
+    """Teacher-forced forward at 160 x 152 (maps [152, 160]; 76x80 / 38x40 / 19x20 inside the spatial tower)."""
+    en = torch.tensor([512, 40, 333])
+    obs = synth_obs(3, seed=81, entity_num=en, hw=(DEFAULT_XY[1], DEFAULT_XY[0]))
+    g = torch.Generator().manual_seed(3)
+    act, num = synth_actions(3, en, g, max_su=7, hw=(DEFAULT_XY[1], DEFAULT_XY[0]))
+    return obs, act, num
+
+
+def default_size_golden():
+    model, cfg, mods = ref_import.load_reference(spatial=DEFAULT_XY, enable_baselines=BASELINES)
+    sd = init_state_dict(seed=WEIGHT_SEED, spatial_x=DEFAULT_XY[0], spatial_y=DEFAULT_XY[1], baselines=BASELINES)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    meta = {'weight_seed': WEIGHT_SEED, 'baselines': list(BASELINES), 'spatial_xy': DEFAULT_XY, 'weights_checksum': checksum(sd),
+            'torch': str(torch.__version__)}
+    obs, act, num = teacher_default_size_case()
+    with torch.no_grad():
+        r = model.compute_teacher_logit(**tree_clone(obs), selected_units_num=num.clone(), action_info=tree_clone(act))
+    torch.save({'meta': meta, 'input_checksum': checksum((obs, act, num)),
+                'logit': {k: compact_logits(v) for k, v in r['logit'].items()}, 'hidden_state': r['hidden_state']},
+               os.path.join(OUT, 'teacher_160x152.pt'))
+
+
 def rl_value_case():
     """learner.use_value_feature: True (bin/rl_user_config.yaml self-play default): 8 rows with the ValueEncoder inputs."""
     return synth_rl_batch(2, 3, seed=71, entity_num='random', max_su=6, value_feature=True)
@@ -118,6 +145,10 @@ def main():
         value_feature_golden()
         print('rl_value_feature.pt', os.path.getsize(os.path.join(OUT, 'rl_value_feature.pt')))
         return
+    if '--only-default-size' in sys.argv:
+        default_size_golden()
+        print('teacher_160x152.pt', os.path.getsize(os.path.join(OUT, 'teacher_160x152.pt')))
+        return
     model, cfg, mods = ref_import.load_reference(spatial=128, enable_baselines=BASELINES)
     sd = init_state_dict(seed=WEIGHT_SEED, baselines=BASELINES)
     model.load_state_dict(sd, strict=True)
@@ -154,6 +185,7 @@ def main():
                 'logit': {k: compact_logits(v) for k, v in r['logit'].items()},
                 'hidden_state': r['hidden_state']}, os.path.join(OUT, 'infer32.pt'))
     value_feature_golden()
+    default_size_golden()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

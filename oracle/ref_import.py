@@ -64,9 +64,10 @@ def load_reference(spatial=128, enable_baselines=('winloss',), seed=0, use_value
     cfg.common.type = 'rl'
     cfg.learner.use_value_feature = bool(use_value_feature)
     cfg.learner.player_id = 'MP0'
-    cfg.model.spatial_x = cfg.model.spatial_y = spatial
+    sx, sy = (spatial, spatial) if isinstance(spatial, int) else spatial          # (spatial_x, spatial_y), e.g. (160, 152)
+    cfg.model.spatial_x, cfg.model.spatial_y = sx, sy
     cfg.model.enable_baselines = list(enable_baselines)
-    F.SPATIAL_SIZE[:] = [spatial, spatial]
+    F.SPATIAL_SIZE[:] = [sy, sx]
     torch.manual_seed(seed)
     model = Model(cfg, use_value_network=True)
     mods = dict(F=F, ReinforcementLoss=ReinforcementLoss, as_rl_utils=as_rl_utils, Model=Model)

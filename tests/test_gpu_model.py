@@ -436,29 +436,3 @@ def test_sl_loss_options_on_gpu(su_mask, label_smooth):
     for k in lg:
         assert torch.allclose(lg[k].grad.cpu(), og[k].grad, rtol=1e-3, atol=1e-6), k
 
-
-def test_rl_step_with_value_feature_vs_golden():
-    """learner.use_value_feature: True (the reference's self-play default): ValueEncoder (value_encoder.py:47-74) in front of
-    the baselines, its spatial tower chunked (encoder_chunk=3 -> 3 chunks over 8 rows) and recomputed in backward."""
-    from golden_util import assert_compact_close
-    g = torch.load(os.path.join(GOLD, 'rl_value_feature.pt'))
-    sd = init_state_dict(seed=G.VALUE_WEIGHT_SEED, baselines=G.VALUE_BASELINES, use_value_feature=True)
-    cfg = {'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': list(G.VALUE_BASELINES)},
-           'learner': {'use_value_feature': True}}
-    m = Model(cfg, use_value_network=True, seed=0, encoder_chunk=3)
-    m.load_state_dict(sd)
-    m = m.cuda()
-    m.zero_grad()
-    batch = G.rl_value_case()
-    out = m.rl_learner_forward(**to_dev(batch))
-    info = ReinforcementLoss(None, 'MP0').compute_loss(out)
-    info['total_loss'].backward()
-    m.raise_on_bad_input()
-    for k in O.HEADS:
-        assert_compact_close(out['target_logit'][k], g['target_logit'][k], 'target_logit/' + k)
-    for k, v in g['value'].items():
-        close(out['value'][k], v, 'value/' + k)
-    for k, v in g['loss'].items():
-        got = info[k].item() if torch.is_tensor(info[k]) else info[k]
-        assert abs(got - v) <= 2e-3 * max(1.0, abs(v)), (k, got, v)
-    _check_gradients(m, g, _oracle_gradients(sd, batch), cos_floor=0.999, frac_4nines=0.90)

@@ -375,3 +375,20 @@ def test_rl_step_with_value_feature_matches_oracle(monkeypatch, chunk):
     # an actor-side model (no value network) has no value encoder even with the flag set (model.py:31-34)
     actor = Model(cfg, use_value_network=False, seed=0)
     assert not any(k.startswith('value_') for k in actor.state_dict())
+
+
+def test_teacher_forward_at_the_default_map_size_matches_oracle():
+    """160 x 152 (the reference default): every map-size dependent shape (fc widths, location logits [N, 24320], build-order
+    location binary split) through the product's host logic."""
+    import make_golden as G
+    sx, sy = G.DEFAULT_XY
+    sd = init_state_dict(seed=G.WEIGHT_SEED, spatial_x=sx, spatial_y=sy, baselines=G.BASELINES)
+    m = Model({'model': {'spatial_x': sx, 'spatial_y': sy, 'enable_baselines': list(G.BASELINES)}}, use_value_network=True, seed=0)
+    m.load_state_dict(sd)
+    obs, act, num = G.teacher_default_size_case()
+    with torch.no_grad():
+        o = O.compute_teacher_logit(sd, **tree_clone(obs), selected_units_num=num.clone(), action_info=tree_clone(act))
+        r = m.compute_teacher_logit(**tree_clone(obs), selected_units_num=num.clone(), action_info=tree_clone(act))
+    for k in O.HEADS:
+        _close(r['logit'][k], o['logit'][k], 'logit/' + k)
+    assert r['logit']['target_location'].shape == (3, sx * sy)

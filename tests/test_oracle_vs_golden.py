@@ -134,3 +134,21 @@ def test_oracle_value_feature_rl_vs_golden():
     for n, v in g['grads'].items():
         close(P[n].grad, v, 'grad/' + n, rtol=1e-3)
     assert any(n.startswith('value_encoder.') for n in g['grads'])
+
+
+def test_oracle_teacher_forward_default_map_size_vs_golden():
+    """The reference's own default map size 160 x 152 (teacher-forced forward dumped from the real reference)."""
+    from golden_util import assert_compact_close
+    g = torch.load(os.path.join(GOLD, 'teacher_160x152.pt'))
+    sx, sy = G.DEFAULT_XY
+    sd = init_state_dict(seed=G.WEIGHT_SEED, spatial_x=sx, spatial_y=sy, baselines=G.BASELINES)
+    obs, act, num = G.teacher_default_size_case()
+    assert G.checksum(sd) == g['meta']['weights_checksum'] and G.checksum((obs, act, num)) == g['input_checksum']
+    with torch.no_grad():
+        o = O.compute_teacher_logit(sd, **tree_clone(obs), selected_units_num=num.clone(), action_info=tree_clone(act))
+    for k in O.HEADS:
+        assert_compact_close(o['logit'][k], g['logit'][k], 'logit/' + k, rtol=1e-4)
+    assert o['logit']['target_location'].shape[-1] == sx * sy
+    for (h, c), (gh, gc) in zip(o['hidden_state'], g['hidden_state']):
+        close(h, gh, 'h')
+        close(c, gc, 'c')

@@ -203,7 +203,7 @@ def tree_bytes(tree):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the two kernels BASELINE.json names, from the committed
 # `ncu --set full --clock-control none` captures of exactly these launches (profiles/r01_summary.md)
-NCU_SOURCE = 'profiles/r02_ncu_raw_{scatter,gemm}.csv'
+NCU_SOURCE = 'profiles/r02_ncu_raw_{scatter,gemm}.csv (the GEMM capture is the single-CTA variant <256,1> of this launch: same operands and output bytes as the CTA-pair variant timed here)'
 NCU_DRAM_BYTES = {'scatter_connection': 70.4e6 + 2155.0e6, 'entity_mlp_gemm_terms3': 139.6e6 + 493.7e6}
 
 

@@ -1690,6 +1690,25 @@ def conv_geometry_supported(H: int, W: int, C: int) -> bool:
     return C % 64 == 0 and W <= 64 and 64 % W == 0 and H % max(1, 128 // W) == 0
 
 
+def _conv1x1_as_fc(x, weight, bias, relu, residual, terms):
+    """A 1x1 convolution at a map size the implicit GEMM's TMA boxes do not cover (e.g. 19x20 at the 160x152 default): it is a
+    plain fc over the pixels, so it stays on the tensor cores; the residual / ReLU are applied after it."""
+    N, H, W, C = x.shape
+    Cout, Cin = weight.shape[:2]
+    cp = _pad_to(Cout, 64)
+    w2 = F.pad(weight.reshape(Cout, Cin), (0, C - Cin, 0, cp - Cout))
+    b2 = F.pad(bias, (0, cp - Cout)) if bias is not None else None
+    x2 = x.reshape(N * H * W, C)
+    sp = getattr(x, '_dsb_split', None)
+    if sp is not None and sp[0].shape == x.shape:
+        x2 = attach_split(x2, sp[0].reshape(x2.shape), sp[1].reshape(x2.shape))
+    y = linear(x2, w2, b2, relu and residual is None, terms, allow_n64=True).view(N, H, W, cp)
+    if residual is not None:
+        y = y + residual
+        y = torch.relu(y) if relu else y
+    return y
+
+
 def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = False,
               residual: Optional[torch.Tensor] = None, terms: int = 3, emit_split: bool = False) -> torch.Tensor:
     """conv2d_block (ctools/torch_utils/network/nn_module.py:119-174) on an NHWC activation [N,H,W,C] whose channel
@@ -1703,21 +1722,7 @@ def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
         y, y_hi, y_lo = _ConvNHWC.apply(x, weight, bias, residual, relu, terms, emit_split)
         return attach_split(y, y_hi, y_lo) if emit_split else y
     if _use_kernel(x) and kh == 1 and C % 64 == 0:
-        # a 1x1 convolution at a map size the implicit GEMM's TMA boxes do not cover (e.g. 19x20 at the 160x152 default):
-        # it is a plain fc over the pixels, so it stays on the tensor cores; the residual / ReLU are applied after it
-        Cout, Cin = weight.shape[:2]
-        cp = _pad_to(Cout, 64)
-        w2 = F.pad(weight.reshape(Cout, Cin), (0, C - Cin, 0, cp - Cout))
-        b2 = F.pad(bias, (0, cp - Cout)) if bias is not None else None
-        x2 = x.reshape(N * H * W, C)
-        sp = getattr(x, '_dsb_split', None)
-        if sp is not None and sp[0].shape == x.shape:
-            x2 = attach_split(x2, sp[0].reshape(x2.shape), sp[1].reshape(x2.shape))
-        y = linear(x2, w2, b2, relu and residual is None, terms, allow_n64=True).view(N, H, W, cp)
-        if residual is not None:
-            y = y + residual
-            y = torch.relu(y) if relu else y
-        return y
+        return _conv1x1_as_fc(x, weight, bias, relu, residual, terms)
     Cout, Cin = weight.shape[:2]
     y = F.conv2d(x[..., :Cin].permute(0, 3, 1, 2), weight, bias, padding=kh // 2).permute(0, 2, 3, 1)
     y = F.pad(y, (0, _pad_to(Cout, 64) - Cout))

@@ -392,3 +392,27 @@ def test_teacher_forward_at_the_default_map_size_matches_oracle():
     for k in O.HEADS:
         _close(r['logit'][k], o['logit'][k], 'logit/' + k)
     assert r['logit']['target_location'].shape == (3, sx * sy)
+
+
+@pytest.mark.parametrize('cout,cin,with_res', [(128, 128, True), (128, 124, False), (32, 128, False)])
+def test_conv1x1_fallback_equals_conv2d(cout, cin, with_res):
+    """ops._conv1x1_as_fc (the 1x1 convolutions of the 160 x 152 map sizes, run as fc over pixels) against F.conv2d, values and
+    gradients, with a residual + ReLU and with input channels padded beyond the weight's."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(cout + cin)
+    N, H, W, C = 2, 19, 20, 128
+    x = torch.randn(N, H, W, C, generator=g, requires_grad=True)
+    w = (torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5).requires_grad_(True)
+    b = torch.randn(cout, generator=g, requires_grad=True)
+    cp = (cout + 63) // 64 * 64
+    res = torch.randn(N, H, W, cp, generator=g) if with_res else None
+    y = ops._conv1x1_as_fc(x, w, b, True, res, 3)
+    ref = F.conv2d(x[..., :cin].permute(0, 3, 1, 2), w, b).permute(0, 2, 3, 1)
+    ref = F.pad(ref, (0, cp - cout))
+    ref = torch.relu(ref + res) if with_res else torch.relu(ref)
+    assert y.shape == ref.shape and (y - ref).abs().max() <= 1e-4 * ref.abs().max()
+    gy = torch.randn(ref.shape, generator=g)
+    gx, gw, gb = torch.autograd.grad(y, (x, w, b), gy)
+    rx, rw, rb = torch.autograd.grad(ref, (x, w, b), gy)
+    for a, r in ((gx, rx), (gw, rw), (gb, rb)):
+        assert (a - r).abs().max() <= 2e-4 * r.abs().max()

@@ -94,13 +94,7 @@ def _expand(src: torch.Tensor, off: torch.Tensor, steps, width: torch.Tensor, ro
         lib.call('dsb_expand_ragged', src, off, steps, width, dst, rows, S, W, src.element_size(), float(fill),
                  1 if src.dtype == torch.float32 else 0)
         return dst
-    s_idx = torch.arange(S).view(1, S, 1)
-    e_idx = torch.arange(W).view(1, 1, W)
-    st = steps.view(-1, 1, 1) if steps is not None else torch.ones(rows, 1, 1, dtype=torch.long)
-    inside = (s_idx < st) & (e_idx < width.view(-1, 1, 1))
-    idx = (off.view(-1, 1, 1) + s_idx * width.view(-1, 1, 1) + e_idx).clamp(0, max(src.numel() - 1, 0))
-    gathered = src[idx] if src.numel() else torch.zeros((rows, S, W), dtype=src.dtype)
-    return torch.where(inside, gathered, torch.full((), fill, dtype=src.dtype))
+    return ops._standin('expand_ragged')(src, off, steps, width, rows, S, W, fill)
 
 
 def _seq_mask(lengths: torch.Tensor, add: int, W: int) -> torch.Tensor:
@@ -108,7 +102,7 @@ def _seq_mask(lengths: torch.Tensor, add: int, W: int) -> torch.Tensor:
         dst = torch.empty((lengths.numel(), W), dtype=torch.uint8, device=lengths.device)
         lib.call('dsb_sequence_mask', lengths.contiguous(), add, dst, lengths.numel(), W)
         return dst.bool()
-    return torch.arange(W).unsqueeze(0) < (lengths + add).unsqueeze(1)
+    return ops._standin('sequence_mask')(lengths, add, W)
 
 
 def expand_rl_batch(compact: Dict, device=None, staged: Dict = None) -> Dict:
@@ -130,9 +124,7 @@ def expand_rl_batch(compact: Dict, device=None, staged: Dict = None) -> Dict:
         for (name, _, _), p in zip(PACKED_PLANES, planes):
             sp[name] = p
     else:
-        v = hw.to(torch.int32) & 0xFFFF
-        for name, bit, bits in PACKED_PLANES:
-            sp[name] = ((v >> bit) & ((1 << bits) - 1)).to(torch.uint8)
+        sp.update(ops._standin('unpack_planes')(hw, PACKED_PLANES))
     sp.update(c['effects'])
     # ---- entity fields: zero-padded to MAX_ENTITY_NUM
     ent_off = _offsets(en_all)

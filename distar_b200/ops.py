@@ -1,10 +1,12 @@
 """Operators of the hot path: autograd wrappers around the C-ABI kernels of libdistar_b200.so.
 
 Every operator here launches hand-written sm_100a kernels when its inputs live on a CUDA device and RAISES
-otherwise — there is no silent fallback.  The only exception is the explicit host-logic test switch
-``enable_host_logic_testing()`` used by the ``-m "not gpu"`` tests: it swaps each kernel for a few lines of plain
-torch so the *Python* control flow around the kernels (shapes, masks, autograd wiring) can be exercised on a
-machine without a GPU.  Product code never turns it on.
+otherwise — there is no silent CPU fallback.  The only exception is the explicit host-logic test switch
+``enable_host_logic_testing()`` used by the tests: CPU tensors then take plain-torch stand-ins so the *Python* control flow
+around the kernels (shapes, masks, autograd wiring) can be exercised on a machine without a GPU.  Product code never turns
+it on.  The stand-ins of the operators that always run a kernel on the GPU live in tests/host_standins.py; torch code that is
+still in this file after an ``if _use_kernel(...)`` is (mostly) also the library path a CUDA tensor takes for a shape the
+kernel does not cover (e.g. ``conv_geometry_supported``).
 """
 import math
 import os
@@ -16,12 +18,23 @@ import torch.nn.functional as F
 from . import lib
 
 _HOST_LOGIC_TESTING = False
+_STANDINS = None          # tests only: operator name -> torch stand-in, loaded from tests/host_standins.py
 
 
 def enable_host_logic_testing(flag: bool = True):
-    """TESTS ONLY: run the torch stand-ins below instead of the CUDA kernels (CPU tensors)."""
-    global _HOST_LOGIC_TESTING
+    """TESTS ONLY: CPU tensors run torch stand-ins instead of raising.  The stand-ins of the operators that ALWAYS take a kernel
+    on the GPU live outside the package, in tests/host_standins.py (imported by name: the tests directory is on sys.path under
+    pytest); most of what remains in this file after an `if _use_kernel(...)` is library code a CUDA tensor can also reach
+    (shapes a kernel does not cover)."""
+    global _HOST_LOGIC_TESTING, _STANDINS
     _HOST_LOGIC_TESTING = flag
+    if flag and _STANDINS is None:
+        import importlib
+        _STANDINS = importlib.import_module('host_standins').TABLE
+
+
+def _standin(name: str):
+    return _STANDINS[name]
 
 
 def _use_kernel(t: torch.Tensor) -> bool:
@@ -67,12 +80,7 @@ def scatter_connection(project: torch.Tensor, ex: torch.Tensor, ey: torch.Tensor
     entity_num = entity_num.to(torch.int64).contiguous()
     if _use_kernel(project):
         return _ScatterConnection.apply(project, ex, ey, entity_num, H, W)
-    N, E, C = project.shape
-    valid = (torch.arange(E, device=project.device).unsqueeze(0) < entity_num.unsqueeze(1)).unsqueeze(-1)
-    idx = ey.long().clamp(0, H - 1) * W + ex.long().clamp(0, W - 1)
-    out = torch.zeros(N, H * W, C, dtype=project.dtype, device=project.device)
-    out = out.scatter_add(1, idx.unsqueeze(-1).expand(-1, -1, C), project * valid)
-    return out.view(N, H, W, C).permute(0, 3, 1, 2).contiguous()
+    return _standin('scatter_connection')(project, ex, ey, entity_num, H, W)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -200,19 +208,7 @@ def spatial_stem(spatial_info, project, ex, ey, entity_num, weight, bias, out_c:
         out, hi, lo = _SpatialStem.apply(project, weight, bias, ex.contiguous(), ey.contiguous(),
                                          entity_num.to(torch.int64).contiguous(), out_c, *planes, *effects)
         return attach_split(out, hi, lo)
-    N, H, W = planes[0].shape
-    scatter_map = scatter_connection(project, ex, ey, entity_num, H, W)
-    chans = [planes[0].float().unsqueeze(1) / 256]
-    for p, n in zip(planes[1:], (4, 2, 5, 2, 2, 2)):
-        chans.append(F.one_hot(p.long(), n).permute(0, 3, 1, 2).float())
-    for e in effects:
-        m = torch.zeros(N, H * W, device=project.device)
-        m.scatter_(1, e.long(), 1.0)
-        chans.append(m.view(N, 1, H, W))
-    chans.append(scatter_map)
-    x = torch.relu(F.conv2d(torch.cat(chans, dim=1), weight, bias))
-    x = F.max_pool2d(x, 2, 2).permute(0, 2, 3, 1)
-    return F.pad(x, (0, out_c - 32)).contiguous()
+    return _standin('spatial_stem')(planes, effects, project, ex, ey, entity_num, weight, bias, out_c)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -235,32 +231,7 @@ def return_scan(reward: torch.Tensor, value: torch.Tensor, rho: torch.Tensor, ga
         td = torch.empty((F_, T, B), dtype=torch.float32, device=reward.device)
         lib.call('dsb_return_scan', reward, value, rho, gamma_td, float(lambda_td), vt, up, td, F_, R, T, B)
         return vt, up, td
-    vt = torch.empty((F_, R, T, B))
-    up = torch.empty((R, T, B))
-    td = torch.empty((F_, T, B))
-    for f in range(F_):
-        v, r = value[f], reward[f]
-        for h in range(R):
-            c = rho[h]
-            vs = v[T].clone()
-            for t in reversed(range(T)):
-                vt[f, h, t] = c[t] * (r[t] + vs - v[t])
-                vs = v[t] + c[t] * (r[t] + v[t + 1] - v[t]) + c[t] * (vs - v[t + 1])
-        g = gamma_td[f]
-        nxt = None
-        for t in reversed(range(T)):
-            nxt = r[t] + g * v[t + 1] if t == T - 1 else r[t] + g * lambda_td * nxt + (g - g * lambda_td) * v[t + 1]
-            td[f, t] = nxt
-    v, r = value[0], reward[0]
-    nxt = None
-    for t in reversed(range(T)):
-        if t == T - 1:
-            nxt = r[t] + v[t + 1]
-        else:
-            lam = ((r[t + 1] + v[t + 2]) >= v[t + 1]).float()
-            nxt = r[t] + lam * nxt + (1 - lam) * v[t + 1]
-        up[:, t] = rho[:, t] * (nxt - v[t])
-    return vt, up, td
+    return _standin('return_scan')(reward, value, rho, gamma_td, lambda_td)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -317,18 +288,7 @@ def categorical_stats(logits: torch.Tensor, action: torch.Tensor, teacher: Optio
         logp, ent, kl, mean_lp, _ = _CategoricalStats.apply(z, t.contiguous() if t is not None else None, a.contiguous(),
                                                             want_mean, flag)
     else:
-        if flag is not None:
-            flag |= 2 * int(((a < 0) | (a >= C)).any())
-        a = a.clamp(0, C - 1)
-        lp = torch.log_softmax(z, -1)
-        logp = lp.gather(-1, a.unsqueeze(-1)).squeeze(-1)
-        ent = -(lp.exp() * lp).sum(-1)
-        mean_lp = lp.mean(-1)
-        if t is not None:
-            tl = torch.log_softmax(t, -1)
-            kl = (tl.exp() * (tl - lp)).sum(-1)
-        else:
-            kl = torch.zeros_like(logp)
+        logp, ent, kl, mean_lp = _standin('categorical_stats')(z, t, a, flag)
     if want_mean:
         return logp.view(shape), ent.view(shape), kl.view(shape), mean_lp.view(shape)
     return logp.view(shape), ent.view(shape), kl.view(shape)
@@ -352,10 +312,7 @@ def sample_categorical(logits: torch.Tensor, generator: Optional[torch.Generator
         logp = torch.empty(rows, dtype=torch.float32, device=logits.device)
         lib.call('dsb_sample_categorical', z, q, index, logp, rows, C)
         return index, logp
-    p = torch.softmax(logits.detach().float(), -1)
-    index = (p / q).argmax(-1)
-    logp = torch.log_softmax(logits.detach().float(), -1).gather(-1, index.unsqueeze(-1)).squeeze(-1)
-    return index, logp
+    return _standin('sample_categorical')(logits, q)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -505,8 +462,7 @@ def split_bf16(x: torch.Tensor):
         lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
         lib.call('dsb_split_bf16', x, hi, lo, x.numel())
         return hi, lo
-    hi = x.to(torch.bfloat16)
-    return hi, (x - hi.float()).to(torch.bfloat16)
+    return _standin('split_bf16')(x)
 
 
 # DEBUG ONLY: DSB_DISABLE_TCGEN05=1 routes every fc_block through the library matmul so the rest of the pipeline
@@ -541,14 +497,7 @@ def gemm_split(a_hi, a_lo, w_hi, w_lo, bias, relu: bool, terms: int = 3, want_sp
         if c is None:
             c = pair_only_placeholder((M, N), a_hi.device)
         return (c, c_hi, c_lo) if want_split else c
-    if terms == 3:
-        c = (a_hi.float() + (a_lo.float() if a_lo is not None else 0)) @ (w_hi.float() + w_lo.float()).t()
-    else:
-        c = a_hi.float() @ w_hi.float().t()
-    if bias is not None:
-        c = c + bias
-    if relu:
-        c = torch.relu(c)
+    c = _standin('gemm_split')(a_hi, a_lo, w_hi, w_lo, bias, relu, terms)
     if want_split:
         h, l = split_bf16(c)
         return c, h, l
@@ -1120,14 +1069,7 @@ def onehot_linear(weight: torch.Tensor, bias: Optional[torch.Tensor], idx: torch
     if _use_kernel(weight):
         out = _OneHotLinear.apply(weight, bias, i64, relu, embedding, clamp_max, flag)
     else:
-        C = weight.shape[0] if embedding else weight.shape[1]
-        if flag is not None:
-            flag |= 4 * int(((i64 < 0) | ((i64 >= C) & (not clamp_max))).any())
-        i64 = i64.clamp(0, C - 1)
-        out = weight[i64] if embedding else weight.t()[i64]
-        if bias is not None:
-            out = out + bias
-        out = torch.relu(out) if relu else out
+        out = _standin('onehot_linear')(weight, bias, i64, relu, embedding, clamp_max, flag)
     return out.view(*shape, out.shape[-1])
 
 
@@ -1775,7 +1717,7 @@ def upsample_bilinear2x_nhwc(x: torch.Tensor) -> torch.Tensor:
     """bilinear x2 (align_corners=False) on a channels-last activation [N,H,W,C]."""
     if _use_kernel(x):
         return _Upsample2xNHWC.apply(x.float())
-    return F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2., mode='bilinear').permute(0, 2, 3, 1).contiguous()
+    return _standin('upsample_bilinear2x_nhwc')(x)
 
 
 class _UpShift9(torch.autograd.Function):
@@ -1834,11 +1776,7 @@ def upsample_conv3x3_single(x: torch.Tensor, weight: torch.Tensor, bias: Optiona
         z = torch.matmul(x, wm)                               # [N,H,W,9]  (small library GEMM, N = 9)
     if _use_kernel(x):
         return _UpShift9.apply(z, bias)
-    up = F.interpolate(z.permute(0, 3, 1, 2), scale_factor=2., mode='bilinear')          # [N,9,2H,2W]
-    up = F.pad(up, (1, 1, 1, 1))
-    H2, W2 = up.shape[2] - 2, up.shape[3] - 2
-    out = sum(up[:, t, t // 3:t // 3 + H2, t % 3:t % 3 + W2] for t in range(9))
-    return out + bias if bias is not None else out
+    return _standin('upshift9')(z, bias)
 
 
 class _MaxPool2(torch.autograd.Function):
@@ -2012,7 +1950,7 @@ def upsample_bilinear2x(x: torch.Tensor) -> torch.Tensor:
     """F.interpolate(x, scale_factor=2., mode='bilinear') (align_corners=False) on [N,C,H,W] fp32."""
     if _use_kernel(x):
         return _Upsample2x.apply(x.float())
-    return F.interpolate(x, scale_factor=2., mode='bilinear')
+    return _standin('upsample_bilinear2x')(x)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -2108,20 +2046,7 @@ class FlatAdam(torch.optim.Optimizer):
                      float(self.max_norm or 0.0), float(grad_scale), lr, float(b1), float(b2), eps, wd, int(self.t), None, None,
                      skip_flag)
             return self.norm
-        if skip_flag is not None and float(skip_flag.reshape(-1)[0]) != 0.0:
-            return self.norm
-        g = self.grad * grad_scale
-        self.norm = g.norm().reshape(1)
-        if self.max_norm is not None:
-            g = g * torch.clamp(self.max_norm / (self.norm + 1e-6), max=1.0)
-        if wd != 0.0:
-            g = g + wd * self.param
-        self.exp_avg.mul_(b1).add_(g, alpha=1 - b1)
-        self.exp_avg_sq.mul_(b2).addcmul_(g, g, value=1 - b2)
-        bc1, bc2 = 1 - b1 ** self.t, 1 - b2 ** self.t
-        denom = self.exp_avg_sq.sqrt() / math.sqrt(bc2) + eps
-        self.param.addcdiv_(self.exp_avg, denom, value=-lr / bc1)
-        return self.norm
+        return _standin('flat_adam_step')(self, grad_scale, skip_flag, lr, b1, b2, eps, wd)
 
     # ---- checkpoint interchange (checkpoint_helper.py:85-140,254: {'model', 'optimizer', 'last_iter'})
     def state_dict(self):

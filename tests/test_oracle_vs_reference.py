@@ -275,3 +275,45 @@ def test_rl_step_with_value_feature_matches_reference():
         _close(P[name].grad, p.grad, rtol=1e-3, atol=1e-4 * max(p.grad.abs().max().item(), 1e-4 * gmax), name='grad/' + name)
         n_ve += name.startswith('value_encoder.')
     assert n_ve > 60
+
+
+def test_default_map_size_matches_reference(su_action_mask):
+    """160 x 152 (the reference's default spatial_x / spatial_y): sampling forward and one RL step, oracle vs the real reference."""
+    sx, sy = 160, 152
+    model, cfg, mods = ref_import.load_reference(spatial=(sx, sy), enable_baselines=('winloss',))
+    sd = init_state_dict(seed=5, spatial_x=sx, spatial_y=sy, baselines=('winloss',))
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    obs = synth_obs(2, seed=91, entity_num=torch.tensor([300, 512]), hw=(sy, sx))
+    torch.manual_seed(9)
+    with torch.no_grad():
+        r = model.compute_logp_action(**tree_clone(obs))
+    torch.manual_seed(9)
+    with torch.no_grad():
+        o = O.compute_logp_action(sd, **tree_clone(obs), su_action_mask=su_action_mask)
+    for k in O.HEADS:
+        assert torch.equal(r['action_info'][k], o['action_info'][k]), k
+        _close(o['logit'][k], r['logit'][k], name='logit/' + k)
+    assert o['logit']['target_location'].shape[-1] == sx * sy
+    # one RL step: the batch generator only knows 128 x 128, so swap in 160 x 152 observations and location labels / teachers
+    batch = synth_rl_batch(2, 2, seed=25, entity_num='random', max_su=5)
+    big = synth_obs(6, seed=25, entity_num=batch['entity_num'], hw=(sy, sx))
+    batch['spatial_info'], batch['scalar_info']['bo_location'] = big['spatial_info'], big['scalar_info']['bo_location']
+    batch['entity_info']['x'], batch['entity_info']['y'] = big['entity_info']['x'], big['entity_info']['y']
+    g = torch.Generator().manual_seed(3)
+    batch['action_info']['target_location'] = torch.randint(0, sx * sy, (2, 2), generator=g)
+    batch['teacher_logit']['target_location'] = torch.randn(2, 2, sx * sy, generator=g)
+    loss_fn = mods['ReinforcementLoss'](cfg.learner, 'MP0')
+    model.zero_grad()
+    r_info = loss_fn.compute_loss(model.rl_learner_forward(**tree_clone(batch)))
+    r_info['total_loss'].backward()
+    P = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    o_info = O.rl_loss(O.rl_learner_forward(P, **tree_clone(batch)))
+    o_info['total_loss'].backward()
+    for k, v in r_info.items():
+        rv = v.item() if torch.is_tensor(v) else v
+        assert abs(o_info[k].item() - rv) <= 1e-4 * max(1.0, abs(rv)), (k, o_info[k].item(), rv)
+    gmax = max(p.grad.abs().max().item() for p in model.parameters() if p.requires_grad)
+    for name, p in model.named_parameters():
+        if p.requires_grad:
+            _close(P[name].grad, p.grad, rtol=1e-3, atol=1e-4 * max(p.grad.abs().max().item(), 1e-4 * gmax), name='grad/' + name)

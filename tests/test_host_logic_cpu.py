@@ -416,3 +416,27 @@ def test_conv1x1_fallback_equals_conv2d(cout, cin, with_res):
     rx, rw, rb = torch.autograd.grad(ref, (x, w, b), gy)
     for a, r in ((gx, rx), (gw, rw), (gb, rb)):
         assert (a - r).abs().max() <= 2e-4 * r.abs().max()
+
+
+def test_bench_runs_every_learner_step_on_every_rank():
+    """A learner step contains the gradient all-reduce of the rank's group: bench.py must never run one on a subset of the
+    ranks (round 2's 8-GPU league run waited 10 minutes in exactly that: an extra traced step on rank 0 only)."""
+    import ast
+    import inspect
+    import bench
+    tree = ast.parse(inspect.getsource(bench.run_b200))
+    step_names = {'step_resident', 'step_e2e', 'timed', 'gemm_family_in_step', 'barrier'}
+
+    def mentions_rank(node):
+        return any(isinstance(n, ast.Name) and n.id in ('rank', 'local_rank') for n in ast.walk(node))
+
+    def uses_step(node):
+        return any(isinstance(n, ast.Name) and n.id in step_names for n in ast.walk(node))
+
+    offenders = []
+    for node in ast.walk(tree):
+        if isinstance(node, ast.If) and mentions_rank(node.test):
+            offenders += [ast.unparse(s)[:80] for s in node.body + node.orelse if uses_step(s)]
+        if isinstance(node, ast.IfExp) and mentions_rank(node.test) and (uses_step(node.body) or uses_step(node.orelse)):
+            offenders.append(ast.unparse(node)[:80])
+    assert not offenders, offenders

@@ -84,18 +84,30 @@ HEADS = ['action_type', 'delay', 'queued', 'selected_units', 'target_unit', 'tar
 # matmul operand rounding emulation (precision study only)
 # --------------------------------------------------------------------------------------------
 _EMU = 'fp32'
+_EMU_LAYERS = None      # None: every product; else a tuple of layer-name prefixes the emulation is limited to
 
 
-def set_matmul_emulation(mode: str):
-    global _EMU
-    assert mode in ('fp32', 'tf32', 'bf16', 'bf16x3')
-    _EMU = mode
+def set_matmul_emulation(mode: str, layers=None):
+    """mode: operand rounding of the emulated products - 'fp32' (none), 'tf32', 'bf16' (both operands: the 1-term tensor-core
+    product), 'bf16_w' / 'bf16_a' (only the weight / only the activation: what a 2-term product a.b_hi / a_hi.b keeps),
+    'bf16x3' (the 3-term split, fp32-class).  layers: limit it to the layers whose parameter name starts with one of these
+    prefixes ('@attention' selects the un-named attention products)."""
+    global _EMU, _EMU_LAYERS
+    assert mode in ('fp32', 'tf32', 'bf16', 'bf16x3', 'bf16_w', 'bf16_a')
+    _EMU, _EMU_LAYERS = mode, (tuple(layers) if layers is not None else None)
 
 
-def _rnd(x: Tensor) -> Tensor:
-    if _EMU == 'fp32' or _EMU == 'bf16x3':
+def _rnd(x: Tensor, name: str = '', operand: str = 'a') -> Tensor:
+    mode = _EMU
+    if _EMU_LAYERS is not None and not name.startswith(_EMU_LAYERS):
+        mode = 'fp32'
+    if mode == 'bf16_w':
+        mode = 'bf16' if operand == 'b' else 'fp32'
+    elif mode == 'bf16_a':
+        mode = 'bf16' if operand == 'a' else 'fp32'
+    if mode == 'fp32' or mode == 'bf16x3':
         return x  # bf16x3 (hi*hi + hi*lo + lo*hi) keeps ~16 mantissa bits: treated as fp32 here
-    if _EMU == 'bf16':
+    if mode == 'bf16':
         return x.to(torch.bfloat16).to(torch.float32)
     # tf32: round-to-nearest-even onto a 10-bit mantissa
     i = x.contiguous().view(torch.int32)
@@ -105,13 +117,13 @@ def _rnd(x: Tensor) -> Tensor:
 
 def _fc(P: Params, name: str, x: Tensor, relu: bool = False) -> Tensor:
     """fc_block(in,out[,ReLU]) — ctools/torch_utils/network/nn_module.py:231-270 (Linear at index 0)."""
-    y = F.linear(_rnd(x), _rnd(P[name + '.0.weight']), P[name + '.0.bias'])
+    y = F.linear(_rnd(x, name, 'a'), _rnd(P[name + '.0.weight'], name, 'b'), P[name + '.0.bias'])
     return torch.relu(y) if relu else y
 
 
 def _conv(P: Params, name: str, x: Tensor, pad: int, relu: bool = False) -> Tensor:
     """conv2d_block(...) — nn_module.py:119-174 (Conv2d at index 0, norm 'none')."""
-    y = F.conv2d(_rnd(x), _rnd(P[name + '.0.weight']), P[name + '.0.bias'], padding=pad)
+    y = F.conv2d(_rnd(x, name, 'a'), _rnd(P[name + '.0.weight'], name, 'b'), P[name + '.0.bias'], padding=pad)
     return torch.relu(y) if relu else y
 
 
@@ -119,8 +131,8 @@ def _ln(P: Params, name: str, x: Tensor) -> Tensor:
     return F.layer_norm(x, (x.shape[-1],), P[name + '.weight'], P[name + '.bias'], 1e-5)
 
 
-def _mm(a: Tensor, b: Tensor) -> Tensor:
-    return torch.matmul(_rnd(a), _rnd(b))
+def _mm(a: Tensor, b: Tensor, name: str = '@attention') -> Tensor:
+    return torch.matmul(_rnd(a, name, 'a'), _rnd(b, name, 'b'))
 
 
 def sequence_mask(lengths: Tensor, max_len: int) -> Tensor:
@@ -340,8 +352,8 @@ def value_encoder(P: Params, vf: Dict[str, Tensor], spatial_x: int) -> Tensor:
 # --------------------------------------------------------------------------------------------
 def lnlstm_cell(P: Params, pre: str, x: Tensor, h: Tensor, c: Tensor) -> Tuple[Tensor, Tensor]:
     """LayerNormLSTMCell.forward, lstm.py:138-153; gate order in/forget/cell/out; carried c is layer-normed."""
-    ig = _ln(P, pre + '.layernorm_i', _mm(x, P[pre + '.weight_ih'].t()))
-    hg = _ln(P, pre + '.layernorm_h', _mm(h, P[pre + '.weight_hh'].t()))
+    ig = _ln(P, pre + '.layernorm_i', _mm(x, P[pre + '.weight_ih'].t(), pre + '.weight_ih'))
+    hg = _ln(P, pre + '.layernorm_h', _mm(h, P[pre + '.weight_hh'].t(), pre + '.weight_hh'))
     i, f, g, o = (ig + hg).chunk(4, 1)
     c2 = _ln(P, pre + '.layernorm_c', torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g))
     h2 = torch.sigmoid(o) * torch.tanh(c2)

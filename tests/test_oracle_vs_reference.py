@@ -317,3 +317,42 @@ def test_default_map_size_matches_reference(su_action_mask):
     for name, p in model.named_parameters():
         if p.requires_grad:
             _close(P[name].grad, p.grad, rtol=1e-3, atol=1e-4 * max(p.grad.abs().max().item(), 1e-4 * gmax), name='grad/' + name)
+
+
+def test_only_update_baseline_with_value_feature_product_vs_reference(monkeypatch):
+    """model.only_update_baseline: True (model.py:138-140): the critic reads DETACHED lstm output / baseline feature, so the value
+    losses train only the value networks and the ValueEncoder.  Product host logic (kernel stand-ins, exact operand split)
+    against the real reference: values and every gradient."""
+    from distar_b200 import ops
+    from distar_b200.model import Model
+    from distar_b200.rl_loss import ReinforcementLoss
+    ref_model, cfg, mods = ref_import.load_reference(spatial=128, enable_baselines=('winloss',), use_value_feature=True)
+    ref_model.only_update_baseline = True
+    sd = init_state_dict(seed=6, baselines=('winloss',), use_value_feature=True)
+    ref_model.load_state_dict(sd, strict=True)
+    batch = synth_rl_batch(2, 2, seed=27, entity_num='random', max_su=5, value_feature=True)
+    ref_model.zero_grad()
+    r_out = ref_model.rl_learner_forward(**tree_clone(batch))
+    r_info = mods['ReinforcementLoss'](cfg.learner, 'MP0').compute_loss(r_out)
+    r_info['total_loss'].backward()
+    ops.enable_host_logic_testing(True)
+    monkeypatch.setattr(ops, 'split_bf16', lambda x: (x.contiguous(), torch.zeros_like(x)))
+    try:
+        mine = Model({'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': ['winloss'], 'only_update_baseline': True},
+                      'learner': {'use_value_feature': True}}, use_value_network=True, seed=0)
+        mine.load_state_dict(sd)
+        mine.zero_grad()
+        out = mine.rl_learner_forward(**tree_clone(batch))
+        info = ReinforcementLoss(None, 'MP0').compute_loss(out)
+        info['total_loss'].backward()
+    finally:
+        ops.enable_host_logic_testing(False)
+    _close(out['value']['winloss'], r_out['value']['winloss'], rtol=1e-3, name='value')
+    ref_grads = dict(ref_model.named_parameters())
+    gmax = max(p.grad.abs().max().item() for p in ref_model.parameters() if p.requires_grad and p.grad is not None)
+    for n, p in mine.named_parameters():
+        if not p.requires_grad:
+            continue
+        rg = ref_grads[n].grad
+        rg = torch.zeros_like(p) if rg is None else rg
+        assert (p.grad - rg).abs().max().item() <= 2e-3 * max(rg.abs().max().item(), 1e-3 * gmax), n

@@ -39,11 +39,26 @@ class SLLearner(BaseLearner):
         self._optimizer = ops.FlatAdam(m.flat_param, m.flat_grad, lr=cfg.learning_rate, betas=(0.9, 0.999), eps=1e-8,
                                        weight_decay=cfg.weight_decay, max_norm=cfg.grad_clip.get('threshold', 1.4),
                                        clip_type=cfg.grad_clip.get('type', 'none'), layout=m.optimizer_layout(), owner=m)
+        # the schedulers are the reference's own (base_learner.py:168-181), acting on FlatAdam's param group
         decay, interval = cfg.get('lr_decay', 1.), int(cfg.get('lr_decay_interval', 1e20))
-        self._lr_scheduler = torch.optim.lr_scheduler.MultiStepLR(
-            self._optimizer, milestones=list(range(0, interval * 20, interval))[1:], gamma=decay)
+        if cfg.get('use_warmup', False):
+            from distar.ctools.torch_utils.lr_scheduler_util import GradualWarmupScheduler
+            decay, interval = cfg.get('lr_decay', 0.9), int(cfg.get('lr_decay_interval', 10000))
+            self._after_lr_scheduler = torch.optim.lr_scheduler.MultiStepLR(
+                self._optimizer, milestones=list(range(0, interval * 40, interval))[1:], gamma=decay)
+            self._lr_scheduler = GradualWarmupScheduler(optimizer=self._optimizer, multiplier=cfg.get('multiplier', 1),
+                                                        total_epoch=cfg.get('warm_up_steps', 10000),
+                                                        after_scheduler=self._after_lr_scheduler)
+        else:
+            self._lr_scheduler = torch.optim.lr_scheduler.MultiStepLR(
+                self._optimizer, milestones=list(range(0, interval * 20, interval))[1:], gamma=decay)
 
-    def _setup_dataloader(self):
+    def _setup_dataloader(self):                                              # sl_learner.py:40-44
+        if self._whole_cfg.learner.job_type == 'train':
+            from distar.agent.default.sl_training.sl_dataloader import SLDataloader     # the reference's replay-decoding loader
+            self._dataloader = SLDataloader(self._whole_cfg)
+            return
+        # any other job type: seeded synthetic batches (the role of the reference's FakeDataloader)
         from distar_b200.synth import synth_sl_batch, tree_map
         cfg = self._whole_cfg.learner.data
         batch = tree_map(lambda t: t.to(self._device), synth_sl_batch(cfg.batch_size, cfg.trajectory_length, seed=0))

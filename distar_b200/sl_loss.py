@@ -49,6 +49,17 @@ class SupervisedLoss:
         self.world_size = get_world_size()
         self.total_batch_size: Optional[torch.Tensor] = None
 
+    LOGGED = ['total_loss', 'action_type_loss', 'delay_loss', 'queued_loss', 'selected_units_loss', 'selected_units_loss_norm',
+              'selected_units_end_flag_loss', 'target_unit_loss', 'target_location_loss', 'action_type_acc', 'delay_distance_L1',
+              'queued_acc', 'selected_units_iou', 'target_unit_acc', 'target_location_distance_L2']
+
+    def register_stats(self, record, tb_logger) -> None:
+        """sl_loss.py:68-98: BaseLearner.register_stats (base_learner.py:235-236) asks the loss to register what compute_loss
+        returns; the framework's variable record raises on any key it has not been told about (log_helper.py:356-364)."""
+        for k in self.LOGGED:
+            record.register_var(k)
+            tb_logger.register_var(k)
+
     # ---- criteria (sl_loss.py:54-58): plain CE for the pointer head, optionally smoothed CE elsewhere
     def _ce(self, logits, labels, smooth: bool = False):
         if smooth:

@@ -76,3 +76,42 @@ def test_b200_pipeline_runs_under_the_reference_learner_framework(pipeline):
     ref_opt = torch.optim.Adam(ref_model.parameters(), lr=1e-5, betas=(0.0, 0.99), eps=1e-5)
     ref_opt.load_state_dict(ck['optimizer'])
     assert len(ref_opt.state_dict()['state']) == len(ck['optimizer']['state'])
+
+
+def test_b200_sl_pipeline_runs_under_the_reference_learner_framework(pipeline):
+    """SLLearner of the b200 pipeline under the reference's BaseLearner on the stock bin/sl_user_config.yaml (momentum_norm clip,
+    warm-up scheduler, weight decay), synthetic batches (job_type != 'train'): the first 6 iterations only carry the LSTM state
+    (sl_learner.py:64-72), then the weights move; the checkpoint hook's file loads back."""
+    from distar.agent.import_helper import import_module
+    from distar.ctools.utils import read_config
+    from distar.ctools.worker.learner.base_learner import BaseLearner
+    cfg = read_config(os.path.join(ref_import.REFERENCE_ROOT, 'distar/bin/sl_user_config.yaml'))
+    cfg.common.experiment_name = 'plug_sl'
+    cfg.common.type = 'sl'
+    cfg.learner.agent = 'b200'
+    cfg.learner.job_type = 'eval'
+    cfg.learner.use_cuda = False
+    cfg.learner.data.batch_size = 1
+    cfg.learner.data.trajectory_length = 2
+    cfg.model = {'spatial_x': 128, 'spatial_y': 128}
+    SLLearner = import_module('b200', 'SLLearner')
+    assert issubclass(SLLearner, BaseLearner)
+    learner = SLLearner(cfg)
+    from distar_b200.ops import FlatAdam
+    assert isinstance(learner.optimizer, FlatAdam) and learner.optimizer.clip_type == 'momentum_norm'
+    w0 = learner.model.flat_param.clone()
+    learner.run(max_iterations=6)
+    assert torch.equal(w0, learner.model.flat_param)              # iterations 0..5: no update yet
+    learner.run(max_iterations=2)
+    assert learner.last_iter.val == 8 and not torch.equal(w0, learner.model.flat_param)
+    # warm-up of the stock config (use_warmup, 20000 steps).  The scheduler is stepped by the framework's LrSchdulerHook after
+    # every iteration (learner_hook.py:111-112) AND by _train after every optimiser step (sl_learner.py:70), as in the reference:
+    # 8 + 2 steps so far
+    from distar.ctools.torch_utils.lr_scheduler_util import GradualWarmupScheduler
+    assert isinstance(learner.lr_scheduler, GradualWarmupScheduler)
+    assert abs(learner.optimizer.param_groups[0]['lr'] - 1e-3 * 10 / 20000) < 1e-12
+    ckpt_dir = os.path.join('experiments', 'plug_sl', 'checkpoint')
+    found = [os.path.join(r, f) for r, _d, fs in os.walk(os.path.join('experiments', 'plug_sl')) for f in fs if f.endswith('.pth.tar') or f.endswith('.pth')]
+    assert found, 'SaveCkptHook wrote nothing (looked under %s)' % ckpt_dir
+    ck = torch.load(found[-1], map_location='cpu', weights_only=False)
+    assert set(ck.keys()) >= {'model', 'optimizer', 'last_iter'}

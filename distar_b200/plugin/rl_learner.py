@@ -69,6 +69,12 @@ class RLLearner(_Base):
     def _get_iter_data(self):
         return next(self._dataloader)
 
+    def _reset_value(self):                                                   # rl_learner.py:225-228
+        """League reset of the critic: fresh value networks (and ValueEncoder), policy untouched."""
+        fresh = Model(self._whole_cfg, use_value_network=True)
+        value_state_dict = {k: v for k, v in fresh.state_dict().items() if 'value' in k or 'auxiliary' in k}
+        self.model.load_state_dict(value_state_dict, strict=False)
+
     @property
     def model(self):
         return self._model

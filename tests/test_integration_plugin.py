@@ -70,6 +70,14 @@ def test_b200_pipeline_runs_under_the_reference_learner_framework(pipeline):
     assert resumed.last_iter.val == 2 and resumed.optimizer.t == learner.optimizer.t == 2
     assert torch.equal(resumed.model.flat_param, learner.model.flat_param)
     assert torch.equal(resumed.optimizer.exp_avg_sq, learner.optimizer.exp_avg_sq)
+    # league value reset (rl_learner.py:225-242): critic re-initialised, policy untouched, optimiser rebuilt
+    before = {k: v.clone() for k, v in resumed.model.state_dict().items()}
+    resumed.reset_value()
+    after = resumed.model.state_dict()
+    assert all(torch.equal(before[k], after[k]) for k in before if 'value' not in k)
+    assert any(not torch.equal(before[k], after[k]) for k in before if k.startswith('value_networks.'))
+    assert any(not torch.equal(before[k], after[k]) for k in before if k.startswith('value_encoder.'))
+    assert resumed.optimizer.t == 0
     # the reference's torch.optim.Adam accepts the optimizer entry of OUR checkpoint (same per-parameter layout)
     ref_model, _cfg_ref, _mods = ref_import.load_reference(spatial=128, enable_baselines=('winloss',), use_value_feature=True)
     ref_model.load_state_dict(ck['model'], strict=True)

@@ -50,6 +50,11 @@ def test_b200_pipeline_runs_under_the_reference_learner_framework(pipeline):
     RLLearner = import_module('b200', 'RLLearner')            # how rl_train.py:43 picks the class
     assert issubclass(RLLearner, BaseLearner)
     assert import_module('b200', 'Agent').__name__ == 'Agent' and import_module('b200', 'SLLearner').__name__ == 'SLLearner'
+    # the b200 Agent computes with our Model; the default pipeline's Agent, importable side by side, keeps the reference's
+    import distar.agent.default.agent as default_agent
+    from distar_b200.model import Model as B200Model
+    assert import_module('b200', 'Agent').__init__.__globals__['Model'] is B200Model
+    assert default_agent.Model is not B200Model and default_agent.Agent.__init__.__globals__['Model'] is default_agent.Model
     learner = RLLearner(_cfg('plug_a'))
     from distar_b200.model import Model
     from distar_b200.ops import FlatAdam

@@ -128,3 +128,50 @@ def test_b200_sl_pipeline_runs_under_the_reference_learner_framework(pipeline):
     assert found, 'SaveCkptHook wrote nothing (looked under %s)' % ckpt_dir
     ck = torch.load(found[-1], map_location='cpu', weights_only=False)
     assert set(ck.keys()) >= {'model', 'optimizer', 'last_iter'}
+
+
+def test_stock_agent_runs_on_the_b200_model(pipeline):
+    """The reference's Agent (agent.py:97-145), built through the b200 pipeline on the stock config at its default 160 x 152 map
+    size: the constructor's realtime warm-up, then compute_logp_action / compute_teacher_logit on the reference's own
+    fake_step_data return exactly the structure (keys, shapes, dtypes) the reference model returns for the same input."""
+    from distar.agent.import_helper import import_module
+    from distar.agent.default.lib.features import fake_step_data
+    from distar.ctools.utils import read_config
+    import distar.agent.default.agent as default_agent
+    cfg = read_config(os.path.join(ref_import.REFERENCE_ROOT, 'distar/bin/rl_user_config.yaml'))
+    cfg.common.type = 'rl'                         # as bin/rl_train.py sets it
+    cfg.actor.use_cuda = False
+    cfg.actor.job_type = 'train'                   # -> a teacher model too (agent.py:142-143)
+    cfg.env.realtime = True                        # -> warm-up forward inside the constructor (agent.py:120-127)
+    cfg.agent.z_path = 'unused.json'
+    from distar.agent.default.lib import features as F
+    F.SPATIAL_SIZE[:] = [152, 160]
+    agent = import_module('b200', 'Agent')(cfg)
+    from distar_b200.model import Model
+    assert isinstance(agent.model, Model) and isinstance(agent.teacher_model, Model)
+    assert (agent.model.spatial_x, agent.model.spatial_y) == (160, 152) and agent._hidden_size == 384 and agent._num_layers == 3
+    ref_model = default_agent.Model(cfg)
+
+    def structure(tree, path=''):
+        if torch.is_tensor(tree):
+            return {path: (tuple(tree.shape), tree.dtype)}
+        out = {}
+        items = tree.items() if isinstance(tree, dict) else enumerate(tree)
+        for k, v in items:
+            out.update(structure(v, '%s/%s' % (path, k)))
+        return out
+    obs = fake_step_data(share_memory=True, batch_size=2, hidden_size=384, hidden_layer=3, train=False)
+    with torch.no_grad():
+        torch.manual_seed(0)
+        mine = agent.model.compute_logp_action(**obs)
+        torch.manual_seed(0)
+        want = ref_model.compute_logp_action(**obs)
+    sm, sw = structure(mine), structure(want)
+    # the number of pointer-network steps depends on the sampled selection (different weights): compare with that dim freed
+    free = lambda d: {k: ((s[0],) + s[2:] if k == '/logit/selected_units' else s, t) for k, (s, t) in d.items()}
+    assert free(sm) == free(sw)
+    tobs = fake_step_data(share_memory=True, batch_size=2, hidden_size=384, hidden_layer=3, train=True)
+    with torch.no_grad():
+        mine_t = agent.teacher_model.compute_teacher_logit(**tobs)
+        want_t = ref_model.compute_teacher_logit(**tobs)
+    assert structure(mine_t) == structure(want_t)

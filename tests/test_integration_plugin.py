@@ -175,3 +175,20 @@ def test_stock_agent_runs_on_the_b200_model(pipeline):
         mine_t = agent.teacher_model.compute_teacher_logit(**tobs)
         want_t = ref_model.compute_teacher_logit(**tobs)
     assert structure(mine_t) == structure(want_t)
+
+
+def test_pipeline_exposes_every_class_import_helper_can_ask_for(pipeline):
+    """import_helper.MODULE_PATHS: RLLearner, SLLearner, Agent, ReplayDecoder.  The replay decoder is game-protocol CPU code the
+    pipeline re-exports from the reference; this image lacks its third-party parsers (mpyq ...), so the lookup must get as far
+    as the STOCK module's own imports."""
+    from distar.agent.import_helper import MODULE_PATHS, import_module
+    assert set(MODULE_PATHS) == {'RLLearner', 'SLLearner', 'Agent', 'ReplayDecoder'}
+    for name in ('RLLearner', 'SLLearner', 'Agent'):
+        assert import_module('b200', name).__name__ == name
+    try:
+        cls = import_module('b200', 'ReplayDecoder')
+    except ModuleNotFoundError as e:
+        assert not (e.name or '').startswith('distar.agent.b200') and not (e.name or '').startswith('distar_b200'), e
+    else:
+        import distar.agent.default.replay_decoder as stock
+        assert cls is stock.ReplayDecoder

@@ -138,7 +138,8 @@ class WeightPublisher:
 
     def __init__(self, model: Model):
         self.model = model
-        self.names = [n for n in model._offsets if not n.startswith('value_networks')]
+        # learner_comm.py:74: actors never see the critic ('value_networks' / 'value_encoder' keys stay on the learner)
+        self.names = [n for n in model._offsets if not n.startswith(('value_networks', 'value_encoder'))]
         segs = sorted((model._offsets[n][0], model._offsets[n][1], n) for n in self.names)
         # coalesce neighbouring slots (16-byte alignment gaps are copied along) into a few contiguous ranges
         self.ranges: List[List[int]] = []

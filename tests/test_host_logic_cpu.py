@@ -325,13 +325,24 @@ def test_sl_learner_steps(sd):
     assert float(h0[0].abs().sum()) > 0
 
 
-def test_weight_publication_maps_between_arena_layouts(sd):
-    """WeightPublisher / WeightSubscriber on CPU tensors: a learner arena (with value networks) into an actor arena (without)."""
+@pytest.mark.parametrize('value_feature', [False, True])
+def test_weight_publication_maps_between_arena_layouts(sd, value_feature):
+    """WeightPublisher / WeightSubscriber on CPU tensors: a learner arena (with value networks, optionally the ValueEncoder) into
+    an actor arena (without); and the actor's own load of a learner checkpoint (actor.py:71-73 strips 'value_networks' only)."""
     from distar_b200.serving import WeightPublisher, WeightSubscriber
-    learner_model = _model(sd)
-    actor = Model({'model': {'spatial_x': 128, 'spatial_y': 128}}, use_value_network=False, seed=1)
+    if value_feature:
+        sd = init_state_dict(seed=3, baselines=('winloss', 'build_order'), use_value_feature=True)
+        learner_model = Model({'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': ['winloss', 'build_order']},
+                               'learner': {'use_value_feature': True}}, use_value_network=True, seed=0)
+        learner_model.load_state_dict(sd)
+    else:
+        learner_model = _model(sd)
+    actor = Model({'model': {'spatial_x': 128, 'spatial_y': 128}, 'learner': {'use_value_feature': value_feature}},
+                  use_value_network=False, seed=1).eval().share_memory()
+    res = actor.load_state_dict({k: v for k, v in learner_model.state_dict().items() if 'value_networks' not in k}, strict=False)
+    assert not res.missing_keys and all(k.startswith('value_encoder.') for k in res.unexpected_keys)
     pub, sub = WeightPublisher(learner_model), WeightSubscriber(actor)
-    assert len(pub.ranges) <= 4 and not any(n.startswith('value_networks') for n in pub.names)
+    assert len(pub.ranges) <= 4 and not any(n.startswith(('value_networks', 'value_encoder')) for n in pub.names)
     with torch.no_grad():
         learner_model.flat_param.add_(0.5)
     assert pub.publish() == 1

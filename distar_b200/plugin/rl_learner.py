@@ -109,7 +109,21 @@ class RLLearner(_Base):
             self._loss.raise_on_bad_action()
             if self._use_distributed:
                 self._model.sync_gradients()
-            gradient = self._optimizer.step(grad_scale=1.0 / self._world_size)      # clip_grad_norm_ + Adam, fused
+            scale = 1.0 / self._world_size                 # the arena holds the SUM over ranks; the step folds the average in
+            save = getattr(self, '_save_grad', False) and self._last_iter.val % self.save_log_freq == 0
+            if save:                                                               # rl_learner.py:118-124
+                for k, param in m.named_parameters():
+                    if param.grad is not None and param.requires_grad:
+                        self.grad_tb_logger.add_scalar(k, torch.norm(param.grad).item() * scale, global_step=self._last_iter.val)
+                        self.model_tb_logger.add_scalar(k, torch.norm(param.data).item(), global_step=self._last_iter.val)
+            gradient = self._optimizer.step(grad_scale=scale)                       # clip_grad_norm_ + Adam, fused
+            if save:                                                               # rl_learner.py:126-130 (gradients after the clip)
+                max_norm = self._optimizer.max_norm
+                coef = min(1.0, max_norm / (float(gradient) + 1e-6)) if max_norm is not None else 1.0
+                for k, param in m.named_parameters():
+                    if param.grad is not None and param.requires_grad:
+                        self.clip_grad_tb_logger.add_scalar(k, torch.norm(param.grad).item() * scale * coef,
+                                                            global_step=self._last_iter.val)
         self._log_buffer['gradient'] = float(gradient)
         self._log_buffer['backward_time'] = self._timer.value
         self._log_buffer.update(log_vars)

@@ -60,8 +60,23 @@ def test_b200_pipeline_runs_under_the_reference_learner_framework(pipeline):
     from distar_b200.ops import FlatAdam
     assert isinstance(learner.model, Model) and isinstance(learner.optimizer, FlatAdam)
     assert isinstance(learner.lr_scheduler, torch.optim.lr_scheduler.MultiStepLR)
+    # save_grad (rl_learner.py:35-47,118-130; set up by the stock constructor in train mode): per-parameter norms before / after
+    # the clip go to the three tensorboard writers
+    class _Writer:
+        def __init__(self):
+            self.rows = {}
+
+        def add_scalar(self, k, v, global_step=None):
+            self.rows[k] = v
+    learner._save_grad, learner.save_log_freq = True, 1
+    learner.grad_tb_logger, learner.clip_grad_tb_logger, learner.model_tb_logger = _Writer(), _Writer(), _Writer()
     w0 = learner.model.flat_param.clone()
     learner.run(max_iterations=2)                             # before_run / after_iter / after_run hooks of the framework
+    names = [n for n, p in learner.model.named_parameters() if p.requires_grad]
+    assert set(learner.grad_tb_logger.rows) == set(names) == set(learner.clip_grad_tb_logger.rows)
+    total = sum(v * v for v in learner.grad_tb_logger.rows.values()) ** 0.5
+    clipped = sum(v * v for v in learner.clip_grad_tb_logger.rows.values()) ** 0.5
+    assert clipped <= total + 1e-6 and clipped <= learner.optimizer.max_norm * 1.001
     assert learner.last_iter.val == 2 and not torch.equal(w0, learner.model.flat_param)
     ckpt_dir = os.path.join('experiments', 'plug_a', 'MP0', 'checkpoint')
     files = sorted(os.listdir(ckpt_dir))

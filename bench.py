@@ -45,6 +45,9 @@ def parse():
                     help='number of encoder chunks whose entity-transformer activations are kept (not recomputed)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--value-feature', action='store_true',
+                    help='rl / league: learner.use_value_feature True (the reference self-play default): ValueEncoder in front of the '
+                         'baselines, value_feature in the batch.  Off by default: BASELINE configs do not include it')
     ap.add_argument('--e2e-format', default='compact', choices=['compact', 'padded'],
                     help='what crosses PCIe every step of the e2e measurement: compact = un-padded trajectories expanded on the '
                          'GPU (distar_b200.batch, the product path); padded = the reference collate layout (1.47 GB / step)')
@@ -390,7 +393,8 @@ def run_b200(args, rank, world, local_rank):
         dist.init_process_group('nccl')
     B, T = args.batch, args.unroll
     rl = args.workload != 'sl'
-    cfg = {'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': ['winloss']}}
+    cfg = {'model': {'spatial_x': 128, 'spatial_y': 128, 'enable_baselines': ['winloss']},
+           'learner': {'use_value_feature': bool(args.value_feature and rl)}}
     model = Model(cfg, use_value_network=rl, seed=0, gemm_terms=args.terms, encoder_chunk=args.encoder_chunk,
                   checkpoint_encoder=not args.no_checkpoint, keep_chunks=args.keep_chunks).cuda()
     player, group, group_ranks = 'MP0', None, list(range(world))
@@ -403,10 +407,10 @@ def run_b200(args, rank, world, local_rank):
                 player, group, group_ranks = pid, g, ranks
         # the exploiters of a league run with DAPO off (rl_loss.py:22-24); MP keeps the user config (use_dapo False by default)
         learner = RLLearner(model, player, dict(USER_LEARNER_CFG), lr=1e-5, max_norm=1.0, group=group)
-        host = synth_rl_batch(B, T, seed=1000 * rank + 17 * LEAGUE_PLAYERS.index(player))
+        host = synth_rl_batch(B, T, seed=1000 * rank + 17 * LEAGUE_PLAYERS.index(player), value_feature=args.value_feature)
     elif rl:
         learner = RLLearner(model, 'MP0', None, lr=1e-5, max_norm=1.0)
-        host = synth_rl_batch(B, T, seed=1000 * rank)
+        host = synth_rl_batch(B, T, seed=1000 * rank, value_feature=args.value_feature)
     else:
         # bin/sl_user_config.yaml: Adam(lr 1e-3, weight_decay 1e-5), clip 'momentum_norm' 1.4, su_mask off, warm-up 20000
         sl_cfg = {'learner': {'su_mask': False, 'learning_rate': 1e-3, 'weight_decay': 1e-5, 'use_warmup': True,
@@ -615,6 +619,7 @@ def run_b200(args, rank, world, local_rank):
         'data': 'synthetic',
         'config': {'workload': workload,
                    'batch_per_gpu': B, 'unroll': T, 'entities': 512, 'spatial': '128x128', 'global_batch': world * B,
+                   'use_value_feature': bool(args.value_feature and rl),
                    'parallelism': 'dp%d' % world if args.workload != 'league' else
                                   '+'.join('dp%d(%s)' % (len(r), p) for p, r in layout),
                    'encoder_chunk': args.encoder_chunk,

@@ -54,6 +54,16 @@ def test_expand_inverts_compact_on_cpu(B, T, entities):
         ops.enable_host_logic_testing(False)
 
 
+def test_value_feature_travels_through_the_compact_format():
+    """learner.use_value_feature: the value_feature entry is already wire-sized (uint8 / bool / int16 fields) and passes through."""
+    ops.enable_host_logic_testing(True)
+    try:
+        batch = synth_rl_batch(2, 3, seed=4, entity_num='random', max_su=5, value_feature=True)
+        _same(expand_rl_batch(compact_rl_batch(batch), 'cpu'), _reference_view(batch))
+    finally:
+        ops.enable_host_logic_testing(False)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('B,T,entities', [(3, 4, 'random'), (4, 8, None)])
 def test_expand_on_device_is_bit_exact(B, T, entities):
